@@ -1,0 +1,351 @@
+"""ctypes binding of the CPU oracle (oracle/myrio_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs; the product package
+(myrio_b200/) must never import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libmyrio_oracle.so")
+
+SIM_COSINE, SIM_JACARD_TANIMOTO, SIM_OVERLAP = 0, 1, 2
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
+    src = os.path.join(_HERE, "myrio_oracle.c")
+    hdr = os.path.join(_HERE, "myrio_oracle.h")
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, hdr)
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u16p = np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+class _ClusterParams(C.Structure):
+    _fields_ = [
+        ("t2", C.c_uint64),
+        ("similarity", C.c_int),
+        ("n_init", C.c_size_t),
+        ("init_row_off", C.c_void_p),
+        ("init_keys", C.c_void_p),
+        ("init_vals", C.c_void_p),
+        ("expected_nb_of_clusters", C.c_size_t),
+        ("eta_improvement", C.c_float),
+        ("nb_iters_max", C.c_size_t),
+        ("has_silhouette", C.c_int),
+        ("ssdcf", C.c_float),
+        ("threads", C.c_int),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.myo_phred_correct_table.restype = C.POINTER(C.c_float)
+        L.myo_kmer_key.restype = C.c_uint64
+        L.myo_kmer_key.argtypes = [_u8p, C.c_int]
+        L.myo_sort_reduce_f32.restype = C.c_size_t
+        L.myo_sort_reduce_f32.argtypes = [_u64p, C.c_size_t, _u64p, _f32p]
+        L.myo_sort_reduce_u16.restype = C.c_size_t
+        L.myo_sort_reduce_u16.argtypes = [_u64p, C.c_size_t, _u64p, _u16p]
+        L.myo_count_reads.restype = C.c_int
+        L.myo_count_reads.argtypes = [_u8p, _u8p, _u64p, C.c_size_t, C.c_int, C.c_float, C.c_int,
+                                      _u64p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.myo_resample_pick.restype = C.c_uint32
+        L.myo_resample_pick.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.myo_count_leaves.restype = C.c_int
+        L.myo_count_leaves.argtypes = [_u8p, _u64p, C.c_size_t, C.c_int, C.c_uint32, C.c_uint64,
+                                       C.c_uint64, C.c_int, _u64p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+        L.myo_normalize_rows_f32.restype = None
+        L.myo_normalize_rows_f32.argtypes = [_u64p, C.c_size_t, _f32p, C.c_int]
+        L.myo_normalize_rows_u16.restype = None
+        L.myo_normalize_rows_u16.argtypes = [_u64p, C.c_size_t, _u16p, _f32p, C.c_int]
+        L.myo_dot.restype = C.c_float
+        L.myo_dot.argtypes = [_u64p, _f32p, C.c_size_t, _u64p, _f32p, C.c_size_t]
+        L.myo_similarity.restype = C.c_float
+        L.myo_similarity.argtypes = [C.c_int, C.c_int, _u64p, _f32p, C.c_size_t, _u64p, _f32p,
+                                     C.c_size_t]
+        L.myo_score_all.restype = None
+        L.myo_score_all.argtypes = [C.c_int, _u64p, _u64p, _f32p, C.c_size_t, _u64p, _f32p,
+                                    C.c_size_t, C.c_int, _f32p]
+        L.myo_topx.restype = None
+        L.myo_topx.argtypes = [_f32p, C.c_size_t, C.c_uint32, C.c_size_t, _f32p, _u32p]
+        L.myo_add.restype = C.c_size_t
+        L.myo_add.argtypes = [_u64p, _f32p, C.c_size_t, _u64p, _f32p, C.c_size_t, _u64p, _f32p]
+        L.myo_centroid.restype = C.c_size_t
+        L.myo_centroid.argtypes = [_u64p, _u64p, _f32p, _u64p, C.c_size_t, _u64p, _f32p]
+        L.myo_invert.restype = None
+        L.myo_invert.argtypes = [_u64p, _u64p, _f32p, C.c_size_t, C.POINTER(C.c_size_t),
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.myo_cluster.restype = C.c_int
+        L.myo_cluster.argtypes = [_u64p, _u64p, _f32p, _u64p, C.c_size_t,
+                                  C.POINTER(_ClusterParams), _i32p, C.POINTER(C.c_uint32),
+                                  C.c_void_p]
+        L.myo_pairwise.restype = None
+        L.myo_pairwise.argtypes = [C.c_int, _u64p, _u64p, _f32p, C.c_size_t, _u64p, _u64p, _f32p,
+                                   C.c_size_t, C.c_int, _f32p]
+        L.myo_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def max_threads() -> int:
+    return int(lib().myo_max_threads())
+
+
+@dataclass
+class Csr:
+    """A batch of sparse vectors: row r = keys[row_off[r]:row_off[r+1]] (sorted) + vals."""
+    row_off: np.ndarray  # uint64 [n+1]
+    keys: np.ndarray     # uint64 [nnz]
+    vals: np.ndarray     # float32 or uint16 [nnz]
+    aux: np.ndarray | None = None  # nb_hck (uint64) for reads, rescale (float32) for leaves
+
+    @property
+    def n_rows(self) -> int:
+        return len(self.row_off) - 1
+
+    def row(self, r: int):
+        b, e = int(self.row_off[r]), int(self.row_off[r + 1])
+        return self.keys[b:e], self.vals[b:e]
+
+
+def phred_correct_table() -> np.ndarray:
+    p = lib().myo_phred_correct_table()
+    return np.ctypeslib.as_array(p, shape=(128,)).copy()
+
+
+def kmer_key(bases: np.ndarray, k: int) -> int:
+    return int(lib().myo_kmer_key(np.ascontiguousarray(bases, np.uint8), k))
+
+
+def sort_reduce_f32(singles):
+    s = np.array(singles, dtype=np.uint64)
+    k = np.zeros(max(1, len(s)), np.uint64)
+    v = np.zeros(max(1, len(s)), np.float32)
+    d = lib().myo_sort_reduce_f32(s, len(s), k, v)
+    return k[:d], v[:d]
+
+
+def sort_reduce_u16(singles):
+    s = np.array(singles, dtype=np.uint64)
+    k = np.zeros(max(1, len(s)), np.uint64)
+    v = np.zeros(max(1, len(s)), np.uint16)
+    d = lib().myo_sort_reduce_u16(s, len(s), k, v)
+    return k[:d], v[:d]
+
+
+def count_reads(bases: np.ndarray, qual: np.ndarray, base_off: np.ndarray, k: int, cutoff: float,
+                threads: int = 0) -> Csr:
+    """data/myrseq.rs:76-111 over a batch. bases: one 2-bit code per byte."""
+    bases = np.ascontiguousarray(bases, np.uint8)
+    qual = np.ascontiguousarray(qual, np.uint8)
+    base_off = np.ascontiguousarray(base_off, np.uint64)
+    n = len(base_off) - 1
+    if len(bases) == 0:
+        bases = np.zeros(1, np.uint8)
+        qual = np.zeros(1, np.uint8)
+    row_off = np.zeros(n + 1, np.uint64)
+    hck = np.zeros(max(1, n), np.uint64)
+    thr = threads if threads > 0 else max_threads()
+    e = lib().myo_count_reads(bases, qual, base_off, n, k, cutoff, thr, row_off, None, None,
+                              hck.ctypes.data)
+    if e:
+        raise ValueError(f"oracle count_reads error {e}")
+    nnz = int(row_off[n])
+    keys = np.zeros(max(1, nnz), np.uint64)
+    vals = np.zeros(max(1, nnz), np.float32)
+    e = lib().myo_count_reads(bases, qual, base_off, n, k, cutoff, thr, row_off,
+                              keys.ctypes.data, vals.ctypes.data, hck.ctypes.data)
+    if e:
+        raise ValueError(f"oracle count_reads error {e}")
+    return Csr(row_off, keys[:nnz], vals[:nnz], hck[:n])
+
+
+def count_leaves(iupac: np.ndarray, base_off: np.ndarray, k: int, nb_resamples: int = 32,
+                 seed: int = 0, leaf_id_base: int = 0, threads: int = 0) -> Csr:
+    """tax/mod.rs:70-148 via tax/store.rs:265-285. iupac: one 4-bit code per byte."""
+    iupac = np.ascontiguousarray(iupac, np.uint8)
+    base_off = np.ascontiguousarray(base_off, np.uint64)
+    n = len(base_off) - 1
+    if len(iupac) == 0:
+        iupac = np.zeros(1, np.uint8)
+    row_off = np.zeros(n + 1, np.uint64)
+    rescale = np.zeros(max(1, n), np.float32)
+    e = lib().myo_count_leaves(iupac, base_off, n, k, nb_resamples, seed, leaf_id_base, threads,
+                               row_off, None, None, rescale.ctypes.data)
+    if e:
+        raise ValueError(f"oracle count_leaves error {e}")
+    nnz = int(row_off[n])
+    keys = np.zeros(max(1, nnz), np.uint64)
+    vals = np.zeros(max(1, nnz), np.uint16)
+    e = lib().myo_count_leaves(iupac, base_off, n, k, nb_resamples, seed, leaf_id_base, threads,
+                               row_off, keys.ctypes.data, vals.ctypes.data, rescale.ctypes.data)
+    if e:
+        raise ValueError(f"oracle count_leaves error {e}")
+    return Csr(row_off, keys[:nnz], vals[:nnz], rescale[:n])
+
+
+def normalize(csr: Csr, threads: int = 0) -> Csr:
+    """f32 rows: data/sparse.rs:380-383; u16 rows: tax/compute.rs:105-106."""
+    n = csr.n_rows
+    if csr.vals.dtype == np.uint16:
+        out = np.zeros(max(1, len(csr.vals)), np.float32)
+        vin = csr.vals if len(csr.vals) else np.zeros(1, np.uint16)
+        lib().myo_normalize_rows_u16(csr.row_off, n, vin, out, threads)
+        return Csr(csr.row_off, csr.keys, out[:len(csr.vals)], csr.aux)
+    vals = np.array(csr.vals, dtype=np.float32, copy=True)
+    if len(vals) == 0:
+        return Csr(csr.row_off, csr.keys, vals, csr.aux)
+    lib().myo_normalize_rows_f32(csr.row_off, n, vals, threads)
+    return Csr(csr.row_off, csr.keys, vals, csr.aux)
+
+
+def _kv(k, v):
+    k = np.ascontiguousarray(k, np.uint64)
+    v = np.ascontiguousarray(v, np.float32)
+    if len(k) == 0:
+        return np.zeros(1, np.uint64), np.zeros(1, np.float32), 0
+    return k, v, len(k)
+
+
+def dot(ak, av, bk, bv) -> np.float32:
+    ak, av, an = _kv(ak, av)
+    bk, bv, bn = _kv(bk, bv)
+    return np.float32(lib().myo_dot(ak, av, an, bk, bv, bn))
+
+
+def similarity(sim: int, pre_normalized: bool, ak, av, bk, bv) -> np.float32:
+    ak, av, an = _kv(ak, av)
+    bk, bv, bn = _kv(bk, bv)
+    return np.float32(lib().myo_similarity(sim, int(pre_normalized), ak, av, an, bk, bv, bn))
+
+
+def score_all(leaves: Csr, qk, qv, sim: int = SIM_COSINE, threads: int = 0) -> np.ndarray:
+    """tax/results.rs:82-93 for one query against normalised leaf vectors."""
+    qk, qv, qn = _kv(qk, qv)
+    out = np.zeros(max(1, leaves.n_rows), np.float32)
+    lk = leaves.keys if len(leaves.keys) else np.zeros(1, np.uint64)
+    lv = leaves.vals if len(leaves.vals) else np.zeros(1, np.float32)
+    lib().myo_score_all(sim, leaves.row_off, lk, lv, leaves.n_rows, qk, qv, qn, threads, out)
+    return out[:leaves.n_rows]
+
+
+def topx(scores: np.ndarray, x: int, id_base: int = 0):
+    scores = np.ascontiguousarray(scores, np.float32)
+    ts = np.zeros(max(1, x), np.float32)
+    ti = np.zeros(max(1, x), np.uint32)
+    s = scores if len(scores) else np.zeros(1, np.float32)
+    lib().myo_topx(s, len(scores), id_base, x, ts, ti)
+    return ts[:x], ti[:x]
+
+
+def add(ak, av, bk, bv):
+    ak, av, an = _kv(ak, av)
+    bk, bv, bn = _kv(bk, bv)
+    ck = np.zeros(an + bn + 1, np.uint64)
+    cv = np.zeros(an + bn + 1, np.float32)
+    n = lib().myo_add(ak, av, an, bk, bv, bn, ck, cv)
+    return ck[:n], cv[:n]
+
+
+def centroid(csr: Csr, member_ids):
+    """clustering.rs:44-53"""
+    ids = np.ascontiguousarray(member_ids, np.uint64)
+    total = int(sum(int(csr.row_off[i + 1] - csr.row_off[i]) for i in ids))
+    ck = np.zeros(total + 1, np.uint64)
+    cv = np.zeros(total + 1, np.float32)
+    idp = ids if len(ids) else np.zeros(1, np.uint64)
+    n = lib().myo_centroid(csr.row_off, csr.keys, np.ascontiguousarray(csr.vals, np.float32), idp,
+                           len(ids), ck, cv)
+    return ck[:n], cv[:n]
+
+
+def invert(leaves: Csr):
+    """Definition of the K3 inverted index: (ukeys, offs, post_leaf, post_val)."""
+    n = leaves.n_rows
+    nu = C.c_size_t(0)
+    lk = leaves.keys if len(leaves.keys) else np.zeros(1, np.uint64)
+    lv = np.ascontiguousarray(leaves.vals, np.float32) if len(leaves.vals) else np.zeros(1, np.float32)
+    lib().myo_invert(leaves.row_off, lk, lv, n, C.byref(nu), None, None, None, None)
+    U, P = nu.value, int(leaves.row_off[n])
+    uk = np.zeros(max(1, U), np.uint64)
+    of = np.zeros(U + 1, np.uint64)
+    pl = np.zeros(max(1, P), np.uint32)
+    pv = np.zeros(max(1, P), np.float32)
+    lib().myo_invert(leaves.row_off, lk, lv, n, C.byref(nu), uk.ctypes.data, of.ctypes.data,
+                     pl.ctypes.data, pv.ctypes.data)
+    return uk[:U], of, pl[:P], pv[:P]
+
+
+def cluster(counts: Csr, t2: int, init: Csr | None, expected_nb_of_clusters: int,
+            eta_improvement: float = 1e-4, nb_iters_max: int = 20, silhouette: float | None = None,
+            sim: int = SIM_COSINE, threads: int = 0):
+    """clustering.rs:55-270 from the step-1 counts. Returns (assign, n_iters, sil)."""
+    n = counts.n_rows
+    p = _ClusterParams()
+    p.t2 = t2
+    p.similarity = sim
+    keep = []
+    if init is not None and init.n_rows > 0:
+        ro = np.ascontiguousarray(init.row_off, np.uint64)
+        ik = np.ascontiguousarray(init.keys, np.uint64)
+        iv = np.ascontiguousarray(init.vals, np.float32)
+        keep += [ro, ik, iv]
+        p.n_init = init.n_rows
+        p.init_row_off = ro.ctypes.data
+        p.init_keys = ik.ctypes.data
+        p.init_vals = iv.ctypes.data
+    else:
+        p.n_init = 0
+    p.expected_nb_of_clusters = expected_nb_of_clusters
+    p.eta_improvement = eta_improvement
+    p.nb_iters_max = nb_iters_max
+    p.has_silhouette = 0 if silhouette is None else 1
+    p.ssdcf = 0.0 if silhouette is None else silhouette
+    p.threads = threads
+    assign = np.zeros(max(1, n), np.int32)
+    sil = np.zeros(max(1, n), np.float32)
+    iters = C.c_uint32(0)
+    ck = counts.keys if len(counts.keys) else np.zeros(1, np.uint64)
+    cv = np.ascontiguousarray(counts.vals, np.float32) if len(counts.vals) else np.zeros(1, np.float32)
+    hck = np.ascontiguousarray(counts.aux, np.uint64) if n else np.zeros(1, np.uint64)
+    e = lib().myo_cluster(counts.row_off, ck, cv, hck, n, C.byref(p), assign, C.byref(iters),
+                          sil.ctypes.data)
+    if e:
+        raise ValueError(f"oracle cluster error {e}")
+    return assign[:n], int(iters.value), sil[:n]
+
+
+def pairwise(rows: Csr, cols: Csr, sim: int = SIM_COSINE, threads: int = 0) -> np.ndarray:
+    out = np.zeros((rows.n_rows, cols.n_rows), np.float32)
+    if out.size == 0:
+        return out
+    lib().myo_pairwise(sim, rows.row_off, rows.keys, np.ascontiguousarray(rows.vals, np.float32),
+                       rows.n_rows, cols.row_off, cols.keys,
+                       np.ascontiguousarray(cols.vals, np.float32), cols.n_rows, threads, out)
+    return out

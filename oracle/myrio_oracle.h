@@ -1,0 +1,160 @@
+/*
+ * myrio_oracle.h -- CPU restatement of Myrio's data-parallel hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under myrio_b200/ (the product) may
+ * include, link or call this.  It is used by tests/, by
+ * __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference
+ * legs, always as the checker or as the timed CPU baseline, never as the
+ * thing shipped.
+ *
+ * Every function restates one reference function and cites it
+ * (paths relative to the reference repository root, Myrio v0.3.0).
+ *
+ * Parity pinning status (see DESIGN.md "Oracle"):
+ *   - pinned by the reference's own known-answer tests (ported verbatim as
+ *     inputs/outputs in tests/test_oracle_golden.py):
+ *       similarity.rs:217-232, sparse.rs:594-656.
+ *   - PARITY UNPINNED (no reference test or golden vector exists, and the
+ *     Rust reference cannot be compiled in this image):
+ *       the integer value of a k-mer key (bio-seq 0.14.2 fork, un-vendored;
+ *       assumed A=0,C=1,G=2,T=3, base i of the window at bits 2i..2i+1),
+ *       the IUPAC 4-bit code (assumed A=8,C=4,G=2,T=1, gap X=0),
+ *       the quality filter, leaf resampling / cut-off / rescale,
+ *       top-x tie order, and every part of cluster().
+ *     For these the oracle is a line-by-line restatement of the cited code.
+ */
+#ifndef MYRIO_ORACLE_H
+#define MYRIO_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Similarity selector, similarity.rs:26-33 */
+enum { MYO_SIM_COSINE = 0, MYO_SIM_JACARD_TANIMOTO = 1, MYO_SIM_OVERLAP = 2 };
+
+/* constants.rs:28  Q_TO_BP_CALL_CORRECT_PROB_MAP as f32 */
+const float *myo_phred_correct_table(void);
+
+/* bio-seq Kmer -> usize (assumed, see header): base j at bits 2j */
+uint64_t myo_kmer_key(const uint8_t *bases, int k);
+
+/* data/sparse.rs:229-272 from_unsorted_singles with value=1.0f (f32 "+=").
+ * keys_out/vals_out capacity n. returns number of distinct keys. */
+size_t myo_sort_reduce_f32(uint64_t *singles, size_t n, uint64_t *keys_out, float *vals_out);
+/* same with value=1u16 and wrapping u16 "+=" (release build semantics) */
+size_t myo_sort_reduce_u16(uint64_t *singles, size_t n, uint64_t *keys_out, uint16_t *vals_out);
+
+/* data/myrseq.rs:76-111  MyrSeq::compute_kmer_counts
+ * bases: one 2-bit code per byte. keys_out/vals_out capacity 2*(n-k+1).
+ * returns 0 ok, <0 error (k out of 2..32, quality >= 128). */
+int myo_count_read(const uint8_t *bases, const uint8_t *qual, size_t n, int k, float cutoff,
+                   uint64_t *keys_out, float *vals_out, size_t *d_out, uint64_t *nb_hck_out);
+
+/* Batch of the above (the reference's callers loop over reads:
+ * clustering.rs:78-90, run.rs:233-241,301-309).  Two-phase: pass
+ * keys_out==NULL to get row_off only.  threads<=1 -> serial like the
+ * reference call sites. */
+int myo_count_reads(const uint8_t *bases, const uint8_t *qual, const uint64_t *base_off,
+                    size_t n_reads, int k, float cutoff, int threads, uint64_t *row_off,
+                    uint64_t *keys_out, float *vals_out, uint64_t *nb_hck_out);
+
+/* Deterministic stand-in for SmallRng in the IUPAC resampler
+ * (tax/mod.rs:77-97).  Shared definition with the CUDA path. */
+uint32_t myo_resample_pick(uint64_t seed, uint64_t leaf, uint32_t resample, uint32_t pos,
+                           uint32_t n_opts);
+
+/* tax/mod.rs:70-148  compute_kmer_store_counts_for_fasta_seq
+ * iupac: one 4-bit code per byte.  capacity of outputs: max(1, 2*(n-k+1)*nb_resamples)
+ * worst case, but never more than 2*(n-k+1)*min(nb_resamples, ...) distinct;
+ * caller passes cap and gets <0 if exceeded. */
+int myo_count_leaf(const uint8_t *iupac, size_t n, int k, uint32_t nb_resamples, uint64_t seed,
+                   uint64_t leaf_id, uint64_t *keys_out, uint16_t *vals_out, size_t cap,
+                   size_t *d_out, float *rescale_out);
+
+/* tax/store.rs:265-285 compute_and_append_kmer_counts: rayon over leaves.
+ * two-phase like myo_count_reads (keys_out==NULL -> sizes only). */
+int myo_count_leaves(const uint8_t *iupac, const uint64_t *base_off, size_t n_leaves, int k,
+                     uint32_t nb_resamples, uint64_t seed, uint64_t leaf_id_base, int threads,
+                     uint64_t *row_off, uint64_t *keys_out, uint16_t *vals_out, float *rescale_out);
+
+/* data/sparse.rs:366-383 normalize_l2 (sum of v*v in key order, sqrt, divide) */
+void myo_normalize_l2(float *vals, size_t n);
+/* tax/compute.rs:100-108  u16 -> f32 -> into_normalized_l2 */
+void myo_normalize_u16(const uint16_t *in, size_t n, float *out);
+/* row-wise over a CSR batch */
+void myo_normalize_rows_f32(const uint64_t *row_off, size_t n_rows, float *vals, int threads);
+void myo_normalize_rows_u16(const uint64_t *row_off, size_t n_rows, const uint16_t *in, float *out,
+                            int threads);
+
+/* data/sparse.rs:317-360  SparseVec<f32>::dot */
+float myo_dot(const uint64_t *ak, const float *av, size_t an, const uint64_t *bk, const float *bv,
+              size_t bn);
+/* similarity.rs:40-182; pre_normalized selects the *_pre_normalized variants */
+float myo_similarity(int sim, int pre_normalized, const uint64_t *ak, const float *av, size_t an,
+                     const uint64_t *bk, const float *bv, size_t bn);
+
+/* tax/results.rs:82-93  score every leaf against one query (rayon -> OpenMP) */
+void myo_score_all(int sim, const uint64_t *leaf_row_off, const uint64_t *leaf_keys,
+                   const float *leaf_vals, size_t n_leaves, const uint64_t *qk, const float *qv,
+                   size_t qn, int threads, float *scores_out);
+
+/* tax/results.rs:310-329 cut(): global top-x, order (score desc, payload_id asc).
+ * Writes min(x,n) entries, pads the rest with (0.0f, 0xFFFFFFFF). */
+void myo_topx(const float *scores, size_t n, uint32_t id_base, size_t x, float *top_scores,
+              uint32_t *top_ids);
+
+/* data/sparse.rs:143-221 + 493-519  a + b */
+size_t myo_add(const uint64_t *ak, const float *av, size_t an, const uint64_t *bk, const float *bv,
+               size_t bn, uint64_t *ck, float *cv);
+
+/* clustering.rs:44-53 compute_cluster_centroid over rows member_ids[0..m) of a CSR batch.
+ * out capacity: sum of member nnz. */
+size_t myo_centroid(const uint64_t *row_off, const uint64_t *keys, const float *vals,
+                    const uint64_t *member_ids, size_t m, uint64_t *ck, float *cv);
+
+/* Reference structure of the inverted index the CUDA path builds (K3).  Not a
+ * reference function: the definition of "posting lists" used for parity.
+ * For leaves [0,n_leaves): unique keys ascending, offsets, and for each key
+ * the (leaf id ascending, value) postings.  Two-phase: ukeys==NULL -> counts. */
+void myo_invert(const uint64_t *row_off, const uint64_t *keys, const float *vals, size_t n_leaves,
+                size_t *n_unique, uint64_t *ukeys, uint64_t *offs, uint32_t *post_leaf,
+                float *post_val);
+
+/* clustering.rs:55-270 cluster(), starting from the per-read counts of step 1.
+ * assign_out[i]: cluster index, -1 = rejected by t2 (clustering.rs:82-87),
+ * -2 = rejected by silhouette trimming (clustering.rs:254-262).
+ * sil_out (optional, n_reads floats): silhouette score of kept reads (NaN if none). */
+typedef struct {
+    uint64_t t2;
+    int similarity;
+    size_t n_init;
+    const uint64_t *init_row_off;
+    const uint64_t *init_keys;
+    const float *init_vals;
+    size_t expected_nb_of_clusters;
+    float eta_improvement;
+    size_t nb_iters_max;
+    int has_silhouette;
+    float ssdcf;
+    int threads;
+} myo_cluster_params;
+
+int myo_cluster(const uint64_t *row_off, const uint64_t *keys, const float *vals,
+                const uint64_t *nb_hck, size_t n_reads, const myo_cluster_params *p,
+                int32_t *assign_out, uint32_t *n_iters_out, float *sil_out);
+
+/* pairwise similarity tile: out[i*n_cols+j] = sim(rows_i, cols_j) on pre-normalised rows */
+void myo_pairwise(int sim, const uint64_t *r_off, const uint64_t *r_keys, const float *r_vals,
+                  size_t n_rows, const uint64_t *c_off, const uint64_t *c_keys, const float *c_vals,
+                  size_t n_cols, int threads, float *out);
+
+int myo_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
