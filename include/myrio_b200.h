@@ -1,0 +1,214 @@
+/*
+ * myrio_b200.h -- C ABI of the B200-native (sm_100a) implementation of Myrio's
+ * data-parallel hot path: k-mer counting of reads and reference leaves, the
+ * inverted index over the leaves, query x leaf similarity scoring with top-x,
+ * and the read-clustering similarity kernels.
+ *
+ * The reference (anesthetice/Myrio v0.3.0) has no FFI; its boundary is the Rust
+ * API of `myrio-core` (myrio-core/src/prelude.rs:1-12).  Each entry point below
+ * names the reference function whose body it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the Rust `extern "C"` block and the
+ * call-site changes; rust/myrio-b200-sys holds that crate as source.
+ *
+ * Conventions
+ *   - plain C types; every function returns a myrio_status (0 = ok);
+ *     myrio_last_error() gives a thread-local message.  No unwinding crosses
+ *     the ABI.
+ *   - all *host* pointers are caller-owned for the duration of the call;
+ *     results with a size known up front are caller-allocated, results with
+ *     a data-dependent size live in opaque device-resident handles
+ *     (myrio_svecs, myrio_index) and are fetched with *_info + *_download.
+ *   - a myrio_ctx is bound to one GPU and one stream and is NOT thread-safe;
+ *     distinct contexts may be used concurrently.  Calls return after the
+ *     work has completed unless the name ends in `_async`.
+ *   - there is no CPU fallback: without a CUDA device myrio_ctx_create fails.
+ *
+ * Encodings (bio-seq 0.14.2, the reference's sequence crate):
+ *   Seq<Dna>   2 bits/base  A=0 C=1 G=2 T=3, base i at bits 2*(i%32) of u64 word i/32
+ *   Seq<Iupac> 4 bits/base  A=8 C=4 G=2 T=1, ambiguity = OR, gap 'X' = 0,
+ *                           symbol i at bits 4*(i%16) of u64 word i/16
+ *   k-mer key  usize::from(&Kmer<Dna,K>): base j of the window at bits 2j..2j+1
+ *   In the packed inputs below every sequence starts at an EVEN word index
+ *   (16-byte aligned) so the kernels can use 128-bit loads.
+ */
+#ifndef MYRIO_B200_H
+#define MYRIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MYRIO_OK = 0,
+    MYRIO_ERR_INVALID_K = 1,   /* k outside 2..32: the reference panics (myrio-proc/src/lib.rs:70) */
+    MYRIO_ERR_BAD_ARG = 2,
+    MYRIO_ERR_CUDA = 3,
+    MYRIO_ERR_OOM = 4,
+    MYRIO_ERR_BAD_QUALITY = 5, /* Phred >= 128: table index out of bounds in the reference */
+    MYRIO_ERR_UNSUPPORTED = 6,
+    MYRIO_ERR_EMPTY = 7,       /* cluster(): no read survives t2 / no centroid (reference panics) */
+    MYRIO_ERR_NONFINITE = 8    /* SimScore::try_new(..).unwrap() would panic (clustering.rs:125) */
+} myrio_status;
+
+/* myrio-core/src/similarity.rs:26-33 */
+typedef enum { MYRIO_SIM_COSINE = 0, MYRIO_SIM_JACARD_TANIMOTO = 1, MYRIO_SIM_OVERLAP = 2 } myrio_similarity;
+
+typedef enum { MYRIO_VAL_F32 = 0, MYRIO_VAL_U16 = 1 } myrio_vtype;
+
+typedef struct myrio_ctx myrio_ctx;       /* one GPU + stream + scratch                     */
+typedef struct myrio_seqs myrio_seqs;     /* device-resident packed sequences (+ quality)   */
+typedef struct myrio_svecs myrio_svecs;   /* device-resident batch of SparseVec<T> (CSR)    */
+typedef struct myrio_index myrio_index;   /* device-resident tiled inverted index of leaves */
+
+const char *myrio_last_error(void);
+int32_t myrio_version(void);
+
+int32_t myrio_ctx_create(int32_t device, myrio_ctx **out);
+void myrio_ctx_destroy(myrio_ctx *ctx);
+int32_t myrio_ctx_sync(myrio_ctx *ctx);
+/* the context's cudaStream_t (as void*), so callers can record their own events on it */
+void *myrio_ctx_stream(const myrio_ctx *ctx);
+/* number of kernels this library has launched on the context so far */
+uint64_t myrio_ctx_launch_count(const myrio_ctx *ctx);
+/* optional per-kernel CUDA-event timing (events on the context's stream) */
+int32_t myrio_prof_enable(myrio_ctx *ctx, int32_t on);
+int32_t myrio_prof_reset(myrio_ctx *ctx);
+/* accumulated device time and launch count of the kernels whose name starts with `prefix` */
+int32_t myrio_prof_query(myrio_ctx *ctx, const char *prefix, double *ms_total, uint64_t *launches);
+
+/* ---- sequences ---------------------------------------------------------- */
+
+/* A batch of MyrSeq (myrio-core/src/data/myrseq.rs:21-33): `sequence` as packed
+ * Seq<Dna> words, `quality` as raw Phred bytes.  base_off[n+1] / word_off[n+1]
+ * are prefix sums; read r has base_off[r+1]-base_off[r] bases. */
+int32_t myrio_reads_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t *word_off,
+                           const uint64_t *base_off, const uint8_t *qual, uint64_t n_reads,
+                           myrio_seqs **out);
+/* The `seq: Seq<Iupac>` of every StorePayload (myrio-core/src/tax/store.rs:28-32)
+ * in payload_id order. */
+int32_t myrio_leaves_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t *word_off,
+                            const uint64_t *base_off, uint64_t n_leaves, myrio_seqs **out);
+void myrio_seqs_free(myrio_seqs *s);
+
+/* ---- k-mer counting ----------------------------------------------------- */
+
+/* MyrSeq::compute_kmer_counts(k, cutoff) for every read
+ * (myrio-core/src/data/myrseq.rs:76-111; callers clustering.rs:78-90,
+ * myrio-cli/src/app/process/run.rs:233-241,301-309).
+ * out: rows = sorted (usize key, f32 count); aux = nb_hck as u64 per read. */
+int32_t myrio_count_reads(myrio_ctx *ctx, const myrio_seqs *reads, uint32_t k, float cutoff,
+                          myrio_svecs **out);
+
+/* compute_kmer_store_counts_for_fasta_seq for every leaf = the body of
+ * TaxTreeStore::compute_and_append_kmer_counts / _overwrite_
+ * (myrio-core/src/tax/mod.rs:70-148, tax/store.rs:265-308).
+ * out: rows = sorted (usize key, u16 count); aux = rescale factor (f32) per leaf.
+ * Ambiguity codes are resampled nb_resamples times with the counter-based
+ * generator documented in DESIGN.md (the reference seeds from the OS). */
+int32_t myrio_count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k,
+                           uint32_t nb_resamples, uint64_t seed, uint64_t leaf_id_base,
+                           myrio_svecs **out);
+
+/* ---- sparse-vector batches ---------------------------------------------- */
+
+int32_t myrio_svecs_info(const myrio_svecs *v, uint64_t *n_rows, uint64_t *nnz, int32_t *vtype);
+/* row_off[n_rows+1], keys[nnz], vals[nnz] (f32 or u16), aux[n_rows] (u64 for f32
+ * batches made by myrio_count_reads, f32 for u16 batches); any pointer may be NULL. */
+int32_t myrio_svecs_download(myrio_ctx *ctx, const myrio_svecs *v, uint64_t *row_off,
+                             uint64_t *keys, void *vals, void *aux);
+/* e.g. the cached `kmer_store_counts_vec[i]` of a loaded .myrtree, or centroids */
+int32_t myrio_svecs_upload(myrio_ctx *ctx, uint64_t n_rows, const uint64_t *row_off,
+                           const uint64_t *keys, const void *vals, int32_t vtype,
+                           myrio_svecs **out);
+/* SparseVec::into_normalized_l2 per row (data/sparse.rs:366-388); u16 input is
+ * first converted with Float::from (tax/compute.rs:100-108). */
+int32_t myrio_svecs_normalize(myrio_ctx *ctx, const myrio_svecs *in, myrio_svecs **out);
+void myrio_svecs_free(myrio_svecs *v);
+
+/* ---- reference index ---------------------------------------------------- */
+
+/* Replaces the `Box<[SFVec]>` payloads built in TaxTreeCompute::from_store_tree
+ * (myrio-core/src/tax/compute.rs:100-118): the normalised leaf vectors are
+ * inverted into per-tile CSR posting lists (key -> (leaf, value)), leaves in
+ * payload_id order.  leaf_id_base is added to reported ids (multi-GPU shards).
+ * tile_leaves = 0 picks the default. */
+int32_t myrio_index_build(myrio_ctx *ctx, const myrio_svecs *leaf_vecs_normalized,
+                          uint32_t leaf_id_base, uint32_t tile_leaves, myrio_index **out);
+int32_t myrio_index_info(const myrio_index *ix, uint64_t *n_leaves, uint64_t *n_tiles,
+                         uint64_t *n_postings, uint64_t *n_unique_total, uint32_t *tile_leaves);
+/* one tile's CSR: ukeys[U], offs[U+1] (relative to the tile), post_leaf[P] (tile-local
+ * leaf index), post_val[P].  Call with NULL arrays to get U and P. */
+int32_t myrio_index_export_tile(myrio_ctx *ctx, const myrio_index *ix, uint64_t tile,
+                                uint64_t *n_unique, uint64_t *n_postings, uint64_t *ukeys,
+                                uint64_t *offs, uint32_t *post_leaf, float *post_val);
+void myrio_index_free(myrio_index *ix);
+
+/* ---- scoring ------------------------------------------------------------ */
+
+/* The loop of TaxTreeResults::from_compute_tree (myrio-core/src/tax/results.rs:82-93):
+ * scores[q*n_leaves + payload_id] = simfunc(leaf, query) for queries
+ * [q_first, q_first+q_count) of `queries` (pre-normalised rows). */
+int32_t myrio_score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                        uint64_t q_first, uint64_t q_count, int32_t similarity, float *scores);
+/* Same scores, reduced on the device to the global top-x of cut()
+ * (tax/results.rs:310-329), order (score desc, payload_id asc); entries past
+ * min(x, n_leaves) are (0.0f, 0xFFFFFFFF).  top_*[q*x + j]. */
+int32_t myrio_score_topx(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                         uint64_t q_first, uint64_t q_count, uint32_t x, int32_t similarity,
+                         float *top_scores, uint32_t *top_ids);
+/* device-output variant (for the NCCL all-gather of shard-local results);
+ * d_* are device pointers of q_count*x elements; asynchronous on the ctx stream */
+int32_t myrio_score_topx_async(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                               uint64_t q_first, uint64_t q_count, uint32_t x, int32_t similarity,
+                               float *d_top_scores, uint32_t *d_top_ids);
+/* merge n_parts shard-local top-x lists laid out [part][q][x] into [q][x] (device pointers) */
+int32_t myrio_topx_merge_async(myrio_ctx *ctx, const float *d_scores_in, const uint32_t *d_ids_in,
+                               uint32_t n_parts, uint64_t q_count, uint32_t x, float *d_scores_out,
+                               uint32_t *d_ids_out);
+/* exact algorithmic work of the last myrio_score_* call: sum over queries of
+ * query keys, of keys found in the index, and of postings touched (T_q) */
+int32_t myrio_score_stats(myrio_ctx *ctx, uint64_t *n_query_keys, uint64_t *n_key_hits,
+                          uint64_t *n_postings_touched);
+
+/* ---- clustering --------------------------------------------------------- */
+
+/* ClusteringParameters (myrio-core/src/clustering.rs:15-36) */
+typedef struct {
+    uint32_t k;
+    float t1;
+    uint64_t t2;
+    int32_t similarity;
+    uint64_t expected_nb_of_clusters;
+    float eta_improvement;
+    uint64_t nb_iters_max;
+    int32_t has_silhouette_trimming;
+    float silhouette_trimming; /* ssdcf */
+} myrio_cluster_params;
+
+/* clustering::cluster (myrio-core/src/clustering.rs:55-270).  initial_centroids
+ * may be NULL (empty).  assign[i] = cluster index of read i, -1 = rejected by t2,
+ * -2 = rejected by silhouette trimming.  silhouette (optional, n_reads floats)
+ * receives the silhouette score of each clustered read (NaN where undefined). */
+int32_t myrio_cluster(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *params,
+                      const myrio_svecs *initial_centroids, int32_t *assign, uint32_t *n_iters,
+                      float *silhouette);
+/* compute_cluster_centroid (clustering.rs:44-53) over rows member_ids[0..m) of
+ * `counts` (raw, un-normalised); out is a 1-row normalised batch. */
+int32_t myrio_compute_cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts,
+                                       const uint64_t *member_ids, uint64_t m, myrio_svecs **out);
+/* the reads x reads (or reads x centroids) similarity tile used by the clustering
+ * loop: out[i*n_cols + j] = simfunc(rows_i, cols_j), rows/cols pre-normalised */
+int32_t myrio_pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols,
+                       int32_t similarity, float *out);
+
+/* device pointers of a batch, for zero-copy interop (torch / NCCL plumbing) */
+int32_t myrio_svecs_device_ptrs(const myrio_svecs *v, const uint64_t **row_off,
+                                const uint64_t **keys, const void **vals, const void **aux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYRIO_B200_H */

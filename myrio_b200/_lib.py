@@ -1,0 +1,117 @@
+"""ctypes binding of libmyrio_b200.so (include/myrio_b200.h).
+
+No fallback of any kind: if the CUDA library has not been built (python
+__graft_entry__.py build / make -C myrio_b200/csrc) loading raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmyrio_b200.so")
+
+OK = 0
+ERR_INVALID_K, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_BAD_QUALITY, ERR_UNSUPPORTED, ERR_EMPTY, ERR_NONFINITE = range(1, 9)
+SIM_COSINE, SIM_JACARD_TANIMOTO, SIM_OVERLAP = 0, 1, 2
+VAL_F32, VAL_U16 = 0, 1
+
+# every symbol include/myrio_b200.h declares (tests/test_capi_symbols.py checks the header against this)
+SYMBOLS = [
+    "myrio_last_error", "myrio_version", "myrio_ctx_create", "myrio_ctx_destroy", "myrio_ctx_sync",
+    "myrio_ctx_launch_count", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query",
+    "myrio_reads_upload", "myrio_leaves_upload", "myrio_seqs_free", "myrio_count_reads",
+    "myrio_count_leaves", "myrio_svecs_info", "myrio_svecs_download", "myrio_svecs_upload",
+    "myrio_svecs_normalize", "myrio_svecs_free", "myrio_index_build", "myrio_index_info",
+    "myrio_index_export_tile", "myrio_index_free", "myrio_score_all", "myrio_score_topx",
+    "myrio_score_topx_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
+    "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_svecs_device_ptrs",
+]
+
+
+class MyrioError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"myrio_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ClusterParams(C.Structure):
+    """myrio_cluster_params (ClusteringParameters, myrio-core/src/clustering.rs:15-36)"""
+    _fields_ = [
+        ("k", C.c_uint32),
+        ("t1", C.c_float),
+        ("t2", C.c_uint64),
+        ("similarity", C.c_int32),
+        ("expected_nb_of_clusters", C.c_uint64),
+        ("eta_improvement", C.c_float),
+        ("nb_iters_max", C.c_uint64),
+        ("has_silhouette_trimming", C.c_int32),
+        ("silhouette_trimming", C.c_float),
+    ]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA library first "
+            "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32
+    P = C.POINTER
+    L.myrio_last_error.restype = C.c_char_p
+    L.myrio_version.restype = i32
+    L.myrio_ctx_create.argtypes = [i32, P(vp)]
+    L.myrio_ctx_destroy.argtypes = [vp]
+    L.myrio_ctx_destroy.restype = None
+    L.myrio_ctx_sync.argtypes = [vp]
+    L.myrio_ctx_launch_count.argtypes = [vp]
+    L.myrio_ctx_launch_count.restype = u64
+    L.myrio_ctx_stream.argtypes = [vp]
+    L.myrio_ctx_stream.restype = vp
+    L.myrio_prof_enable.argtypes = [vp, i32]
+    L.myrio_prof_reset.argtypes = [vp]
+    L.myrio_prof_query.argtypes = [vp, C.c_char_p, P(C.c_double), P(u64)]
+    L.myrio_reads_upload.argtypes = [vp, vp, vp, vp, vp, u64, P(vp)]
+    L.myrio_leaves_upload.argtypes = [vp, vp, vp, vp, u64, P(vp)]
+    L.myrio_seqs_free.argtypes = [vp]
+    L.myrio_seqs_free.restype = None
+    L.myrio_count_reads.argtypes = [vp, vp, u32, C.c_float, P(vp)]
+    L.myrio_count_leaves.argtypes = [vp, vp, u32, u32, u64, u64, P(vp)]
+    L.myrio_svecs_info.argtypes = [vp, P(u64), P(u64), P(i32)]
+    L.myrio_svecs_download.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.myrio_svecs_upload.argtypes = [vp, u64, vp, vp, vp, i32, P(vp)]
+    L.myrio_svecs_normalize.argtypes = [vp, vp, P(vp)]
+    L.myrio_svecs_free.argtypes = [vp]
+    L.myrio_svecs_free.restype = None
+    L.myrio_svecs_device_ptrs.argtypes = [vp, P(vp), P(vp), P(vp), P(vp)]
+    L.myrio_index_build.argtypes = [vp, vp, u32, u32, P(vp)]
+    L.myrio_index_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u64), P(u32)]
+    L.myrio_index_export_tile.argtypes = [vp, vp, u64, P(u64), P(u64), vp, vp, vp, vp]
+    L.myrio_index_free.argtypes = [vp]
+    L.myrio_index_free.restype = None
+    L.myrio_score_all.argtypes = [vp, vp, vp, u64, u64, i32, vp]
+    L.myrio_score_topx.argtypes = [vp, vp, vp, u64, u64, u32, i32, vp, vp]
+    L.myrio_score_topx_async.argtypes = [vp, vp, vp, u64, u64, u32, i32, vp, vp]
+    L.myrio_topx_merge_async.argtypes = [vp, vp, vp, u32, u64, u32, vp, vp]
+    L.myrio_score_stats.argtypes = [vp, P(u64), P(u64), P(u64)]
+    L.myrio_cluster.argtypes = [vp, vp, P(ClusterParams), vp, vp, P(u32), vp]
+    L.myrio_compute_cluster_centroid.argtypes = [vp, vp, vp, u64, P(vp)]
+    L.myrio_pairwise.argtypes = [vp, vp, vp, i32, vp]
+    for name in SYMBOLS:
+        f = getattr(L, name)
+        if name not in ("myrio_last_error", "myrio_ctx_destroy", "myrio_ctx_launch_count", "myrio_seqs_free",
+                        "myrio_svecs_free", "myrio_index_free", "myrio_version", "myrio_ctx_stream"):
+            f.restype = i32
+    _lib = L
+    return L
+
+
+def check(status: int) -> None:
+    if status != OK:
+        msg = load().myrio_last_error()
+        raise MyrioError(status, msg.decode() if msg else "")

@@ -1,0 +1,371 @@
+"""Host-side mirror of the `myrio-core` API for the hot path (prelude.rs:1-12),
+over the C ABI of include/myrio_b200.h.  Names, argument meaning and error
+behaviour follow the reference; batches replace per-item calls
+(`MyrSeqs.compute_kmer_counts` == `MyrSeq::compute_kmer_counts` for every read).
+
+Every call runs on the GPU through libmyrio_b200.so; nothing here computes on
+the CPU and nothing imports the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import MyrioError, SIM_COSINE, SIM_JACARD_TANIMOTO, SIM_OVERLAP  # noqa: F401
+from .synth import SeqSet, pack_dna2, pack_iupac4, tree_to_iupac
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU + stream (myrio_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._L.myrio_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.myrio_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _lib.check(self._L.myrio_ctx_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t of the context as an integer (torch.cuda.ExternalStream(ctx.stream))."""
+        return int(self._L.myrio_ctx_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.myrio_ctx_launch_count(self.h))
+
+    def prof_enable(self, on: bool = True):
+        _lib.check(self._L.myrio_prof_enable(self.h, int(on)))
+
+    def prof_reset(self):
+        _lib.check(self._L.myrio_prof_reset(self.h))
+
+    def prof_query(self, prefix: str = ""):
+        ms, n = C.c_double(0), C.c_uint64(0)
+        _lib.check(self._L.myrio_prof_query(self.h, prefix.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
+    def score_stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _lib.check(self._L.myrio_score_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"query_keys": int(a.value), "key_hits": int(b.value), "postings_touched": int(c.value)}
+
+
+class SFVecs:
+    """Device-resident batch of SparseVec<T> (myrio_svecs): row r is one sorted
+    (usize key, value) vector -- SFVec for f32, SparseVec<u16> for leaf counts."""
+
+    aux_is_u64 = True
+
+    def __init__(self, ctx: Context, handle, has_aux: bool = False):
+        self.ctx, self.h, self.has_aux = ctx, handle, has_aux
+        n, nnz, vt = C.c_uint64(0), C.c_uint64(0), C.c_int32(0)
+        _lib.check(ctx._L.myrio_svecs_info(handle, C.byref(n), C.byref(nnz), C.byref(vt)))
+        self.n_rows, self.nnz, self.vtype = int(n.value), int(nnz.value), int(vt.value)
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx._L.myrio_svecs_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    @classmethod
+    def upload(cls, ctx: Context, row_off, keys, vals) -> "SFVecs":
+        row_off = np.ascontiguousarray(row_off, np.uint64)
+        keys = np.ascontiguousarray(keys, np.uint64)
+        vals = np.ascontiguousarray(vals)
+        if vals.dtype == np.uint16:
+            vt = _lib.VAL_U16
+        else:
+            vals = np.ascontiguousarray(vals, np.float32)
+            vt = _lib.VAL_F32
+        h = C.c_void_p()
+        _lib.check(ctx._L.myrio_svecs_upload(ctx.h, len(row_off) - 1, _p(row_off), _p(keys), _p(vals), vt,
+                                             C.byref(h)))
+        return cls(ctx, h)
+
+    def download(self, aux: bool = True):
+        """(row_off, keys, vals, aux) as numpy arrays."""
+        row_off = np.zeros(self.n_rows + 1, np.uint64)
+        keys = np.zeros(self.nnz, np.uint64)
+        vals = np.zeros(self.nnz, np.float32 if self.vtype == _lib.VAL_F32 else np.uint16)
+        ax = None
+        if aux and self.has_aux:
+            # nb_hck (u64) for read counts, rescale factor (f32) for leaf counts
+            ax = np.zeros(self.n_rows, np.uint64 if self.aux_is_u64 else np.float32)
+        _lib.check(self.ctx._L.myrio_svecs_download(self.ctx.h, self.h, _p(row_off), _p(keys), _p(vals),
+                                                    _p(ax)))
+        return row_off, keys, vals, ax
+
+    def into_normalized_l2(self) -> "SFVecs":
+        """SparseVec::into_normalized_l2 per row (data/sparse.rs:385-388)."""
+        h = C.c_void_p()
+        _lib.check(self.ctx._L.myrio_svecs_normalize(self.ctx.h, self.h, C.byref(h)))
+        out = SFVecs(self.ctx, h, self.has_aux)
+        out.aux_is_u64 = getattr(self, "aux_is_u64", True)
+        return out
+
+
+class MyrSeqs:
+    """A batch of MyrSeq (data/myrseq.rs:21-33) resident on the GPU."""
+
+    def __init__(self, ctx: Context, seqs: SeqSet):
+        if seqs.qual is None:
+            raise ValueError("reads need quality scores")
+        self.ctx, self.n = ctx, seqs.n
+        words, word_off = pack_dna2(seqs)
+        self._upload(words, word_off, np.ascontiguousarray(seqs.base_off, np.uint64),
+                     np.ascontiguousarray(seqs.qual, np.uint8))
+
+    def _upload(self, words, word_off, base_off, qual):
+        h = C.c_void_p()
+        _lib.check(self.ctx._L.myrio_reads_upload(self.ctx.h, _p(words), _p(word_off), _p(base_off), _p(qual),
+                                                  self.n, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_packed(cls, ctx, words, word_off, base_off, qual) -> "MyrSeqs":
+        self = cls.__new__(cls)
+        self.ctx, self.n = ctx, len(base_off) - 1
+        self._upload(words, word_off, base_off, qual)
+        return self
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx._L.myrio_seqs_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    def compute_kmer_counts(self, k: int, cutoff: float) -> SFVecs:
+        """MyrSeq::compute_kmer_counts for every read (data/myrseq.rs:76-111);
+        the returned batch carries nb_hck as its aux column."""
+        h = C.c_void_p()
+        _lib.check(self.ctx._L.myrio_count_reads(self.ctx.h, self.h, k, cutoff, C.byref(h)))
+        out = SFVecs(self.ctx, h, True)
+        out.aux_is_u64 = True
+        return out
+
+
+class TaxTreeStore:
+    """The leaf sequences + cached k-mer counts of a .myrtree (tax/store.rs:28-50);
+    the taxonomy itself stays on the host (out of scope)."""
+
+    def __init__(self, ctx: Context, leaves: SeqSet | None = None, *, iupac=None, base_off=None,
+                 gene: str = "", leaf_id_base: int = 0):
+        self.ctx, self.gene, self.leaf_id_base = ctx, gene, leaf_id_base
+        if leaves is not None:
+            iupac, base_off = tree_to_iupac(leaves), leaves.base_off
+        base_off = np.ascontiguousarray(base_off, np.uint64)
+        words, word_off = pack_iupac4(np.ascontiguousarray(iupac, np.uint8), base_off)
+        self.n_leaves = len(base_off) - 1
+        h = C.c_void_p()
+        _lib.check(ctx._L.myrio_leaves_upload(ctx.h, _p(words), _p(word_off), _p(base_off), self.n_leaves,
+                                              C.byref(h)))
+        self.h = h
+        self.k_precomputed: list[int] = []
+        self.kmer_store_counts_vec: list[SFVecs] = []
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx._L.myrio_seqs_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    def _count(self, k: int, nb_resamples: int, seed: int) -> SFVecs:
+        h = C.c_void_p()
+        _lib.check(self.ctx._L.myrio_count_leaves(self.ctx.h, self.h, k, nb_resamples, seed, self.leaf_id_base,
+                                                  C.byref(h)))
+        out = SFVecs(self.ctx, h, True)
+        out.aux_is_u64 = False
+        return out
+
+    def compute_and_append_kmer_counts(self, k: int, nb_resamples: int, seed: int = 0):
+        """tax/store.rs:265-285"""
+        self.kmer_store_counts_vec.append(self._count(k, nb_resamples, seed))
+        self.k_precomputed.append(k)
+
+    def compute_and_overwrite_kmer_counts(self, k: int, nb_resamples: int, seed: int = 0):
+        """tax/store.rs:287-308"""
+        self.kmer_store_counts_vec = [self._count(k, nb_resamples, seed)]
+        self.k_precomputed = [k]
+
+
+class TaxTreeCompute:
+    """tax/compute.rs:13-20 -- the normalised leaf vectors, held as a tiled inverted index."""
+
+    def __init__(self, ctx, index_handle, n_leaves, leaf_id_base, leaf_vecs: SFVecs | None):
+        self.ctx, self.h, self.n_leaves, self.leaf_id_base = ctx, index_handle, n_leaves, leaf_id_base
+        self.leaf_vecs = leaf_vecs
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx._L.myrio_index_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    @classmethod
+    def from_store_tree(cls, ttstore: TaxTreeStore, search_k: int, fasta_nb_resamples: int = 32, *,
+                        cache_counts: bool = True, seed: int = 0, tile_leaves: int = 0,
+                        keep_leaf_vecs: bool = False) -> "TaxTreeCompute":
+        """tax/compute.rs:80-118: pick (or compute) the cached counts for search_k, convert
+        each leaf to an L2-normalised f32 vector, and build the index the score loop runs on."""
+        if search_k in ttstore.k_precomputed:
+            idx = ttstore.k_precomputed.index(search_k)
+        elif cache_counts:
+            ttstore.compute_and_append_kmer_counts(search_k, fasta_nb_resamples, seed)
+            idx = len(ttstore.k_precomputed) - 1
+        else:
+            ttstore.compute_and_overwrite_kmer_counts(search_k, fasta_nb_resamples, seed)
+            idx = 0
+        counts = ttstore.kmer_store_counts_vec[idx]
+        return cls.from_counts(counts, ttstore.leaf_id_base, tile_leaves=tile_leaves,
+                               keep_leaf_vecs=keep_leaf_vecs)
+
+    @classmethod
+    def from_counts(cls, counts: SFVecs, leaf_id_base: int = 0, *, tile_leaves: int = 0,
+                    keep_leaf_vecs: bool = False) -> "TaxTreeCompute":
+        ctx = counts.ctx
+        normalized = counts.into_normalized_l2()
+        h = C.c_void_p()
+        _lib.check(ctx._L.myrio_index_build(ctx.h, normalized.h, leaf_id_base, tile_leaves, C.byref(h)))
+        return cls(ctx, h, counts.n_rows, leaf_id_base, normalized if keep_leaf_vecs else None)
+
+    def info(self):
+        a, b, c, d, e = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        _lib.check(self.ctx._L.myrio_index_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d),
+                                                C.byref(e)))
+        return {"n_leaves": int(a.value), "n_tiles": int(b.value), "n_postings": int(c.value),
+                "n_unique_total": int(d.value), "tile_leaves": int(e.value)}
+
+    def export_tile(self, tile: int):
+        nu, npst = C.c_uint64(0), C.c_uint64(0)
+        L = self.ctx._L
+        _lib.check(L.myrio_index_export_tile(self.ctx.h, self.h, tile, C.byref(nu), C.byref(npst), None, None,
+                                             None, None))
+        uk = np.zeros(nu.value, np.uint64)
+        of = np.zeros(nu.value + 1, np.uint64)
+        pl = np.zeros(npst.value, np.uint32)
+        pv = np.zeros(npst.value, np.float32)
+        _lib.check(L.myrio_index_export_tile(self.ctx.h, self.h, tile, C.byref(nu), C.byref(npst), _p(uk),
+                                             _p(of), _p(pl), _p(pv)))
+        return uk, of, pl, pv
+
+
+@dataclass
+class TaxTreeResults:
+    """The scoring part of tax/results.rs: full score rows and/or the cut() top-x."""
+    scores: np.ndarray | None      # [Q, n_leaves] in payload order (results.rs:82-93)
+    top_scores: np.ndarray | None  # [Q, x]  (results.rs:310-329; score desc, payload_id asc)
+    top_ids: np.ndarray | None     # [Q, x]
+
+    @classmethod
+    def from_compute_tree(cls, queries: SFVecs, ttcompute: TaxTreeCompute, similarity: int = SIM_COSINE,
+                          nb_best_analysis: int = 100, *, q_first: int = 0, q_count: int | None = None,
+                          full_scores: bool = False) -> "TaxTreeResults":
+        ctx = ttcompute.ctx
+        q_count = queries.n_rows - q_first if q_count is None else q_count
+        scores = ts = ti = None
+        if full_scores:
+            scores = np.zeros((q_count, ttcompute.n_leaves), np.float32)
+            _lib.check(ctx._L.myrio_score_all(ctx.h, ttcompute.h, queries.h, q_first, q_count, similarity,
+                                              _p(scores)))
+        if nb_best_analysis:
+            ts = np.zeros((q_count, nb_best_analysis), np.float32)
+            ti = np.zeros((q_count, nb_best_analysis), np.uint32)
+            _lib.check(ctx._L.myrio_score_topx(ctx.h, ttcompute.h, queries.h, q_first, q_count,
+                                               nb_best_analysis, similarity, _p(ts), _p(ti)))
+        return cls(scores, ts, ti)
+
+
+@dataclass
+class ClusteringParameters:
+    """myrio-core/src/clustering.rs:15-36 (defaults: myrio-cli/src/app/config.rs:107-119)"""
+    k: int = 6
+    t1: float = 0.2
+    t2: int = 20
+    similarity: int = SIM_COSINE
+    intial_centroids: SFVecs | None = None  # (sic) spelled as in the reference
+    expected_nb_of_clusters: int = 1
+    eta_improvement: float = 1e-4
+    nb_iters_max: int = 20
+    silhouette_trimming: float | None = None
+
+
+@dataclass
+class ClusteringOutput:
+    """clustering.rs:38-41 as index lists: clusters[c] = read indices in input order;
+    rejected = reads dropped by t2 (first) then by silhouette trimming."""
+    clusters: list
+    rejected: np.ndarray
+    assign: np.ndarray
+    n_iters: int
+    silhouette: np.ndarray = field(default=None)
+
+
+def cluster(myrseqs: MyrSeqs, params: ClusteringParameters) -> ClusteringOutput:
+    """clustering::cluster (myrio-core/src/clustering.rs:55-270)."""
+    ctx = myrseqs.ctx
+    p = _lib.ClusterParams()
+    p.k, p.t1, p.t2, p.similarity = params.k, params.t1, params.t2, params.similarity
+    p.expected_nb_of_clusters = params.expected_nb_of_clusters
+    p.eta_improvement, p.nb_iters_max = params.eta_improvement, params.nb_iters_max
+    p.has_silhouette_trimming = int(params.silhouette_trimming is not None)
+    p.silhouette_trimming = params.silhouette_trimming or 0.0
+    assign = np.zeros(max(1, myrseqs.n), np.int32)
+    sil = np.zeros(max(1, myrseqs.n), np.float32)
+    iters = C.c_uint32(0)
+    init = params.intial_centroids.h if params.intial_centroids is not None else None
+    _lib.check(ctx._L.myrio_cluster(ctx.h, myrseqs.h, C.byref(p), init, _p(assign), C.byref(iters), _p(sil)))
+    assign, sil = assign[:myrseqs.n], sil[:myrseqs.n]
+    nc = int(assign.max()) + 1 if (assign >= 0).any() else 0
+    nc = max(nc, params.expected_nb_of_clusters,
+             params.intial_centroids.n_rows if params.intial_centroids is not None else 0)
+    clusters = [np.nonzero(assign == c)[0] for c in range(nc)]
+    rejected = np.concatenate([np.nonzero(assign == -1)[0], np.nonzero(assign == -2)[0]])
+    return ClusteringOutput(clusters, rejected, assign, int(iters.value), sil)
+
+
+def compute_cluster_centroid(counts: SFVecs, member_ids) -> SFVecs:
+    """clustering::compute_cluster_centroid (clustering.rs:44-53) over rows of a raw count batch."""
+    ids = np.ascontiguousarray(member_ids, np.uint64)
+    h = C.c_void_p()
+    _lib.check(counts.ctx._L.myrio_compute_cluster_centroid(counts.ctx.h, counts.h, _p(ids), len(ids),
+                                                            C.byref(h)))
+    return SFVecs(counts.ctx, h)
+
+
+def pairwise(rows: SFVecs, cols: SFVecs, similarity: int = SIM_COSINE) -> np.ndarray:
+    """The reads x reads / reads x centroids similarity tile of the clustering loop."""
+    out = np.zeros((rows.n_rows, cols.n_rows), np.float32)
+    if out.size:
+        _lib.check(rows.ctx._L.myrio_pairwise(rows.ctx.h, rows.h, cols.h, similarity, _p(out)))
+    return out

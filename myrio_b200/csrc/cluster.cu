@@ -1,0 +1,670 @@
+// cluster.cu -- K6: the reads x centroids / reads x reads similarity kernels and the
+// host loop of clustering::cluster (myrio-core/src/clustering.rs:55-270).
+//
+// At the clustering k (default 6) a k-mer vector has at most 4^k = 4096
+// dimensions, so the column side of a similarity tile is kept DENSE in shared
+// memory (transposed [key][column]) while every thread walks one sparse row in
+// ascending key order: acc_c = acc_c + row_val * col_c[key], separate multiply and
+// add.  A key missing from the column contributes +0.0, which leaves an f32
+// accumulator unchanged, so the result is bit-identical to the reference's
+// sparse merge-join (data/sparse.rs:317-360).  No tensor cores: the sum order is
+// part of the result.
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+#include "cluster.cuh"
+#include "index.cuh"
+#include "kmer_count.cuh"
+
+namespace myrio {
+
+static constexpr int PK_THREADS = 256;
+enum { PK_STORE = 0, PK_SILSUM = 1, PK_ARGMAX = 2 };
+
+struct PairArgs {
+    const uint64_t *r_off;
+    const uint64_t *r_keys;
+    const float *r_vals;
+    const uint32_t *row_ids;  // rows of the CSR batch to use (NULL = identity)
+    uint32_t n_rows;
+    const uint64_t *c_off;  // sparse columns (CSR batch + id list) ...
+    const uint64_t *c_keys;
+    const float *c_vals;
+    const uint32_t *col_ids;
+    const float *c_dense;  // ... or dense columns [n_cols][dim]
+    uint32_t n_cols;
+    uint32_t dim;
+    uint32_t split;  // PK_SILSUM: columns [0,split) feed sum a, the rest sum b
+    int sim;
+    float *out;         // STORE: [n_rows][n_cols]; SILSUM: [n_rows][2]; ARGMAX: best sim [n_rows]
+    uint32_t *out_idx;  // ARGMAX: best column (last maximum)
+};
+
+__device__ __forceinline__ float pk_finite_or_zero(float x) { return (fabsf(x) <= 3.402823466e+38f) ? x : 0.0f; }
+
+__device__ __forceinline__ float pk_sim(int sim, float dot) {
+    if (sim == MYRIO_SIM_JACARD_TANIMOTO) return pk_finite_or_zero(__fdiv_rn(dot, __fsub_rn(2.0f, dot)));
+    return dot;
+}
+
+template <int MODE, int CB>
+__global__ void __launch_bounds__(PK_THREADS) pair_kernel(PairArgs a) {
+    extern __shared__ __align__(16) float colT[];  // [dim][CB]
+    const uint32_t tid = threadIdx.x;
+    const uint32_t ri = blockIdx.x * PK_THREADS + tid;
+    const bool row_ok = ri < a.n_rows;
+    uint64_t rb = 0, re = 0;
+    if (row_ok) {
+        const uint32_t r = a.row_ids ? a.row_ids[ri] : ri;
+        rb = a.r_off[r];
+        re = a.r_off[r + 1];
+    }
+    for (uint32_t i = tid; i < a.dim * CB; i += PK_THREADS) colT[i] = 0.0f;
+    __syncthreads();
+
+    float sum_a = 0.0f, sum_b = 0.0f;  // SILSUM
+    float best = 0.0f;                  // ARGMAX
+    uint32_t best_idx = 0;
+
+    for (uint32_t c0 = 0; c0 < a.n_cols; c0 += CB) {
+        const uint32_t nc = min((uint32_t)CB, a.n_cols - c0);
+        // stage the chunk's columns
+        if (a.c_dense) {
+            for (uint32_t i = tid; i < a.dim * nc; i += PK_THREADS) {
+                const uint32_t c = i / a.dim, key = i % a.dim;
+                colT[key * CB + c] = a.c_dense[(size_t)(c0 + c) * a.dim + key];
+            }
+        } else {
+            for (uint32_t c = 0; c < nc; ++c) {
+                const uint32_t cr = a.col_ids ? a.col_ids[c0 + c] : (c0 + c);
+                const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
+                for (uint64_t j = b + tid; j < e; j += PK_THREADS) colT[(uint32_t)a.c_keys[j] * CB + c] = a.c_vals[j];
+            }
+        }
+        __syncthreads();
+        float acc[CB];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) acc[c] = 0.0f;
+        for (uint64_t j = rb; j < re; ++j) {  // ascending key order
+            const uint32_t key = (uint32_t)a.r_keys[j];
+            const float v = a.r_vals[j];
+            const float *cp = colT + (size_t)key * CB;
+#pragma unroll
+            for (int c = 0; c < CB; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(v, cp[c]));
+        }
+        if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                if ((uint32_t)c < nc) {
+                    const float s = pk_sim(a.sim, acc[c]);
+                    if (MODE == PK_STORE) {
+                        a.out[(size_t)ri * a.n_cols + c0 + c] = s;
+                    } else if (MODE == PK_SILSUM) {
+                        const float d = __fsub_rn(1.0f, s);  // Similarity::dist, similarity.rs:53-56
+                        if (c0 + c < a.split)
+                            sum_a = __fadd_rn(sum_a, d);
+                        else
+                            sum_b = __fadd_rn(sum_b, d);
+                    } else {
+                        if ((c0 + c) == 0 || s >= best) {  // max_by_key keeps the LAST maximum
+                            best = s;
+                            best_idx = c0 + c;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // un-stage (sparse columns only touch their own entries)
+        if (!a.c_dense) {
+            for (uint32_t c = 0; c < nc; ++c) {
+                const uint32_t cr = a.col_ids ? a.col_ids[c0 + c] : (c0 + c);
+                const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
+                for (uint64_t j = b + tid; j < e; j += PK_THREADS) colT[(uint32_t)a.c_keys[j] * CB + c] = 0.0f;
+            }
+            __syncthreads();
+        }
+    }
+    if (row_ok) {
+        if (MODE == PK_SILSUM) {
+            a.out[(size_t)ri * 2] = sum_a;
+            a.out[(size_t)ri * 2 + 1] = sum_b;
+        } else if (MODE == PK_ARGMAX) {
+            a.out[ri] = best;
+            a.out_idx[ri] = best_idx;
+        }
+    }
+}
+
+// generic fallback for myrio_pairwise at large k: one thread per pair, two-pointer merge
+__global__ void __launch_bounds__(128) pair_merge_kernel(const uint64_t *__restrict__ r_off,
+                                                         const uint64_t *__restrict__ r_keys,
+                                                         const float *__restrict__ r_vals, uint32_t n_rows,
+                                                         const uint64_t *__restrict__ c_off,
+                                                         const uint64_t *__restrict__ c_keys,
+                                                         const float *__restrict__ c_vals, uint32_t n_cols,
+                                                         int sim, float *__restrict__ out) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (uint64_t)n_rows * n_cols) return;
+    const uint32_t r = (uint32_t)(p / n_cols), c = (uint32_t)(p % n_cols);
+    uint64_t i = r_off[r], ie = r_off[r + 1], j = c_off[c], je = c_off[c + 1];
+    float acc = 0.0f;
+    while (i < ie && j < je) {
+        const uint64_t a = r_keys[i], b = c_keys[j];
+        if (a < b)
+            ++i;
+        else if (a > b)
+            ++j;
+        else {
+            acc = __fadd_rn(acc, __fmul_rn(r_vals[i], c_vals[j]));
+            ++i;
+            ++j;
+        }
+    }
+    out[p] = pk_sim(sim, acc);
+}
+
+template <int MODE>
+static void launch_pair(myrio_ctx *ctx, const PairArgs &a, const char *name) {
+    if (a.n_rows == 0 || a.n_cols == 0) return;
+    const unsigned grid = (a.n_rows + PK_THREADS - 1) / PK_THREADS;
+    if (a.dim <= 4096) {
+        const size_t smem = (size_t)a.dim * 8 * sizeof(float);
+        MYRIO_CK(cudaFuncSetAttribute(pair_kernel<MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, name, (pair_kernel<MODE, 8>), grid, PK_THREADS, smem, a);
+    } else {
+        const size_t smem = (size_t)a.dim * 2 * sizeof(float);
+        MYRIO_CK(cudaFuncSetAttribute(pair_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, name, (pair_kernel<MODE, 2>), grid, PK_THREADS, smem, a);
+    }
+}
+
+// ---------------------------------------------------------------- recentering
+
+// one warp per kept read: sums[c][key] += raw count (integer-valued, exact)
+__global__ void __launch_bounds__(256) recenter_accumulate_kernel(const uint64_t *__restrict__ r_off,
+                                                                  const uint64_t *__restrict__ r_keys,
+                                                                  const float *__restrict__ raw,
+                                                                  const uint32_t *__restrict__ kept,
+                                                                  const uint32_t *__restrict__ target,
+                                                                  uint32_t n_kept, uint32_t dim,
+                                                                  uint32_t *__restrict__ sums,
+                                                                  uint32_t *__restrict__ members) {
+    const uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_kept) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t r = kept[i], c = target[i];
+    const uint64_t b = r_off[r], e = r_off[r + 1];
+    for (uint64_t j = b + lane; j < e; j += 32)
+        atomicAdd(&sums[(size_t)c * dim + (uint32_t)r_keys[j]], (uint32_t)raw[j]);
+    if (lane == 0) atomicAdd(&members[c], 1u);
+}
+
+// one thread per cluster: centroid = normalize_l2(sum of raw member counts)
+// (clustering.rs:44-53, 288-295); empty clusters keep their centroid.
+__global__ void recenter_finalize_kernel(const uint32_t *__restrict__ sums, const uint32_t *__restrict__ members,
+                                         uint32_t n_clusters, uint32_t dim, float *__restrict__ cen) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_clusters || members[c] == 0) return;
+    const uint32_t *s = sums + (size_t)c * dim;
+    float *o = cen + (size_t)c * dim;
+    float nrm = 0.0f;
+    for (uint32_t k = 0; k < dim; ++k) {
+        const float v = (float)s[k];
+        nrm = __fadd_rn(nrm, __fmul_rn(v, v));
+    }
+    const float m = __fsqrt_rn(nrm);
+    for (uint32_t k = 0; k < dim; ++k) {
+        const uint32_t u = s[k];
+        o[k] = u ? __fdiv_rn((float)u, m) : 0.0f;
+    }
+}
+
+// ----------------------------------------------------------------- host side
+
+static void host_normalize(std::vector<float> &v) {  // data/sparse.rs:366-383
+    float s = 0.0f;
+    for (float x : v) {
+        const float sq = x * x;
+        s = s + sq;
+    }
+    const float m = sqrtf(s);
+    for (float &x : v) x = x / m;
+}
+
+static float host_dense_dot(const float *a, const float *b, uint32_t dim) {
+    float acc = 0.0f;
+    for (uint32_t k = 0; k < dim; ++k) {
+        const float p = a[k] * b[k];
+        acc = acc + p;
+    }
+    return acc;
+}
+
+static float host_sim(int sim, float dot) {
+    if (sim == MYRIO_SIM_JACARD_TANIMOTO) {
+        const float s = dot / (2.0f - dot);
+        return std::isfinite(s) ? s : 0.0f;
+    }
+    return dot;
+}
+
+static uint64_t max_key_of(myrio_ctx *ctx, const myrio_svecs *v);
+
+void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *p,
+                   const myrio_svecs *init, int32_t *assign, uint32_t *n_iters, float *silhouette) {
+    const uint64_t n_init = init ? init->n_rows : 0;
+    if (n_init == 0 && p->expected_nb_of_clusters == 0)
+        fail(MYRIO_ERR_BAD_ARG, "Ensure `initial_centroids` is not empty or `expected_nb_of_clusters` > 0");
+    if (p->k < 2 || p->k > 32) fail(MYRIO_ERR_INVALID_K, "k=%u: only k in 2..32 is supported", p->k);
+    if (p->k > 7)
+        fail(MYRIO_ERR_UNSUPPORTED, "GPU clustering keeps 4^k dense columns in shared memory: k <= 7 (got %u)", p->k);
+    if (p->similarity != MYRIO_SIM_COSINE && p->similarity != MYRIO_SIM_JACARD_TANIMOTO)
+        fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path", p->similarity);
+    if (init && init->vtype != MYRIO_VAL_F32) fail(MYRIO_ERR_BAD_ARG, "initial centroids must be f32");
+    const uint64_t N = reads->n;
+    const uint32_t dim = 1u << (2 * p->k);
+    const int sim = p->similarity;
+    if (n_iters) *n_iters = 0;
+
+    // Step 1 (clustering.rs:78-90)
+    std::unique_ptr<myrio_svecs> counts(count_reads(ctx, reads, p->k, p->t1));
+    std::vector<uint64_t> hck(N);
+    d2h(ctx, hck.data(), counts->aux_u64.p, N);
+    sync(ctx);
+    std::vector<uint32_t> kept;
+    for (uint64_t r = 0; r < N; ++r) {
+        if (silhouette) silhouette[r] = NAN;
+        if (hck[r] > p->t2) {
+            kept.push_back((uint32_t)r);
+            assign[r] = 0;
+        } else {
+            assign[r] = -1;
+        }
+    }
+    const uint32_t nk = (uint32_t)kept.size();
+    if (nk == 0) fail(MYRIO_ERR_EMPTY, "no read has more than t2=%llu high-confidence k-mers", (unsigned long long)p->t2);
+    std::unique_ptr<myrio_svecs> norm(svecs_normalize(ctx, counts.get()));  // :93-94
+    DevBuf<uint32_t> d_kept(nk);
+    h2d(ctx, d_kept.p, kept.data(), nk);
+
+    // Step 2 (:99-129): centroids live as dense rows
+    const uint64_t cmax = std::max<uint64_t>(std::max<uint64_t>(n_init, p->expected_nb_of_clusters), 1);
+    DevBuf<float> cen(cmax * dim);
+    MYRIO_CK(cudaMemsetAsync(cen.p, 0, cmax * dim * sizeof(float), ctx->stream));
+    uint32_t nc = 0;
+    std::vector<float> dense(dim);
+    if (n_init) {
+        std::vector<uint64_t> ro(n_init + 1), ik(init->nnz);
+        std::vector<float> iv(init->nnz);
+        d2h(ctx, ro.data(), init->row_off.p, n_init + 1);
+        d2h(ctx, ik.data(), init->keys.p, init->nnz);
+        d2h(ctx, iv.data(), init->vals_f32.p, init->nnz);
+        sync(ctx);
+        for (uint64_t c = 0; c < n_init; ++c) {
+            std::fill(dense.begin(), dense.end(), 0.0f);
+            for (uint64_t j = ro[c]; j < ro[c + 1]; ++j) {
+                if (ik[j] >= dim) fail(MYRIO_ERR_BAD_ARG, "initial centroid key out of range for k=%u", p->k);
+                dense[ik[j]] = iv[j];
+            }
+            h2d(ctx, cen.p + (size_t)nc * dim, dense.data(), dim);
+            sync(ctx);
+            ++nc;
+        }
+    }
+    // Cluster::from_normalized_centroid (:281-286): clone the normalised read and normalise AGAIN
+    auto push_centroid_from_read = [&](uint32_t r) {
+        uint64_t be[2];
+        d2h(ctx, be, norm->row_off.p + r, 2);
+        sync(ctx);
+        const uint64_t n = be[1] - be[0];
+        std::vector<uint64_t> kk(n);
+        std::vector<float> vv(n);
+        d2h(ctx, kk.data(), norm->keys.p + be[0], n);
+        d2h(ctx, vv.data(), norm->vals_f32.p + be[0], n);
+        sync(ctx);
+        host_normalize(vv);
+        std::fill(dense.begin(), dense.end(), 0.0f);
+        for (uint64_t j = 0; j < n; ++j) dense[kk[j]] = vv[j];
+        h2d(ctx, cen.p + (size_t)nc * dim, dense.data(), dim);
+        sync(ctx);
+        ++nc;
+    };
+    uint32_t max_idx = 0;  // :106-108 max_by_key -> last maximum
+    uint64_t max_hck = 0;
+    for (uint32_t i = 0; i < nk; ++i)
+        if (i == 0 || hck[kept[i]] >= max_hck) {
+            max_hck = hck[kept[i]];
+            max_idx = i;
+        }
+    const float max_nb_hck = (float)max_hck;
+    if (nc == 0) push_centroid_from_read(kept[max_idx]);
+
+    PairArgs pa{};
+    pa.r_off = norm->row_off.p;
+    pa.r_keys = norm->keys.p;
+    pa.r_vals = norm->vals_f32.p;
+    pa.row_ids = d_kept.p;
+    pa.n_rows = nk;
+    pa.c_dense = cen.p;
+    pa.dim = dim;
+    pa.sim = sim;
+
+    while (nc < p->expected_nb_of_clusters) {  // :114-129
+        DevBuf<float> d_dots((size_t)nk * nc);
+        pa.n_cols = nc;
+        pa.out = d_dots.p;
+        launch_pair<PK_STORE>(ctx, pa, "k6_pair_store");
+        std::vector<float> dots((size_t)nk * nc);
+        d2h(ctx, dots.data(), d_dots.p, dots.size());
+        sync(ctx);
+        uint32_t best = 0;
+        float best_score = 0.0f;
+        for (uint32_t i = 0; i < nk; ++i) {
+            float s = 0.0f;
+            for (uint32_t c = 0; c < nc; ++c) s = s + dots[(size_t)i * nc + c];
+            s = s / (float)nc;
+            const float h = (float)hck[kept[i]];
+            const float pen = 0.8f + 0.2f * (1.0f - h / max_nb_hck);
+            s = s * pen;
+            if (!std::isfinite(s)) fail(MYRIO_ERR_NONFINITE, "non-finite centroid-selection score");
+            if (i == 0 || s < best_score) {  // min_by_key -> first minimum
+                best_score = s;
+                best = i;
+            }
+        }
+        push_centroid_from_read(kept[best]);
+    }
+
+    // Step 3 (:132-169)
+    DevBuf<float> d_best(nk);
+    DevBuf<uint32_t> d_target(nk), d_sums((size_t)nc * dim), d_members(nc);
+    std::vector<float> best(nk);
+    std::vector<uint32_t> target(nk);
+    pa.n_cols = nc;
+    pa.out = d_best.p;
+    pa.out_idx = d_target.p;
+    float previous_mean_wcsss = 1E-6f;
+    float improvement_score = 3.40282347e+38f;
+    uint64_t nb_iters = 0;
+    while (improvement_score > p->eta_improvement && nb_iters < p->nb_iters_max) {
+        launch_pair<PK_ARGMAX>(ctx, pa, "k6_pair_argmax");
+        d2h(ctx, best.data(), d_best.p, nk);
+        d2h(ctx, target.data(), d_target.p, nk);
+        sync(ctx);
+        // wcsss (:307-316): sum1 over members (push order = read order)
+        std::vector<float> w(nc, 0.0f);
+        std::vector<uint8_t> seen(nc, 0);
+        for (uint32_t i = 0; i < nk; ++i) {
+            const uint32_t c = target[i];
+            if (!seen[c]) {
+                w[c] = best[i];
+                seen[c] = 1;
+            } else {
+                w[c] = w[c] + best[i];
+            }
+        }
+        float sum_w = 0.0f;
+        for (uint32_t c = 0; c < nc; ++c) sum_w = sum_w + w[c];
+        const float current_mean_wcsss = sum_w / (float)p->expected_nb_of_clusters;
+        improvement_score = (current_mean_wcsss - previous_mean_wcsss) / previous_mean_wcsss;
+        previous_mean_wcsss = current_mean_wcsss;
+        // recenter (:167)
+        MYRIO_CK(cudaMemsetAsync(d_sums.p, 0, (size_t)nc * dim * sizeof(uint32_t), ctx->stream));
+        MYRIO_CK(cudaMemsetAsync(d_members.p, 0, nc * sizeof(uint32_t), ctx->stream));
+        MYRIO_LAUNCH(ctx, "k6_recenter_accumulate", recenter_accumulate_kernel, (nk + 7) / 8, 256, 0,
+                     counts->row_off.p, counts->keys.p, counts->vals_f32.p, d_kept.p, d_target.p, nk, dim,
+                     d_sums.p, d_members.p);
+        MYRIO_LAUNCH(ctx, "k6_recenter_finalize", recenter_finalize_kernel, (nc + 31) / 32, 32, 0, d_sums.p,
+                     d_members.p, nc, dim, cen.p);
+        nb_iters += 1;
+    }
+    if (n_iters) *n_iters = (uint32_t)nb_iters;
+
+    // Step 5 / first half of step 4 (:200-233): final assignment
+    launch_pair<PK_ARGMAX>(ctx, pa, "k6_pair_argmax");
+    d2h(ctx, target.data(), d_target.p, nk);
+    sync(ctx);
+    for (uint32_t i = 0; i < nk; ++i) assign[kept[i]] = (int32_t)target[i];
+    if (!p->has_silhouette_trimming || nc == 1) return;
+
+    // Step 4 (:235-267) with compute_silhouette_scores_vec (:318-365)
+    std::vector<std::vector<uint32_t>> members(nc);
+    for (uint32_t i = 0; i < nk; ++i) members[target[i]].push_back(kept[i]);
+    std::vector<float> hcen((size_t)nc * dim);
+    d2h(ctx, hcen.data(), cen.p, hcen.size());
+    sync(ctx);
+    const float ssdcf = p->silhouette_trimming;
+    for (uint32_t c = 0; c < nc; ++c) {
+        const uint32_t nm = (uint32_t)members[c].size();
+        if (nm == 0) continue;
+        // neighbour: last maximum over j != c of sim(centroid_c, centroid_j) (:345-351)
+        uint32_t nb = 0xFFFFFFFFu;
+        float bs = 0.0f;
+        for (uint32_t j = 0; j < nc; ++j) {
+            if (j == c) continue;
+            const float s = host_sim(sim, host_dense_dot(&hcen[(size_t)c * dim], &hcen[(size_t)j * dim], dim));
+            if (nb == 0xFFFFFFFFu || s >= bs) {
+                bs = s;
+                nb = j;
+            }
+        }
+        const uint32_t nn = (uint32_t)members[nb].size();
+        std::vector<uint32_t> cols(members[c]);
+        cols.insert(cols.end(), members[nb].begin(), members[nb].end());
+        DevBuf<uint32_t> d_rows(nm), d_cols(cols.size());
+        DevBuf<float> d_sums2((size_t)nm * 2);
+        h2d(ctx, d_rows.p, members[c].data(), nm);
+        h2d(ctx, d_cols.p, cols.data(), cols.size());
+        PairArgs sa{};
+        sa.r_off = norm->row_off.p;
+        sa.r_keys = norm->keys.p;
+        sa.r_vals = norm->vals_f32.p;
+        sa.row_ids = d_rows.p;
+        sa.n_rows = nm;
+        sa.c_off = norm->row_off.p;
+        sa.c_keys = norm->keys.p;
+        sa.c_vals = norm->vals_f32.p;
+        sa.col_ids = d_cols.p;
+        sa.n_cols = (uint32_t)cols.size();
+        sa.dim = dim;
+        sa.split = nm;
+        sa.sim = sim;
+        sa.out = d_sums2.p;
+        launch_pair<PK_SILSUM>(ctx, sa, "k6_pair_silhouette");
+        std::vector<float> sums((size_t)nm * 2);
+        d2h(ctx, sums.data(), d_sums2.p, sums.size());
+        sync(ctx);
+        std::vector<float> sil(nm);
+        for (uint32_t t = 0; t < nm; ++t) {  // inner() :323-336
+            const float a = sums[(size_t)t * 2] / (float)(nm - 1);
+            const float b = sums[(size_t)t * 2 + 1] / (float)nn;
+            sil[t] = (b - a) / fmaxf(a, b);
+        }
+        const float n = (float)nm;  // :244-249
+        float sum = 0.0f;
+        for (uint32_t t = 0; t < nm; ++t) sum = sum + sil[t];
+        const float mean = sum / n;
+        float sq = 0.0f;
+        for (uint32_t t = 0; t < nm; ++t) {
+            const float d = sil[t] - mean;
+            sq = sq + d * d;
+        }
+        const float sd = sqrtf((1.0f / n) * sq);
+        const float left_cutoff = mean - sd * ssdcf;
+        for (uint32_t t = 0; t < nm; ++t) {
+            const uint32_t r = members[c][t];
+            if (silhouette) silhouette[r] = sil[t];
+            if (sil[t] < left_cutoff) assign[r] = -2;  // :257-262
+        }
+    }
+}
+
+// ------------------------------------------------ compute_cluster_centroid
+
+__global__ void __launch_bounds__(256) gather_members_kernel(const uint64_t *__restrict__ r_off,
+                                                             const uint64_t *__restrict__ r_keys,
+                                                             const float *__restrict__ r_vals,
+                                                             const uint64_t *__restrict__ ids,
+                                                             const uint64_t *__restrict__ dst_off, uint64_t m,
+                                                             uint64_t *__restrict__ okeys,
+                                                             uint64_t *__restrict__ ovals) {
+    const uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= m) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t r = ids[i], b = r_off[r], n = r_off[r + 1] - b, d = dst_off[i];
+    for (uint64_t j = lane; j < n; j += 32) {
+        okeys[d + j] = r_keys[b + j];
+        ovals[d + j] = (uint64_t)r_vals[b + j];  // raw counts are integer-valued
+    }
+}
+
+__global__ void __launch_bounds__(256) cc_mark_heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
+                                                            uint32_t *__restrict__ flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) cc_reduce_runs_kernel(const uint64_t *__restrict__ keys,
+                                                             const uint64_t *__restrict__ vals, uint64_t n,
+                                                             const uint32_t *__restrict__ flags,
+                                                             const uint64_t *__restrict__ uidx,
+                                                             uint64_t *__restrict__ ukeys,
+                                                             float *__restrict__ usum) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flags[i]) return;
+    const uint64_t key = keys[i];
+    uint64_t s = 0;
+    for (uint64_t j = i; j < n && keys[j] == key; ++j) s += vals[j];
+    const uint64_t u = uidx[i];
+    ukeys[u] = key;
+    usum[u] = (float)s;
+}
+
+__global__ void cc_norm_kernel(const float *__restrict__ v, uint64_t n, float *__restrict__ magn) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float s = 0.0f;
+        for (uint64_t i = 0; i < n; ++i) s = __fadd_rn(s, __fmul_rn(v[i], v[i]));
+        *magn = __fsqrt_rn(s);
+    }
+}
+
+__global__ void __launch_bounds__(256) cc_scale_kernel(float *__restrict__ v, uint64_t n,
+                                                       const float *__restrict__ magn) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = __fdiv_rn(v[i], *magn);
+}
+
+myrio_svecs *cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts, const uint64_t *member_ids,
+                              uint64_t m) {
+    if (counts->vtype != MYRIO_VAL_F32) fail(MYRIO_ERR_BAD_ARG, "counts must be an f32 batch");
+    for (uint64_t i = 0; i < m; ++i)
+        if (member_ids[i] >= counts->n_rows) fail(MYRIO_ERR_BAD_ARG, "member id out of range");
+    auto out = std::make_unique<myrio_svecs>();
+    out->n_rows = 1;
+    out->vtype = MYRIO_VAL_F32;
+    out->row_off.alloc(2);
+    std::vector<uint64_t> ro(counts->n_rows + 1);
+    d2h(ctx, ro.data(), counts->row_off.p, counts->n_rows + 1);
+    sync(ctx);
+    std::vector<uint64_t> dst(m + 1, 0);
+    for (uint64_t i = 0; i < m; ++i) dst[i + 1] = dst[i] + (ro[member_ids[i] + 1] - ro[member_ids[i]]);
+    const uint64_t total = dst[m];
+    uint64_t U = 0;
+    if (total) {
+        DevBuf<uint64_t> d_ids(m), d_dst(m + 1), k1(total), v1(total), k2(total), v2(total), uidx(total + 1);
+        DevBuf<uint32_t> hist, flags(total);
+        DevBuf<uint64_t> offs;
+        h2d(ctx, d_ids.p, member_ids, m);
+        h2d(ctx, d_dst.p, dst.data(), m + 1);
+        MYRIO_LAUNCH(ctx, "cc_gather", gather_members_kernel, (unsigned)((m + 7) / 8), 256, 0, counts->row_off.p,
+                     counts->keys.p, counts->vals_f32.p, d_ids.p, d_dst.p, m, k1.p, v1.p);
+        const bool in_tmp = radix_sort_pairs_raw(ctx, k1.p, v1.p, k2.p, v2.p, total, 64, hist, offs);
+        const uint64_t *sk = in_tmp ? k2.p : k1.p, *sv = in_tmp ? v2.p : v1.p;
+        const unsigned g = (unsigned)((total + 255) / 256);
+        MYRIO_LAUNCH(ctx, "cc_mark_heads", cc_mark_heads_kernel, g, 256, 0, sk, total, flags.p);
+        exclusive_scan_u32_to_u64(ctx, flags.p, uidx.p, total);
+        d2h(ctx, &U, uidx.p + total, 1);
+        sync(ctx);
+        out->keys.alloc(U);
+        out->vals_f32.alloc(U);
+        MYRIO_LAUNCH(ctx, "cc_reduce_runs", cc_reduce_runs_kernel, g, 256, 0, sk, sv, total, flags.p, uidx.p,
+                     out->keys.p, out->vals_f32.p);
+        DevBuf<float> magn(1);
+        MYRIO_LAUNCH(ctx, "cc_norm", cc_norm_kernel, 1, 32, 0, out->vals_f32.p, U, magn.p);
+        MYRIO_LAUNCH(ctx, "cc_scale", cc_scale_kernel, (unsigned)((U + 255) / 256), 256, 0, out->vals_f32.p, U,
+                     magn.p);
+        sync(ctx);
+    } else {
+        out->keys.alloc(1);
+        out->vals_f32.alloc(1);
+    }
+    out->nnz = U;
+    const uint64_t h_ro[2] = {0, U};
+    h2d(ctx, out->row_off.p, h_ro, 2);
+    sync(ctx);
+    return out.release();
+}
+
+// --------------------------------------------------------------- pairwise
+
+__global__ void __launch_bounds__(256) max_key_kernel(const uint64_t *__restrict__ keys, uint64_t n,
+                                                      unsigned long long *__restrict__ out) {
+    uint64_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        m = max(m, keys[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, (unsigned long long)m);
+}
+
+static uint64_t max_key_of(myrio_ctx *ctx, const myrio_svecs *v) {
+    if (v->nnz == 0) return 0;
+    DevBuf<unsigned long long> d(1);
+    MYRIO_CK(cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+    MYRIO_LAUNCH(ctx, "max_key", max_key_kernel, (unsigned)std::min<uint64_t>(1024, (v->nnz + 255) / 256), 256, 0,
+                 v->keys.p, v->nnz, d.p);
+    unsigned long long h = 0;
+    d2h(ctx, &h, d.p, 1);
+    sync(ctx);
+    return h;
+}
+
+void pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols, int32_t sim, float *out) {
+    if (rows->vtype != MYRIO_VAL_F32 || cols->vtype != MYRIO_VAL_F32)
+        fail(MYRIO_ERR_BAD_ARG, "pairwise needs f32 (pre-normalised) batches");
+    if (sim != MYRIO_SIM_COSINE && sim != MYRIO_SIM_JACARD_TANIMOTO)
+        fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path", sim);
+    const uint64_t nr = rows->n_rows, ncol = cols->n_rows;
+    if (nr == 0 || ncol == 0) return;
+    if (nr > 0xFFFFFFFFull || ncol > 0xFFFFFFFFull) fail(MYRIO_ERR_BAD_ARG, "too many rows/cols");
+    const uint64_t mk = std::max(max_key_of(ctx, rows), max_key_of(ctx, cols));
+    DevBuf<float> d_out(nr * ncol);
+    if (mk < 16384) {
+        uint32_t dim = 16;
+        while (dim <= mk) dim <<= 2;
+        PairArgs a{};
+        a.r_off = rows->row_off.p;
+        a.r_keys = rows->keys.p;
+        a.r_vals = rows->vals_f32.p;
+        a.n_rows = (uint32_t)nr;
+        a.c_off = cols->row_off.p;
+        a.c_keys = cols->keys.p;
+        a.c_vals = cols->vals_f32.p;
+        a.n_cols = (uint32_t)ncol;
+        a.dim = dim;
+        a.sim = sim;
+        a.out = d_out.p;
+        launch_pair<PK_STORE>(ctx, a, "k6_pair_store");
+    } else {
+        const uint64_t np = nr * ncol;
+        MYRIO_LAUNCH(ctx, "k6_pair_merge", pair_merge_kernel, (unsigned)((np + 127) / 128), 128, 0,
+                     rows->row_off.p, rows->keys.p, rows->vals_f32.p, (uint32_t)nr, cols->row_off.p,
+                     cols->keys.p, cols->vals_f32.p, (uint32_t)ncol, sim, d_out.p);
+    }
+    d2h(ctx, out, d_out.p, nr * ncol);
+    sync(ctx);
+}
+
+}  // namespace myrio

@@ -1,0 +1,213 @@
+// common.cuh -- context, error handling, device buffers, launch bookkeeping.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/myrio_b200.h"
+
+namespace myrio {
+
+struct Error {
+    int32_t code;
+    std::string msg;
+};
+
+void set_last_error(const std::string &msg);
+
+[[noreturn]] inline void fail(int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    throw Error{code, std::string(buf)};
+}
+
+#define MYRIO_CK(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            ::myrio::fail(e__ == cudaErrorMemoryAllocation ? MYRIO_ERR_OOM : MYRIO_ERR_CUDA,    \
+                          "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+        }                                                                                       \
+    } while (0)
+
+// Runs `f`, translating exceptions into a status + thread-local message.
+template <typename F>
+inline int32_t guarded(F &&f) {
+    try {
+        f();
+        return MYRIO_OK;
+    } catch (const Error &e) {
+        set_last_error(e.msg);
+        return e.code;
+    } catch (const std::exception &e) {
+        set_last_error(e.what());
+        return MYRIO_ERR_BAD_ARG;
+    } catch (...) {
+        set_last_error("unknown error");
+        return MYRIO_ERR_BAD_ARG;
+    }
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) {
+        o.p = nullptr;
+        o.n = 0;
+    }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) MYRIO_CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    // grow-only scratch
+    void reserve(size_t count) {
+        if (count > n) alloc(count + count / 8);
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct ProfEntry {
+    std::string name;
+    cudaEvent_t start, stop;
+};
+
+}  // namespace myrio
+
+struct myrio_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    uint64_t launches = 0;
+    bool prof_on = false;
+    std::vector<myrio::ProfEntry> prof;
+    // scoring scratch (grow-only)
+    myrio::DevBuf<float> score_rows;
+    myrio::DevBuf<unsigned long long> score_counters;
+    uint64_t last_stats[3] = {0, 0, 0};
+    // pinned staging for small D2H reads
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+struct myrio_seqs {
+    int kind = 0;  // 0 reads (2-bit + qual), 1 leaves (4-bit)
+    uint64_t n = 0;
+    myrio::DevBuf<uint64_t> words, word_off, base_off;
+    myrio::DevBuf<uint8_t> qual;
+    std::vector<uint64_t> h_base_off;  // host copy of the lengths (classification)
+    std::vector<uint32_t> h_aux;       // leaves: number of ambiguity codes per sequence
+};
+
+struct myrio_svecs {
+    uint64_t n_rows = 0, nnz = 0;
+    int32_t vtype = MYRIO_VAL_F32;
+    int aux_kind = 0;  // 0 none, 1 u64 (nb_hck), 2 f32 (rescale)
+    myrio::DevBuf<uint64_t> row_off, keys;
+    myrio::DevBuf<float> vals_f32;
+    myrio::DevBuf<uint16_t> vals_u16;
+    myrio::DevBuf<uint64_t> aux_u64;
+    myrio::DevBuf<float> aux_f32;
+};
+
+namespace myrio {
+
+struct ScopedDevice {
+    int prev = 0;
+    explicit ScopedDevice(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        cur = dev;
+    }
+    ~ScopedDevice() {
+        if (prev != cur) cudaSetDevice(prev);
+    }
+    int cur;
+};
+
+// Bookkeeping around every kernel launch: count it, optionally time it with
+// CUDA events on the context's stream, and surface launch errors.
+struct LaunchScope {
+    myrio_ctx *ctx;
+    bool timed;
+    cudaEvent_t stop = nullptr;
+    LaunchScope(myrio_ctx *c, const char *name) : ctx(c), timed(c->prof_on) {
+        ctx->launches++;
+        if (timed) {
+            ProfEntry e;
+            e.name = name;
+            MYRIO_CK(cudaEventCreate(&e.start));
+            MYRIO_CK(cudaEventCreate(&e.stop));
+            MYRIO_CK(cudaEventRecord(e.start, ctx->stream));
+            stop = e.stop;
+            ctx->prof.push_back(e);
+        }
+    }
+    void done() {
+        if (timed) MYRIO_CK(cudaEventRecord(stop, ctx->stream));
+        MYRIO_CK(cudaGetLastError());
+    }
+};
+
+#define MYRIO_LAUNCH(ctx, name, kernel, grid, block, smem, ...)                      \
+    do {                                                                             \
+        ::myrio::LaunchScope ls__((ctx), (name));                                    \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+        ls__.done();                                                                 \
+    } while (0)
+
+inline void sync(myrio_ctx *ctx) { MYRIO_CK(cudaStreamSynchronize(ctx->stream)); }
+
+template <typename T>
+inline void h2d(myrio_ctx *ctx, T *dst, const T *src, size_t n) {
+    if (n) MYRIO_CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+}
+template <typename T>
+inline void d2h(myrio_ctx *ctx, T *dst, const T *src, size_t n) {
+    if (n) MYRIO_CK(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+}
+
+// --- device-wide primitives (scan.cu) ---
+// out[i] = sum_{j<i} in[j] for i in [0, n]; out has n+1 elements.
+void exclusive_scan_u32_to_u64(myrio_ctx *ctx, const uint32_t *in, uint64_t *out, size_t n);
+void exclusive_scan_u64(myrio_ctx *ctx, const uint64_t *in, uint64_t *out, size_t n);
+
+// --- LSD radix sort of (u64 key, u64 payload) pairs, stable (radix_sort.cu) ---
+// Sorts by key bits [0, key_bits).  keys/vals are overwritten with the result.
+void radix_sort_pairs(myrio_ctx *ctx, uint64_t *keys, uint64_t *vals, uint64_t *keys_tmp,
+                      uint64_t *vals_tmp, size_t n, int key_bits);
+
+}  // namespace myrio

@@ -1,0 +1,66 @@
+// index.cuh -- the tiled inverted index over the reference leaves (K3 output).
+#pragma once
+#include "common.cuh"
+
+namespace myrio {
+
+// Dictionary slot of a tile: open addressing, linear probing. len == 0 <=> empty.
+struct __align__(16) DictSlot {
+    uint64_t key;
+    uint32_t begin;  // first posting, relative to the tile's posting range
+    uint32_t len;    // number of postings (document frequency inside the tile)
+};
+
+struct TileInfo {
+    uint64_t post_begin;  // offset of the tile's postings in the global posting array
+    uint64_t n_post;
+    uint64_t n_unique;
+    uint32_t leaf_begin;  // first leaf (shard-local payload index) of the tile
+    uint32_t n_leaves;
+    const DictSlot *dict;
+    uint32_t dict_mask;  // table size - 1 (power of two)
+    uint32_t pad_;
+    const uint64_t *ukeys;    // sorted unique keys of the tile        (export / tests)
+    const uint32_t *ubegin;   // first posting of each unique key, +1 sentinel
+};
+
+__device__ __forceinline__ uint32_t dict_hash(uint64_t key) {
+    key ^= key >> 33;
+    key *= 0xff51afd7ed558ccdull;
+    key ^= key >> 33;
+    key *= 0xc4ceb9fe1a85ec53ull;
+    key ^= key >> 33;
+    return (uint32_t)key;
+}
+
+// posting = (value bits, tile-local leaf) packed as one 8-byte word
+struct __align__(8) Posting {
+    float val;
+    uint32_t leaf;
+};
+
+}  // namespace myrio
+
+struct myrio_index {
+    uint64_t n_leaves = 0;
+    uint32_t leaf_id_base = 0;
+    uint32_t tile_leaves = 0;
+    uint64_t n_postings = 0, n_unique_total = 0;
+    myrio::DevBuf<uint64_t> postings;  // Posting[n_postings]
+    std::vector<myrio::TileInfo> tiles;
+    myrio::DevBuf<myrio::TileInfo> d_tiles;
+    std::vector<myrio::DevBuf<myrio::DictSlot>> dicts;
+    std::vector<myrio::DevBuf<uint64_t>> ukeys;
+    std::vector<myrio::DevBuf<uint32_t>> ubegin;
+};
+
+namespace myrio {
+myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t leaf_id_base,
+                         uint32_t tile_leaves);
+void index_export_tile(myrio_ctx *ctx, const myrio_index *ix, uint64_t tile, uint64_t *n_unique,
+                       uint64_t *n_postings, uint64_t *ukeys, uint64_t *offs, uint32_t *post_leaf,
+                       float *post_val);
+bool radix_sort_pairs_raw(myrio_ctx *ctx, uint64_t *keys, uint64_t *vals, uint64_t *keys_tmp,
+                          uint64_t *vals_tmp, size_t n, int key_bits, DevBuf<uint32_t> &hist,
+                          DevBuf<uint64_t> &offs);
+}  // namespace myrio

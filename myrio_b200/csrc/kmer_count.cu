@@ -1,0 +1,791 @@
+// kmer_count.cu -- K1 (read k-mer counting) and K2 (reference-leaf k-mer counting).
+//
+// One CTA per sequence.  The packed sequence is staged in shared memory with
+// 16-byte loads, every window's key is produced by a funnel shift over the 2-bit
+// words (forward key + reverse-complement key via brev), the keys are sorted in
+// shared memory (bitonic network) and run-length reduced into a sorted
+// (key, count) row.  Rows go to an over-allocated scratch at a per-row offset
+// known up front (2*(n-k+1) keys at most); compact_rows_kernel then packs them
+// into the final CSR once the exact row sizes have been prefix-summed.
+//
+// Reference semantics restated here:
+//   reads : MyrSeq::compute_kmer_counts      myrio-core/src/data/myrseq.rs:76-111
+//   leaves: compute_kmer_store_counts_for_fasta_seq  myrio-core/src/tax/mod.rs:70-148
+//   reduce: SparseVec::from_unsorted_singles  myrio-core/src/data/sparse.rs:229-272
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kmer_count.cuh"
+
+namespace myrio {
+
+static constexpr int KC_THREADS = 256;
+
+static const uint32_t h_phred_bits[128] = {
+#include "phred_table.inc"
+};
+
+__device__ float g_phred[128];
+
+void upload_phred_table(myrio_ctx *ctx) {
+    MYRIO_CK(cudaMemcpyToSymbolAsync(g_phred, h_phred_bits, sizeof(h_phred_bits), 0,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+}
+
+// ----------------------------------------------------------------- helpers
+
+// key of the window starting at base i: bits [2i, 2i+2k) of the LSB-first packed words
+__device__ __forceinline__ uint64_t window_key(const uint64_t *w, uint32_t i, uint32_t k) {
+    const uint32_t wi = i >> 5, sh = (i & 31u) * 2u;
+    uint64_t key = w[wi] >> sh;
+    if (sh) key |= w[wi + 1] << (64u - sh);
+    if (k < 32) key &= (1ull << (2u * k)) - 1ull;
+    return key;
+}
+
+// key of the reverse complement of a window: complement (3-b == ~b per 2-bit
+// group), reverse the order of the groups, realign to bit 0
+__device__ __forceinline__ uint64_t revcomp_key(uint64_t key, uint32_t k) {
+    uint64_t x = __brevll(~key);
+    x = ((x & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((x & 0x5555555555555555ull) << 1);
+    return x >> (64u - 2u * k);
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v) {
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one u32 per thread (KC_THREADS threads); wbuf: 33 u32
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *wbuf, uint32_t *total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = warp_incl_scan_u32(v);
+    if (lane == 31) wbuf[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (KC_THREADS / 32) ? wbuf[lane] : 0;
+        uint32_t wi = warp_incl_scan_u32(w);
+        if (lane < (KC_THREADS / 32)) wbuf[lane] = wi - w;
+        if (lane == 31) wbuf[32] = wi;
+    }
+    __syncthreads();
+    uint32_t res = wbuf[warp] + inc - v;
+    *total = wbuf[32];
+    __syncthreads();
+    return res;
+}
+
+// Bitonic sort of S (power of two) keys, ascending; optional u16 payload moves along.
+template <bool HAS_W>
+__device__ __forceinline__ void bitonic_sort(uint64_t *keys, uint16_t *w, uint32_t S) {
+    for (uint32_t size = 2; size <= S; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (S >> 1); t += KC_THREADS) {
+                uint32_t lo = 2u * t - (t & (stride - 1u));
+                uint32_t hi = lo + stride;
+                bool asc = (lo & size) == 0u;
+                uint64_t a = keys[lo], b = keys[hi];
+                if ((a > b) == asc) {
+                    keys[lo] = b;
+                    keys[hi] = a;
+                    if (HAS_W) {
+                        uint16_t t0 = w[lo];
+                        w[lo] = w[hi];
+                        w[hi] = t0;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint32_t pow2_ceil(uint32_t v) {
+    if (v <= 2) return 2;
+    return 1u << (32 - __clz(v - 1));
+}
+
+// Marks run heads of the sorted keys[0..E) and records their positions:
+// headpos[idx] = index of the idx-th distinct key; returns D (number of runs).
+// Each thread owns a contiguous chunk so the scan keeps the order.
+__device__ __forceinline__ uint32_t find_run_heads(const uint64_t *keys, uint32_t E,
+                                                   uint32_t *headpos, uint32_t *wbuf) {
+    const uint32_t C = (E + KC_THREADS - 1) / KC_THREADS;
+    const uint32_t b = min(E, threadIdx.x * C), e = min(E, b + C);
+    uint32_t cnt = 0;
+    for (uint32_t i = b; i < e; ++i) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+    uint32_t D;
+    uint32_t pos = block_excl_scan_u32(cnt, wbuf, &D);
+    for (uint32_t i = b; i < e; ++i)
+        if (i == 0 || keys[i] != keys[i - 1]) headpos[pos++] = i;
+    __syncthreads();
+    return D;
+}
+
+// ------------------------------------------------------------- K1: reads
+
+struct ReadCountArgs {
+    const uint64_t *words;
+    const uint64_t *word_off;
+    const uint64_t *base_off;
+    const uint8_t *qual;
+    const uint32_t *ids;  // rows handled by this launch
+    uint32_t k;
+    float cutoff;
+    uint32_t ecap;         // sort capacity (power of two) >= 2*(n-k+1) for every row of the launch
+    const uint64_t *eoff;  // scratch offset of every row
+    uint64_t *skeys;
+    float *svals;
+    uint32_t *d_out;    // distinct keys per row
+    uint64_t *hck_out;  // nb_hck per row
+    int *err;
+    uint8_t *gscratch;  // GLOBAL variant: per-CTA work area
+    uint64_t gstride;
+};
+
+// shared/global work area: keys[ecap] u64 | aux[ecap+64] u32 (conf factors, then run heads)
+//                          | words[ecap/64+4] u64
+__host__ __device__ inline size_t read_work_bytes(uint32_t ecap) {
+    return (size_t)ecap * 8 + ((size_t)ecap + 64) * 4 + ((size_t)ecap / 64 + 4) * 8;
+}
+
+template <bool GLOBAL>
+__global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ float s_phred[128];
+    __shared__ uint32_t s_wbuf[33];
+    __shared__ uint32_t s_cnt;
+
+    uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(work);
+    uint32_t *aux = reinterpret_cast<uint32_t *>(work + (size_t)a.ecap * 8);
+    uint64_t *words = reinterpret_cast<uint64_t *>(work + (size_t)a.ecap * 8 + ((size_t)a.ecap + 64) * 4);
+    float *pfac = reinterpret_cast<float *>(aux);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t r = a.ids[blockIdx.x];
+    const uint64_t b0 = a.base_off[r];
+    const uint32_t n = (uint32_t)(a.base_off[r + 1] - b0);
+    const uint32_t k = a.k;
+
+    if (tid < 128) s_phred[tid] = g_phred[tid];
+    if (tid == 0) s_cnt = 0;
+    if (n < k) {  // kmers::<K>() yields nothing
+        if (tid == 0) {
+            a.d_out[r] = 0;
+            a.hck_out[r] = 0;
+        }
+        return;
+    }
+    const uint32_t nb = n - k + 1;
+
+    // packed bases: 16-byte loads (every read starts on an even word)
+    {
+        const uint64_t w0 = a.word_off[r];
+        const uint32_t nw = (n + 31) >> 5;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.words + w0);
+        uint4 *dst = reinterpret_cast<uint4 *>(words);
+        for (uint32_t i = tid; i < (nw + 1) / 2; i += KC_THREADS) dst[i] = __ldg(src + i);
+        if (tid == 0) {  // window_key may touch one word past the end
+            words[((nw + 1) / 2) * 2] = 0;
+        }
+    }
+    __syncthreads();  // s_phred ready
+    // quality bytes -> per-base probability of a correct call, 16-byte loads
+    {
+        const uint8_t *qp = a.qual + b0;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(qp) & 15u);
+        const uint4 *q4 = reinterpret_cast<const uint4 *>(qp - mis);
+        const uint32_t nchunks = (mis + n + 15) >> 4;
+        bool bad = false;
+        for (uint32_t c = tid; c < nchunks; c += KC_THREADS) {
+            uint4 v = __ldg(q4 + c);
+            uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                int idx = (int)(c * 16 + j) - (int)mis;
+                if (idx >= 0 && idx < (int)n) {
+                    uint32_t q = (wv[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                    bad |= q >= 128u;
+                    pfac[idx] = s_phred[q & 127u];
+                }
+            }
+        }
+        if (bad) atomicMax(a.err, MYRIO_ERR_BAD_QUALITY);
+    }
+    __syncthreads();
+
+    // windows: confidence = product of k factors (sequential f32, as the reference);
+    // every passing window emits its key and its reverse complement's key
+    for (uint32_t base = 0; base < nb; base += KC_THREADS) {
+        const uint32_t i = base + tid;
+        bool pass = false;
+        uint64_t kf = 0, kr = 0;
+        if (i < nb) {
+            float conf = 1.0f;
+            for (uint32_t j = 0; j < k; ++j) conf = __fmul_rn(conf, pfac[i + j]);
+            pass = conf > a.cutoff;
+            if (pass) {
+                kf = window_key(words, i, k);
+                kr = revcomp_key(kf, k);
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            const unsigned lane = tid & 31;
+            const int leader = __ffs(m) - 1;
+            uint32_t slot = 0;
+            if ((int)lane == leader) slot = atomicAdd(&s_cnt, 2u * __popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, leader);
+            if (pass) {
+                slot += 2u * __popc(m & ((1u << lane) - 1u));
+                keys[slot] = kf;
+                keys[slot + 1] = kr;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t E = s_cnt;  // == nb_hck
+    if (E == 0) {
+        if (tid == 0) {
+            a.d_out[r] = 0;
+            a.hck_out[r] = 0;
+        }
+        return;
+    }
+    const uint32_t S = pow2_ceil(E);
+    for (uint32_t i = E + tid; i < S; i += KC_THREADS) keys[i] = ~0ull;
+    bitonic_sort<false>(keys, nullptr, S);
+
+    uint32_t *headpos = aux;  // conf factors are dead
+    const uint32_t D = find_run_heads(keys, E, headpos, s_wbuf);
+    const uint64_t o = a.eoff[r];
+    for (uint32_t idx = tid; idx < D; idx += KC_THREADS) {
+        const uint32_t i = headpos[idx];
+        const uint32_t nx = (idx + 1 < D) ? headpos[idx + 1] : E;
+        a.skeys[o + idx] = keys[i];
+        a.svals[o + idx] = (float)(nx - i);  // value += 1.0 per occurrence: exact
+    }
+    if (tid == 0) {
+        a.d_out[r] = D;
+        a.hck_out[r] = E;
+    }
+}
+
+// ------------------------------------------------------------ K2: leaves
+
+// shared definition with oracle/myrio_oracle.c:myo_resample_pick
+__device__ __forceinline__ uint32_t resample_pick(uint64_t seed, uint64_t leaf, uint32_t resample,
+                                                  uint32_t pos, uint32_t n_opts) {
+    uint64_t x = seed;
+    x ^= leaf * 0x9E3779B97F4A7C15ull;
+    x ^= ((uint64_t)resample << 32 | (uint64_t)pos) * 0xD1B54A32D192ED03ull;
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x = x ^ (x >> 31);
+    return (uint32_t)(((x >> 32) * (uint64_t)n_opts) >> 32);
+}
+
+// tax/mod.rs:77-97: options in ascending Dna order = descending bit of the 4-bit code
+__device__ __forceinline__ uint32_t resolve_iupac(uint32_t code, uint64_t seed, uint64_t leaf,
+                                                  uint32_t resample, uint32_t pos) {
+    const uint32_t nopt = __popc(code);
+    if (nopt == 1) return (uint32_t)__clz(code) - 28u;
+    uint32_t pick = resample_pick(seed, leaf, resample, pos, nopt);
+    // pick-th set bit counted from bit 3 downwards
+    for (uint32_t b = 0; b < 4; ++b) {
+        if (code & (8u >> b)) {
+            if (pick == 0) return b;
+            --pick;
+        }
+    }
+    return 0;
+}
+
+struct LeafCountArgs {
+    const uint64_t *words;  // 4-bit packed
+    const uint64_t *word_off;
+    const uint64_t *base_off;
+    const uint32_t *ids;
+    uint32_t k;
+    uint32_t nb_resamples;
+    uint64_t seed;
+    uint64_t leaf_id_base;
+    uint32_t ecap;  // sort capacity and max symbols of every row of the launch
+    const uint64_t *eoff;
+    uint64_t *skeys;
+    uint16_t *svals;
+    uint32_t *d_out;
+    float *rescale_out;
+    int *err;
+    uint8_t *gscratch;
+    uint64_t gstride;
+};
+
+// work area: keys[ecap] u64 | aux[ecap+64] u32 | wts[ecap] u16 | raw[ecap+16] u8 | comp[ecap+16] u8
+//            | words2[ecap/32+4] u64
+__host__ __device__ inline size_t leaf_work_bytes(uint32_t ecap) {
+    return (size_t)ecap * 8 + ((size_t)ecap + 64) * 4 + (size_t)ecap * 2 + 2 * ((size_t)ecap + 16) +
+           ((size_t)ecap / 32 + 4) * 8;
+}
+
+template <bool GLOBAL>
+__global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ uint32_t s_wbuf[33];
+    __shared__ uint32_t s_cnt, s_namb, s_over;
+    __shared__ uint32_t s_sum;
+
+    uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
+    size_t o_ = 0;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(work + o_);
+    o_ += (size_t)a.ecap * 8;
+    uint32_t *aux = reinterpret_cast<uint32_t *>(work + o_);
+    o_ += ((size_t)a.ecap + 64) * 4;
+    uint16_t *wts = reinterpret_cast<uint16_t *>(work + o_);
+    o_ += (size_t)a.ecap * 2;
+    uint8_t *raw = work + o_;
+    o_ += (size_t)a.ecap + 16;
+    uint8_t *comp = work + o_;
+    o_ += (size_t)a.ecap + 16;
+    uint64_t *words2 = reinterpret_cast<uint64_t *>(work + o_);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t r = a.ids[blockIdx.x];
+    const uint64_t b0 = a.base_off[r];
+    const uint32_t n_in = (uint32_t)(a.base_off[r + 1] - b0);
+    const uint32_t k = a.k, R = a.nb_resamples;
+    const uint64_t leaf = a.leaf_id_base + r;
+    const uint64_t o = a.eoff[r];
+
+    if (tid == 0) {
+        s_cnt = 0;
+        s_namb = 0;
+        s_over = 0;
+        s_sum = 0;
+    }
+    // unpack 4-bit symbols (16-byte loads: 32 symbols each)
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.words + a.word_off[r]);
+        const uint32_t nchunks = (n_in + 31) >> 5;
+        for (uint32_t c = tid; c < nchunks; c += KC_THREADS) {
+            uint4 v = __ldg(src + c);
+            uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                uint32_t idx = c * 32 + j;
+                if (idx < n_in) raw[idx] = (uint8_t)((wv[j >> 3] >> ((j & 7) * 4)) & 15u);
+            }
+        }
+    }
+    __syncthreads();
+    // drop gaps (Iupac::X == 0), tax/mod.rs:98 -- ordered compaction
+    uint32_t n;
+    {
+        const uint32_t C = (n_in + KC_THREADS - 1) / KC_THREADS;
+        const uint32_t b = min(n_in, tid * C), e = min(n_in, b + C);
+        uint32_t cnt = 0, amb = 0;
+        for (uint32_t i = b; i < e; ++i) {
+            cnt += raw[i] != 0;
+            amb += __popc((uint32_t)raw[i]) > 1;
+        }
+        uint32_t pos = block_excl_scan_u32(cnt, s_wbuf, &n);
+        for (uint32_t i = b; i < e; ++i)
+            if (raw[i] != 0) comp[pos++] = raw[i];
+        if (amb) atomicAdd(&s_namb, amb);
+    }
+    __syncthreads();
+    const uint32_t cutoff = (R + 5u) >> 3;  // tax/mod.rs:130
+    if (n < k || R == 0) {                  // :99-102 / empty singles -> :136-139
+        if (tid == 0) {
+            a.skeys[o] = 0;
+            a.svals[o] = 1;
+            a.d_out[r] = 1;
+            a.rescale_out[r] = 1.0f;
+        }
+        return;
+    }
+    const uint32_t nb = n - k + 1;
+    const bool ambiguous = s_namb != 0;
+    uint32_t E;
+    if (!ambiguous) {
+        // all resamples are identical: count once, scale by R (wrapping u16 like the
+        // release-mode `+=` of from_unsorted_singles)
+        const uint32_t nw = (n + 31) >> 5;
+        for (uint32_t wi = tid; wi <= nw; wi += KC_THREADS) {
+            uint64_t w = 0;
+            const uint32_t lim = min(32u, n > wi * 32 ? n - wi * 32 : 0u);
+            for (uint32_t j = 0; j < lim; ++j)
+                w |= (uint64_t)((uint32_t)__clz((uint32_t)comp[wi * 32 + j]) - 28u) << (2 * j);
+            words2[wi] = w;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < nb; i += KC_THREADS) {
+            uint64_t kf = window_key(words2, i, k);
+            keys[2 * i] = kf;
+            keys[2 * i + 1] = revcomp_key(kf, k);
+        }
+        E = 2 * nb;
+    } else {
+        // prefix count of ambiguous symbols -> window i is ambiguous iff pre[i+k] > pre[i]
+        uint32_t *pre = aux;
+        {
+            const uint32_t C = (n + KC_THREADS - 1) / KC_THREADS;
+            const uint32_t b = min(n, tid * C), e = min(n, b + C);
+            uint32_t cnt = 0;
+            for (uint32_t i = b; i < e; ++i) cnt += __popc((uint32_t)comp[i]) > 1;
+            uint32_t tot;
+            uint32_t pos = block_excl_scan_u32(cnt, s_wbuf, &tot);
+            for (uint32_t i = b; i < e; ++i) {
+                pre[i] = pos;
+                pos += __popc((uint32_t)comp[i]) > 1;
+            }
+            if (tid == KC_THREADS - 1 || e == n) pre[n] = tot;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < nb; i += KC_THREADS) {
+            const bool amb = pre[i + k] != pre[i];
+            const uint32_t need = amb ? 2 * R : 2;
+            const uint32_t slot = atomicAdd(&s_cnt, need);
+            if (slot + need > a.ecap) {
+                s_over = 1;
+                continue;
+            }
+            if (!amb) {
+                uint64_t kf = 0;
+                for (uint32_t j = 0; j < k; ++j)
+                    kf |= (uint64_t)((uint32_t)__clz((uint32_t)comp[i + j]) - 28u) << (2 * j);
+                keys[slot] = kf;
+                wts[slot] = (uint16_t)R;
+                keys[slot + 1] = revcomp_key(kf, k);
+                wts[slot + 1] = (uint16_t)R;
+            } else {
+                for (uint32_t rs = 0; rs < R; ++rs) {
+                    uint64_t kf = 0;
+                    for (uint32_t j = 0; j < k; ++j)
+                        kf |= (uint64_t)resolve_iupac(comp[i + j], a.seed, leaf, rs, i + j) << (2 * j);
+                    keys[slot + 2 * rs] = kf;
+                    wts[slot + 2 * rs] = 1;
+                    keys[slot + 2 * rs + 1] = revcomp_key(kf, k);
+                    wts[slot + 2 * rs + 1] = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_over) {
+            if (tid == 0) atomicMax(a.err, MYRIO_ERR_UNSUPPORTED);
+            return;
+        }
+        E = s_cnt;
+    }
+    __syncthreads();
+    const uint32_t S = pow2_ceil(E);
+    for (uint32_t i = E + tid; i < S; i += KC_THREADS) {
+        keys[i] = ~0ull;
+        if (ambiguous) wts[i] = 0;
+    }
+    if (ambiguous)
+        bitonic_sort<true>(keys, wts, S);
+    else
+        bitonic_sort<false>(keys, nullptr, S);
+
+    uint32_t *headpos = aux;
+    const uint32_t Dall = find_run_heads(keys, E, headpos, s_wbuf);
+    // value per run, strip values <= cutoff (:130-134), ordered compaction of the survivors
+    {
+        const uint32_t C = (Dall + KC_THREADS - 1) / KC_THREADS;
+        const uint32_t b = min(Dall, tid * C), e = min(Dall, b + C);
+        uint32_t kept = 0, sum = 0;
+        // pass 1: count survivors of this thread's chunk
+        for (uint32_t idx = b; idx < e; ++idx) {
+            const uint32_t i = headpos[idx];
+            const uint32_t nx = (idx + 1 < Dall) ? headpos[idx + 1] : E;
+            uint32_t v;
+            if (ambiguous) {
+                v = 0;
+                for (uint32_t j = i; j < nx; ++j) v += wts[j];
+            } else {
+                v = (nx - i) * R;
+            }
+            v &= 0xFFFFu;
+            kept += v > cutoff;
+        }
+        uint32_t D;
+        uint32_t pos = block_excl_scan_u32(kept, s_wbuf, &D);
+        for (uint32_t idx = b; idx < e; ++idx) {
+            const uint32_t i = headpos[idx];
+            const uint32_t nx = (idx + 1 < Dall) ? headpos[idx + 1] : E;
+            uint32_t v;
+            if (ambiguous) {
+                v = 0;
+                for (uint32_t j = i; j < nx; ++j) v += wts[j];
+            } else {
+                v = (nx - i) * R;
+            }
+            v &= 0xFFFFu;
+            if (v > cutoff) {
+                a.skeys[o + pos] = keys[i];
+                a.svals[o + pos] = (uint16_t)v;
+                sum += v;
+                ++pos;
+            }
+        }
+        if (sum) atomicAdd(&s_sum, sum);  // u32 wrapping like sum::<u32>() in release
+        __syncthreads();
+        if (tid == 0) {
+            if (D == 0) {  // :136-139
+                a.skeys[o] = 0;
+                a.svals[o] = 1;
+                a.d_out[r] = 1;
+                a.rescale_out[r] = 1.0f;
+            } else {
+                a.d_out[r] = D;
+                a.rescale_out[r] = __fdiv_rn((float)(2u * nb), (float)s_sum);  // :144-145
+            }
+        }
+    }
+}
+
+// ------------------------------------------------- scratch -> CSR compaction
+
+template <typename VT>
+__global__ void __launch_bounds__(256) compact_rows_kernel(const uint64_t *__restrict__ eoff,
+                                                           const uint64_t *__restrict__ row_off,
+                                                           const uint64_t *__restrict__ skeys,
+                                                           const VT *__restrict__ svals,
+                                                           uint64_t *__restrict__ keys,
+                                                           VT *__restrict__ vals, uint64_t n_rows) {
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t src = eoff[row], dst = row_off[row];
+    const uint32_t d = (uint32_t)(row_off[row + 1] - dst);
+    for (uint32_t i = lane; i < d; i += 32) {
+        keys[dst + i] = skeys[src + i];
+        vals[dst + i] = svals[src + i];
+    }
+}
+
+// ------------------------------------------------------------ host drivers
+
+static const uint32_t kSmemClasses[] = {1024, 2048, 4096, 8192, 16384};
+
+template <typename KernelT>
+static void allow_smem(KernelT kernel, size_t bytes) {
+    MYRIO_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+static uint32_t host_pow2_ceil(uint64_t v) {
+    uint32_t p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+myrio_svecs *count_reads(myrio_ctx *ctx, const myrio_seqs *reads, uint32_t k, float cutoff) {
+    if (k < 2 || k > 32) fail(MYRIO_ERR_INVALID_K, "k=%u: only k in 2..32 is supported", k);
+    if (reads->kind != 0) fail(MYRIO_ERR_BAD_ARG, "count_reads needs a reads batch");
+    const uint64_t N = reads->n;
+    auto *out = new myrio_svecs();
+    std::unique_ptr<myrio_svecs> guard(out);
+    out->n_rows = N;
+    out->vtype = MYRIO_VAL_F32;
+    out->aux_kind = 1;
+    out->row_off.alloc(N + 1);
+    out->aux_u64.alloc(std::max<uint64_t>(N, 1));
+    if (N == 0) {
+        MYRIO_CK(cudaMemsetAsync(out->row_off.p, 0, sizeof(uint64_t), ctx->stream));
+        sync(ctx);
+        return guard.release();
+    }
+    // scratch row offsets + size classes from the host copy of the lengths
+    std::vector<uint64_t> eoff(N + 1);
+    std::vector<std::vector<uint32_t>> cls(sizeof(kSmemClasses) / sizeof(uint32_t) + 1);
+    uint64_t acc = 0, max_e = 0;
+    for (uint64_t r = 0; r < N; ++r) {
+        uint64_t n = reads->h_base_off[r + 1] - reads->h_base_off[r];
+        uint64_t e = n >= k ? 2 * (n - k + 1) : 0;
+        eoff[r] = acc;
+        acc += e;
+        max_e = std::max(max_e, e);
+        size_t c = 0;
+        while (c < sizeof(kSmemClasses) / sizeof(uint32_t) && e > kSmemClasses[c]) ++c;
+        cls[c].push_back((uint32_t)r);
+    }
+    eoff[N] = acc;
+    DevBuf<uint64_t> d_eoff(N + 1), skeys(std::max<uint64_t>(acc, 1));
+    DevBuf<float> svals(std::max<uint64_t>(acc, 1));
+    DevBuf<uint32_t> d_d(N);
+    DevBuf<int> d_err(1);
+    h2d(ctx, d_eoff.p, eoff.data(), N + 1);
+    MYRIO_CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+
+    std::vector<DevBuf<uint32_t>> id_bufs;
+    DevBuf<uint8_t> gscratch;
+    for (size_t c = 0; c < cls.size(); ++c) {
+        if (cls[c].empty()) continue;
+        id_bufs.emplace_back(cls[c].size());
+        h2d(ctx, id_bufs.back().p, cls[c].data(), cls[c].size());
+        ReadCountArgs a{};
+        a.words = reads->words.p;
+        a.word_off = reads->word_off.p;
+        a.base_off = reads->base_off.p;
+        a.qual = reads->qual.p;
+        a.ids = id_bufs.back().p;
+        a.k = k;
+        a.cutoff = cutoff;
+        a.eoff = d_eoff.p;
+        a.skeys = skeys.p;
+        a.svals = svals.p;
+        a.d_out = d_d.p;
+        a.hck_out = out->aux_u64.p;
+        a.err = d_err.p;
+        if (c < sizeof(kSmemClasses) / sizeof(uint32_t)) {
+            a.ecap = kSmemClasses[c];
+            size_t smem = read_work_bytes(a.ecap);
+            allow_smem(count_reads_kernel<false>, smem);
+            MYRIO_LAUNCH(ctx, "k1_count_reads", count_reads_kernel<false>, (unsigned)cls[c].size(),
+                         KC_THREADS, smem, a);
+        } else {
+            // sequences too long for shared memory: same algorithm on a global work area,
+            // processed in waves to bound the scratch
+            a.ecap = host_pow2_ceil(max_e);
+            a.gstride = (read_work_bytes(a.ecap) + 255) / 256 * 256;
+            const size_t wave = std::max<size_t>(1, std::min<size_t>(cls[c].size(), (1ull << 30) / a.gstride));
+            gscratch.alloc(wave * a.gstride);
+            a.gscratch = gscratch.p;
+            for (size_t b = 0; b < cls[c].size(); b += wave) {
+                a.ids = id_bufs.back().p + b;
+                unsigned g = (unsigned)std::min(wave, cls[c].size() - b);
+                MYRIO_LAUNCH(ctx, "k1_count_reads_long", count_reads_kernel<true>, g, KC_THREADS, 0, a);
+            }
+        }
+    }
+    exclusive_scan_u32_to_u64(ctx, d_d.p, out->row_off.p, N);
+    int h_err = 0;
+    uint64_t nnz = 0;
+    d2h(ctx, &h_err, d_err.p, 1);
+    d2h(ctx, &nnz, out->row_off.p + N, 1);
+    sync(ctx);
+    if (h_err == MYRIO_ERR_BAD_QUALITY)
+        fail(MYRIO_ERR_BAD_QUALITY, "a quality score >= 128 indexes past the Phred table");
+    if (h_err) fail(h_err, "read counting failed (%d)", h_err);
+    out->nnz = nnz;
+    out->keys.alloc(std::max<uint64_t>(nnz, 1));
+    out->vals_f32.alloc(std::max<uint64_t>(nnz, 1));
+    MYRIO_LAUNCH(ctx, "compact_rows", compact_rows_kernel<float>, (unsigned)((N + 7) / 8), 256, 0,
+                 d_eoff.p, out->row_off.p, skeys.p, svals.p, out->keys.p, out->vals_f32.p, N);
+    sync(ctx);
+    return guard.release();
+}
+
+myrio_svecs *count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k, uint32_t nb_resamples,
+                          uint64_t seed, uint64_t leaf_id_base) {
+    if (k < 2 || k > 32) fail(MYRIO_ERR_INVALID_K, "k=%u: only k in 2..32 is supported", k);
+    if (leaves->kind != 1) fail(MYRIO_ERR_BAD_ARG, "count_leaves needs a leaves batch");
+    if (nb_resamples > 65535) fail(MYRIO_ERR_BAD_ARG, "nb_resamples must fit in u16");
+    const uint64_t L = leaves->n;
+    auto *out = new myrio_svecs();
+    std::unique_ptr<myrio_svecs> guard(out);
+    out->n_rows = L;
+    out->vtype = MYRIO_VAL_U16;
+    out->aux_kind = 2;
+    out->row_off.alloc(L + 1);
+    out->aux_f32.alloc(std::max<uint64_t>(L, 1));
+    if (L == 0) {
+        MYRIO_CK(cudaMemsetAsync(out->row_off.p, 0, sizeof(uint64_t), ctx->stream));
+        sync(ctx);
+        return guard.release();
+    }
+    // Capacity per row.  ACGT-only leaves need 2*(n-k+1) keys; a leaf with `amb`
+    // ambiguity codes needs at most 2*(nb + (R-1)*min(nb, k*amb)).
+    const std::vector<uint32_t> &amb = leaves->h_aux;
+    std::vector<uint64_t> eoff(L + 1);
+    const size_t n_cls = sizeof(kSmemClasses) / sizeof(uint32_t);
+    std::vector<std::vector<uint32_t>> cls(n_cls + 1);
+    uint64_t acc = 0, max_cap = 0;
+    for (uint64_t r = 0; r < L; ++r) {
+        uint64_t n = leaves->h_base_off[r + 1] - leaves->h_base_off[r];
+        uint64_t nb = n >= k ? n - k + 1 : 0;
+        uint64_t na = amb.empty() ? 0 : amb[r];
+        uint64_t e = 2 * (nb + (uint64_t)(nb_resamples > 0 ? nb_resamples - 1 : 0) * std::min<uint64_t>(nb, (uint64_t)k * na));
+        uint64_t cap = std::max<uint64_t>(std::max<uint64_t>(e, n), 1);
+        eoff[r] = acc;
+        acc += std::max<uint64_t>(e, 1);
+        max_cap = std::max(max_cap, cap);
+        size_t c = 0;
+        while (c < n_cls && cap > kSmemClasses[c]) ++c;
+        cls[c].push_back((uint32_t)r);
+    }
+    eoff[L] = acc;
+    DevBuf<uint64_t> d_eoff(L + 1), skeys(acc);
+    DevBuf<uint16_t> svals(acc);
+    DevBuf<uint32_t> d_d(L);
+    DevBuf<int> d_err(1);
+    h2d(ctx, d_eoff.p, eoff.data(), L + 1);
+    MYRIO_CK(cudaMemsetAsync(d_err.p, 0, sizeof(int), ctx->stream));
+
+    std::vector<DevBuf<uint32_t>> id_bufs;
+    DevBuf<uint8_t> gscratch;
+    for (size_t c = 0; c < cls.size(); ++c) {
+        if (cls[c].empty()) continue;
+        id_bufs.emplace_back(cls[c].size());
+        h2d(ctx, id_bufs.back().p, cls[c].data(), cls[c].size());
+        LeafCountArgs a{};
+        a.words = leaves->words.p;
+        a.word_off = leaves->word_off.p;
+        a.base_off = leaves->base_off.p;
+        a.ids = id_bufs.back().p;
+        a.k = k;
+        a.nb_resamples = nb_resamples;
+        a.seed = seed;
+        a.leaf_id_base = leaf_id_base;
+        a.eoff = d_eoff.p;
+        a.skeys = skeys.p;
+        a.svals = svals.p;
+        a.d_out = d_d.p;
+        a.rescale_out = out->aux_f32.p;
+        a.err = d_err.p;
+        if (c < n_cls) {
+            a.ecap = kSmemClasses[c];
+            size_t smem = leaf_work_bytes(a.ecap);
+            allow_smem(count_leaves_kernel<false>, smem);
+            MYRIO_LAUNCH(ctx, "k2_count_leaves", count_leaves_kernel<false>, (unsigned)cls[c].size(),
+                         KC_THREADS, smem, a);
+        } else {
+            a.ecap = host_pow2_ceil(max_cap);
+            a.gstride = (leaf_work_bytes(a.ecap) + 255) / 256 * 256;
+            const size_t wave = std::max<size_t>(1, std::min<size_t>(cls[c].size(), (1ull << 30) / a.gstride));
+            gscratch.alloc(wave * a.gstride);
+            a.gscratch = gscratch.p;
+            for (size_t b = 0; b < cls[c].size(); b += wave) {
+                a.ids = id_bufs.back().p + b;
+                unsigned g = (unsigned)std::min(wave, cls[c].size() - b);
+                MYRIO_LAUNCH(ctx, "k2_count_leaves_long", count_leaves_kernel<true>, g, KC_THREADS, 0, a);
+            }
+        }
+    }
+    exclusive_scan_u32_to_u64(ctx, d_d.p, out->row_off.p, L);
+    int h_err = 0;
+    uint64_t nnz = 0;
+    d2h(ctx, &h_err, d_err.p, 1);
+    d2h(ctx, &nnz, out->row_off.p + L, 1);
+    sync(ctx);
+    if (h_err) fail(h_err, "leaf counting failed (%d)", h_err);
+    out->nnz = nnz;
+    out->keys.alloc(std::max<uint64_t>(nnz, 1));
+    out->vals_u16.alloc(std::max<uint64_t>(nnz, 1));
+    MYRIO_LAUNCH(ctx, "compact_rows", compact_rows_kernel<uint16_t>, (unsigned)((L + 7) / 8), 256, 0,
+                 d_eoff.p, out->row_off.p, skeys.p, svals.p, out->keys.p, out->vals_u16.p, L);
+    sync(ctx);
+    return guard.release();
+}
+
+}  // namespace myrio

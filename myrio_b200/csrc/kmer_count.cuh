@@ -1,0 +1,20 @@
+// internal entry points of the library (one per translation unit)
+#pragma once
+#include <memory>
+
+#include "common.cuh"
+
+namespace myrio {
+
+// kmer_count.cu
+void upload_phred_table(myrio_ctx *ctx);
+myrio_svecs *count_reads(myrio_ctx *ctx, const myrio_seqs *reads, uint32_t k, float cutoff);
+myrio_svecs *count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k, uint32_t nb_resamples,
+                          uint64_t seed, uint64_t leaf_id_base);
+
+// svecs.cu
+myrio_svecs *svecs_normalize(myrio_ctx *ctx, const myrio_svecs *in);
+
+// index.cu / score.cu / cluster.cu: see their own headers
+
+}  // namespace myrio

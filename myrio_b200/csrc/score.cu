@@ -1,0 +1,393 @@
+// score.cu -- K4 (query x leaf similarity over the inverted index), K5 (top-x
+// select) and K7 (merge of shard-local top-x lists).
+//
+// Reference semantics (myrio-core/src/tax/results.rs:82-93 with
+// similarity.rs:87-92 and data/sparse.rs:317-360): score[leaf] = sum over the
+// keys shared by query and leaf, in ASCENDING KEY ORDER, of q_val * leaf_val,
+// accumulated in f32 with separate multiply and add (Rust never fuses).  The
+// rounding of that sequential sum is part of the result, so the
+// kernel keeps the order: one warp owns the accumulators of one (query, tile)
+// pair and walks the query's keys in ascending order; the lanes fan out over
+// the posting list of ONE key at a time (a leaf occurs at most once per list),
+// so no two lanes ever update the same accumulator and no atomics are needed.
+#include <algorithm>
+
+#include "index.cuh"
+#include "kmer_count.cuh"
+#include "score.cuh"
+
+namespace myrio {
+
+struct ScoreArgs {
+    const TileInfo *tiles;
+    const uint64_t *postings;
+    const uint64_t *q_row_off;
+    const uint64_t *q_keys;
+    const float *q_vals;
+    uint64_t q_first;
+    uint32_t q_count;
+    uint32_t tile_leaves;
+    unsigned long long n_tasks;
+    float *scores;  // [q_count][ld]
+    uint64_t ld;
+    unsigned long long *counters;  // [0] task counter, [1..3] stats
+};
+
+__device__ __forceinline__ float finite_or_zero(float x) {
+    return (fabsf(x) <= 3.402823466e+38f) ? x : 0.0f;  // false for NaN and inf
+}
+
+template <int SIM>
+__device__ __forceinline__ float sim_transform(float dot) {
+    if (SIM == MYRIO_SIM_JACARD_TANIMOTO)  // similarity.rs:143-149 (pre-normalised)
+        return finite_or_zero(__fdiv_rn(dot, __fsub_rn(2.0f, dot)));
+    return dot;  // similarity.rs:87-92
+}
+
+template <int SIM>
+__global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
+    extern __shared__ float acc_all[];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *acc = acc_all + (size_t)warp * a.tile_leaves;
+    unsigned long long st_keys = 0, st_hits = 0, st_post = 0;
+
+    for (;;) {
+        unsigned long long task = 0;
+        if (lane == 0) task = atomicAdd(a.counters, 1ull);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= a.n_tasks) break;
+        const uint32_t t = (uint32_t)(task / a.q_count);  // tile-major: a tile's postings stay hot in L2
+        const uint32_t ql = (uint32_t)(task % a.q_count);
+        const TileInfo *ti = a.tiles + t;
+        const uint32_t nl = ti->n_leaves;
+        const uint32_t mask = ti->dict_mask;
+        const uint4 *dict = reinterpret_cast<const uint4 *>(ti->dict);
+        const uint64_t *post = a.postings + ti->post_begin;
+
+        for (uint32_t i = lane; i < nl; i += 32) acc[i] = 0.0f;
+        __syncwarp();
+
+        const uint64_t qb = a.q_row_off[a.q_first + ql], qe = a.q_row_off[a.q_first + ql + 1];
+        st_keys += (lane == 0) ? (qe - qb) : 0;
+        for (uint64_t base = qb; base < qe; base += 32) {
+            const uint64_t idx = base + lane;
+            const bool valid = idx < qe;
+            uint64_t key = 0;
+            float qv = 0.0f;
+            uint32_t begin = 0, len = 0;
+            if (valid) {
+                key = a.q_keys[idx];
+                qv = a.q_vals[idx];
+                uint32_t h = dict_hash(key) & mask;
+                for (;;) {
+                    const uint4 s = __ldg(dict + h);
+                    if (s.w == 0u) break;  // empty slot: key absent from this tile
+                    if ((((uint64_t)s.y << 32) | s.x) == key) {
+                        begin = s.z;
+                        len = s.w;
+                        break;
+                    }
+                    h = (h + 1) & mask;
+                }
+            }
+            unsigned hits = __ballot_sync(0xffffffffu, len != 0u);
+            st_hits += (lane == 0) ? __popc(hits) : 0;
+            while (hits) {  // lanes hold ascending keys: walk them in lane order
+                const int src = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const uint32_t b = __shfl_sync(0xffffffffu, begin, src);
+                const uint32_t l = __shfl_sync(0xffffffffu, len, src);
+                const float v = __shfl_sync(0xffffffffu, qv, src);
+                for (uint32_t i = lane; i < l; i += 32) {
+                    const uint64_t p = __ldg(post + b + i);
+                    const uint32_t leaf = (uint32_t)(p >> 32);
+                    const float prod = __fmul_rn(v, __uint_as_float((uint32_t)p));
+                    acc[leaf] = __fadd_rn(acc[leaf], prod);
+                }
+                st_post += (lane == 0) ? l : 0;
+                __syncwarp();  // the next key may touch the same leaves from other lanes
+            }
+        }
+        float *out = a.scores + (size_t)ql * a.ld + ti->leaf_begin;
+        for (uint32_t i = lane; i < nl; i += 32) out[i] = sim_transform<SIM>(acc[i]);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (st_keys) atomicAdd(a.counters + 1, st_keys);
+        if (st_hits) atomicAdd(a.counters + 2, st_hits);
+        if (st_post) atomicAdd(a.counters + 3, st_post);
+    }
+}
+
+// ------------------------------------------------------------------ K5: top-x
+
+static constexpr int TX_THREADS = 256;
+static constexpr int TX_MAX_X = 1024;
+
+// larger composite = better rank: score bits (scores are >= +0) then smaller id first
+__device__ __forceinline__ uint64_t topx_composite(float s, uint32_t i) {
+    return ((uint64_t)__float_as_uint(s) << 32) | (uint64_t)(0xFFFFFFFFu - i);
+}
+
+// descending bitonic sort of S (pow2) u64 in shared memory
+__device__ __forceinline__ void bitonic_desc(uint64_t *k, uint32_t S) {
+    for (uint32_t size = 2; size <= S; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (uint32_t t = threadIdx.x; t < (S >> 1); t += blockDim.x) {
+                uint32_t lo = 2u * t - (t & (stride - 1u)), hi = lo + stride;
+                bool desc = (lo & size) == 0u;
+                uint64_t x = k[lo], y = k[hi];
+                if ((x < y) == desc) {
+                    k[lo] = y;
+                    k[hi] = x;
+                }
+            }
+        }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TX_THREADS) topx_kernel(const float *__restrict__ scores, uint64_t ld,
+                                                          uint32_t n, uint32_t x, uint32_t id_base,
+                                                          float *__restrict__ out_s,
+                                                          uint32_t *__restrict__ out_i) {
+    __shared__ uint32_t hist[2048];
+    __shared__ uint64_t cand[TX_MAX_X];
+    __shared__ uint32_t s_scan[TX_THREADS];
+    __shared__ uint32_t s_bin, s_need, s_cnt, s_done;
+    const float *row = scores + (size_t)blockIdx.x * ld;
+    float *os = out_s + (size_t)blockIdx.x * x;
+    uint32_t *oi = out_i + (size_t)blockIdx.x * x;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t xx = min(x, n);
+
+    uint64_t thr = 0;  // take every element whose composite >= thr
+    if (xx < n) {
+        // radix select of the xx-th largest composite, 11-bit digits from the top
+        uint64_t prefix = 0;
+        int hi_bits = 0;  // number of leading bits already fixed
+        if (tid == 0) {
+            s_need = xx;
+            s_done = 0;
+        }
+        __syncthreads();
+        while (hi_bits < 64) {
+            const int nb = min(11, 64 - hi_bits);
+            const int shift = 64 - hi_bits - nb;
+            const uint32_t nbins = 1u << nb;
+            for (uint32_t i = tid; i < nbins; i += TX_THREADS) hist[i] = 0;
+            __syncthreads();
+            for (uint32_t base = 0; base < n; base += TX_THREADS) {
+                const uint32_t i = base + tid;
+                uint32_t bin = 0xFFFFFFFFu;
+                if (i < n) {
+                    const uint64_t c = topx_composite(row[i], i);
+                    if (hi_bits == 0 || (c >> (64 - hi_bits)) == prefix) bin = (uint32_t)(c >> shift) & (nbins - 1u);
+                }
+                // warp-aggregated histogram update (scores cluster in a few bins)
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (bin != 0xFFFFFFFFu && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+            }
+            __syncthreads();
+            // find the bin (from the top) where the running count reaches `need`
+            const uint32_t per = nbins / TX_THREADS ? nbins / TX_THREADS : 1;
+            uint32_t local = 0;
+            if (tid * per < nbins)
+                for (uint32_t j = 0; j < per; ++j) local += hist[nbins - 1 - (tid * per + j)];
+            s_scan[tid] = local;
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t need = s_need, run = 0, seg = 0;
+                while (seg < TX_THREADS && run + s_scan[seg] < need) run += s_scan[seg++];
+                // inside segment `seg`
+                uint32_t j = 0, b = nbins - 1 - seg * per;
+                while (run + hist[b] < need) {
+                    run += hist[b];
+                    ++j;
+                    --b;
+                }
+                s_bin = b;
+                s_need = need - run;
+                s_done = (hist[b] == need - run) ? 1u : 0u;  // the whole bin is taken
+            }
+            __syncthreads();
+            prefix = (prefix << nb) | s_bin;
+            hi_bits += nb;
+            const bool done = s_done != 0;
+            __syncthreads();
+            if (done) break;
+        }
+        thr = hi_bits < 64 ? prefix << (64 - hi_bits) : prefix;
+    }
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += TX_THREADS) {
+        const uint64_t c = topx_composite(row[i], i);
+        if (c >= thr) {
+            const uint32_t slot = atomicAdd(&s_cnt, 1u);
+            if (slot < TX_MAX_X) cand[slot] = c;
+        }
+    }
+    __syncthreads();
+    const uint32_t m = min(s_cnt, (uint32_t)TX_MAX_X);  // == xx
+    uint32_t S = 2;
+    while (S < m) S <<= 1;
+    for (uint32_t i = m + tid; i < S; i += TX_THREADS) cand[i] = 0;
+    bitonic_desc(cand, S);
+    for (uint32_t j = tid; j < x; j += TX_THREADS) {
+        if (j < m) {
+            const uint64_t c = cand[j];
+            os[j] = __uint_as_float((uint32_t)(c >> 32));
+            oi[j] = id_base + (0xFFFFFFFFu - (uint32_t)c);
+        } else {
+            os[j] = 0.0f;
+            oi[j] = 0xFFFFFFFFu;
+        }
+    }
+}
+
+// ------------------------------------------------------- K7: merge of shards
+
+// in: [n_parts][q][x] ; ids are global payload ids, padding = (0.0f, 0xFFFFFFFF)
+__global__ void __launch_bounds__(256) topx_merge_kernel(const float *__restrict__ in_s,
+                                                         const uint32_t *__restrict__ in_i,
+                                                         uint32_t n_parts, uint64_t q_count, uint32_t x,
+                                                         float *__restrict__ out_s,
+                                                         uint32_t *__restrict__ out_i) {
+    extern __shared__ uint64_t mk[];
+    const uint64_t q = blockIdx.x;
+    const uint32_t total = n_parts * x;
+    uint32_t S = 2;
+    while (S < total) S <<= 1;
+    for (uint32_t j = threadIdx.x; j < S; j += blockDim.x) {
+        uint64_t c = 0;
+        if (j < total) {
+            const uint32_t p = j / x, e = j % x;
+            const size_t src = ((size_t)p * q_count + q) * x + e;
+            const uint32_t id = in_i[src];
+            // padding (id 0xFFFFFFFF, score 0) maps to composite 0 = worst
+            c = ((uint64_t)__float_as_uint(in_s[src]) << 32) | (uint64_t)(0xFFFFFFFFu - id);
+        }
+        mk[j] = c;
+    }
+    bitonic_desc(mk, S);
+    for (uint32_t j = threadIdx.x; j < x; j += blockDim.x) {
+        const uint64_t c = mk[j];
+        out_s[q * x + j] = __uint_as_float((uint32_t)(c >> 32));
+        out_i[q * x + j] = 0xFFFFFFFFu - (uint32_t)c;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+
+static void check_queries(const myrio_svecs *q, uint64_t q_first, uint64_t q_count) {
+    if (q->vtype != MYRIO_VAL_F32) fail(MYRIO_ERR_BAD_ARG, "queries must be f32 (pre-normalised) vectors");
+    if (q_first + q_count > q->n_rows) fail(MYRIO_ERR_BAD_ARG, "query range out of bounds");
+}
+
+static uint64_t rows_per_batch(const myrio_index *ix, uint64_t q_count) {
+    const uint64_t budget = 1ull << 31;  // bytes of score rows kept on the device at once
+    uint64_t per = std::max<uint64_t>(1, budget / (std::max<uint64_t>(ix->n_leaves, 1) * 4));
+    return std::min(per, std::max<uint64_t>(q_count, 1));
+}
+
+// scores rows [qn][L] for queries [q0, q0+qn) into ctx->score_rows
+static void score_rows(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q0,
+                       uint64_t qn, int32_t sim) {
+    if (sim != MYRIO_SIM_COSINE && sim != MYRIO_SIM_JACARD_TANIMOTO)
+        fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path (Cosine, JacardTanimoto are)", sim);
+    const uint64_t L = ix->n_leaves;
+    ctx->score_rows.reserve(std::max<uint64_t>(qn * L, 1));
+    ctx->score_counters.reserve(4);
+    if (qn == 0 || L == 0) return;
+    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+    ScoreArgs a{};
+    a.tiles = ix->d_tiles.p;
+    a.postings = ix->postings.p;
+    a.q_row_off = queries->row_off.p;
+    a.q_keys = queries->keys.p;
+    a.q_vals = queries->vals_f32.p;
+    a.q_first = q0;
+    a.q_count = (uint32_t)qn;
+    a.tile_leaves = ix->tile_leaves;
+    a.n_tasks = (unsigned long long)qn * ix->tiles.size();
+    a.scores = ctx->score_rows.p;
+    a.ld = L;
+    a.counters = ctx->score_counters.p;
+    const size_t per_warp = (size_t)ix->tile_leaves * sizeof(float);
+    int warps = (int)std::min<size_t>(16, (ctx->smem_optin - 1024) / per_warp);
+    if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
+    const size_t smem = per_warp * warps;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(a.n_tasks, (unsigned long long)ctx->sm_count);
+    if (sim == MYRIO_SIM_COSINE) {
+        MYRIO_CK(cudaFuncSetAttribute(score_tiles_kernel<MYRIO_SIM_COSINE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, "k4_score_tiles", score_tiles_kernel<MYRIO_SIM_COSINE>, grid, warps * 32, smem, a);
+    } else {
+        MYRIO_CK(cudaFuncSetAttribute(score_tiles_kernel<MYRIO_SIM_JACARD_TANIMOTO>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, "k4_score_tiles", score_tiles_kernel<MYRIO_SIM_JACARD_TANIMOTO>, grid, warps * 32,
+                     smem, a);
+    }
+}
+
+static void accumulate_stats(myrio_ctx *ctx) {
+    unsigned long long h[4] = {0, 0, 0, 0};
+    d2h(ctx, h, ctx->score_counters.p, 4);
+    sync(ctx);
+    ctx->last_stats[0] += h[1];
+    ctx->last_stats[1] += h[2];
+    ctx->last_stats[2] += h[3];
+    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+}
+
+void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
+               uint64_t q_count, int32_t sim, float *scores_host) {
+    check_queries(queries, q_first, q_count);
+    const uint64_t L = ix->n_leaves;
+    ctx->last_stats[0] = ctx->last_stats[1] = ctx->last_stats[2] = 0;
+    ctx->score_counters.reserve(4);
+    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const uint64_t per = rows_per_batch(ix, q_count);
+    for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
+        const uint64_t qn = std::min(per, q_count - q0);
+        score_rows(ctx, ix, queries, q_first + q0, qn, sim);
+        d2h(ctx, scores_host + q0 * L, ctx->score_rows.p, qn * L);
+        accumulate_stats(ctx);
+    }
+    sync(ctx);
+}
+
+void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                       uint64_t q_first, uint64_t q_count, uint32_t x, int32_t sim, float *d_top_scores,
+                       uint32_t *d_top_ids, bool collect_stats) {
+    check_queries(queries, q_first, q_count);
+    if (x == 0 || x > TX_MAX_X) fail(MYRIO_ERR_BAD_ARG, "x must be in 1..%d", TX_MAX_X);
+    const uint64_t L = ix->n_leaves;
+    ctx->last_stats[0] = ctx->last_stats[1] = ctx->last_stats[2] = 0;
+    ctx->score_counters.reserve(4);
+    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    const uint64_t per = rows_per_batch(ix, q_count);
+    for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
+        const uint64_t qn = std::min(per, q_count - q0);
+        score_rows(ctx, ix, queries, q_first + q0, qn, sim);
+        MYRIO_LAUNCH(ctx, "k5_topx", topx_kernel, (unsigned)qn, TX_THREADS, 0, ctx->score_rows.p, L,
+                     (uint32_t)L, x, ix->leaf_id_base, d_top_scores + q0 * x, d_top_ids + q0 * x);
+        if (collect_stats) accumulate_stats(ctx);
+    }
+}
+
+void topx_merge_device(myrio_ctx *ctx, const float *d_scores_in, const uint32_t *d_ids_in, uint32_t n_parts,
+                       uint64_t q_count, uint32_t x, float *d_scores_out, uint32_t *d_ids_out) {
+    if (x == 0 || n_parts == 0) fail(MYRIO_ERR_BAD_ARG, "x and n_parts must be > 0");
+    uint64_t total = (uint64_t)n_parts * x, S = 2;
+    while (S < total) S <<= 1;
+    const size_t smem = S * sizeof(uint64_t);
+    if (smem > ctx->smem_optin) fail(MYRIO_ERR_UNSUPPORTED, "n_parts*x=%llu too large to merge", (unsigned long long)total);
+    if (q_count == 0) return;
+    MYRIO_CK(cudaFuncSetAttribute(topx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYRIO_LAUNCH(ctx, "k7_topx_merge", topx_merge_kernel, (unsigned)q_count, 256, smem, d_scores_in, d_ids_in,
+                 n_parts, q_count, x, d_scores_out, d_ids_out);
+}
+
+}  // namespace myrio

@@ -1,0 +1,13 @@
+// score.cuh -- scoring entry points (score.cu)
+#pragma once
+#include "index.cuh"
+
+namespace myrio {
+void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
+               uint64_t q_count, int32_t sim, float *scores_host);
+void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                       uint64_t q_first, uint64_t q_count, uint32_t x, int32_t sim, float *d_top_scores,
+                       uint32_t *d_top_ids, bool collect_stats);
+void topx_merge_device(myrio_ctx *ctx, const float *d_scores_in, const uint32_t *d_ids_in, uint32_t n_parts,
+                       uint64_t q_count, uint32_t x, float *d_scores_out, uint32_t *d_ids_out);
+}  // namespace myrio

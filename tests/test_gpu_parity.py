@@ -1,0 +1,361 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+the same seeded inputs.  Integer/byte/index results must be bit-exact; f32 scores
+are compared bit-exactly too (the kernels keep the reference's summation order,
+which is stricter than the 1e-6 relative tolerance north_star allows)."""
+import numpy as np
+import pytest
+
+import oracle
+from myrio_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from myrio_b200 import api as _api
+    return _api
+
+
+@pytest.fixture(scope="module")
+def ctx(api):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def seqset(seqs, quals=None):
+    codes = np.concatenate([np.array(["ACGT".index(c) for c in s], np.uint8) for s in seqs]) if seqs else np.zeros(0, np.uint8)
+    off = np.zeros(len(seqs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    q = None
+    if quals is not None:
+        q = np.concatenate([np.array(x, np.uint8) for x in quals]) if quals else np.zeros(0, np.uint8)
+    return synth.SeqSet(codes, off, q)
+
+
+def assert_reads_parity(api, ctx, reads, k, cutoff):
+    got = api.MyrSeqs(ctx, reads).compute_kmer_counts(k, cutoff)
+    ro, keys, vals, hck = got.download()
+    exp = oracle.count_reads(reads.codes, reads.qual, reads.base_off, k, cutoff)
+    assert (ro == exp.row_off).all()
+    assert (keys == exp.keys).all()
+    assert (bits(vals) == bits(exp.vals)).all()
+    assert (hck == exp.aux).all()
+    return got, exp
+
+
+# ---------------------------------------------------------------- K1 reads
+
+def test_reference_kat_simfunc(api, ctx):
+    # myrio-core/src/similarity.rs:217-232 through the GPU path
+    f32_min = float(np.finfo(np.float32).min)
+    s = seqset(["ACTG", "ACTC"], [[0] * 4, [0] * 4])
+    got = api.MyrSeqs(ctx, s).compute_kmer_counts(2, f32_min)
+    ro, keys, vals, hck = got.download()
+    assert hck.tolist() == [6, 6]
+    a = (keys[ro[0]:ro[1]], vals[ro[0]:ro[1]])
+    b = (keys[ro[1]:ro[2]], vals[ro[1]:ro[2]])
+    cos = oracle.similarity(oracle.SIM_COSINE, False, a[0], a[1], b[0], b[1])
+    assert abs(cos - np.float32(2 / 3)) < np.finfo(np.float32).eps
+    nro, nkeys, nvals, _ = got.into_normalized_l2().download()
+    tile = api.pairwise(got.into_normalized_l2(), got.into_normalized_l2())
+    assert abs(tile[0, 1] - cos) < np.finfo(np.float32).eps
+    assert tile[0, 1] == tile[1, 0]
+
+
+@pytest.mark.parametrize("k", [2, 6, 12, 18, 24, 31, 32])
+def test_count_reads_k_sweep(api, ctx, k):
+    tree = synth.make_tree(50, 5)
+    reads = synth.make_reads(tree, 300, 6)
+    cutoff = 0.1 if k >= 12 else 0.2
+    assert_reads_parity(api, ctx, reads, k, cutoff)
+
+
+def test_count_reads_edge_cases(api, ctx):
+    rng = np.random.default_rng(1)
+
+    def rnd(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+
+    seqs = ["ACGT", "A", rnd(17), rnd(18), rnd(19), "A" * 200, "T" * 64, rnd(31), rnd(32), rnd(33), rnd(64),
+            rnd(65), rnd(700), "ACGT" * 100]
+    quals = [[40] * len(s) for s in seqs]
+    quals[3] = [1] * 18          # every window fails
+    quals[12] = list(rng.integers(1, 41, 700))
+    s = seqset(seqs, quals)
+    for k in (2, 18, 32):
+        assert_reads_parity(api, ctx, s, k, 0.1)
+    # cutoff extremes
+    assert_reads_parity(api, ctx, s, 18, float(np.finfo(np.float32).min))
+    assert_reads_parity(api, ctx, s, 18, 1.0)
+
+
+def test_count_reads_empty_batch(api, ctx):
+    s = seqset([], [])
+    got = api.MyrSeqs(ctx, s).compute_kmer_counts(18, 0.1)
+    assert got.n_rows == 0 and got.nnz == 0
+
+
+def test_count_reads_long_reads_use_every_size_class(api, ctx):
+    rng = np.random.default_rng(2)
+    lens = [400, 600, 1100, 2300, 4500, 8800, 20000]   # 1k..16k shared-memory classes + global fallback
+    codes = rng.integers(0, 4, sum(lens), dtype=np.uint8)
+    qual = rng.integers(20, 41, sum(lens)).astype(np.uint8)
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    assert_reads_parity(api, ctx, synth.SeqSet(codes, off, qual), 18, 0.1)
+
+
+def test_count_reads_errors(api, ctx):
+    s = seqset(["ACGTACGT"], [[40] * 8])
+    m = api.MyrSeqs(ctx, s)
+    for k in (0, 1, 33):
+        with pytest.raises(api.MyrioError) as e:
+            m.compute_kmer_counts(k, 0.1)
+        assert e.value.code == 1  # MYRIO_ERR_INVALID_K (the reference panics)
+    bad = seqset(["ACGTACGT"], [[40] * 7 + [128]])
+    with pytest.raises(api.MyrioError) as e:
+        api.MyrSeqs(ctx, bad).compute_kmer_counts(2, 0.1)
+    assert e.value.code == 5  # MYRIO_ERR_BAD_QUALITY
+
+
+# --------------------------------------------------------------- K2 leaves
+
+def assert_leaves_parity(api, ctx, iupac, base_off, k, R, seed=0, base=0):
+    st = api.TaxTreeStore(ctx, iupac=iupac, base_off=base_off, leaf_id_base=base)
+    st.compute_and_append_kmer_counts(k, R, seed)
+    ro, keys, vals, rescale = st.kmer_store_counts_vec[0].download()
+    exp = oracle.count_leaves(iupac, base_off, k, R, seed, base)
+    assert (ro == exp.row_off).all()
+    assert (keys == exp.keys).all()
+    assert (vals == exp.vals).all()
+    assert (bits(rescale) == bits(exp.aux)).all()
+    return st, exp
+
+
+@pytest.mark.parametrize("k", [2, 6, 18, 32])
+def test_count_leaves_acgt(api, ctx, k):
+    tree = synth.make_tree(200, 9)
+    assert_leaves_parity(api, ctx, synth.tree_to_iupac(tree), tree.base_off, k, 32)
+
+
+@pytest.mark.parametrize("R", [0, 1, 3, 32, 100])
+def test_count_leaves_resample_counts(api, ctx, R):
+    tree = synth.make_tree(20, 10)
+    assert_leaves_parity(api, ctx, synth.tree_to_iupac(tree), tree.base_off, 12, R)
+
+
+def test_count_leaves_gaps_ambiguity_and_sentinels(api, ctx):
+    rng = np.random.default_rng(3)
+    tree = synth.make_tree(30, 11)
+    iu = synth.tree_to_iupac(tree).copy()
+    # sprinkle gaps (0) and ambiguity codes over some leaves
+    for leaf in range(0, 30, 3):
+        b, e = int(tree.base_off[leaf]), int(tree.base_off[leaf + 1])
+        pos = rng.integers(b, e, 12)
+        iu[pos[:6]] = 0
+        iu[pos[6:]] = rng.choice([3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15], 6)
+    # an all-gap leaf, a too-short leaf, a heavily ambiguous leaf
+    extra = [np.zeros(40, np.uint8), np.array([8, 4, 2], np.uint8), np.full(60, 15, np.uint8)]
+    iu2 = np.concatenate([iu] + extra)
+    off = np.concatenate([tree.base_off, tree.base_off[-1] + np.cumsum([40, 3, 60]).astype(np.uint64)])
+    for k, seed in ((6, 1), (18, 2)):
+        assert_leaves_parity(api, ctx, iu2, off, k, 32, seed=seed, base=1000)
+
+
+def test_count_leaves_long_leaf(api, ctx):
+    rng = np.random.default_rng(4)
+    lens = [700, 3000, 9000, 30000]
+    iu = synth.DNA_TO_IUPAC[rng.integers(0, 4, sum(lens))]
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    assert_leaves_parity(api, ctx, iu, off, 18, 32)
+
+
+# -------------------------------------------------- normalise + K3 index
+
+def test_normalize_and_index_match_oracle(api, ctx):
+    tree = synth.make_tree(700, 12)
+    st, exp = assert_leaves_parity(api, ctx, synth.tree_to_iupac(tree), tree.base_off, 18, 32)
+    nro, nkeys, nvals, _ = st.kmer_store_counts_vec[0].into_normalized_l2().download()
+    oln = oracle.normalize(exp)
+    assert (bits(nvals) == bits(oln.vals)).all()
+    ttc = api.TaxTreeCompute.from_store_tree(st, 18, 32, tile_leaves=256)
+    info = ttc.info()
+    assert info["n_tiles"] == 3 and info["n_postings"] == len(exp.keys)
+    for t in range(info["n_tiles"]):
+        lo, hi = t * 256, min(700, (t + 1) * 256)
+        sub = oracle.Csr(oln.row_off[lo:hi + 1] - oln.row_off[lo], oln.keys[int(oln.row_off[lo]):int(oln.row_off[hi])],
+                         oln.vals[int(oln.row_off[lo]):int(oln.row_off[hi])])
+        uk, of, pl, pv = oracle.invert(sub)
+        guk, gof, gpl, gpv = ttc.export_tile(t)
+        assert (guk == uk).all() and (gof == of).all() and (gpl == pl).all() and (bits(gpv) == bits(pv)).all()
+
+
+# ----------------------------------------------------- K4 / K5 scoring
+
+def build_case(api, ctx, n_leaves, n_reads, seed, k=18, tile_leaves=0):
+    tree = synth.make_tree(n_leaves, seed)
+    reads = synth.make_reads(tree, n_reads, seed + 1)
+    st = api.TaxTreeStore(ctx, tree)
+    ttc = api.TaxTreeCompute.from_store_tree(st, k, 32, tile_leaves=tile_leaves)
+    q = api.MyrSeqs(ctx, reads).compute_kmer_counts(k, 0.1).into_normalized_l2()
+    oln = oracle.normalize(oracle.count_leaves(synth.tree_to_iupac(tree), tree.base_off, k, 32))
+    oqn = oracle.normalize(oracle.count_reads(reads.codes, reads.qual, reads.base_off, k, 0.1))
+    return tree, reads, ttc, q, oln, oqn
+
+
+@pytest.mark.parametrize("tile_leaves", [64, 1000, 0])
+def test_score_all_and_topx_bit_exact(api, ctx, tile_leaves):
+    tree, reads, ttc, q, oln, oqn = build_case(api, ctx, 1500, 40, 21, tile_leaves=tile_leaves)
+    res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 100, full_scores=True)
+    for i in range(reads.n):
+        k, v = oqn.row(i)
+        s = oracle.score_all(oln, k, v)
+        assert (bits(s) == bits(res.scores[i])).all()
+        ts, ti = oracle.topx(s, 100)
+        assert (ti == res.top_ids[i]).all()
+        assert (bits(ts) == bits(res.top_scores[i])).all()
+    st = ctx.score_stats()
+    assert st["query_keys"] == int(oqn.row_off[-1]) * ttc.info()["n_tiles"]
+
+
+def test_score_jacard_tanimoto_and_k12(api, ctx):
+    tree, reads, ttc, q, oln, oqn = build_case(api, ctx, 400, 12, 31, k=12)
+    res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_JACARD_TANIMOTO, 7, full_scores=True)
+    for i in range(reads.n):
+        k, v = oqn.row(i)
+        s = oracle.score_all(oln, k, v, sim=oracle.SIM_JACARD_TANIMOTO)
+        assert (bits(s) == bits(res.scores[i])).all()
+        ts, ti = oracle.topx(s, 7)
+        assert (ti == res.top_ids[i]).all()
+    with pytest.raises(api.MyrioError) as e:
+        api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_OVERLAP, 7)
+    assert e.value.code == 6
+
+
+def test_topx_ties_zero_rows_and_padding(api, ctx):
+    # handcrafted leaf vectors: duplicates give exact ties, unrelated leaves give zeros
+    keys = [[1, 2, 3], [1, 2, 3], [7, 8], [1, 2, 3], [9], [2, 3, 4]]
+    row_off = np.zeros(len(keys) + 1, np.uint64)
+    row_off[1:] = np.cumsum([len(x) for x in keys])
+    k = np.concatenate([np.array(x, np.uint64) for x in keys])
+    v = np.ones(len(k), np.uint16)
+    counts = api.SFVecs.upload(ctx, row_off, k, v)
+    ttc = api.TaxTreeCompute.from_counts(counts, leaf_id_base=100, tile_leaves=4)
+    q = api.SFVecs.upload(ctx, np.array([0, 3, 4], np.uint64), np.array([1, 2, 3, 50], np.uint64),
+                          np.array([1, 1, 1, 1], np.float32)).into_normalized_l2()
+    res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 8, full_scores=True)
+    oln = oracle.normalize(oracle.Csr(row_off, k, v))
+    for i, (qk, qv) in enumerate([([1, 2, 3], [1, 1, 1]), ([50], [1])]):
+        qv = np.array(qv, np.float32) / np.sqrt(np.float32(len(qv)))
+        s = oracle.score_all(oln, np.array(qk, np.uint64), qv.astype(np.float32))
+        assert (bits(s) == bits(res.scores[i])).all()
+        ts, ti = oracle.topx(s, 8, id_base=100)
+        assert (ti == res.top_ids[i]).all() and (bits(ts) == bits(res.top_scores[i])).all()
+    assert res.top_ids[0][:3].tolist() == [100, 101, 103]      # ties: payload_id ascending
+    assert res.top_ids[1][:6].tolist() == [100, 101, 102, 103, 104, 105] and res.top_ids[1][6] == 0xFFFFFFFF
+
+
+def test_topx_merge_matches_single_shard(api, ctx):
+    import ctypes as C
+    import torch
+    tree, reads, ttc, q, oln, oqn = build_case(api, ctx, 900, 16, 41)
+    full = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 20)
+    # two shards of the same leaves: [0,450) and [450,900)
+    x, Q = 20, reads.n
+    parts_s = torch.zeros((2, Q, x), dtype=torch.float32, device="cuda")
+    parts_i = torch.zeros((2, Q, x), dtype=torch.int32, device="cuda")
+    keep = []
+    for p, (lo, hi) in enumerate([(0, 450), (450, 900)]):
+        sub = tree.subset(np.arange(lo, hi))
+        st = api.TaxTreeStore(ctx, sub, leaf_id_base=lo)
+        shard = api.TaxTreeCompute.from_store_tree(st, 18, 32, tile_leaves=128)
+        keep.append((st, shard))
+        from myrio_b200 import _lib
+        _lib.check(ctx._L.myrio_score_topx_async(ctx.h, shard.h, q.h, 0, Q, x, 0, C.c_void_p(parts_s[p].data_ptr()),
+                                                 C.c_void_p(parts_i[p].data_ptr())))
+    out_s = torch.zeros((Q, x), dtype=torch.float32, device="cuda")
+    out_i = torch.zeros((Q, x), dtype=torch.int32, device="cuda")
+    _lib.check(ctx._L.myrio_topx_merge_async(ctx.h, C.c_void_p(parts_s.data_ptr()), C.c_void_p(parts_i.data_ptr()),
+                                             2, Q, x, C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr())))
+    ctx.sync()
+    assert (out_i.cpu().numpy().view(np.uint32) == full.top_ids).all()
+    assert (bits(out_s.cpu().numpy()) == bits(full.top_scores)).all()
+
+
+# ------------------------------------------------------------ K6 cluster
+
+def two_gene_reads(n_each, seed):
+    t1, t2 = synth.make_tree(80, seed), synth.make_tree(80, seed + 1)
+    r1, r2 = synth.make_reads(t1, n_each, seed + 2), synth.make_reads(t2, n_each, seed + 3)
+    codes = np.concatenate([r1.codes, r2.codes])
+    qual = np.concatenate([r1.qual, r2.qual])
+    off = np.concatenate([r1.base_off, r2.base_off[1:] + r1.base_off[-1]])
+    return synth.SeqSet(codes, off, qual)
+
+
+def test_pairwise_tile_bit_exact(api, ctx):
+    reads = two_gene_reads(40, 51)
+    oc = oracle.normalize(oracle.count_reads(reads.codes, reads.qual, reads.base_off, 6, 0.2))
+    g = api.MyrSeqs(ctx, reads).compute_kmer_counts(6, 0.2).into_normalized_l2()
+    for sim in (api.SIM_COSINE, api.SIM_JACARD_TANIMOTO):
+        assert (bits(api.pairwise(g, g, sim)) == bits(oracle.pairwise(oc, oc, sim))).all()
+    # large k takes the merge-join fallback
+    oc18 = oracle.normalize(oracle.count_reads(reads.codes, reads.qual, reads.base_off, 18, 0.1))
+    g18 = api.MyrSeqs(ctx, reads).compute_kmer_counts(18, 0.1).into_normalized_l2()
+    assert (bits(api.pairwise(g18, g18)) == bits(oracle.pairwise(oc18, oc18))).all()
+
+
+@pytest.mark.parametrize("silhouette", [None, 1.4])
+@pytest.mark.parametrize("with_init", [False, True])
+def test_cluster_matches_oracle(api, ctx, silhouette, with_init):
+    reads = two_gene_reads(150, 61)
+    m = api.MyrSeqs(ctx, reads)
+    oc = oracle.count_reads(reads.codes, reads.qual, reads.base_off, 6, 0.2)
+    init_g = init_o = None
+    if with_init:
+        # centroids of the first/last 20 reads as supplied initial centroids
+        ck1, cv1 = oracle.centroid(oc, np.arange(0, 20))
+        ck2, cv2 = oracle.centroid(oc, np.arange(280, 300))
+        ro = np.array([0, len(ck1), len(ck1) + len(ck2)], np.uint64)
+        init_o = oracle.Csr(ro, np.concatenate([ck1, ck2]), np.concatenate([cv1, cv2]))
+        init_g = api.SFVecs.upload(ctx, ro, init_o.keys, init_o.vals)
+    for expected in (2, 3):
+        oassign, oiters, osil = oracle.cluster(oc, 20, init_o, expected, silhouette=silhouette)
+        out = api.cluster(m, api.ClusteringParameters(k=6, t1=0.2, t2=20, intial_centroids=init_g,
+                                                      expected_nb_of_clusters=expected,
+                                                      silhouette_trimming=silhouette))
+        assert (out.assign == oassign).all()
+        assert out.n_iters == oiters
+        if silhouette is not None:
+            both = ~np.isnan(osil)
+            assert (np.isnan(out.silhouette) == np.isnan(osil)).all()
+            assert (bits(out.silhouette[both]) == bits(osil[both])).all()
+
+
+def test_cluster_errors(api, ctx):
+    reads = two_gene_reads(10, 71)
+    m = api.MyrSeqs(ctx, reads)
+    with pytest.raises(api.MyrioError) as e:
+        api.cluster(m, api.ClusteringParameters(expected_nb_of_clusters=0))
+    assert e.value.code == 2
+    with pytest.raises(api.MyrioError) as e:
+        api.cluster(m, api.ClusteringParameters(t2=10 ** 9, expected_nb_of_clusters=2))
+    assert e.value.code == 7
+
+
+def test_compute_cluster_centroid_search_k(api, ctx):
+    # run.rs:301-309: the query of a cluster is the centroid of its reads at search_k
+    reads = two_gene_reads(30, 81)
+    oc = oracle.count_reads(reads.codes, reads.qual, reads.base_off, 18, 0.1)
+    g = api.MyrSeqs(ctx, reads).compute_kmer_counts(18, 0.1)
+    ids = np.arange(0, 30)
+    ck, cv = oracle.centroid(oc, ids)
+    ro, keys, vals, _ = api.compute_cluster_centroid(g, ids).download(aux=False)
+    assert ro.tolist() == [0, len(ck)] and (keys == ck).all() and (bits(vals) == bits(cv)).all()
