@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py -- the Myrio hot path on N B200s (BASELINE.json: query x reference-leaf
+similarity scores/s and k-mers counted/s).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
+
+Workload (BASELINE.json configs[1]): a synthetic BOLD-scale ITS tree of 100 000
+leaves per GPU x 100 000 simulated reads, k = 18.  One STEP = one pass of the hot
+path over the read batch: 2-bit k-mer counting of every read (K1), L2
+normalisation, scoring of every read against every leaf of the rank's shard over
+the inverted index (K4), top-100 per read (K5) and -- for N > 1 -- the NCCL
+all-gather of the shard-local top-x plus the merge kernel (K7).  The reference
+tree is counted (K2) and indexed (K3) once before the timed region; both are
+timed separately and reported in the same JSON line.
+
+`value` has the reads resident in HBM; `e2e` goes through the public API with
+pinned host buffers (H2D of the packed reads and D2H of the top-x inside the
+timed region).  Inputs (index ~1 GB/GPU) are larger than the 126 MB L2.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "query_x_leaf_similarity_scores_per_s"
+UNIT = "scores/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--leaves", type=int, default=100_000, help="reference leaves per GPU")
+    ap.add_argument("--reads", type=int, default=100_000, help="reads (queries), total")
+    ap.add_argument("--k", type=int, default=18)
+    ap.add_argument("--x", type=int, default=100)
+    ap.add_argument("--tile-leaves", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, world):
+    return {
+        "workload": f"configs[1]: synthetic BOLD-Plantae-scale ITS tree, {args.leaves} leaves per GPU x "
+                    f"{args.reads} reads, k={args.k}, top-{args.x}, cosine",
+        "leaves_per_gpu": args.leaves, "leaves_total": args.leaves * world, "reads": args.reads,
+        "k": args.k, "x": args.x, "read_cutoff_t1": 0.1, "nb_resamples": 32,
+        "parallelism": f"leaf-shard x{world}, queries replicated, NCCL all-gather of top-x",
+        "l2_policy": "inputs larger than L2 (index >= 1 GB per GPU vs 126 MB L2); no explicit flush",
+        "seeds": {"tree": 1002, "reads": 2002},
+    }
+
+
+# ------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------- data
+
+def make_data(args, rank, world):
+    from myrio_b200 import synth
+    tree = synth.make_tree(args.leaves, 1002, root_seed=1002, shard=rank)
+    lo = rank * args.reads // world
+    hi = (rank + 1) * args.reads // world
+    reads_local = synth.make_reads(tree, hi - lo, 2002 + rank)
+    return tree, reads_local
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles():
+    """dram bytes per K4 launch from the committed ncu capture, if any (profiles/*k4*traffic*.json)."""
+    d = os.path.join(ROOT, "profiles")
+    best = None
+    if os.path.isdir(d):
+        for f in sorted(os.listdir(d)):
+            if f.endswith(".json") and "traffic" in f:
+                try:
+                    best = json.load(open(os.path.join(d, f)))
+                except Exception:
+                    pass
+    return best
+
+
+# ------------------------------------------------------------- CPU arms
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    import oracle
+    from myrio_b200 import synth
+    threads = oracle.max_threads()
+    tree, reads_local = make_data(args, 0, 1 if world == 1 else world)
+    # leaf vectors (the reference's "index" is the list of normalised leaf vectors)
+    t0 = time.perf_counter()
+    lc = oracle.count_leaves(synth.tree_to_iupac(tree), tree.base_off, args.k, 32, threads=threads)
+    t_leaves = time.perf_counter() - t0
+    ln = oracle.normalize(lc, threads)
+    # queries
+    nq_probe = min(reads_local.n, 8)
+    sub = reads_local.subset(np.arange(min(reads_local.n, 4096)))
+    t0 = time.perf_counter()
+    rc = oracle.count_reads(sub.codes, sub.qual, sub.base_off, args.k, 0.1, threads=1)  # serial like the reference
+    t_reads = time.perf_counter() - t0
+    qn = oracle.normalize(rc, threads)
+
+    def score_n(n):
+        t0 = time.perf_counter()
+        for i in range(n):
+            k, v = qn.row(i)
+            s = oracle.score_all(ln, k, v, threads=threads)
+            oracle.topx(s, args.x)
+        return time.perf_counter() - t0
+
+    t_probe = score_n(nq_probe)
+    per_q = t_probe / nq_probe
+    n_step = int(max(4, min(qn.n_rows, args.cpu_seconds / max(per_q, 1e-9) / max(1, args.steps + args.warmup))))
+    for _ in range(args.warmup):
+        score_n(n_step)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        score_n(n_step)
+    dt = time.perf_counter() - t0
+    value = n_step * args.steps * tree.n / dt
+    sample = (f"{n_step} queries x {tree.n} leaves per step (first reads of the seed-2002 batch), "
+              f"{threads} OpenMP threads over leaves like rayon (tax/results.rs:89-93)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "kmers_counted_per_s": {
+            "reads_serial": float(rc.aux.sum()) / t_reads,
+            "leaves_reference_equivalent_x32": float(2 * (tree.lengths() - args.k + 1).clip(0).sum() * 32) / t_leaves,
+            "leaves_logical": float(2 * (tree.lengths() - args.k + 1).clip(0).sum()) / t_leaves,
+            "cores": threads,
+        },
+        "note": "CPU restatement of the reference algorithm (the Rust binary cannot be built: no cargo/rustc)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------- GPU arm
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from myrio_b200 import _lib, api, synth
+    from myrio_b200 import dist as mdist
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = api.Context(local_rank)
+    L = ctx._L
+    dev = torch.device("cuda", local_rank)
+    ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    tree, reads_local = make_data(args, rank, world)
+    reads = mdist.allgather_reads(reads_local) if world > 1 else reads_local
+    Q, x, k = reads.n, args.x, args.k
+
+    # ---- setup (timed separately): K2 leaf counting, normalise, K3 index build
+    ctx.prof_enable(True)
+    t0 = time.perf_counter()
+    store = api.TaxTreeStore(ctx, tree, leaf_id_base=rank * args.leaves)
+    t_upload_leaves = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    store.compute_and_append_kmer_counts(k, 32)
+    ctx.sync()
+    t_count_leaves = time.perf_counter() - t0
+    k2_ms, _ = ctx.prof_query("k2_")
+    t0 = time.perf_counter()
+    ttc = api.TaxTreeCompute.from_store_tree(store, k, 32, tile_leaves=args.tile_leaves)
+    ctx.sync()
+    t_index = time.perf_counter() - t0
+    info = ttc.info()
+    leaf_kmers = float(2 * (tree.lengths() - k + 1).clip(0).sum())
+    ctx.prof_enable(False)
+    ctx.prof_reset()
+
+    # ---- pinned host copies of the packed reads (e2e path) and resident reads (value path)
+    words, word_off = synth.pack_dna2(reads)
+    base_off = np.ascontiguousarray(reads.base_off, np.uint64)
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    keep = [pinned(words), pinned(word_off), pinned(base_off), pinned(reads.qual)]
+    p_words, p_woff, p_boff, p_qual = (kp[1] for kp in keep)
+    h2d_bytes = int(p_words.nbytes + p_woff.nbytes + p_boff.nbytes + p_qual.nbytes)
+    out_s_t = torch.empty((Q, x), dtype=torch.float32).pin_memory()
+    out_i_t = torch.empty((Q, x), dtype=torch.int32).pin_memory()
+    d2h_bytes = int(out_s_t.numel() * 4 + out_i_t.numel() * 4)
+    resident = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)
+
+    def step_resident():
+        counts = resident.compute_kmer_counts(k, 0.1)
+        qn = counts.into_normalized_l2()
+        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE)
+        return counts, s, i
+
+    def step_e2e():
+        m = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)      # H2D from pinned memory
+        counts = m.compute_kmer_counts(k, 0.1)
+        qn = counts.into_normalized_l2()
+        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE)
+        out_s_t.copy_(s, non_blocking=True)                                    # D2H of the step's result
+        out_i_t.copy_(i, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return counts
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        ctx.sync()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        ctx.sync()
+        torch.cuda.synchronize(dev)
+        e1.record(ext)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    # ---- warm-up (both paths), then the timed regions
+    for _ in range(args.warmup):
+        step_resident()
+    for _ in range(max(1, min(args.warmup, 2))):
+        step_e2e()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.prof_reset()
+    ctx.prof_enable(True)
+    launches0 = ctx.launch_count
+    ms_value = timed(step_resident, args.steps)
+    launches = ctx.launch_count - launches0
+    k4_ms, k4_n = ctx.prof_query("k4_")
+    k1_ms, k1_n = ctx.prof_query("k1_")
+    k5_ms, k5_n = ctx.prof_query("k5_")
+    all_ms, all_n = ctx.prof_query("")
+    ctx.prof_enable(False)
+    ctx.prof_reset()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- exact algorithmic work of one step (one untimed pass with the counters on)
+    counts = resident.compute_kmer_counts(k, 0.1)
+    qn = counts.into_normalized_l2()
+    ts = np.zeros((Q, x), np.float32)
+    ti = np.zeros((Q, x), np.uint32)
+    _lib.check(L.myrio_score_topx(ctx.h, ttc.h, qn.h, 0, Q, x, api.SIM_COSINE, ts.ctypes.data_as(C.c_void_p),
+                                  ti.ctypes.data_as(C.c_void_p)))
+    st = ctx.score_stats()
+    _, _, _, hck = counts.download()
+    nq_sum = st["query_keys"] // max(info["n_tiles"], 1)
+    t_q = st["postings_touched"]
+    read_kmers = float(hck.sum())
+
+    n_gpu_scores = float(Q) * float(args.leaves) * world
+    value = n_gpu_scores * args.steps / (ms_value * 1e-3)
+    e2e_value = n_gpu_scores * args.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (K4), per launch, SURVEY §8d bytes
+    peak, peak_src = peaks()
+    alg_bytes_step = 12 * nq_sum + 16 * nq_sum + 8 * t_q + 8 * x * Q
+    k4_per_step = max(k4_n // max(args.steps, 1), 1)
+    alg_bytes_launch = alg_bytes_step / k4_per_step
+    k4_avg_ms = k4_ms / max(k4_n, 1)
+    achieved = alg_bytes_launch / (k4_avg_ms * 1e-3) / 1e9 if k4_avg_ms > 0 else 0.0
+    tr = traffic_from_profiles()
+    roofline = {
+        "bound": "hbm", "kernel": "k4_score_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": (tr or {}).get("dram_bytes_per_launch"),
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
+        "launch_ms_avg": k4_avg_ms, "launches_per_step": k4_per_step,
+        "postings_touched_per_step": t_q, "query_keys_per_step": nq_sum,
+        "kernel_share_of_step": k4_ms / max(all_ms, 1e-9),
+        "note": "achieved counts every posting a query touches (8 B each); posting lists are re-used across "
+                "queries from L2, so achieved can exceed the HBM peak -- `traffic` is the measured DRAM bytes",
+    }
+    if tr:
+        roofline["traffic_source"] = tr.get("source")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": clocks,
+        "kmers_counted_per_s": {
+            "reads_k1_kernel": read_kmers * args.steps / (k1_ms * 1e-3) if k1_ms > 0 else None,
+            "reads_count_call": None,
+            "leaves_k2_kernel_logical": leaf_kmers / (k2_ms * 1e-3) if k2_ms > 0 else None,
+            "leaves_k2_kernel_reference_equivalent_x32": leaf_kmers * 32 / (k2_ms * 1e-3) if k2_ms > 0 else None,
+            "leaves_count_call_logical": leaf_kmers / t_count_leaves,
+            "read_kmers_per_step": read_kmers, "leaf_kmers_logical": leaf_kmers,
+        },
+        "setup_s": {"leaves_upload": t_upload_leaves, "k2_count_leaves": t_count_leaves, "k3_index_build": t_index},
+        "index": info,
+        "kernel_ms_per_step": {"k1_count_reads": k1_ms / args.steps, "k4_score_tiles": k4_ms / args.steps,
+                               "k5_topx": k5_ms / args.steps, "all_kernels": all_ms / args.steps},
+    }
+
+    # ---- CPU baseline: the oracle on the host cores, rank 0, N=1 only, bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        threads = oracle.max_threads()
+        nleaf = min(tree.n, 2048)
+        sub_tree = tree.subset(np.arange(nleaf))
+        t0 = time.perf_counter()
+        oracle.count_leaves(synth.tree_to_iupac(sub_tree), sub_tree.base_off, k, 32, threads=threads)
+        t_cl = time.perf_counter() - t0
+        # leaf vectors for the score sample come from the GPU counts (already parity-checked in tests/)
+        lro, lkeys, lvals, _ = store.kmer_store_counts_vec[0].download(aux=False)
+        oln = oracle.normalize(oracle.Csr(lro, lkeys, lvals), threads)
+        qro, qkeys, qvals, _ = qn.download(aux=False)
+        oq = oracle.Csr(qro, qkeys, qvals)
+        t0 = time.perf_counter()
+        kq, vq = oq.row(0)
+        oracle.score_all(oln, kq, vq, threads=threads)
+        per_q = max(time.perf_counter() - t0, 1e-6)
+        n_s = int(max(4, min(Q, args.cpu_seconds / per_q)))
+        t0 = time.perf_counter()
+        mism = 0
+        for i in range(n_s):
+            kq, vq = oq.row(i)
+            s = oracle.score_all(oln, kq, vq, threads=threads)
+            es, ei = oracle.topx(s, x, id_base=rank * args.leaves)
+            mism += int((ei != ti[i]).any() or (es.view(np.uint32) != ts[i].view(np.uint32)).any())
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": n_s * tree.n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n_s} of {Q} queries x all {tree.n} leaves (merge-join dots + top-{x}), "
+                      f"{threads} OpenMP threads over leaves like rayon",
+            "leaf_kmers_per_s_reference_equivalent_x32": float(2 * (sub_tree.lengths() - k + 1).clip(0).sum() * 32) / t_cl,
+            "leaf_count_sample": f"{nleaf} leaves, {threads} threads",
+        }
+        line["parity_in_bench"] = {"queries_checked": n_s, "topx_mismatches": mism}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+"""Multi-GPU plumbing: reference leaves are sharded across ranks in
+contiguous payload-id blocks, queries are replicated (all-gathered once), every
+rank produces a shard-local top-x and ONE exchange step -- an all-gather of
+Q x x (score, global payload id) pairs -- feeds the merge kernel (K7).
+
+torch.distributed is used for the rendezvous and the collectives only
+(NCCL on GPUs; gloo in the CPU tests of this module's host logic)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .synth import SeqSet
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block partition of n units (leaves / reads) over `world` ranks."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _device_for_backend() -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def allgather_ragged(local: np.ndarray, group=None) -> list[np.ndarray]:
+    """All-gather 1-D arrays of different lengths (one per rank), same dtype."""
+    world = dist.get_world_size(group)
+    dev = _device_for_backend()
+    n = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(max(sizes), 1)
+    raw = np.zeros(m * local.dtype.itemsize, np.uint8)
+    raw[:local.nbytes] = np.ascontiguousarray(local).view(np.uint8).reshape(-1)
+    mine = torch.from_numpy(raw).to(dev)
+    bufs = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(bufs, mine, group=group)
+    out = []
+    for s, b in zip(sizes, bufs):
+        out.append(b.cpu().numpy()[:s * local.dtype.itemsize].view(local.dtype).copy())
+    return out
+
+
+def allgather_reads(local: SeqSet, group=None) -> SeqSet:
+    """Queries are broadcast: every rank ends up with the reads of all ranks, in rank order."""
+    codes = allgather_ragged(local.codes, group)
+    quals = allgather_ragged(local.qual, group)
+    lens = allgather_ragged(local.lengths().astype(np.int64), group)
+    all_lens = np.concatenate(lens)
+    off = np.zeros(len(all_lens) + 1, np.uint64)
+    off[1:] = np.cumsum(all_lens)
+    return SeqSet(np.concatenate(codes), off, np.concatenate(quals), {"kind": "reads"})
+
+
+def allgather_topx(scores: torch.Tensor, ids: torch.Tensor, group=None):
+    """The one exchange step: [Q, x] per rank -> [world, Q, x] on every rank."""
+    world = dist.get_world_size(group)
+    gs = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    gi = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(gs.view(-1), scores.contiguous().view(-1), group=group) \
+        if dist.get_backend() == "nccl" else dist.all_gather(list(gs.unbind(0)), scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(gi.view(-1), ids.contiguous().view(-1), group=group) \
+        if dist.get_backend() == "nccl" else dist.all_gather(list(gi.unbind(0)), ids.contiguous(), group=group)
+    return gs, gi
+
+
+def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None):
+    """Shard-local top-x on this rank's leaves (K4+K5), NCCL all-gather, merge (K7).
+    Returns device tensors (scores [Q,x] f32, ids [Q,x] i32 holding u32 payload ids),
+    identical on every rank and identical to the single-GPU result."""
+    from . import _lib
+    Q = queries.n_rows
+    dev = torch.device("cuda", ctx.device)
+    ls = torch.empty((Q, x), dtype=torch.float32, device=dev)
+    li = torch.empty((Q, x), dtype=torch.int32, device=dev)
+    torch.cuda.current_stream(dev).synchronize()
+    _lib.check(ctx._L.myrio_score_topx_async(ctx.h, ttcompute.h, queries.h, 0, Q, x, similarity,
+                                             C.c_void_p(ls.data_ptr()), C.c_void_p(li.data_ptr())))
+    ctx.sync()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return ls, li
+    gs, gi = allgather_topx(ls, li, group)
+    torch.cuda.current_stream(dev).synchronize()
+    out_s, out_i = torch.empty_like(ls), torch.empty_like(li)
+    _lib.check(ctx._L.myrio_topx_merge_async(ctx.h, C.c_void_p(gs.data_ptr()), C.c_void_p(gi.data_ptr()),
+                                             gs.shape[0], Q, x, C.c_void_p(out_s.data_ptr()),
+                                             C.c_void_p(out_i.data_ptr())))
+    ctx.sync()
+    return out_s, out_i
