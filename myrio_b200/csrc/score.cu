@@ -44,11 +44,19 @@ __device__ __forceinline__ float sim_transform(float dot) {
     return dot;  // similarity.rs:87-92
 }
 
+// Postings fetched per lane and chunk: a chunk is up to 32*SC_U postings of ONE key
+// (distinct leaves => SC_U*32 independent accumulator updates => full ILP), and two
+// chunks are kept in flight (registers) so that the L2/HBM latency of chunk n+1
+// hides behind the shared-memory updates of chunk n, across key boundaries too.
+static constexpr int SC_U = 8;
+
 template <int SIM>
 __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
     extern __shared__ float acc_all[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float *acc = acc_all + (size_t)warp * a.tile_leaves;
+    const uint32_t acc_stride = a.tile_leaves + 32;  // + dummy slot for masked-off lanes
+    float *acc = acc_all + (size_t)warp * acc_stride;
+    const uint64_t dummy_posting = (uint64_t)a.tile_leaves << 32;  // leaf = dummy slot, val = +0.0
     unsigned long long st_keys = 0, st_hits = 0, st_post = 0;
 
     for (;;) {
@@ -65,48 +73,111 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
         const uint64_t *post = a.postings + ti->post_begin;
 
         for (uint32_t i = lane; i < nl; i += 32) acc[i] = 0.0f;
+        if (lane == 0) acc[a.tile_leaves] = 0.0f;
         __syncwarp();
 
         const uint64_t qb = a.q_row_off[a.q_first + ql], qe = a.q_row_off[a.q_first + ql + 1];
         st_keys += (lane == 0) ? (qe - qb) : 0;
+
+        // software-pipelined dictionary probe: the first slot of batch n+1 is in flight
+        // while the posting lists of batch n are processed
+        uint64_t key = 0, nkey = 0;
+        float qv = 0.0f, nqv = 0.0f;
+        uint32_t h = 0, nh = 0;
+        uint4 slot = make_uint4(0, 0, 0, 0), nslot = make_uint4(0, 0, 0, 0);
+        if (qb + lane < qe) {
+            key = a.q_keys[qb + lane];
+            qv = a.q_vals[qb + lane];
+            h = dict_hash(key) & mask;
+            slot = __ldg(dict + h);
+        }
         for (uint64_t base = qb; base < qe; base += 32) {
-            const uint64_t idx = base + lane;
-            const bool valid = idx < qe;
-            uint64_t key = 0;
-            float qv = 0.0f;
+            const bool valid = base + lane < qe;
+            {  // prefetch the next batch of query keys and their first dictionary slot
+                const uint64_t nidx = base + 32 + lane;
+                nslot = make_uint4(0, 0, 0, 0);
+                if (nidx < qe) {
+                    nkey = a.q_keys[nidx];
+                    nqv = a.q_vals[nidx];
+                    nh = dict_hash(nkey) & mask;
+                    nslot = __ldg(dict + nh);
+                }
+            }
             uint32_t begin = 0, len = 0;
             if (valid) {
-                key = a.q_keys[idx];
-                qv = a.q_vals[idx];
-                uint32_t h = dict_hash(key) & mask;
                 for (;;) {
-                    const uint4 s = __ldg(dict + h);
-                    if (s.w == 0u) break;  // empty slot: key absent from this tile
-                    if ((((uint64_t)s.y << 32) | s.x) == key) {
-                        begin = s.z;
-                        len = s.w;
+                    if (slot.w == 0u) break;  // empty slot: key absent from this tile
+                    if ((((uint64_t)slot.y << 32) | slot.x) == key) {
+                        begin = slot.z;
+                        len = slot.w;
                         break;
                     }
                     h = (h + 1) & mask;
+                    slot = __ldg(dict + h);
                 }
             }
             unsigned hits = __ballot_sync(0xffffffffu, len != 0u);
             st_hits += (lane == 0) ? __popc(hits) : 0;
-            while (hits) {  // lanes hold ascending keys: walk them in lane order
-                const int src = __ffs(hits) - 1;
-                hits &= hits - 1;
-                const uint32_t b = __shfl_sync(0xffffffffu, begin, src);
-                const uint32_t l = __shfl_sync(0xffffffffu, len, src);
-                const float v = __shfl_sync(0xffffffffu, qv, src);
-                for (uint32_t i = lane; i < l; i += 32) {
-                    const uint64_t p = __ldg(post + b + i);
-                    const uint32_t leaf = (uint32_t)(p >> 32);
-                    const float prod = __fmul_rn(v, __uint_as_float((uint32_t)p));
-                    acc[leaf] = __fadd_rn(acc[leaf], prod);
+
+            // cursor over the hit lists, in lane (= ascending key) order
+            int src = -1;
+            uint32_t cb = 0, cl = 0, coff = 0;
+            float cv = 0.0f;
+            auto next_hit = [&]() {
+                if (!hits) {
+                    src = -1;
+                    return;
                 }
-                st_post += (lane == 0) ? l : 0;
-                __syncwarp();  // the next key may touch the same leaves from other lanes
+                src = __ffs(hits) - 1;
+                hits &= hits - 1;
+                cb = __shfl_sync(0xffffffffu, begin, src);
+                cl = __shfl_sync(0xffffffffu, len, src);
+                cv = __shfl_sync(0xffffffffu, qv, src);
+                coff = 0;
+                st_post += (lane == 0) ? cl : 0;
+            };
+            auto fetch = [&](uint64_t(&p)[SC_U], uint32_t &n, float &v) -> bool {
+                if (src < 0) return false;
+                n = min(cl - coff, 32u * SC_U);
+                v = cv;
+                const uint64_t *ptr = post + cb + coff;
+#pragma unroll
+                for (int u = 0; u < SC_U; ++u) {
+                    const uint32_t idx = u * 32 + lane;
+                    p[u] = (u * 32u < n && idx < n) ? __ldg(ptr + idx) : dummy_posting;
+                }
+                coff += n;
+                if (coff >= cl) next_hit();
+                return true;
+            };
+            auto process = [&](const uint64_t(&p)[SC_U], uint32_t n, float v) {
+                float tacc[SC_U];
+#pragma unroll
+                for (int u = 0; u < SC_U; ++u)
+                    if (u * 32u < n) tacc[u] = acc[(uint32_t)(p[u] >> 32)];
+#pragma unroll
+                for (int u = 0; u < SC_U; ++u)
+                    if (u * 32u < n)
+                        acc[(uint32_t)(p[u] >> 32)] =
+                            __fadd_rn(tacc[u], __fmul_rn(v, __uint_as_float((uint32_t)p[u])));
+                __syncwarp();  // the next chunk may belong to another key and hit the same leaves
+            };
+            next_hit();
+            uint64_t pa[SC_U], pb[SC_U];
+            uint32_t na = 0, nb = 0;
+            float va = 0.0f, vb = 0.0f;
+            bool have_a = fetch(pa, na, va);
+            while (have_a) {
+                const bool have_b = fetch(pb, nb, vb);
+                process(pa, na, va);
+                if (!have_b) break;
+                have_a = fetch(pa, na, va);
+                process(pb, nb, vb);
             }
+            key = nkey;
+            qv = nqv;
+            h = nh;
+            slot = nslot;
         }
         float *out = a.scores + (size_t)ql * a.ld + ti->leaf_begin;
         for (uint32_t i = lane; i < nl; i += 32) out[i] = sim_transform<SIM>(acc[i]);
@@ -314,7 +385,7 @@ static void score_rows(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     a.scores = ctx->score_rows.p;
     a.ld = L;
     a.counters = ctx->score_counters.p;
-    const size_t per_warp = (size_t)ix->tile_leaves * sizeof(float);
+    const size_t per_warp = ((size_t)ix->tile_leaves + 32) * sizeof(float);
     int warps = (int)std::min<size_t>(16, (ctx->smem_optin - 1024) / per_warp);
     if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
     const size_t smem = per_warp * warps;
