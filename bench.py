@@ -357,7 +357,7 @@ def run_ours(args, rank, local_rank, world):
     achieved = alg_bytes_launch / (k4_avg_ms * 1e-3) / 1e9 if k4_avg_ms > 0 else 0.0
     tr = traffic_from_profiles()
     roofline = {
-        "bound": "hbm", "kernel": "k4_score_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "k4_score_tiles_topx (score_tiles_kernel<COSINE, fused top-x>)", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": (tr or {}).get("dram_bytes_per_launch"),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
         "launch_ms_avg": k4_avg_ms, "launches_per_step": k4_per_step,
@@ -389,8 +389,8 @@ def run_ours(args, rank, local_rank, world):
         },
         "setup_s": {"leaves_upload": t_upload_leaves, "k2_count_leaves": t_count_leaves, "k3_index_build": t_index},
         "index": info,
-        "kernel_ms_per_step": {"k1_count_reads": k1_ms / args.steps, "k4_score_tiles": k4_ms / args.steps,
-                               "k5_topx": k5_ms / args.steps, "all_kernels": all_ms / args.steps},
+        "kernel_ms_per_step": {"k1_count_reads": k1_ms / args.steps, "k4_score_tiles_topx": k4_ms / args.steps,
+                               "k5_topx_merge_tiles": k5_ms / args.steps, "all_kernels": all_ms / args.steps},
     }
 
     # ---- CPU baseline: the oracle on the host cores, rank 0, N=1 only, bounded sample

@@ -10,6 +10,10 @@
 namespace myrio {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &msg) { g_last_error = msg; }
+cudaStream_t &alloc_stream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
 }  // namespace myrio
 
 using namespace myrio;
@@ -39,6 +43,13 @@ int32_t myrio_ctx_create(int32_t device, myrio_ctx **out) {
         ctx->sm_count = prop.multiProcessorCount;
         ctx->smem_optin = prop.sharedMemPerBlockOptin;
         MYRIO_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        {  // keep freed scratch cached in the pool instead of returning it to the OS
+            cudaMemPool_t pool;
+            MYRIO_CK(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t threshold = UINT64_MAX;
+            MYRIO_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        }
+        ScopedCtx sc(ctx.get());
         upload_phred_table(ctx.get());
         sync(ctx.get());
         *out = ctx.release();
@@ -49,19 +60,22 @@ void myrio_ctx_destroy(myrio_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    alloc_stream() = ctx->stream;
     for (auto &e : ctx->prof) {
         cudaEventDestroy(e.start);
         cudaEventDestroy(e.stop);
     }
     ctx->score_rows.release();
     ctx->score_counters.release();
+    cudaStreamSynchronize(ctx->stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    alloc_stream() = nullptr;
     delete ctx;
 }
 
 int32_t myrio_ctx_sync(myrio_ctx *ctx) {
     return guarded([&] {
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         sync(ctx);
     });
 }
@@ -76,7 +90,7 @@ int32_t myrio_prof_enable(myrio_ctx *ctx, int32_t on) {
 
 int32_t myrio_prof_reset(myrio_ctx *ctx) {
     return guarded([&] {
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         sync(ctx);
         for (auto &e : ctx->prof) {
             cudaEventDestroy(e.start);
@@ -88,7 +102,7 @@ int32_t myrio_prof_reset(myrio_ctx *ctx) {
 
 int32_t myrio_prof_query(myrio_ctx *ctx, const char *prefix, double *ms_total, uint64_t *launches) {
     return guarded([&] {
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         sync(ctx);
         double ms = 0;
         uint64_t n = 0;
@@ -168,7 +182,7 @@ int32_t myrio_reads_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t
                            myrio_seqs **out) {
     return guarded([&] {
         if (!ctx || !out) fail(MYRIO_ERR_BAD_ARG, "NULL ctx/out");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         *out = upload_seqs(ctx, 0, words, word_off, base_off, qual, n_reads);
     });
 }
@@ -177,7 +191,7 @@ int32_t myrio_leaves_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_
                             const uint64_t *base_off, uint64_t n_leaves, myrio_seqs **out) {
     return guarded([&] {
         if (!ctx || !out) fail(MYRIO_ERR_BAD_ARG, "NULL ctx/out");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         *out = upload_seqs(ctx, 1, words, word_off, base_off, nullptr, n_leaves);
     });
 }
@@ -190,7 +204,7 @@ int32_t myrio_count_reads(myrio_ctx *ctx, const myrio_seqs *reads, uint32_t k, f
                           myrio_svecs **out) {
     return guarded([&] {
         if (!ctx || !reads || !out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         *out = count_reads(ctx, reads, k, cutoff);
     });
 }
@@ -199,7 +213,7 @@ int32_t myrio_count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k,
                            uint64_t seed, uint64_t leaf_id_base, myrio_svecs **out) {
     return guarded([&] {
         if (!ctx || !leaves || !out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         *out = count_leaves(ctx, leaves, k, nb_resamples, seed, leaf_id_base);
     });
 }
@@ -219,7 +233,7 @@ int32_t myrio_svecs_download(myrio_ctx *ctx, const myrio_svecs *v, uint64_t *row
                              void *vals, void *aux) {
     return guarded([&] {
         if (!ctx || !v) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         if (row_off) d2h(ctx, row_off, v->row_off.p, v->n_rows + 1);
         if (keys) d2h(ctx, keys, v->keys.p, v->nnz);
         if (vals) {
@@ -245,7 +259,7 @@ int32_t myrio_svecs_upload(myrio_ctx *ctx, uint64_t n_rows, const uint64_t *row_
     return guarded([&] {
         if (!ctx || !out || !row_off) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
         if (vtype != MYRIO_VAL_F32 && vtype != MYRIO_VAL_U16) fail(MYRIO_ERR_BAD_ARG, "bad vtype");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         const uint64_t nnz = row_off[n_rows];
         if (nnz && (!keys || !vals)) fail(MYRIO_ERR_BAD_ARG, "NULL keys/vals");
         auto v = std::make_unique<myrio_svecs>();
@@ -271,7 +285,7 @@ int32_t myrio_svecs_upload(myrio_ctx *ctx, uint64_t n_rows, const uint64_t *row_
 int32_t myrio_svecs_normalize(myrio_ctx *ctx, const myrio_svecs *in, myrio_svecs **out) {
     return guarded([&] {
         if (!ctx || !in || !out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         *out = svecs_normalize(ctx, in);
     });
 }
@@ -295,7 +309,7 @@ int32_t myrio_index_build(myrio_ctx *ctx, const myrio_svecs *leaf_vecs_normalize
                           uint32_t tile_leaves, myrio_index **out) {
     return guarded([&] {
         if (!ctx || !leaf_vecs_normalized || !out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         *out = index_build(ctx, leaf_vecs_normalized, leaf_id_base, tile_leaves);
     });
 }
@@ -317,7 +331,7 @@ int32_t myrio_index_export_tile(myrio_ctx *ctx, const myrio_index *ix, uint64_t 
                                 float *post_val) {
     return guarded([&] {
         if (!ctx || !ix) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         index_export_tile(ctx, ix, tile, n_unique, n_postings, ukeys, offs, post_leaf, post_val);
     });
 }
@@ -330,7 +344,7 @@ int32_t myrio_score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs
                         uint64_t q_count, int32_t similarity, float *scores) {
     return guarded([&] {
         if (!ctx || !ix || !queries || (!scores && q_count)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         score_all(ctx, ix, queries, q_first, q_count, similarity, scores);
     });
 }
@@ -340,7 +354,7 @@ int32_t myrio_score_topx_async(myrio_ctx *ctx, const myrio_index *ix, const myri
                                float *d_top_scores, uint32_t *d_top_ids) {
     return guarded([&] {
         if (!ctx || !ix || !queries || !d_top_scores || !d_top_ids) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         score_topx_device(ctx, ix, queries, q_first, q_count, x, similarity, d_top_scores, d_top_ids, false);
     });
 }
@@ -350,7 +364,7 @@ int32_t myrio_score_topx(myrio_ctx *ctx, const myrio_index *ix, const myrio_svec
                          uint32_t *top_ids) {
     return guarded([&] {
         if (!ctx || !ix || !queries || !top_scores || !top_ids) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         DevBuf<float> ds(std::max<uint64_t>(q_count * x, 1));
         DevBuf<uint32_t> di(std::max<uint64_t>(q_count * x, 1));
         score_topx_device(ctx, ix, queries, q_first, q_count, x, similarity, ds.p, di.p, true);
@@ -365,7 +379,7 @@ int32_t myrio_topx_merge_async(myrio_ctx *ctx, const float *d_scores_in, const u
                                uint32_t *d_ids_out) {
     return guarded([&] {
         if (!ctx || !d_scores_in || !d_ids_in || !d_scores_out || !d_ids_out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         topx_merge_device(ctx, d_scores_in, d_ids_in, n_parts, q_count, x, d_scores_out, d_ids_out);
     });
 }
@@ -387,7 +401,7 @@ int32_t myrio_cluster(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_clust
                       float *silhouette) {
     return guarded([&] {
         if (!ctx || !reads || !params || (!assign && reads->n)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         cluster_reads(ctx, reads, params, initial_centroids, assign, n_iters, silhouette);
     });
 }
@@ -396,7 +410,7 @@ int32_t myrio_compute_cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts
                                        uint64_t m, myrio_svecs **out) {
     return guarded([&] {
         if (!ctx || !counts || !out || (!member_ids && m)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         *out = cluster_centroid(ctx, counts, member_ids, m);
     });
 }
@@ -405,7 +419,7 @@ int32_t myrio_pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svec
                        float *out) {
     return guarded([&] {
         if (!ctx || !rows || !cols || !out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
-        ScopedDevice sd(ctx->device);
+        ScopedCtx sc(ctx);
         pairwise(ctx, rows, cols, similarity, out);
     });
 }

@@ -59,15 +59,23 @@ inline int32_t guarded(F &&f) {
     }
 }
 
+// Stream of the context whose API call is running on this thread (set by ScopedCtx).
+// Device buffers are stream-ordered allocations from the device's default memory
+// pool (cudaMallocAsync): scratch of one call is recycled by the next without
+// going back to the driver, and a buffer may be released while kernels that use it
+// are still queued on the same stream.
+cudaStream_t &alloc_stream();
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t s = nullptr;
     DevBuf() = default;
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) {
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) {
         o.p = nullptr;
         o.n = 0;
     }
@@ -76,6 +84,7 @@ struct DevBuf {
             release();
             p = o.p;
             n = o.n;
+            s = o.s;
             o.p = nullptr;
             o.n = 0;
         }
@@ -85,14 +94,21 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) MYRIO_CK(cudaMalloc(&p, count * sizeof(T)));
+        s = alloc_stream();
+        if (count) MYRIO_CK(cudaMallocAsync(&p, count * sizeof(T), s));
     }
     // grow-only scratch
     void reserve(size_t count) {
         if (count > n) alloc(count + count / 8);
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            // the owning context (and its stream) may already be gone: fall back to cudaFree
+            if (cudaFreeAsync(p, s) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(p);
+            }
+        }
         p = nullptr;
         n = 0;
     }
@@ -145,17 +161,20 @@ struct myrio_svecs {
 
 namespace myrio {
 
-struct ScopedDevice {
-    int prev = 0;
-    explicit ScopedDevice(int dev) {
+// Makes `ctx` current for the calling thread: device + allocation stream.
+struct ScopedCtx {
+    int prev = 0, cur = 0;
+    cudaStream_t prev_stream;
+    explicit ScopedCtx(const myrio_ctx *ctx) : prev_stream(alloc_stream()) {
         cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        cur = dev;
+        cur = ctx->device;
+        if (prev != cur) cudaSetDevice(cur);
+        alloc_stream() = ctx->stream;
     }
-    ~ScopedDevice() {
+    ~ScopedCtx() {
+        alloc_stream() = prev_stream;
         if (prev != cur) cudaSetDevice(prev);
     }
-    int cur;
 };
 
 // Bookkeeping around every kernel launch: count it, optionally time it with

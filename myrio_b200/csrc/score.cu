@@ -28,9 +28,16 @@ struct ScoreArgs {
     uint32_t q_count;
     uint32_t tile_leaves;
     unsigned long long n_tasks;
-    float *scores;  // [q_count][ld]
+    float *scores;  // [q_count][ld]            (full-row mode)
     uint64_t ld;
     unsigned long long *counters;  // [0] task counter, [1..3] stats
+    // fused top-x mode: every (query, tile) task leaves its candidates for the global top-x
+    uint32_t x;
+    uint32_t n_tiles;
+    uint32_t leaf_id_base;
+    uint64_t *cand;      // composites [q_count][n_tiles][x]
+    uint32_t *cand_cnt;  // [q_count][n_tiles]
+    uint32_t *gthr;      // [q_count] running lower bound (score bits) of the query's x-th best score
 };
 
 __device__ __forceinline__ float finite_or_zero(float x) {
@@ -44,18 +51,137 @@ __device__ __forceinline__ float sim_transform(float dot) {
     return dot;  // similarity.rs:87-92
 }
 
+// larger composite = better rank: score bits (scores are >= +0) then smaller id first
+__device__ __forceinline__ uint64_t topx_composite(uint32_t score_bits, uint32_t id) {
+    return ((uint64_t)score_bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+}
+
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan_u32s(uint32_t v, unsigned lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+
+// K5, fused into K4: with one tile's scores still in shared memory the warp keeps the
+// tile's candidates for the query's global top-x (tax/results.rs:310-329).  A running
+// per-query lower bound on the x-th best score (max over finished tiles of the tile's
+// own x-th best) prunes later tiles: most tasks take the "few survivors" path (one
+// pass); only the first tiles of a query run the 4 x 8-bit warp radix select.
+// Pruning never drops a member of the global top-x: an element below the bound has
+// at least x better elements in the tile that produced the bound.
+template <int SIM>
+__device__ __forceinline__ void tile_topx(float *acc, uint32_t *hist, uint32_t nl, uint32_t x,
+                                          uint32_t gid_base, uint32_t *gthr_q, uint64_t *cand,
+                                          uint32_t *cand_cnt, unsigned lane) {
+    uint32_t thr = 0;
+    if (lane == 0) thr = *reinterpret_cast<volatile uint32_t *>(gthr_q);
+    thr = __shfl_sync(0xffffffffu, thr, 0);
+    uint32_t cnt = 0;
+    for (uint32_t i = lane; i < nl; i += 32) {
+        const float s = sim_transform<SIM>(acc[i]);
+        acc[i] = s;
+        cnt += (__float_as_uint(s) >= thr) ? 1u : 0u;
+    }
+    cnt = warp_sum_u32(cnt);
+    __syncwarp();
+    const bool select = cnt > x;
+    uint32_t T = thr, need_eq = 0;
+    if (select) {
+        // x-th largest score among the survivors: radix select on the f32 bit pattern
+        uint32_t prefix = 0, need = x;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+            __syncwarp();
+            for (uint32_t base = 0; base < nl; base += 32) {
+                const uint32_t i = base + lane;
+                uint32_t bin = 0xFFFFFFFFu;
+                if (i < nl) {
+                    const uint32_t b = __float_as_uint(acc[i]);
+                    if (b >= thr && (pass == 0 || (b >> (shift + 8)) == prefix)) bin = (b >> shift) & 255u;
+                }
+                const unsigned peers = __match_any_sync(0xffffffffu, bin);
+                if (bin != 0xFFFFFFFFu && (int)lane == __ffs(peers) - 1) hist[bin] += __popc(peers);
+                __syncwarp();
+            }
+            // lane l owns bins 255-8l .. 248-8l (descending); find where the running count reaches need
+            uint32_t local[8], lsum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                local[j] = hist[255 - 8 * lane - j];
+                lsum += local[j];
+            }
+            const uint32_t incl = warp_incl_scan_u32s(lsum, lane);
+            const unsigned reach = __ballot_sync(0xffffffffu, incl >= need);
+            const int owner = __ffs(reach) - 1;
+            uint32_t bin = 0, rest = 0;
+            if ((int)lane == owner) {
+                uint32_t run = incl - lsum;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (run + local[j] >= need) {
+                        bin = 255 - 8 * lane - j;
+                        rest = need - run;
+                        break;
+                    }
+                    run += local[j];
+                }
+            }
+            bin = __shfl_sync(0xffffffffu, bin, owner);
+            need = __shfl_sync(0xffffffffu, rest, owner);
+            prefix = (prefix << 8) | bin;
+            __syncwarp();
+        }
+        T = prefix;
+        need_eq = need;  // how many elements equal to T are taken (smallest ids first)
+        if (lane == 0 && T > thr) atomicMax(gthr_q, T);
+    }
+    uint32_t out = 0, eq_taken = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t base = 0; base < nl; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < nl;
+        const uint32_t b = valid ? __float_as_uint(acc[i]) : 0u;
+        bool take;
+        if (select) {
+            const bool eq = valid && b == T;
+            const unsigned m_eq = __ballot_sync(0xffffffffu, eq);
+            take = (valid && b > T) || (eq && eq_taken + __popc(m_eq & lt) < need_eq);
+            eq_taken += __popc(m_eq);
+        } else {
+            take = valid && b >= thr;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (take) cand[out + __popc(m & lt)] = topx_composite(b, gid_base + i);
+        out += __popc(m);
+    }
+    if (lane == 0) *cand_cnt = out;
+}
+
 // Postings fetched per lane and chunk: a chunk is up to 32*SC_U postings of ONE key
 // (distinct leaves => SC_U*32 independent accumulator updates => full ILP), and two
 // chunks are kept in flight (registers) so that the L2/HBM latency of chunk n+1
 // hides behind the shared-memory updates of chunk n, across key boundaries too.
 static constexpr int SC_U = 8;
 
-template <int SIM>
+template <int SIM, bool FUSED>
 __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
     extern __shared__ float acc_all[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t acc_stride = a.tile_leaves + 32;  // + dummy slot for masked-off lanes
+    // per warp: tile accumulators + dummy slot for masked-off lanes (+ 256-bin histogram)
+    const uint32_t acc_stride = a.tile_leaves + 32 + (FUSED ? 256 : 0);
     float *acc = acc_all + (size_t)warp * acc_stride;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(acc + a.tile_leaves + 32);
     const uint64_t dummy_posting = (uint64_t)a.tile_leaves << 32;  // leaf = dummy slot, val = +0.0
     unsigned long long st_keys = 0, st_hits = 0, st_post = 0;
 
@@ -179,8 +305,14 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
             h = nh;
             slot = nslot;
         }
-        float *out = a.scores + (size_t)ql * a.ld + ti->leaf_begin;
-        for (uint32_t i = lane; i < nl; i += 32) out[i] = sim_transform<SIM>(acc[i]);
+        if (FUSED) {
+            const size_t slot = (size_t)ql * a.n_tiles + t;
+            tile_topx<SIM>(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
+                           a.cand + slot * a.x, a.cand_cnt + slot, lane);
+        } else {
+            float *out = a.scores + (size_t)ql * a.ld + ti->leaf_begin;
+            for (uint32_t i = lane; i < nl; i += 32) out[i] = sim_transform<SIM>(acc[i]);
+        }
         __syncwarp();
     }
     if (lane == 0) {
@@ -194,11 +326,7 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
 
 static constexpr int TX_THREADS = 256;
 static constexpr int TX_MAX_X = 1024;
-
-// larger composite = better rank: score bits (scores are >= +0) then smaller id first
-__device__ __forceinline__ uint64_t topx_composite(float s, uint32_t i) {
-    return ((uint64_t)__float_as_uint(s) << 32) | (uint64_t)(0xFFFFFFFFu - i);
-}
+static constexpr int TX_SORT_CAP = 4096;  // composites sorted at once per query (32 KB)
 
 // descending bitonic sort of S (pow2) u64 in shared memory
 __device__ __forceinline__ void bitonic_desc(uint64_t *k, uint32_t S) {
@@ -218,101 +346,40 @@ __device__ __forceinline__ void bitonic_desc(uint64_t *k, uint32_t S) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TX_THREADS) topx_kernel(const float *__restrict__ scores, uint64_t ld,
-                                                          uint32_t n, uint32_t x, uint32_t id_base,
-                                                          float *__restrict__ out_s,
-                                                          uint32_t *__restrict__ out_i) {
-    __shared__ uint32_t hist[2048];
-    __shared__ uint64_t cand[TX_MAX_X];
-    __shared__ uint32_t s_scan[TX_THREADS];
-    __shared__ uint32_t s_bin, s_need, s_cnt, s_done;
-    const float *row = scores + (size_t)blockIdx.x * ld;
-    float *os = out_s + (size_t)blockIdx.x * x;
-    uint32_t *oi = out_i + (size_t)blockIdx.x * x;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t xx = min(x, n);
-
-    uint64_t thr = 0;  // take every element whose composite >= thr
-    if (xx < n) {
-        // radix select of the xx-th largest composite, 11-bit digits from the top
-        uint64_t prefix = 0;
-        int hi_bits = 0;  // number of leading bits already fixed
-        if (tid == 0) {
-            s_need = xx;
-            s_done = 0;
+// One CTA per query: merges the per-tile candidate lists into the final top-x,
+// order (score desc, payload_id asc) == descending composite.
+__global__ void __launch_bounds__(TX_THREADS) topx_cand_merge_kernel(const uint64_t *__restrict__ cand,
+                                                                     const uint32_t *__restrict__ cand_cnt,
+                                                                     uint32_t n_tiles, uint32_t x,
+                                                                     float *__restrict__ out_s,
+                                                                     uint32_t *__restrict__ out_i) {
+    __shared__ uint64_t buf[TX_SORT_CAP];
+    const size_t q = blockIdx.x;
+    uint32_t filled = 0;  // buf[0..filled) = best so far (sorted) + appended candidates
+    for (uint32_t t = 0; t <= n_tiles; ++t) {
+        const uint32_t cnt = t < n_tiles ? cand_cnt[q * n_tiles + t] : 0u;
+        if (t == n_tiles || filled + cnt > TX_SORT_CAP) {
+            uint32_t S = 2;
+            while (S < filled) S <<= 1;
+            for (uint32_t j = filled + threadIdx.x; j < S; j += TX_THREADS) buf[j] = 0;
+            bitonic_desc(buf, S);
+            filled = min(filled, x);
         }
-        __syncthreads();
-        while (hi_bits < 64) {
-            const int nb = min(11, 64 - hi_bits);
-            const int shift = 64 - hi_bits - nb;
-            const uint32_t nbins = 1u << nb;
-            for (uint32_t i = tid; i < nbins; i += TX_THREADS) hist[i] = 0;
+        if (t < n_tiles) {
+            const uint64_t *src = cand + (q * n_tiles + t) * x;
+            for (uint32_t j = threadIdx.x; j < cnt; j += TX_THREADS) buf[filled + j] = src[j];
+            filled += cnt;
             __syncthreads();
-            for (uint32_t base = 0; base < n; base += TX_THREADS) {
-                const uint32_t i = base + tid;
-                uint32_t bin = 0xFFFFFFFFu;
-                if (i < n) {
-                    const uint64_t c = topx_composite(row[i], i);
-                    if (hi_bits == 0 || (c >> (64 - hi_bits)) == prefix) bin = (uint32_t)(c >> shift) & (nbins - 1u);
-                }
-                // warp-aggregated histogram update (scores cluster in a few bins)
-                const unsigned peers = __match_any_sync(0xffffffffu, bin);
-                if (bin != 0xFFFFFFFFu && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
-            }
-            __syncthreads();
-            // find the bin (from the top) where the running count reaches `need`
-            const uint32_t per = nbins / TX_THREADS ? nbins / TX_THREADS : 1;
-            uint32_t local = 0;
-            if (tid * per < nbins)
-                for (uint32_t j = 0; j < per; ++j) local += hist[nbins - 1 - (tid * per + j)];
-            s_scan[tid] = local;
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t need = s_need, run = 0, seg = 0;
-                while (seg < TX_THREADS && run + s_scan[seg] < need) run += s_scan[seg++];
-                // inside segment `seg`
-                uint32_t j = 0, b = nbins - 1 - seg * per;
-                while (run + hist[b] < need) {
-                    run += hist[b];
-                    ++j;
-                    --b;
-                }
-                s_bin = b;
-                s_need = need - run;
-                s_done = (hist[b] == need - run) ? 1u : 0u;  // the whole bin is taken
-            }
-            __syncthreads();
-            prefix = (prefix << nb) | s_bin;
-            hi_bits += nb;
-            const bool done = s_done != 0;
-            __syncthreads();
-            if (done) break;
-        }
-        thr = hi_bits < 64 ? prefix << (64 - hi_bits) : prefix;
-    }
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    for (uint32_t i = tid; i < n; i += TX_THREADS) {
-        const uint64_t c = topx_composite(row[i], i);
-        if (c >= thr) {
-            const uint32_t slot = atomicAdd(&s_cnt, 1u);
-            if (slot < TX_MAX_X) cand[slot] = c;
         }
     }
-    __syncthreads();
-    const uint32_t m = min(s_cnt, (uint32_t)TX_MAX_X);  // == xx
-    uint32_t S = 2;
-    while (S < m) S <<= 1;
-    for (uint32_t i = m + tid; i < S; i += TX_THREADS) cand[i] = 0;
-    bitonic_desc(cand, S);
-    for (uint32_t j = tid; j < x; j += TX_THREADS) {
-        if (j < m) {
-            const uint64_t c = cand[j];
-            os[j] = __uint_as_float((uint32_t)(c >> 32));
-            oi[j] = id_base + (0xFFFFFFFFu - (uint32_t)c);
+    for (uint32_t j = threadIdx.x; j < x; j += TX_THREADS) {
+        if (j < filled) {
+            const uint64_t c = buf[j];
+            out_s[q * x + j] = __uint_as_float((uint32_t)(c >> 32));
+            out_i[q * x + j] = 0xFFFFFFFFu - (uint32_t)c;
         } else {
-            os[j] = 0.0f;
-            oi[j] = 0xFFFFFFFFu;
+            out_s[q * x + j] = 0.0f;
+            out_i[q * x + j] = 0xFFFFFFFFu;
         }
     }
 }
@@ -356,22 +423,32 @@ static void check_queries(const myrio_svecs *q, uint64_t q_first, uint64_t q_cou
     if (q_first + q_count > q->n_rows) fail(MYRIO_ERR_BAD_ARG, "query range out of bounds");
 }
 
-static uint64_t rows_per_batch(const myrio_index *ix, uint64_t q_count) {
-    const uint64_t budget = 1ull << 31;  // bytes of score rows kept on the device at once
-    uint64_t per = std::max<uint64_t>(1, budget / (std::max<uint64_t>(ix->n_leaves, 1) * 4));
-    return std::min(per, std::max<uint64_t>(q_count, 1));
-}
-
-// scores rows [qn][L] for queries [q0, q0+qn) into ctx->score_rows
-static void score_rows(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q0,
-                       uint64_t qn, int32_t sim) {
+static void check_sim(int32_t sim) {
     if (sim != MYRIO_SIM_COSINE && sim != MYRIO_SIM_JACARD_TANIMOTO)
         fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path (Cosine, JacardTanimoto are)", sim);
-    const uint64_t L = ix->n_leaves;
-    ctx->score_rows.reserve(std::max<uint64_t>(qn * L, 1));
-    ctx->score_counters.reserve(4);
-    if (qn == 0 || L == 0) return;
-    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+}
+
+template <bool FUSED>
+static void launch_score(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a, int32_t sim) {
+    const size_t per_warp = ((size_t)ix->tile_leaves + 32 + (FUSED ? 256 : 0)) * sizeof(float);
+    int warps = (int)std::min<size_t>(16, (ctx->smem_optin - 1024) / per_warp);
+    if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
+    const size_t smem = per_warp * warps;
+    const unsigned grid = (unsigned)std::min<unsigned long long>(a.n_tasks, (unsigned long long)ctx->sm_count);
+    const char *name = FUSED ? "k4_score_tiles_topx" : "k4_score_tiles_rows";
+    if (sim == MYRIO_SIM_COSINE) {
+        auto kern = score_tiles_kernel<MYRIO_SIM_COSINE, FUSED>;
+        MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, name, kern, grid, warps * 32, smem, a);
+    } else {
+        auto kern = score_tiles_kernel<MYRIO_SIM_JACARD_TANIMOTO, FUSED>;
+        MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, name, kern, grid, warps * 32, smem, a);
+    }
+}
+
+static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q0,
+                           uint64_t qn) {
     ScoreArgs a{};
     a.tiles = ix->d_tiles.p;
     a.postings = ix->postings.p;
@@ -381,25 +458,18 @@ static void score_rows(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     a.q_first = q0;
     a.q_count = (uint32_t)qn;
     a.tile_leaves = ix->tile_leaves;
+    a.n_tiles = (uint32_t)ix->tiles.size();
     a.n_tasks = (unsigned long long)qn * ix->tiles.size();
-    a.scores = ctx->score_rows.p;
-    a.ld = L;
+    a.ld = ix->n_leaves;
+    a.leaf_id_base = ix->leaf_id_base;
     a.counters = ctx->score_counters.p;
-    const size_t per_warp = ((size_t)ix->tile_leaves + 32) * sizeof(float);
-    int warps = (int)std::min<size_t>(16, (ctx->smem_optin - 1024) / per_warp);
-    if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
-    const size_t smem = per_warp * warps;
-    const unsigned grid = (unsigned)std::min<unsigned long long>(a.n_tasks, (unsigned long long)ctx->sm_count);
-    if (sim == MYRIO_SIM_COSINE) {
-        MYRIO_CK(cudaFuncSetAttribute(score_tiles_kernel<MYRIO_SIM_COSINE>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MYRIO_LAUNCH(ctx, "k4_score_tiles", score_tiles_kernel<MYRIO_SIM_COSINE>, grid, warps * 32, smem, a);
-    } else {
-        MYRIO_CK(cudaFuncSetAttribute(score_tiles_kernel<MYRIO_SIM_JACARD_TANIMOTO>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MYRIO_LAUNCH(ctx, "k4_score_tiles", score_tiles_kernel<MYRIO_SIM_JACARD_TANIMOTO>, grid, warps * 32,
-                     smem, a);
-    }
+    return a;
+}
+
+static void reset_stats(myrio_ctx *ctx) {
+    ctx->last_stats[0] = ctx->last_stats[1] = ctx->last_stats[2] = 0;
+    ctx->score_counters.reserve(4);
+    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
 }
 
 static void accumulate_stats(myrio_ctx *ctx) {
@@ -415,14 +485,19 @@ static void accumulate_stats(myrio_ctx *ctx) {
 void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
                uint64_t q_count, int32_t sim, float *scores_host) {
     check_queries(queries, q_first, q_count);
+    check_sim(sim);
     const uint64_t L = ix->n_leaves;
-    ctx->last_stats[0] = ctx->last_stats[1] = ctx->last_stats[2] = 0;
-    ctx->score_counters.reserve(4);
-    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    const uint64_t per = rows_per_batch(ix, q_count);
+    reset_stats(ctx);
+    if (q_count == 0 || L == 0) return;
+    const uint64_t budget = 1ull << 31;  // bytes of score rows kept on the device at once
+    const uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, budget / (L * 4)), q_count);
+    ctx->score_rows.reserve(per * L);
     for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
         const uint64_t qn = std::min(per, q_count - q0);
-        score_rows(ctx, ix, queries, q_first + q0, qn, sim);
+        MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+        ScoreArgs a = base_args(ctx, ix, queries, q_first + q0, qn);
+        a.scores = ctx->score_rows.p;
+        launch_score<false>(ctx, ix, a, sim);
         d2h(ctx, scores_host + q0 * L, ctx->score_rows.p, qn * L);
         accumulate_stats(ctx);
     }
@@ -433,17 +508,30 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
                        uint64_t q_first, uint64_t q_count, uint32_t x, int32_t sim, float *d_top_scores,
                        uint32_t *d_top_ids, bool collect_stats) {
     check_queries(queries, q_first, q_count);
+    check_sim(sim);
     if (x == 0 || x > TX_MAX_X) fail(MYRIO_ERR_BAD_ARG, "x must be in 1..%d", TX_MAX_X);
-    const uint64_t L = ix->n_leaves;
-    ctx->last_stats[0] = ctx->last_stats[1] = ctx->last_stats[2] = 0;
-    ctx->score_counters.reserve(4);
-    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
-    const uint64_t per = rows_per_batch(ix, q_count);
+    reset_stats(ctx);
+    if (q_count == 0) return;
+    const uint64_t n_tiles = std::max<uint64_t>(ix->tiles.size(), 1);
+    const uint64_t budget = 4ull << 30;  // bytes of per-tile candidates kept at once
+    const uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, budget / (n_tiles * x * 8)), q_count);
+    DevBuf<uint64_t> cand(per * n_tiles * x);
+    DevBuf<uint32_t> cand_cnt(per * n_tiles), gthr(per);
     for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
         const uint64_t qn = std::min(per, q_count - q0);
-        score_rows(ctx, ix, queries, q_first + q0, qn, sim);
-        MYRIO_LAUNCH(ctx, "k5_topx", topx_kernel, (unsigned)qn, TX_THREADS, 0, ctx->score_rows.p, L,
-                     (uint32_t)L, x, ix->leaf_id_base, d_top_scores + q0 * x, d_top_ids + q0 * x);
+        MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+        MYRIO_CK(cudaMemsetAsync(gthr.p, 0, qn * sizeof(uint32_t), ctx->stream));
+        MYRIO_CK(cudaMemsetAsync(cand_cnt.p, 0, qn * n_tiles * sizeof(uint32_t), ctx->stream));
+        if (!ix->tiles.empty()) {
+            ScoreArgs a = base_args(ctx, ix, queries, q_first + q0, qn);
+            a.x = x;
+            a.cand = cand.p;
+            a.cand_cnt = cand_cnt.p;
+            a.gthr = gthr.p;
+            launch_score<true>(ctx, ix, a, sim);
+        }
+        MYRIO_LAUNCH(ctx, "k5_topx_merge_tiles", topx_cand_merge_kernel, (unsigned)qn, TX_THREADS, 0, cand.p,
+                     cand_cnt.p, (uint32_t)ix->tiles.size(), x, d_top_scores + q0 * x, d_top_ids + q0 * x);
         if (collect_stats) accumulate_stats(ctx);
     }
 }
