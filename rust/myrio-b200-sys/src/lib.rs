@@ -1,0 +1,102 @@
+//! Raw bindings of `include/myrio_b200.h` (kept in sync by hand; every item cites the header).
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_void};
+
+#[repr(C)] pub struct myrio_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct myrio_seqs { _p: [u8; 0] }
+#[repr(C)] pub struct myrio_svecs { _p: [u8; 0] }
+#[repr(C)] pub struct myrio_index { _p: [u8; 0] }
+
+pub const MYRIO_OK: i32 = 0;
+pub const MYRIO_ERR_INVALID_K: i32 = 1;
+pub const MYRIO_ERR_BAD_ARG: i32 = 2;
+pub const MYRIO_ERR_CUDA: i32 = 3;
+pub const MYRIO_ERR_OOM: i32 = 4;
+pub const MYRIO_ERR_BAD_QUALITY: i32 = 5;
+pub const MYRIO_ERR_UNSUPPORTED: i32 = 6;
+pub const MYRIO_ERR_EMPTY: i32 = 7;
+pub const MYRIO_ERR_NONFINITE: i32 = 8;
+
+pub const MYRIO_SIM_COSINE: i32 = 0;
+pub const MYRIO_SIM_JACARD_TANIMOTO: i32 = 1;
+pub const MYRIO_SIM_OVERLAP: i32 = 2;
+pub const MYRIO_VAL_F32: i32 = 0;
+pub const MYRIO_VAL_U16: i32 = 1;
+
+/// `ClusteringParameters` (myrio-core/src/clustering.rs:15-36) without the centroids.
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct myrio_cluster_params {
+    pub k: u32,
+    pub t1: f32,
+    pub t2: u64,
+    pub similarity: i32,
+    pub expected_nb_of_clusters: u64,
+    pub eta_improvement: f32,
+    pub nb_iters_max: u64,
+    pub has_silhouette_trimming: i32,
+    pub silhouette_trimming: f32,
+}
+
+unsafe extern "C" {
+    pub fn myrio_last_error() -> *const c_char;
+    pub fn myrio_version() -> i32;
+    pub fn myrio_ctx_create(device: i32, out: *mut *mut myrio_ctx) -> i32;
+    pub fn myrio_ctx_destroy(ctx: *mut myrio_ctx);
+    pub fn myrio_ctx_sync(ctx: *mut myrio_ctx) -> i32;
+    pub fn myrio_ctx_stream(ctx: *const myrio_ctx) -> *mut c_void;
+    pub fn myrio_ctx_launch_count(ctx: *const myrio_ctx) -> u64;
+    pub fn myrio_prof_enable(ctx: *mut myrio_ctx, on: i32) -> i32;
+    pub fn myrio_prof_reset(ctx: *mut myrio_ctx) -> i32;
+    pub fn myrio_prof_query(ctx: *mut myrio_ctx, prefix: *const c_char, ms_total: *mut f64, launches: *mut u64) -> i32;
+
+    pub fn myrio_reads_upload(ctx: *mut myrio_ctx, words: *const u64, word_off: *const u64, base_off: *const u64,
+                              qual: *const u8, n_reads: u64, out: *mut *mut myrio_seqs) -> i32;
+    pub fn myrio_leaves_upload(ctx: *mut myrio_ctx, words: *const u64, word_off: *const u64, base_off: *const u64,
+                               n_leaves: u64, out: *mut *mut myrio_seqs) -> i32;
+    pub fn myrio_seqs_free(s: *mut myrio_seqs);
+
+    pub fn myrio_count_reads(ctx: *mut myrio_ctx, reads: *const myrio_seqs, k: u32, cutoff: f32,
+                             out: *mut *mut myrio_svecs) -> i32;
+    pub fn myrio_count_leaves(ctx: *mut myrio_ctx, leaves: *const myrio_seqs, k: u32, nb_resamples: u32, seed: u64,
+                              leaf_id_base: u64, out: *mut *mut myrio_svecs) -> i32;
+
+    pub fn myrio_svecs_info(v: *const myrio_svecs, n_rows: *mut u64, nnz: *mut u64, vtype: *mut i32) -> i32;
+    pub fn myrio_svecs_download(ctx: *mut myrio_ctx, v: *const myrio_svecs, row_off: *mut u64, keys: *mut u64,
+                                vals: *mut c_void, aux: *mut c_void) -> i32;
+    pub fn myrio_svecs_upload(ctx: *mut myrio_ctx, n_rows: u64, row_off: *const u64, keys: *const u64,
+                              vals: *const c_void, vtype: i32, out: *mut *mut myrio_svecs) -> i32;
+    pub fn myrio_svecs_normalize(ctx: *mut myrio_ctx, input: *const myrio_svecs, out: *mut *mut myrio_svecs) -> i32;
+    pub fn myrio_svecs_free(v: *mut myrio_svecs);
+    pub fn myrio_svecs_device_ptrs(v: *const myrio_svecs, row_off: *mut *const u64, keys: *mut *const u64,
+                                   vals: *mut *const c_void, aux: *mut *const c_void) -> i32;
+
+    pub fn myrio_index_build(ctx: *mut myrio_ctx, leaf_vecs_normalized: *const myrio_svecs, leaf_id_base: u32,
+                             tile_leaves: u32, out: *mut *mut myrio_index) -> i32;
+    pub fn myrio_index_info(ix: *const myrio_index, n_leaves: *mut u64, n_tiles: *mut u64, n_postings: *mut u64,
+                            n_unique_total: *mut u64, tile_leaves: *mut u32) -> i32;
+    pub fn myrio_index_export_tile(ctx: *mut myrio_ctx, ix: *const myrio_index, tile: u64, n_unique: *mut u64,
+                                   n_postings: *mut u64, ukeys: *mut u64, offs: *mut u64, post_leaf: *mut u32,
+                                   post_val: *mut f32) -> i32;
+    pub fn myrio_index_free(ix: *mut myrio_index);
+
+    pub fn myrio_score_all(ctx: *mut myrio_ctx, ix: *const myrio_index, queries: *const myrio_svecs, q_first: u64,
+                           q_count: u64, similarity: i32, scores: *mut f32) -> i32;
+    pub fn myrio_score_topx(ctx: *mut myrio_ctx, ix: *const myrio_index, queries: *const myrio_svecs, q_first: u64,
+                            q_count: u64, x: u32, similarity: i32, top_scores: *mut f32, top_ids: *mut u32) -> i32;
+    pub fn myrio_score_topx_async(ctx: *mut myrio_ctx, ix: *const myrio_index, queries: *const myrio_svecs,
+                                  q_first: u64, q_count: u64, x: u32, similarity: i32, d_top_scores: *mut f32,
+                                  d_top_ids: *mut u32) -> i32;
+    pub fn myrio_topx_merge_async(ctx: *mut myrio_ctx, d_scores_in: *const f32, d_ids_in: *const u32, n_parts: u32,
+                                  q_count: u64, x: u32, d_scores_out: *mut f32, d_ids_out: *mut u32) -> i32;
+    pub fn myrio_score_stats(ctx: *mut myrio_ctx, n_query_keys: *mut u64, n_key_hits: *mut u64,
+                             n_postings_touched: *mut u64) -> i32;
+
+    pub fn myrio_cluster(ctx: *mut myrio_ctx, reads: *const myrio_seqs, params: *const myrio_cluster_params,
+                         initial_centroids: *const myrio_svecs, assign: *mut i32, n_iters: *mut u32,
+                         silhouette: *mut f32) -> i32;
+    pub fn myrio_compute_cluster_centroid(ctx: *mut myrio_ctx, counts: *const myrio_svecs, member_ids: *const u64,
+                                          m: u64, out: *mut *mut myrio_svecs) -> i32;
+    pub fn myrio_pairwise(ctx: *mut myrio_ctx, rows: *const myrio_svecs, cols: *const myrio_svecs, similarity: i32,
+                          out: *mut f32) -> i32;
+}
