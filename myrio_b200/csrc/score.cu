@@ -266,11 +266,14 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
                 if (src < 0) return false;
                 n = min(cl - coff, 32u * SC_U);
                 v = cv;
-                const uint64_t *ptr = post + cb + coff;
+                const uint64_t *ptr = post + cb + coff + lane;
+                if (n == 32u * SC_U) {  // full chunk: unpredicated loads
 #pragma unroll
-                for (int u = 0; u < SC_U; ++u) {
-                    const uint32_t idx = u * 32 + lane;
-                    p[u] = (u * 32u < n && idx < n) ? __ldg(ptr + idx) : dummy_posting;
+                    for (int u = 0; u < SC_U; ++u) p[u] = __ldg(ptr + u * 32);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < SC_U; ++u)
+                        p[u] = (u * 32u + lane < n) ? __ldg(ptr + u * 32) : dummy_posting;
                 }
                 coff += n;
                 if (coff >= cl) next_hit();
@@ -278,14 +281,23 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
             };
             auto process = [&](const uint64_t(&p)[SC_U], uint32_t n, float v) {
                 float tacc[SC_U];
+                if (n == 32u * SC_U) {
 #pragma unroll
-                for (int u = 0; u < SC_U; ++u)
-                    if (u * 32u < n) tacc[u] = acc[(uint32_t)(p[u] >> 32)];
+                    for (int u = 0; u < SC_U; ++u) tacc[u] = acc[(uint32_t)(p[u] >> 32)];
 #pragma unroll
-                for (int u = 0; u < SC_U; ++u)
-                    if (u * 32u < n)
+                    for (int u = 0; u < SC_U; ++u)
                         acc[(uint32_t)(p[u] >> 32)] =
                             __fadd_rn(tacc[u], __fmul_rn(v, __uint_as_float((uint32_t)p[u])));
+                } else {
+#pragma unroll
+                    for (int u = 0; u < SC_U; ++u)
+                        if (u * 32u < n) tacc[u] = acc[(uint32_t)(p[u] >> 32)];
+#pragma unroll
+                    for (int u = 0; u < SC_U; ++u)
+                        if (u * 32u < n)
+                            acc[(uint32_t)(p[u] >> 32)] =
+                                __fadd_rn(tacc[u], __fmul_rn(v, __uint_as_float((uint32_t)p[u])));
+                }
                 __syncwarp();  // the next chunk may belong to another key and hit the same leaves
             };
             next_hit();
