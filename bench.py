@@ -223,6 +223,8 @@ def run_ours(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        os.environ["NCCL_DEBUG"] = os.environ.get("MYRIO_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = api.Context(local_rank)
     L = ctx._L
