@@ -107,6 +107,56 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *keys, uint16_t *w, uint32
     __syncthreads();
 }
 
+// Sort of E u64 keys (values < 2^key_bits) for the common case of keys spread over
+// their leading bits: one MSD counting pass into 256 order-preserving buckets
+// (a handful of keys each), then every thread insertion-sorts one bucket.  About
+// 8x fewer instructions than the bitonic network at E ~ 1000.  Returns false -- and
+// leaves `keys` untouched -- if some bucket holds more than 32 keys (low-complexity
+// sequence); the caller then falls back to the bitonic network.
+__device__ __forceinline__ bool bucket_sort(uint64_t *keys, uint64_t *keys2, uint32_t E, uint32_t key_bits,
+                                            uint32_t *s_hist, uint32_t *s_start, uint32_t *wbuf) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t shift = key_bits > 8 ? key_bits - 8 : 0;
+    s_hist[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < E; i += KC_THREADS) atomicAdd(&s_hist[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    const uint32_t c = s_hist[tid];
+    uint32_t total;
+    const uint32_t start = block_excl_scan_u32(c, wbuf, &total);
+    const int too_big = __syncthreads_or(c > 32u);
+    if (too_big) return false;
+    s_start[tid] = start;
+    if (tid == KC_THREADS - 1) s_start[KC_THREADS] = E;
+    s_hist[tid] = 0;  // becomes the per-bucket cursor
+    __syncthreads();
+    for (uint32_t i = tid; i < E; i += KC_THREADS) {
+        const uint64_t key = keys[i];
+        const uint32_t d = (uint32_t)(key >> shift) & 255u;
+        keys2[s_start[d] + atomicAdd(&s_hist[d], 1u)] = key;
+    }
+    __syncthreads();
+    {
+        const uint32_t b = start, e = start + c;
+        for (uint32_t i = b + 1; i < e; ++i) {
+            const uint64_t x = keys2[i];
+            uint32_t j = i;
+            while (j > b && keys2[j - 1] > x) {
+                keys2[j] = keys2[j - 1];
+                --j;
+            }
+            keys2[j] = x;
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < E; i += KC_THREADS) keys[i] = keys2[i];
+    __syncthreads();
+    return true;
+}
+
+// bucket sort needs a second key buffer: only the small size classes carry one
+__host__ __device__ inline bool has_bucket_buffer(uint32_t ecap) { return ecap <= 4096; }
+
 __device__ __forceinline__ uint32_t pow2_ceil(uint32_t v) {
     if (v <= 2) return 2;
     return 1u << (32 - __clz(v - 1));
@@ -152,8 +202,10 @@ struct ReadCountArgs {
 
 // shared/global work area: keys[ecap] u64 | aux[ecap+64] u32 (conf factors, then run heads)
 //                          | words[ecap/64+4] u64
+//                          | keys2[ecap] u64 (bucket-sort buffer, small classes only)
 __host__ __device__ inline size_t read_work_bytes(uint32_t ecap) {
-    return (size_t)ecap * 8 + ((size_t)ecap + 64) * 4 + ((size_t)ecap / 64 + 4) * 8;
+    return (size_t)ecap * 8 + ((size_t)ecap + 64) * 4 + ((size_t)ecap / 64 + 4) * 8 +
+           (has_bucket_buffer(ecap) ? (size_t)ecap * 8 : 0);
 }
 
 template <bool GLOBAL>
@@ -162,11 +214,13 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
     __shared__ float s_phred[128];
     __shared__ uint32_t s_wbuf[33];
     __shared__ uint32_t s_cnt;
+    __shared__ uint32_t s_hist[KC_THREADS], s_start[KC_THREADS + 1];
 
     uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
     uint64_t *keys = reinterpret_cast<uint64_t *>(work);
     uint32_t *aux = reinterpret_cast<uint32_t *>(work + (size_t)a.ecap * 8);
     uint64_t *words = reinterpret_cast<uint64_t *>(work + (size_t)a.ecap * 8 + ((size_t)a.ecap + 64) * 4);
+    uint64_t *keys2 = words + ((size_t)a.ecap / 64 + 4);
     float *pfac = reinterpret_cast<float *>(aux);
 
     const uint32_t tid = threadIdx.x;
@@ -260,9 +314,11 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
         }
         return;
     }
-    const uint32_t S = pow2_ceil(E);
-    for (uint32_t i = E + tid; i < S; i += KC_THREADS) keys[i] = ~0ull;
-    bitonic_sort<false>(keys, nullptr, S);
+    if (!(has_bucket_buffer(a.ecap) && bucket_sort(keys, keys2, E, 2u * k, s_hist, s_start, s_wbuf))) {
+        const uint32_t S = pow2_ceil(E);
+        for (uint32_t i = E + tid; i < S; i += KC_THREADS) keys[i] = ~0ull;
+        bitonic_sort<false>(keys, nullptr, S);
+    }
 
     uint32_t *headpos = aux;  // conf factors are dead
     const uint32_t D = find_run_heads(keys, E, headpos, s_wbuf);
@@ -334,7 +390,7 @@ struct LeafCountArgs {
 //            | words2[ecap/32+4] u64
 __host__ __device__ inline size_t leaf_work_bytes(uint32_t ecap) {
     return (size_t)ecap * 8 + ((size_t)ecap + 64) * 4 + (size_t)ecap * 2 + 2 * ((size_t)ecap + 16) +
-           ((size_t)ecap / 32 + 4) * 8;
+           ((size_t)ecap / 32 + 4) * 8 + 16 + (has_bucket_buffer(ecap) ? (size_t)ecap * 8 : 0);
 }
 
 template <bool GLOBAL>
@@ -343,6 +399,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     __shared__ uint32_t s_wbuf[33];
     __shared__ uint32_t s_cnt, s_namb, s_over;
     __shared__ uint32_t s_sum;
+    __shared__ uint32_t s_hist[KC_THREADS], s_start[KC_THREADS + 1];
 
     uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
     size_t o_ = 0;
@@ -356,7 +413,9 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     o_ += (size_t)a.ecap + 16;
     uint8_t *comp = work + o_;
     o_ += (size_t)a.ecap + 16;
+    o_ = (o_ + 15) & ~(size_t)15;
     uint64_t *words2 = reinterpret_cast<uint64_t *>(work + o_);
+    uint64_t *keys2 = words2 + ((size_t)a.ecap / 32 + 4);
 
     const uint32_t tid = threadIdx.x;
     const uint32_t r = a.ids[blockIdx.x];
@@ -487,15 +546,18 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
         E = s_cnt;
     }
     __syncthreads();
-    const uint32_t S = pow2_ceil(E);
-    for (uint32_t i = E + tid; i < S; i += KC_THREADS) {
-        keys[i] = ~0ull;
-        if (ambiguous) wts[i] = 0;
+    if (!(!ambiguous && has_bucket_buffer(a.ecap) &&
+          bucket_sort(keys, keys2, E, 2u * k, s_hist, s_start, s_wbuf))) {
+        const uint32_t S = pow2_ceil(E);
+        for (uint32_t i = E + tid; i < S; i += KC_THREADS) {
+            keys[i] = ~0ull;
+            if (ambiguous) wts[i] = 0;
+        }
+        if (ambiguous)
+            bitonic_sort<true>(keys, wts, S);
+        else
+            bitonic_sort<false>(keys, nullptr, S);
     }
-    if (ambiguous)
-        bitonic_sort<true>(keys, wts, S);
-    else
-        bitonic_sort<false>(keys, nullptr, S);
 
     uint32_t *headpos = aux;
     const uint32_t Dall = find_run_heads(keys, E, headpos, s_wbuf);
