@@ -67,6 +67,9 @@ void myrio_ctx_destroy(myrio_ctx *ctx) {
     }
     ctx->score_rows.release();
     ctx->score_counters.release();
+    ctx->topx_cand.release();
+    ctx->topx_cand_cnt.release();
+    ctx->topx_gthr.release();
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     alloc_stream() = nullptr;

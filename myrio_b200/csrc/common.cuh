@@ -133,6 +133,8 @@ struct myrio_ctx {
     // scoring scratch (grow-only)
     myrio::DevBuf<float> score_rows;
     myrio::DevBuf<unsigned long long> score_counters;
+    myrio::DevBuf<uint64_t> topx_cand;
+    myrio::DevBuf<uint32_t> topx_cand_cnt, topx_gthr;
     uint64_t last_stats[3] = {0, 0, 0};
     // pinned staging for small D2H reads
     void *pinned = nullptr;

@@ -61,14 +61,69 @@ __global__ void __launch_bounds__(256) emit_unique_kernel(const uint64_t *__rest
     if (i == 0) ubegin[uidx[n]] = (uint32_t)n;
 }
 
+// unit[leaf] = smallest normalised value of the leaf's row (count == common count)
+__global__ void __launch_bounds__(256) row_min_kernel(const uint64_t *__restrict__ row_off,
+                                                      const float *__restrict__ vals, uint64_t n_rows,
+                                                      float *__restrict__ unit) {
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const unsigned lane = threadIdx.x & 31;
+    float m = 3.402823466e+38f;
+    for (uint64_t i = row_off[row] + lane; i < row_off[row + 1]; i += 32) m = fminf(m, vals[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (lane == 0) unit[row] = (row_off[row + 1] > row_off[row]) ? m : 0.0f;
+}
+
+// A unique key is DENSE when it occurs in at least dense_min leaves of the tile and every
+// one of its postings carries exactly unit[leaf]; flags[u] = 1 then.
+__global__ void __launch_bounds__(256) classify_dense_kernel(const uint64_t *__restrict__ postings,
+                                                             const uint32_t *__restrict__ ubegin,
+                                                             uint64_t n_unique, const float *__restrict__ unit,
+                                                             uint32_t dense_min, uint32_t *__restrict__ flags) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_unique) return;
+    const uint32_t b = ubegin[u], e = ubegin[u + 1];
+    uint32_t dense = (e - b) >= dense_min ? 1u : 0u;
+    for (uint32_t i = b; dense && i < e; ++i) {
+        const uint64_t p = postings[i];
+        if ((uint32_t)p != __float_as_uint(unit[(uint32_t)(p >> 32)])) dense = 0u;
+    }
+    flags[u] = dense;
+}
+
+// one warp per dense key: fill its 32-word bitmap (word = leaf & 31, bit = leaf >> 5)
+__global__ void __launch_bounds__(256) fill_bitmaps_kernel(const uint64_t *__restrict__ postings,
+                                                           const uint32_t *__restrict__ ubegin,
+                                                           uint64_t n_unique, const uint32_t *__restrict__ flags,
+                                                           const uint64_t *__restrict__ didx,
+                                                           uint32_t *__restrict__ bitmaps) {
+    const uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (u >= n_unique || !flags[u]) return;
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t *bm = bitmaps + didx[u] * 32;
+    uint32_t w = 0;
+    // lane l owns word l: scan the key's postings and keep the leaves with leaf & 31 == l
+    for (uint32_t i = ubegin[u]; i < ubegin[u + 1]; ++i) {
+        const uint32_t leaf = (uint32_t)(postings[i] >> 32);
+        if ((leaf & 31u) == lane) w |= 1u << (leaf >> 5);
+    }
+    bm[lane] = w;
+}
+
 __global__ void __launch_bounds__(256) dict_insert_kernel(const uint64_t *__restrict__ ukeys,
                                                           const uint32_t *__restrict__ ubegin,
-                                                          uint64_t n_unique, DictSlot *dict,
+                                                          uint64_t n_unique, const uint32_t *__restrict__ flags,
+                                                          const uint64_t *__restrict__ didx, DictSlot *dict,
                                                           uint32_t mask) {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_unique) return;
     const uint64_t key = ukeys[u];
-    const uint32_t begin = ubegin[u], len = ubegin[u + 1] - begin;
+    uint32_t begin = ubegin[u], len = ubegin[u + 1] - begin;
+    if (flags && flags[u]) {
+        begin = (uint32_t)didx[u];
+        len |= DENSE_FLAG;
+    }
     uint32_t h = dict_hash(key) & mask;
     for (;;) {
         // claim an empty slot through its `len` word (len != 0 for every real entry)
@@ -85,7 +140,7 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
                          uint32_t tile_leaves) {
     if (leaves->vtype != MYRIO_VAL_F32)
         fail(MYRIO_ERR_BAD_ARG, "index_build needs normalised f32 leaf vectors (myrio_svecs_normalize)");
-    if (tile_leaves == 0) tile_leaves = 4096;
+    if (tile_leaves == 0) tile_leaves = 1024;
     if (tile_leaves > 49152) fail(MYRIO_ERR_BAD_ARG, "tile_leaves must be <= 49152");
     if (leaves->n_rows >= 0xFFFFFFFFull) fail(MYRIO_ERR_BAD_ARG, "too many leaves for u32 payload ids");
     auto ix = std::make_unique<myrio_index>();
@@ -121,8 +176,14 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
     while (key_bits < 64 && (h_or >> key_bits) != 0) ++key_bits;
     if (key_bits == 0) key_bits = 1;
 
-    DevBuf<uint32_t> hist, flags;
-    DevBuf<uint64_t> offs, uidx;
+    ix->unit.alloc(L);
+    MYRIO_LAUNCH(ctx, "k3_row_min", row_min_kernel, (unsigned)((L + 7) / 8), 256, 0, leaves->row_off.p,
+                 leaves->vals_f32.p, L, ix->unit.p);
+    ix->bitmaps.resize(n_tiles);
+    const bool dense_ok = tile_leaves <= DENSE_MAX_TILE;
+
+    DevBuf<uint32_t> hist, flags, dflags;
+    DevBuf<uint64_t> offs, uidx, didx;
     bool in_tmp = false;
     uint64_t max_tile_post = 0;
     for (uint64_t t = 0; t < n_tiles; ++t) max_tile_post = std::max(max_tile_post, bounds[t + 1] - bounds[t]);
@@ -155,18 +216,41 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
             ix->ubegin[t].alloc(1);
             MYRIO_CK(cudaMemsetAsync(ix->ubegin[t].p, 0, sizeof(uint32_t), ctx->stream));
         }
+        // dense keys -> bitmaps
+        uint64_t n_dense = 0;
+        const uint64_t *sv = (in_tmp ? pv2.p : pv.p) + pb;
+        if (dense_ok && U) {
+            const uint32_t dense_min = std::max<uint32_t>(32u, ti.n_leaves / 4u);
+            dflags.reserve(U);
+            didx.reserve(U + 1);
+            MYRIO_LAUNCH(ctx, "k3_classify_dense", classify_dense_kernel, (unsigned)((U + 255) / 256), 256, 0, sv,
+                         ix->ubegin[t].p, U, ix->unit.p + ti.leaf_begin, dense_min, dflags.p);
+            exclusive_scan_u32_to_u64(ctx, dflags.p, didx.p, U);
+            d2h(ctx, &n_dense, didx.p + U, 1);
+            sync(ctx);
+            if (n_dense) {
+                ix->bitmaps[t].alloc(n_dense * 32);
+                MYRIO_LAUNCH(ctx, "k3_fill_bitmaps", fill_bitmaps_kernel, (unsigned)((U + 7) / 8), 256, 0, sv,
+                             ix->ubegin[t].p, U, dflags.p, didx.p, ix->bitmaps[t].p);
+            }
+        }
         uint32_t cap = 16;
         while (cap < 2 * U) cap <<= 1;
         ix->dicts[t].alloc(cap);
         MYRIO_CK(cudaMemsetAsync(ix->dicts[t].p, 0, (size_t)cap * sizeof(DictSlot), ctx->stream));
         if (U)
             MYRIO_LAUNCH(ctx, "k3_dict_insert", dict_insert_kernel, (unsigned)((U + 255) / 256), 256, 0,
-                         ix->ukeys[t].p, ix->ubegin[t].p, U, ix->dicts[t].p, cap - 1);
+                         ix->ukeys[t].p, ix->ubegin[t].p, U, n_dense ? dflags.p : nullptr, didx.p,
+                         ix->dicts[t].p, cap - 1);
         ti.n_unique = U;
         ti.dict = ix->dicts[t].p;
         ti.dict_mask = cap - 1;
         ti.ukeys = ix->ukeys[t].p;
         ti.ubegin = ix->ubegin[t].p;
+        ti.bitmaps = ix->bitmaps[t].p;
+        ti.unit = ix->unit.p + ti.leaf_begin;
+        ti.n_dense = n_dense;
+        ix->n_dense_total += n_dense;
         ix->n_unique_total += U;
     }
     sync(ctx);

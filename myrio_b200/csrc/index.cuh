@@ -5,11 +5,17 @@
 namespace myrio {
 
 // Dictionary slot of a tile: open addressing, linear probing. len == 0 <=> empty.
+// Sparse key: begin = first posting (relative to the tile's posting range), len = df.
+// Dense key (DENSE_FLAG set in len): begin = index of the key's 32-word bitmap in the
+// tile's bitmap array, len & ~DENSE_FLAG = df.
 struct __align__(16) DictSlot {
     uint64_t key;
-    uint32_t begin;  // first posting, relative to the tile's posting range
-    uint32_t len;    // number of postings (document frequency inside the tile)
+    uint32_t begin;
+    uint32_t len;
 };
+static constexpr uint32_t DENSE_FLAG = 0x80000000u;
+// dense keys need lane-owned accumulators: leaf = 32*r + lane with r < 32
+static constexpr uint32_t DENSE_MAX_TILE = 1024;
 
 struct TileInfo {
     uint64_t post_begin;  // offset of the tile's postings in the global posting array
@@ -22,6 +28,11 @@ struct TileInfo {
     uint32_t pad_;
     const uint64_t *ukeys;    // sorted unique keys of the tile        (export / tests)
     const uint32_t *ubegin;   // first posting of each unique key, +1 sentinel
+    // dense keys: a posting whose value equals unit[leaf] (the leaf's smallest normalised
+    // value, i.e. count == the common count) is one bit: word `leaf & 31`, bit `leaf >> 5`
+    const uint32_t *bitmaps;  // [n_dense][32]
+    const float *unit;        // [n_leaves] (slice of the index-wide array)
+    uint64_t n_dense;
 };
 
 __device__ __forceinline__ uint32_t dict_hash(uint64_t key) {
@@ -52,6 +63,9 @@ struct myrio_index {
     std::vector<myrio::DevBuf<myrio::DictSlot>> dicts;
     std::vector<myrio::DevBuf<uint64_t>> ukeys;
     std::vector<myrio::DevBuf<uint32_t>> ubegin;
+    std::vector<myrio::DevBuf<uint32_t>> bitmaps;
+    myrio::DevBuf<float> unit;  // [n_leaves]
+    uint64_t n_dense_total = 0;
 };
 
 namespace myrio {

@@ -93,6 +93,10 @@ __device__ __forceinline__ void tile_topx(float *acc, uint32_t *hist, uint32_t n
     }
     cnt = warp_sum_u32(cnt);
     __syncwarp();
+    if (cnt == 0) {  // nothing in this tile can enter the query's top-x
+        if (lane == 0) *cand_cnt = 0;
+        return;
+    }
     const bool select = cnt > x;
     uint32_t T = thr, need_eq = 0;
     if (select) {
@@ -168,20 +172,43 @@ __device__ __forceinline__ void tile_topx(float *acc, uint32_t *hist, uint32_t n
     if (lane == 0) *cand_cnt = out;
 }
 
-// Postings fetched per lane and chunk: a chunk is up to 32*SC_U postings of ONE key
-// (distinct leaves => SC_U*32 independent accumulator updates => full ILP), and two
-// chunks are kept in flight (registers) so that the L2/HBM latency of chunk n+1
-// hides behind the shared-memory updates of chunk n, across key boundaries too.
-static constexpr int SC_U = 8;
+// K4.  One warp owns one (query, tile) task.
+//
+// Phase A -- probe: the query's keys are looked up in the tile's dictionary, four
+// rounds of 32 keys at a time (four independent 16-byte loads per lane in flight),
+// and the hits are appended IN KEY ORDER to a per-warp list in shared memory.
+// Phase B -- accumulate: the hit list is walked in order.  A sparse key is streamed in
+// chunks of up to 32*SC_U postings (distinct leaves => independent updates, full ILP);
+// a dense key is one 128-byte bitmap applied to lane-owned accumulators that stay in
+// registers while dense keys follow one another.  Two chunks are kept in flight so the
+// load of chunk n+1 (possibly of the next key) hides behind the updates of chunk n.
+static constexpr int SC_U = 2;
+static constexpr int SC_MAX_WARPS = 20;  // 96 registers per thread (racc[32] in registers), ~11 KB of smem per warp
+static constexpr int SC_PROBE_ROUNDS = 2;
+static constexpr uint32_t SC_HITS = 160;  // hit-list capacity per warp (drained when nearly full)
+
+struct __align__(4) HitRec {
+    uint32_t begin;
+    uint32_t len;  // DENSE_FLAG | df
+    float qv;
+};
+
+__host__ __device__ inline size_t score_warp_smem_bytes(uint32_t tile_leaves, bool fused) {
+    return ((size_t)tile_leaves + 32 + (fused ? 256 : 0) + DENSE_MAX_TILE) * sizeof(float) +
+           SC_HITS * sizeof(HitRec);
+}
 
 template <int SIM, bool FUSED>
-__global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
-    extern __shared__ float acc_all[];
+__global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per warp: tile accumulators + dummy slot for masked-off lanes (+ 256-bin histogram)
-    const uint32_t acc_stride = a.tile_leaves + 32 + (FUSED ? 256 : 0);
-    float *acc = acc_all + (size_t)warp * acc_stride;
+    const unsigned lt = (1u << lane) - 1u;
+    // per warp: tile accumulators + dummy slot for masked-off lanes (+ 256-bin histogram) + hit list
+    uint8_t *wbase = smem_raw + (size_t)warp * score_warp_smem_bytes(a.tile_leaves, FUSED);
+    float *acc = reinterpret_cast<float *>(wbase);
     uint32_t *hist = reinterpret_cast<uint32_t *>(acc + a.tile_leaves + 32);
+    float *usm = acc + a.tile_leaves + 32 + (FUSED ? 256 : 0);  // unit values of the lane-owned leaves
+    HitRec *hits = reinterpret_cast<HitRec *>(usm + DENSE_MAX_TILE);
     const uint64_t dummy_posting = (uint64_t)a.tile_leaves << 32;  // leaf = dummy slot, val = +0.0
     unsigned long long st_keys = 0, st_hits = 0, st_post = 0;
 
@@ -190,82 +217,82 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
         if (lane == 0) task = atomicAdd(a.counters, 1ull);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
-        const uint32_t t = (uint32_t)(task / a.q_count);  // tile-major: a tile's postings stay hot in L2
+        const uint32_t t = (uint32_t)(task / a.q_count);  // tile-major: a tile's index stays hot in L2
         const uint32_t ql = (uint32_t)(task % a.q_count);
         const TileInfo *ti = a.tiles + t;
         const uint32_t nl = ti->n_leaves;
         const uint32_t mask = ti->dict_mask;
         const uint4 *dict = reinterpret_cast<const uint4 *>(ti->dict);
         const uint64_t *post = a.postings + ti->post_begin;
+        const uint32_t *bitmaps = ti->bitmaps;
 
-        for (uint32_t i = lane; i < nl; i += 32) acc[i] = 0.0f;
+        // Dense keys (tiles of <= 1024 leaves): this lane owns leaves 32*r + lane.  Their
+        // accumulators live in registers while dense keys follow one another (flushed to /
+        // reloaded from shared memory around sparse chunks); their unit values sit in shared
+        // memory (bank == lane, conflict-free) -- keeping them in registers too costs a quarter
+        // of the resident warps and measured slower (profiles/r01_k4_variants.md).
+        const bool dense_tile = ti->n_dense != 0;  // implies tile_leaves <= DENSE_MAX_TILE
+        float racc[32];
+        bool in_regs = dense_tile;
+        if (dense_tile) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                usm[32 * r + lane] = (32u * r + lane < nl) ? __ldg(ti->unit + 32 * r + lane) : 0.0f;
+                racc[r] = 0.0f;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) racc[r] = 0.0f;
+            for (uint32_t i = lane; i < nl; i += 32) acc[i] = 0.0f;
+        }
         if (lane == 0) acc[a.tile_leaves] = 0.0f;
         __syncwarp();
+        auto flush_regs = [&]() {  // registers -> shared memory (slot 32*r + lane, bank == lane)
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+                if (32u * r < a.tile_leaves) acc[32 * r + lane] = racc[r];
+            in_regs = false;
+            __syncwarp();
+        };
+        auto reload_regs = [&]() {
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+                if (32u * r < a.tile_leaves) racc[r] = acc[32 * r + lane];
+            in_regs = true;
+        };
 
-        const uint64_t qb = a.q_row_off[a.q_first + ql], qe = a.q_row_off[a.q_first + ql + 1];
-        st_keys += (lane == 0) ? (qe - qb) : 0;
-
-        // software-pipelined dictionary probe: the first slot of batch n+1 is in flight
-        // while the posting lists of batch n are processed
-        uint64_t key = 0, nkey = 0;
-        float qv = 0.0f, nqv = 0.0f;
-        uint32_t h = 0, nh = 0;
-        uint4 slot = make_uint4(0, 0, 0, 0), nslot = make_uint4(0, 0, 0, 0);
-        if (qb + lane < qe) {
-            key = a.q_keys[qb + lane];
-            qv = a.q_vals[qb + lane];
-            h = dict_hash(key) & mask;
-            slot = __ldg(dict + h);
-        }
-        for (uint64_t base = qb; base < qe; base += 32) {
-            const bool valid = base + lane < qe;
-            {  // prefetch the next batch of query keys and their first dictionary slot
-                const uint64_t nidx = base + 32 + lane;
-                nslot = make_uint4(0, 0, 0, 0);
-                if (nidx < qe) {
-                    nkey = a.q_keys[nidx];
-                    nqv = a.q_vals[nidx];
-                    nh = dict_hash(nkey) & mask;
-                    nslot = __ldg(dict + nh);
-                }
-            }
-            uint32_t begin = 0, len = 0;
-            if (valid) {
-                for (;;) {
-                    if (slot.w == 0u) break;  // empty slot: key absent from this tile
-                    if ((((uint64_t)slot.y << 32) | slot.x) == key) {
-                        begin = slot.z;
-                        len = slot.w;
-                        break;
-                    }
-                    h = (h + 1) & mask;
-                    slot = __ldg(dict + h);
-                }
-            }
-            unsigned hits = __ballot_sync(0xffffffffu, len != 0u);
-            st_hits += (lane == 0) ? __popc(hits) : 0;
-
-            // cursor over the hit lists, in lane (= ascending key) order
-            int src = -1;
+        // ---- phase B: walk hits[0..n_hits) in order
+        auto process_hits = [&](uint32_t n_hits) {
+            uint32_t hi = 0;  // next hit to open
             uint32_t cb = 0, cl = 0, coff = 0;
             float cv = 0.0f;
+            bool cdense = false, open = false;
             auto next_hit = [&]() {
-                if (!hits) {
-                    src = -1;
+                if (hi >= n_hits) {
+                    open = false;
                     return;
                 }
-                src = __ffs(hits) - 1;
-                hits &= hits - 1;
-                cb = __shfl_sync(0xffffffffu, begin, src);
-                cl = __shfl_sync(0xffffffffu, len, src);
-                cv = __shfl_sync(0xffffffffu, qv, src);
+                const HitRec h = hits[hi++];  // same address for all lanes: broadcast
+                cb = h.begin;
+                cdense = (h.len & DENSE_FLAG) != 0u;
+                cl = h.len & ~DENSE_FLAG;
+                cv = h.qv;
                 coff = 0;
+                open = true;
                 st_post += (lane == 0) ? cl : 0;
             };
+            constexpr uint32_t DENSE_CHUNK = 0xFFFFFFFFu;  // chunk-size marker of a dense key
             auto fetch = [&](uint64_t(&p)[SC_U], uint32_t &n, float &v) -> bool {
-                if (src < 0) return false;
-                n = min(cl - coff, 32u * SC_U);
+                if (!open) return false;
                 v = cv;
+                if (cdense) {  // the whole key is one 128-byte bitmap: word `lane`
+                    n = DENSE_CHUNK;
+                    p[0] = __ldg(bitmaps + (size_t)cb * 32 + lane);
+                    next_hit();
+                    return true;
+                }
+                n = min(cl - coff, 32u * SC_U);
                 const uint64_t *ptr = post + cb + coff + lane;
                 if (n == 32u * SC_U) {  // full chunk: unpredicated loads
 #pragma unroll
@@ -280,6 +307,19 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
                 return true;
             };
             auto process = [&](const uint64_t(&p)[SC_U], uint32_t n, float v) {
+                if (n == DENSE_CHUNK) {
+                    // lane-owned leaves in registers: no shared-memory traffic, no ordering hazard
+                    // with other dense keys; branch-free select per slot
+                    if (!in_regs) reload_regs();
+                    const uint32_t w = (uint32_t)p[0];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        const float s2 = __fadd_rn(racc[r], __fmul_rn(v, usm[32 * r + lane]));
+                        racc[r] = (w & (1u << r)) ? s2 : racc[r];
+                    }
+                    return;
+                }
+                if (in_regs) flush_regs();
                 float tacc[SC_U];
                 if (n == 32u * SC_U) {
 #pragma unroll
@@ -312,11 +352,69 @@ __global__ void __launch_bounds__(512) score_tiles_kernel(ScoreArgs a) {
                 have_a = fetch(pa, na, va);
                 process(pb, nb, vb);
             }
-            key = nkey;
-            qv = nqv;
-            h = nh;
-            slot = nslot;
-        }
+        };
+
+        // ---- phase A: probe
+        const uint64_t qb = a.q_row_off[a.q_first + ql], qe = a.q_row_off[a.q_first + ql + 1];
+        st_keys += (lane == 0) ? (qe - qb) : 0;
+        // Probe until the hit list is nearly full (or the keys are exhausted), then walk it.
+        // ONE textual call of process_hits keeps the lambda (and racc/unit) in registers.
+        uint64_t base = qb;
+        do {
+            uint32_t n_hits = 0;
+            while (base < qe && n_hits <= SC_HITS - 32 * SC_PROBE_ROUNDS) {
+                uint64_t key[SC_PROBE_ROUNDS];
+                float qv[SC_PROBE_ROUNDS];
+                uint32_t h[SC_PROBE_ROUNDS];
+                uint4 slot[SC_PROBE_ROUNDS];
+#pragma unroll
+                for (int j = 0; j < SC_PROBE_ROUNDS; ++j) {
+                    const uint64_t idx = base + 32 * j + lane;
+                    key[j] = 0;
+                    qv[j] = 0.0f;
+                    h[j] = 0;
+                    slot[j] = make_uint4(0, 0, 0, 0);
+                    if (idx < qe) {
+                        key[j] = a.q_keys[idx];
+                        qv[j] = a.q_vals[idx];
+                        h[j] = dict_hash(key[j]) & mask;
+                        slot[j] = __ldg(dict + h[j]);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < SC_PROBE_ROUNDS; ++j) {
+                    uint32_t begin = 0, len = 0;
+                    if (base + 32 * j + lane < qe) {
+                        for (;;) {
+                            if (slot[j].w == 0u) break;  // empty slot: key absent from this tile
+                            if ((((uint64_t)slot[j].y << 32) | slot[j].x) == key[j]) {
+                                begin = slot[j].z;
+                                len = slot[j].w;
+                                break;
+                            }
+                            h[j] = (h[j] + 1) & mask;
+                            slot[j] = __ldg(dict + h[j]);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, len != 0u);
+                    if (len != 0u) {  // lanes hold ascending keys: append in lane order
+                        HitRec r;
+                        r.begin = begin;
+                        r.len = len;
+                        r.qv = qv[j];
+                        hits[n_hits + __popc(m & lt)] = r;
+                    }
+                    n_hits += __popc(m);
+                }
+                base += 32 * SC_PROBE_ROUNDS;
+            }
+            __syncwarp();
+            st_hits += (lane == 0) ? n_hits : 0;
+            process_hits(n_hits);
+            __syncwarp();
+        } while (base < qe);
+
+        if (in_regs) flush_regs();
         if (FUSED) {
             const size_t slot = (size_t)ql * a.n_tiles + t;
             tile_topx<SIM>(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
@@ -442,8 +540,8 @@ static void check_sim(int32_t sim) {
 
 template <bool FUSED>
 static void launch_score(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a, int32_t sim) {
-    const size_t per_warp = ((size_t)ix->tile_leaves + 32 + (FUSED ? 256 : 0)) * sizeof(float);
-    int warps = (int)std::min<size_t>(16, (ctx->smem_optin - 1024) / per_warp);
+    const size_t per_warp = score_warp_smem_bytes(ix->tile_leaves, FUSED);
+    int warps = (int)std::min<size_t>(SC_MAX_WARPS, (ctx->smem_optin - 1024) / per_warp);
     if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
     const size_t smem = per_warp * warps;
     const unsigned grid = (unsigned)std::min<unsigned long long>(a.n_tasks, (unsigned long long)ctx->sm_count);
@@ -525,10 +623,14 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     reset_stats(ctx);
     if (q_count == 0) return;
     const uint64_t n_tiles = std::max<uint64_t>(ix->tiles.size(), 1);
-    const uint64_t budget = 4ull << 30;  // bytes of per-tile candidates kept at once
+    const uint64_t budget = 8ull << 30;  // bytes of per-tile candidates kept at once
     const uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, budget / (n_tiles * x * 8)), q_count);
-    DevBuf<uint64_t> cand(per * n_tiles * x);
-    DevBuf<uint32_t> cand_cnt(per * n_tiles), gthr(per);
+    // grow-only scratch of the context: a steady-state step never goes back to the allocator
+    DevBuf<uint64_t> &cand = ctx->topx_cand;
+    DevBuf<uint32_t> &cand_cnt = ctx->topx_cand_cnt, &gthr = ctx->topx_gthr;
+    cand.reserve(per * n_tiles * x);
+    cand_cnt.reserve(per * n_tiles);
+    gthr.reserve(per);
     for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
         const uint64_t qn = std::min(per, q_count - q0);
         MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
