@@ -457,32 +457,74 @@ __device__ __forceinline__ void bitonic_desc(uint64_t *k, uint32_t S) {
 }
 
 // One CTA per query: merges the per-tile candidate lists into the final top-x,
-// order (score desc, payload_id asc) == descending composite.
+// order (score desc, payload_id asc) == descending composite.  The candidate counts
+// are prefix-summed so that the (few hundred) survivors are gathered in one go and
+// sorted once; only a query with more than TX_SORT_CAP candidates takes the chunked path.
 __global__ void __launch_bounds__(TX_THREADS) topx_cand_merge_kernel(const uint64_t *__restrict__ cand,
                                                                      const uint32_t *__restrict__ cand_cnt,
                                                                      uint32_t n_tiles, uint32_t x,
                                                                      float *__restrict__ out_s,
                                                                      uint32_t *__restrict__ out_i) {
     __shared__ uint64_t buf[TX_SORT_CAP];
+    __shared__ uint32_t s_warp[TX_THREADS / 32 + 1];
+    __shared__ uint32_t s_total;
     const size_t q = blockIdx.x;
-    uint32_t filled = 0;  // buf[0..filled) = best so far (sorted) + appended candidates
-    for (uint32_t t = 0; t <= n_tiles; ++t) {
-        const uint32_t cnt = t < n_tiles ? cand_cnt[q * n_tiles + t] : 0u;
-        if (t == n_tiles || filled + cnt > TX_SORT_CAP) {
-            uint32_t S = 2;
-            while (S < filled) S <<= 1;
-            for (uint32_t j = filled + threadIdx.x; j < S; j += TX_THREADS) buf[j] = 0;
-            bitonic_desc(buf, S);
-            filled = min(filled, x);
-        }
-        if (t < n_tiles) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t *cnts = cand_cnt + q * n_tiles;
+    // pass 1: total number of candidates
+    uint32_t local = 0;
+    for (uint32_t t = tid; t < n_tiles; t += TX_THREADS) local += cnts[t];
+    local = warp_sum_u32(local);
+    if (lane == 0) s_warp[warp] = local;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < TX_THREADS / 32; ++w) s += s_warp[w];
+        s_total = s;
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    __syncthreads();  // everyone has read the total before the cursor below reuses s_total
+    uint32_t filled = 0;
+    if (total <= TX_SORT_CAP) {
+        // gather: one warp per tile, positions from an atomic cursor (order is fixed by the sort)
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        for (uint32_t t = warp; t < n_tiles; t += TX_THREADS / 32) {
+            const uint32_t cnt = cnts[t];
+            if (cnt == 0) continue;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_total, cnt);
+            base = __shfl_sync(0xffffffffu, base, 0);
             const uint64_t *src = cand + (q * n_tiles + t) * x;
-            for (uint32_t j = threadIdx.x; j < cnt; j += TX_THREADS) buf[filled + j] = src[j];
-            filled += cnt;
-            __syncthreads();
+            for (uint32_t j = lane; j < cnt; j += 32) buf[base + j] = src[j];
+        }
+        __syncthreads();
+        filled = total;
+        uint32_t S = 2;
+        while (S < filled) S <<= 1;
+        for (uint32_t j = filled + tid; j < S; j += TX_THREADS) buf[j] = 0;
+        bitonic_desc(buf, S);
+        filled = min(filled, x);
+    } else {
+        for (uint32_t t = 0; t <= n_tiles; ++t) {
+            const uint32_t cnt = t < n_tiles ? cnts[t] : 0u;
+            if (t == n_tiles || filled + cnt > TX_SORT_CAP) {
+                uint32_t S = 2;
+                while (S < filled) S <<= 1;
+                for (uint32_t j = filled + tid; j < S; j += TX_THREADS) buf[j] = 0;
+                bitonic_desc(buf, S);
+                filled = min(filled, x);
+            }
+            if (t < n_tiles) {
+                const uint64_t *src = cand + (q * n_tiles + t) * x;
+                for (uint32_t j = tid; j < cnt; j += TX_THREADS) buf[filled + j] = src[j];
+                filled += cnt;
+                __syncthreads();
+            }
         }
     }
-    for (uint32_t j = threadIdx.x; j < x; j += TX_THREADS) {
+    for (uint32_t j = tid; j < x; j += TX_THREADS) {
         if (j < filled) {
             const uint64_t c = buf[j];
             out_s[q * x + j] = __uint_as_float((uint32_t)(c >> 32));

@@ -359,3 +359,94 @@ def test_compute_cluster_centroid_search_k(api, ctx):
     ck, cv = oracle.centroid(oc, ids)
     ro, keys, vals, _ = api.compute_cluster_centroid(g, ids).download(aux=False)
     assert ro.tolist() == [0, len(ck)] and (keys == ck).all() and (bits(vals) == bits(cv)).all()
+
+
+# ------------------------------------------- long queries, dense keys, properties
+
+def test_leaves_as_queries_self_score_and_long_hit_lists(api, ctx):
+    # every leaf vector scored against the tree: ~1266 keys per query, all present in the
+    # query's own tile (hit list drained several times), top-1 must be the leaf itself
+    tree = synth.make_tree(2500, 91)
+    st = api.TaxTreeStore(ctx, tree)
+    ttc = api.TaxTreeCompute.from_store_tree(st, 18, 32, keep_leaf_vecs=True)
+    q = ttc.leaf_vecs
+    res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 5, q_first=1000, q_count=200,
+                                               full_scores=True)
+    oln = oracle.normalize(oracle.count_leaves(synth.tree_to_iupac(tree), tree.base_off, 18, 32))
+    for j in range(0, 200, 7):
+        k, v = oln.row(1000 + j)
+        s = oracle.score_all(oln, k, v)
+        assert (bits(s) == bits(res.scores[j])).all()
+        ts, ti = oracle.topx(s, 5)
+        assert (ti == res.top_ids[j]).all() and (bits(ts) == bits(res.top_scores[j])).all()
+    assert (res.top_ids[:, 0] == np.arange(1000, 1200)).all()
+    # ~1266 sequential f32 additions: the self-score is 1 only up to the rounding the reference has too
+    assert np.allclose(res.top_scores[:, 0], 1.0, atol=1e-4)
+
+
+def test_cluster_centroid_query_against_tree(api, ctx):
+    # run.rs:301-309 + results.rs:82-93: the query is the centroid of a cluster's reads at
+    # search_k (thousands of keys), scored against every leaf
+    tree = synth.make_tree(1800, 93)
+    reads = synth.make_reads(tree, 120, 94, leaf_ids=np.arange(600, 640))
+    st = api.TaxTreeStore(ctx, tree)
+    ttc = api.TaxTreeCompute.from_store_tree(st, 18, 32)
+    counts = api.MyrSeqs(ctx, reads).compute_kmer_counts(18, 0.1)
+    cen = api.compute_cluster_centroid(counts, np.arange(reads.n))
+    res = api.TaxTreeResults.from_compute_tree(cen, ttc, api.SIM_COSINE, 100, full_scores=True)
+    oc = oracle.count_reads(reads.codes, reads.qual, reads.base_off, 18, 0.1)
+    ck, cv = oracle.centroid(oc, np.arange(reads.n))
+    assert len(ck) > 3000
+    oln = oracle.normalize(oracle.count_leaves(synth.tree_to_iupac(tree), tree.base_off, 18, 32))
+    s = oracle.score_all(oln, ck, cv)
+    assert (bits(s) == bits(res.scores[0])).all()
+    ts, ti = oracle.topx(s, 100)
+    assert (ti == res.top_ids[0]).all() and (bits(ts) == bits(res.top_scores[0])).all()
+    assert 600 <= ti[0] < 640
+
+
+def test_dense_and_sparse_tilings_agree(api, ctx):
+    # the same tree indexed with tiles that allow dense keys (<= 1024 leaves) and with tiles
+    # that do not (> 1024) must give identical bits; also non-ACGT-style counts (values that
+    # are not all unit[leaf]) must demote keys to the sparse form, not change results
+    tree = synth.make_tree(3000, 95)
+    reads = synth.make_reads(tree, 30, 96)
+    st = api.TaxTreeStore(ctx, tree)
+    q = api.MyrSeqs(ctx, reads).compute_kmer_counts(18, 0.1).into_normalized_l2()
+    outs = []
+    for tl in (1024, 512, 2048, 4096):
+        ttc = api.TaxTreeCompute.from_store_tree(st, 18, 32, tile_leaves=tl)
+        outs.append(api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 50, full_scores=True))
+    for o in outs[1:]:
+        assert (bits(o.scores) == bits(outs[0].scores)).all()
+        assert (o.top_ids == outs[0].top_ids).all() and (bits(o.top_scores) == bits(outs[0].top_scores)).all()
+    # perturbed counts: bump a few counts so that conserved keys carry non-unit values
+    ro, keys, vals, _ = st.kmer_store_counts_vec[0].download(aux=False)
+    vals = vals.copy()
+    rng = np.random.default_rng(3)
+    vals[rng.integers(0, len(vals), len(vals) // 50)] = 64
+    pert = api.SFVecs.upload(ctx, ro, keys, vals)
+    ttc = api.TaxTreeCompute.from_counts(pert)
+    res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 20, full_scores=True)
+    oln = oracle.normalize(oracle.Csr(ro, keys, vals))
+    qro, qk, qv, _ = q.download(aux=False)
+    for i in range(0, 30, 3):
+        s = oracle.score_all(oln, qk[int(qro[i]):int(qro[i + 1])], qv[int(qro[i]):int(qro[i + 1])])
+        assert (bits(s) == bits(res.scores[i])).all()
+        ts, ti = oracle.topx(s, 20)
+        assert (ti == res.top_ids[i]).all()
+
+
+def test_topx_many_candidates_chunked_merge(api, ctx):
+    # x = 1024 with many tiles: more than 4096 candidates per query reach the merge kernel
+    tree = synth.make_tree(9000, 97)
+    reads = synth.make_reads(tree, 6, 98)
+    st = api.TaxTreeStore(ctx, tree)
+    ttc = api.TaxTreeCompute.from_store_tree(st, 18, 32)
+    q = api.MyrSeqs(ctx, reads).compute_kmer_counts(18, 0.1).into_normalized_l2()
+    res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 1024, full_scores=True)
+    for i in range(reads.n):
+        ts, ti = oracle.topx(res.scores[i], 1024)
+        assert (ti == res.top_ids[i]).all() and (bits(ts) == bits(res.top_scores[i])).all()
+    with pytest.raises(api.MyrioError):
+        api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 1025)
