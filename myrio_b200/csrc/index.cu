@@ -1,4 +1,4 @@
-// index.cu -- K3: build the tiled CSR inverted index (k-mer key -> posting list of
+// index.cu -- K3: build the tiled inverted index (k-mer key -> posting list of
 // (leaf, normalised count)) from the per-leaf sorted sparse vectors.
 //
 // Replaces the `Box<[SFVec]>` of L2-normalised leaf vectors that
@@ -6,10 +6,15 @@
 // as the structure the score loop (tax/results.rs:82-93) runs against.
 //
 // Leaves are cut into tiles of `tile_leaves` consecutive payload ids (the scoring
-// kernel keeps one tile's accumulators in shared memory).  Per tile: stable LSD
-// radix sort of (key, (leaf,value)) pairs -> posting lists ordered by leaf inside
-// each key; run heads -> unique keys + offsets; open-addressing dictionary
-// key -> (begin, len).
+// kernel keeps one tile's accumulators on chip).  The whole index is built at once,
+// whatever the number of tiles:
+//   1. (key, (leaf, value)) pairs in leaf order;
+//   2. ONE stable LSD radix sort: by key, then by tile -> postings grouped by tile and,
+//      inside a tile, ordered by (key, leaf);
+//   3. run heads -> unique (tile, key) entries + absolute posting offsets;
+//   4. unit[leaf] = smallest value of the leaf; a key that occurs in >= 1/4 of a tile's
+//      leaves, always with value == unit[leaf], is DENSE: one 128-byte bitmap;
+//   5. per-tile open-addressing dictionaries key -> (begin, len | DENSE_FLAG).
 #include <algorithm>
 
 #include "index.cuh"
@@ -17,34 +22,79 @@
 
 namespace myrio {
 
+// payload = (shard-local leaf << 32) | value bits; key_or collects the key bits in use
 __global__ void __launch_bounds__(256) make_pairs_kernel(const uint64_t *__restrict__ row_off,
                                                          const uint64_t *__restrict__ keys,
                                                          const float *__restrict__ vals,
-                                                         uint64_t n_rows, uint32_t tile_leaves,
-                                                         uint64_t *__restrict__ pkeys,
+                                                         uint64_t n_rows, uint64_t *__restrict__ pkeys,
                                                          uint64_t *__restrict__ pvals,
-                                                         unsigned long long *__restrict__ key_or) {
+                                                         unsigned long long *__restrict__ key_or,
+                                                         float *__restrict__ unit) {
     const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const unsigned lane = threadIdx.x & 31;
     const uint64_t b = row_off[row], e = row_off[row + 1];
-    const uint64_t leaf_local = row % tile_leaves;
     uint64_t acc = 0;
+    float m = 3.402823466e+38f;
     for (uint64_t i = b + lane; i < e; i += 32) {
         const uint64_t k = keys[i];
+        const float v = vals[i];
         acc |= k;
+        m = fminf(m, v);
         pkeys[i] = k;
-        pvals[i] = (leaf_local << 32) | (uint64_t)__float_as_uint(vals[i]);
+        pvals[i] = (row << 32) | (uint64_t)__float_as_uint(v);
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) acc |= __shfl_xor_sync(0xffffffffu, acc, d);
-    if (lane == 0 && acc) atomicOr(key_or, (unsigned long long)acc);
+    for (int d = 16; d > 0; d >>= 1) {
+        acc |= __shfl_xor_sync(0xffffffffu, acc, d);
+        m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
+    }
+    if (lane == 0) {
+        if (acc) atomicOr(key_or, (unsigned long long)acc);
+        unit[row] = e > b ? m : 0.0f;  // the leaf's smallest normalised value (count == common count)
+    }
 }
 
+__global__ void __launch_bounds__(256) gather_u64_kernel(const uint64_t *__restrict__ src,
+                                                         const uint64_t *__restrict__ idx, uint64_t n,
+                                                         uint64_t *__restrict__ dst) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+
+// tile of a posting position / unique-entry index: last t with bounds[t] <= pos
+__device__ __forceinline__ uint32_t tile_of(const uint64_t *__restrict__ bounds, uint32_t n_tiles, uint64_t pos) {
+    uint32_t lo = 0, hi = n_tiles;  // invariant: bounds[lo] <= pos < bounds[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (bounds[mid] <= pos)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// heads of the key runs (tile starts are added by mark_tile_starts_kernel)
 __global__ void __launch_bounds__(256) mark_heads_kernel(const uint64_t *__restrict__ keys, uint64_t n,
                                                          uint32_t *__restrict__ flags) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) mark_tile_starts_kernel(const uint64_t *__restrict__ bounds,
+                                                               uint32_t n_tiles, uint64_t n,
+                                                               uint32_t *__restrict__ flags) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_tiles && bounds[t] < n) flags[bounds[t]] = 1u;
+}
+
+__global__ void __launch_bounds__(256) localize_leaves_kernel(uint64_t *__restrict__ payload, uint64_t n,
+                                                              uint32_t tile_leaves) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t p = payload[i];
+    payload[i] = ((uint64_t)((uint32_t)(p >> 32) % tile_leaves) << 32) | (p & 0xFFFFFFFFull);
 }
 
 __global__ void __launch_bounds__(256) emit_unique_kernel(const uint64_t *__restrict__ keys, uint64_t n,
@@ -61,38 +111,37 @@ __global__ void __launch_bounds__(256) emit_unique_kernel(const uint64_t *__rest
     if (i == 0) ubegin[uidx[n]] = (uint32_t)n;
 }
 
-// unit[leaf] = smallest normalised value of the leaf's row (count == common count)
-__global__ void __launch_bounds__(256) row_min_kernel(const uint64_t *__restrict__ row_off,
-                                                      const float *__restrict__ vals, uint64_t n_rows,
-                                                      float *__restrict__ unit) {
-    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const unsigned lane = threadIdx.x & 31;
-    float m = 3.402823466e+38f;
-    for (uint64_t i = row_off[row] + lane; i < row_off[row + 1]; i += 32) m = fminf(m, vals[i]);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if (lane == 0) unit[row] = (row_off[row + 1] > row_off[row]) ? m : 0.0f;
-}
-
-// A unique key is DENSE when it occurs in at least dense_min leaves of the tile and every
-// one of its postings carries exactly unit[leaf]; flags[u] = 1 then.
+// A unique (tile, key) entry is DENSE when the key occurs in at least max(32, n_leaves/4)
+// leaves of the tile and every one of its postings carries exactly unit[leaf].
 __global__ void __launch_bounds__(256) classify_dense_kernel(const uint64_t *__restrict__ postings,
                                                              const uint32_t *__restrict__ ubegin,
-                                                             uint64_t n_unique, const float *__restrict__ unit,
-                                                             uint32_t dense_min, uint32_t *__restrict__ flags) {
+                                                             uint64_t n_unique,
+                                                             const uint64_t *__restrict__ ustart,
+                                                             uint32_t n_tiles, uint64_t n_leaves,
+                                                             uint32_t tile_leaves,
+                                                             const float *__restrict__ unit,
+                                                             uint32_t *__restrict__ flags) {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_unique) return;
     const uint32_t b = ubegin[u], e = ubegin[u + 1];
-    uint32_t dense = (e - b) >= dense_min ? 1u : 0u;
-    for (uint32_t i = b; dense && i < e; ++i) {
-        const uint64_t p = postings[i];
-        if ((uint32_t)p != __float_as_uint(unit[(uint32_t)(p >> 32)])) dense = 0u;
+    uint32_t dense = 0;
+    if (e - b >= 32u) {
+        const uint32_t t = tile_of(ustart, n_tiles, u);
+        const uint64_t leaf0 = (uint64_t)t * tile_leaves;
+        const uint32_t nl = (uint32_t)min((uint64_t)tile_leaves, n_leaves - leaf0);
+        if (e - b >= max(32u, nl / 4u)) {
+            dense = 1;
+            const float *un = unit + leaf0;
+            for (uint32_t i = b; dense && i < e; ++i) {
+                const uint64_t p = postings[i];
+                if ((uint32_t)p != __float_as_uint(un[(uint32_t)(p >> 32)])) dense = 0u;
+            }
+        }
     }
     flags[u] = dense;
 }
 
-// one warp per dense key: fill its 32-word bitmap (word = leaf & 31, bit = leaf >> 5)
+// one warp per dense entry: lane l builds word l (leaves with leaf & 31 == l, bit = leaf >> 5)
 __global__ void __launch_bounds__(256) fill_bitmaps_kernel(const uint64_t *__restrict__ postings,
                                                            const uint32_t *__restrict__ ubegin,
                                                            uint64_t n_unique, const uint32_t *__restrict__ flags,
@@ -101,30 +150,41 @@ __global__ void __launch_bounds__(256) fill_bitmaps_kernel(const uint64_t *__res
     const uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (u >= n_unique || !flags[u]) return;
     const unsigned lane = threadIdx.x & 31;
-    uint32_t *bm = bitmaps + didx[u] * 32;
     uint32_t w = 0;
-    // lane l owns word l: scan the key's postings and keep the leaves with leaf & 31 == l
     for (uint32_t i = ubegin[u]; i < ubegin[u + 1]; ++i) {
         const uint32_t leaf = (uint32_t)(postings[i] >> 32);
         if ((leaf & 31u) == lane) w |= 1u << (leaf >> 5);
     }
-    bm[lane] = w;
+    bitmaps[didx[u] * 32 + lane] = w;
 }
+
+struct TileBuildMeta {
+    uint64_t post_begin;   // first posting of the tile
+    uint64_t dict_begin;   // first slot of the tile's dictionary
+    uint64_t dense_begin;  // first bitmap of the tile
+    uint32_t dict_mask;
+    uint32_t pad_;
+};
 
 __global__ void __launch_bounds__(256) dict_insert_kernel(const uint64_t *__restrict__ ukeys,
                                                           const uint32_t *__restrict__ ubegin,
                                                           uint64_t n_unique, const uint32_t *__restrict__ flags,
-                                                          const uint64_t *__restrict__ didx, DictSlot *dict,
-                                                          uint32_t mask) {
+                                                          const uint64_t *__restrict__ didx,
+                                                          const uint64_t *__restrict__ ustart, uint32_t n_tiles,
+                                                          const TileBuildMeta *__restrict__ meta,
+                                                          DictSlot *dict_all) {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_unique) return;
+    const uint32_t t = tile_of(ustart, n_tiles, u);
+    const TileBuildMeta m = meta[t];
     const uint64_t key = ukeys[u];
-    uint32_t begin = ubegin[u], len = ubegin[u + 1] - begin;
-    if (flags && flags[u]) {
-        begin = (uint32_t)didx[u];
+    uint32_t begin = (uint32_t)(ubegin[u] - m.post_begin), len = ubegin[u + 1] - ubegin[u];
+    if (flags[u]) {
+        begin = (uint32_t)(didx[u] - m.dense_begin);
         len |= DENSE_FLAG;
     }
-    uint32_t h = dict_hash(key) & mask;
+    DictSlot *dict = dict_all + m.dict_begin;
+    uint32_t h = dict_hash(key) & m.dict_mask;
     for (;;) {
         // claim an empty slot through its `len` word (len != 0 for every real entry)
         if (atomicCAS(&dict[h].len, 0u, len) == 0u) {
@@ -132,7 +192,7 @@ __global__ void __launch_bounds__(256) dict_insert_kernel(const uint64_t *__rest
             dict[h].begin = begin;
             return;
         }
-        h = (h + 1) & mask;
+        h = (h + 1) & m.dict_mask;
     }
 }
 
@@ -143,6 +203,9 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
     if (tile_leaves == 0) tile_leaves = 1024;
     if (tile_leaves > 49152) fail(MYRIO_ERR_BAD_ARG, "tile_leaves must be <= 49152");
     if (leaves->n_rows >= 0xFFFFFFFFull) fail(MYRIO_ERR_BAD_ARG, "too many leaves for u32 payload ids");
+    if (leaves->nnz >= 0xFFFFFFFFull)
+        fail(MYRIO_ERR_UNSUPPORTED, "an index shard holds at most 2^32-1 postings (got %llu): shard the leaves",
+             (unsigned long long)leaves->nnz);
     auto ix = std::make_unique<myrio_index>();
     const uint64_t L = leaves->n_rows, P = leaves->nnz;
     ix->n_leaves = L;
@@ -151,24 +214,26 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
     ix->n_postings = P;
     const uint64_t n_tiles = (L + tile_leaves - 1) / tile_leaves;
     ix->tiles.resize(n_tiles);
-    ix->dicts.resize(n_tiles);
-    ix->ukeys.resize(n_tiles);
-    ix->ubegin.resize(n_tiles);
     if (L == 0) return ix.release();
 
-    // tile boundaries in posting space
-    std::vector<uint64_t> bounds(n_tiles + 1);
-    for (uint64_t t = 0; t <= n_tiles; ++t) {
-        const uint64_t row = std::min<uint64_t>(t * tile_leaves, L);
-        d2h(ctx, &bounds[t], leaves->row_off.p + row, 1);
-    }
+    // tile boundaries in posting space (the sort keeps the number of postings per tile)
+    std::vector<uint64_t> rows(n_tiles + 1), bounds(n_tiles + 1);
+    for (uint64_t t = 0; t <= n_tiles; ++t) rows[t] = std::min<uint64_t>(t * tile_leaves, L);
+    DevBuf<uint64_t> d_rows(n_tiles + 1), d_bounds(n_tiles + 1);
+    h2d(ctx, d_rows.p, rows.data(), n_tiles + 1);
+    MYRIO_LAUNCH(ctx, "k3_gather", gather_u64_kernel, (unsigned)((n_tiles + 256) / 256), 256, 0,
+                 leaves->row_off.p, d_rows.p, n_tiles + 1, d_bounds.p);
+    d2h(ctx, bounds.data(), d_bounds.p, n_tiles + 1);
+
+    // 1. pairs + unit values
     DevBuf<uint64_t> pk(std::max<uint64_t>(P, 1)), pv(std::max<uint64_t>(P, 1)),
         pk2(std::max<uint64_t>(P, 1)), pv2(std::max<uint64_t>(P, 1));
     DevBuf<unsigned long long> key_or(1);
+    ix->unit.alloc(L);
     MYRIO_CK(cudaMemsetAsync(key_or.p, 0, sizeof(unsigned long long), ctx->stream));
     MYRIO_LAUNCH(ctx, "k3_make_pairs", make_pairs_kernel, (unsigned)((L + 7) / 8), 256, 0,
-                 leaves->row_off.p, leaves->keys.p, leaves->vals_f32.p, L, tile_leaves, pk.p, pv.p,
-                 key_or.p);
+                 leaves->row_off.p, leaves->keys.p, leaves->vals_f32.p, L, pk.p, pv.p, key_or.p,
+                 ix->unit.p);
     unsigned long long h_or = 0;
     d2h(ctx, &h_or, key_or.p, 1);
     sync(ctx);
@@ -176,84 +241,107 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
     while (key_bits < 64 && (h_or >> key_bits) != 0) ++key_bits;
     if (key_bits == 0) key_bits = 1;
 
-    ix->unit.alloc(L);
-    MYRIO_LAUNCH(ctx, "k3_row_min", row_min_kernel, (unsigned)((L + 7) / 8), 256, 0, leaves->row_off.p,
-                 leaves->vals_f32.p, L, ix->unit.p);
-    ix->bitmaps.resize(n_tiles);
-    const bool dense_ok = tile_leaves <= DENSE_MAX_TILE;
+    // 2. one stable sort: by key, then by tile
+    DevBuf<uint32_t> hist;
+    DevBuf<uint64_t> offs;
+    const bool in_tmp = radix_sort_pairs_raw(ctx, pk.p, pv.p, pk2.p, pv2.p, P, key_bits, hist, offs,
+                                             tile_leaves, n_tiles);
+    uint64_t *sk = in_tmp ? pk2.p : pk.p, *sv = in_tmp ? pv2.p : pv.p;
+    hist.release();
+    offs.release();
+    (in_tmp ? pk : pk2).release();  // the other key buffer is no longer needed
 
-    DevBuf<uint32_t> hist, flags, dflags;
-    DevBuf<uint64_t> offs, uidx, didx;
-    bool in_tmp = false;
-    uint64_t max_tile_post = 0;
-    for (uint64_t t = 0; t < n_tiles; ++t) max_tile_post = std::max(max_tile_post, bounds[t + 1] - bounds[t]);
-    flags.alloc(std::max<uint64_t>(max_tile_post, 1));
-    uidx.alloc(max_tile_post + 1);
+    uint64_t U = 0, n_dense = 0;
+    std::vector<uint64_t> ustart(n_tiles + 1, 0), dstart(n_tiles + 1, 0);
+    DevBuf<uint64_t> d_ustart(n_tiles + 1);
+    DevBuf<uint32_t> dflags;
+    DevBuf<uint64_t> didx;
+    if (P) {
+        // 3. run heads -> unique entries
+        const unsigned g = (unsigned)((P + 255) / 256);
+        DevBuf<uint32_t> flags(P);
+        DevBuf<uint64_t> uidx(P + 1);
+        MYRIO_LAUNCH(ctx, "k3_mark_heads", mark_heads_kernel, g, 256, 0, sk, P, flags.p);
+        MYRIO_LAUNCH(ctx, "k3_mark_tile_starts", mark_tile_starts_kernel, (unsigned)((n_tiles + 255) / 256), 256,
+                     0, d_bounds.p, (uint32_t)n_tiles, P, flags.p);
+        MYRIO_LAUNCH(ctx, "k3_localize_leaves", localize_leaves_kernel, g, 256, 0, sv, P, tile_leaves);
+        exclusive_scan_u32_to_u64(ctx, flags.p, uidx.p, P);
+        MYRIO_LAUNCH(ctx, "k3_gather", gather_u64_kernel, (unsigned)((n_tiles + 256) / 256), 256, 0, uidx.p,
+                     d_bounds.p, n_tiles + 1, d_ustart.p);
+        d2h(ctx, ustart.data(), d_ustart.p, n_tiles + 1);
+        sync(ctx);
+        U = ustart[n_tiles];
+        ix->ukeys.alloc(U);
+        ix->ubegin.alloc(U + 1);
+        MYRIO_LAUNCH(ctx, "k3_emit_unique", emit_unique_kernel, g, 256, 0, sk, P, flags.p, uidx.p, ix->ukeys.p,
+                     ix->ubegin.p);
+        // 4. dense entries -> bitmaps
+        dflags.alloc(U);
+        didx.alloc(U + 1);
+        if (tile_leaves <= DENSE_MAX_TILE) {
+            MYRIO_LAUNCH(ctx, "k3_classify_dense", classify_dense_kernel, (unsigned)((U + 255) / 256), 256, 0, sv,
+                         ix->ubegin.p, U, d_ustart.p, (uint32_t)n_tiles, L, tile_leaves, ix->unit.p, dflags.p);
+        } else {
+            MYRIO_CK(cudaMemsetAsync(dflags.p, 0, U * sizeof(uint32_t), ctx->stream));
+        }
+        exclusive_scan_u32_to_u64(ctx, dflags.p, didx.p, U);
+        DevBuf<uint64_t> d_dstart(n_tiles + 1);
+        MYRIO_LAUNCH(ctx, "k3_gather", gather_u64_kernel, (unsigned)((n_tiles + 256) / 256), 256, 0, didx.p,
+                     d_ustart.p, n_tiles + 1, d_dstart.p);
+        d2h(ctx, dstart.data(), d_dstart.p, n_tiles + 1);
+        sync(ctx);
+        n_dense = dstart[n_tiles];
+        if (n_dense) {
+            ix->bitmaps.alloc(n_dense * 32);
+            MYRIO_LAUNCH(ctx, "k3_fill_bitmaps", fill_bitmaps_kernel, (unsigned)((U + 7) / 8), 256, 0, sv,
+                         ix->ubegin.p, U, dflags.p, didx.p, ix->bitmaps.p);
+        }
+    } else {
+        ix->ubegin.alloc(1);
+        MYRIO_CK(cudaMemsetAsync(ix->ubegin.p, 0, sizeof(uint32_t), ctx->stream));
+    }
+    ix->n_unique_total = U;
+    ix->n_dense_total = n_dense;
 
+    // 5. per-tile dictionaries in one slot array
+    std::vector<TileBuildMeta> meta(n_tiles);
+    uint64_t slots = 0;
     for (uint64_t t = 0; t < n_tiles; ++t) {
-        const uint64_t pb = bounds[t], np = bounds[t + 1] - pb;
+        const uint64_t ut = ustart[t + 1] - ustart[t];
+        uint32_t cap = 16;
+        while (cap < 2 * ut) cap <<= 1;
+        meta[t].post_begin = bounds[t];
+        meta[t].dict_begin = slots;
+        meta[t].dense_begin = dstart[t];
+        meta[t].dict_mask = cap - 1;
+        meta[t].pad_ = 0;
+        slots += cap;
+    }
+    ix->dicts.alloc(slots);
+    MYRIO_CK(cudaMemsetAsync(ix->dicts.p, 0, slots * sizeof(DictSlot), ctx->stream));
+    if (U) {
+        DevBuf<TileBuildMeta> d_meta(n_tiles);
+        h2d(ctx, d_meta.p, meta.data(), n_tiles);
+        MYRIO_LAUNCH(ctx, "k3_dict_insert", dict_insert_kernel, (unsigned)((U + 255) / 256), 256, 0, ix->ukeys.p,
+                     ix->ubegin.p, U, dflags.p, didx.p, d_ustart.p, (uint32_t)n_tiles, d_meta.p, ix->dicts.p);
+        sync(ctx);  // meta (host vector) and d_meta stay alive until the kernel has run
+    }
+    for (uint64_t t = 0; t < n_tiles; ++t) {
         TileInfo &ti = ix->tiles[t];
-        ti.post_begin = pb;
-        ti.n_post = np;
+        ti.post_begin = bounds[t];
+        ti.n_post = bounds[t + 1] - bounds[t];
+        ti.n_unique = ustart[t + 1] - ustart[t];
         ti.leaf_begin = (uint32_t)(t * tile_leaves);
         ti.n_leaves = (uint32_t)(std::min<uint64_t>(L, (t + 1) * tile_leaves) - t * tile_leaves);
-        if (np >= 0xFFFFFFFFull) fail(MYRIO_ERR_UNSUPPORTED, "tile with >= 2^32 postings; lower tile_leaves");
-        in_tmp = radix_sort_pairs_raw(ctx, pk.p + pb, pv.p + pb, pk2.p + pb, pv2.p + pb, np, key_bits,
-                                      hist, offs);
-        const uint64_t *sk = (in_tmp ? pk2.p : pk.p) + pb;
-        uint64_t U = 0;
-        if (np) {
-            const unsigned g = (unsigned)((np + 255) / 256);
-            MYRIO_LAUNCH(ctx, "k3_mark_heads", mark_heads_kernel, g, 256, 0, sk, np, flags.p);
-            exclusive_scan_u32_to_u64(ctx, flags.p, uidx.p, np);
-            d2h(ctx, &U, uidx.p + np, 1);
-            sync(ctx);
-            ix->ukeys[t].alloc(U);
-            ix->ubegin[t].alloc(U + 1);
-            MYRIO_LAUNCH(ctx, "k3_emit_unique", emit_unique_kernel, g, 256, 0, sk, np, flags.p, uidx.p,
-                         ix->ukeys[t].p, ix->ubegin[t].p);
-        } else {
-            ix->ubegin[t].alloc(1);
-            MYRIO_CK(cudaMemsetAsync(ix->ubegin[t].p, 0, sizeof(uint32_t), ctx->stream));
-        }
-        // dense keys -> bitmaps
-        uint64_t n_dense = 0;
-        const uint64_t *sv = (in_tmp ? pv2.p : pv.p) + pb;
-        if (dense_ok && U) {
-            const uint32_t dense_min = std::max<uint32_t>(32u, ti.n_leaves / 4u);
-            dflags.reserve(U);
-            didx.reserve(U + 1);
-            MYRIO_LAUNCH(ctx, "k3_classify_dense", classify_dense_kernel, (unsigned)((U + 255) / 256), 256, 0, sv,
-                         ix->ubegin[t].p, U, ix->unit.p + ti.leaf_begin, dense_min, dflags.p);
-            exclusive_scan_u32_to_u64(ctx, dflags.p, didx.p, U);
-            d2h(ctx, &n_dense, didx.p + U, 1);
-            sync(ctx);
-            if (n_dense) {
-                ix->bitmaps[t].alloc(n_dense * 32);
-                MYRIO_LAUNCH(ctx, "k3_fill_bitmaps", fill_bitmaps_kernel, (unsigned)((U + 7) / 8), 256, 0, sv,
-                             ix->ubegin[t].p, U, dflags.p, didx.p, ix->bitmaps[t].p);
-            }
-        }
-        uint32_t cap = 16;
-        while (cap < 2 * U) cap <<= 1;
-        ix->dicts[t].alloc(cap);
-        MYRIO_CK(cudaMemsetAsync(ix->dicts[t].p, 0, (size_t)cap * sizeof(DictSlot), ctx->stream));
-        if (U)
-            MYRIO_LAUNCH(ctx, "k3_dict_insert", dict_insert_kernel, (unsigned)((U + 255) / 256), 256, 0,
-                         ix->ukeys[t].p, ix->ubegin[t].p, U, n_dense ? dflags.p : nullptr, didx.p,
-                         ix->dicts[t].p, cap - 1);
-        ti.n_unique = U;
-        ti.dict = ix->dicts[t].p;
-        ti.dict_mask = cap - 1;
-        ti.ukeys = ix->ukeys[t].p;
-        ti.ubegin = ix->ubegin[t].p;
-        ti.bitmaps = ix->bitmaps[t].p;
+        ti.dict = ix->dicts.p + meta[t].dict_begin;
+        ti.dict_mask = meta[t].dict_mask;
+        ti.pad_ = 0;
+        ti.ukeys = ix->ukeys.p + ustart[t];
+        ti.ubegin = ix->ubegin.p + ustart[t];
+        ti.bitmaps = ix->bitmaps.p + dstart[t] * 32;
         ti.unit = ix->unit.p + ti.leaf_begin;
-        ti.n_dense = n_dense;
-        ix->n_dense_total += n_dense;
-        ix->n_unique_total += U;
+        ti.n_dense = dstart[t + 1] - dstart[t];
     }
-    sync(ctx);
     ix->postings = std::move(in_tmp ? pv2 : pv);
     ix->d_tiles.alloc(n_tiles);
     h2d(ctx, ix->d_tiles.p, ix->tiles.data(), n_tiles);
@@ -284,7 +372,8 @@ void index_export_tile(myrio_ctx *ctx, const myrio_index *ix, uint64_t tile, uin
         std::vector<uint32_t> tmp(ti.n_unique + 1);
         d2h(ctx, tmp.data(), ti.ubegin, ti.n_unique + 1);
         sync(ctx);
-        for (uint64_t i = 0; i <= ti.n_unique; ++i) offs[i] = tmp[i];
+        for (uint64_t i = 0; i <= ti.n_unique; ++i) offs[i] = tmp[i] - ti.post_begin;  // tile-relative
+        if (ti.n_unique == 0) offs[0] = 0;
     }
     if ((post_leaf || post_val) && ti.n_post) {
         DevBuf<uint32_t> dl(ti.n_post);

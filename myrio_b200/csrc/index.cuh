@@ -27,7 +27,7 @@ struct TileInfo {
     uint32_t dict_mask;  // table size - 1 (power of two)
     uint32_t pad_;
     const uint64_t *ukeys;    // sorted unique keys of the tile        (export / tests)
-    const uint32_t *ubegin;   // first posting of each unique key, +1 sentinel
+    const uint32_t *ubegin;   // ABSOLUTE first posting of each unique key, +1 sentinel
     // dense keys: a posting whose value equals unit[leaf] (the leaf's smallest normalised
     // value, i.e. count == the common count) is one bit: word `leaf & 31`, bit `leaf >> 5`
     const uint32_t *bitmaps;  // [n_dense][32]
@@ -60,11 +60,12 @@ struct myrio_index {
     myrio::DevBuf<uint64_t> postings;  // Posting[n_postings]
     std::vector<myrio::TileInfo> tiles;
     myrio::DevBuf<myrio::TileInfo> d_tiles;
-    std::vector<myrio::DevBuf<myrio::DictSlot>> dicts;
-    std::vector<myrio::DevBuf<uint64_t>> ukeys;
-    std::vector<myrio::DevBuf<uint32_t>> ubegin;
-    std::vector<myrio::DevBuf<uint32_t>> bitmaps;
-    myrio::DevBuf<float> unit;  // [n_leaves]
+    // index-wide arrays; every TileInfo points at its slice
+    myrio::DevBuf<myrio::DictSlot> dicts;
+    myrio::DevBuf<uint64_t> ukeys;    // [n_unique_total]
+    myrio::DevBuf<uint32_t> ubegin;   // [n_unique_total + 1], absolute posting offsets
+    myrio::DevBuf<uint32_t> bitmaps;  // [n_dense_total][32]
+    myrio::DevBuf<float> unit;        // [n_leaves]
     uint64_t n_dense_total = 0;
 };
 
@@ -76,5 +77,5 @@ void index_export_tile(myrio_ctx *ctx, const myrio_index *ix, uint64_t tile, uin
                        float *post_val);
 bool radix_sort_pairs_raw(myrio_ctx *ctx, uint64_t *keys, uint64_t *vals, uint64_t *keys_tmp,
                           uint64_t *vals_tmp, size_t n, int key_bits, DevBuf<uint32_t> &hist,
-                          DevBuf<uint64_t> &offs);
+                          DevBuf<uint64_t> &offs, uint32_t group_div = 0, uint64_t n_groups = 0);
 }  // namespace myrio
