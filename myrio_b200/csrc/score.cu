@@ -462,6 +462,7 @@ __device__ __forceinline__ void bitonic_desc(uint64_t *k, uint32_t S) {
 // sorted once; only a query with more than TX_SORT_CAP candidates takes the chunked path.
 __global__ void __launch_bounds__(TX_THREADS) topx_cand_merge_kernel(const uint64_t *__restrict__ cand,
                                                                      const uint32_t *__restrict__ cand_cnt,
+                                                                     const uint32_t *__restrict__ gthr,
                                                                      uint32_t n_tiles, uint32_t x,
                                                                      float *__restrict__ out_s,
                                                                      uint32_t *__restrict__ out_i) {
@@ -485,6 +486,10 @@ __global__ void __launch_bounds__(TX_THREADS) topx_cand_merge_kernel(const uint6
     __syncthreads();
     const uint32_t total = s_total;
     __syncthreads();  // everyone has read the total before the cursor below reuses s_total
+    // The FINAL bound of the query (max over its tiles of the tile's x-th best score) is known
+    // now: the early tiles wrote their candidates against a looser bound, most of which fall
+    // below it and cannot be in the top-x (at least x scores are >= the bound).
+    const uint32_t thr = gthr[q];
     uint32_t filled = 0;
     if (total <= TX_SORT_CAP) {
         // gather: one warp per tile, positions from an atomic cursor (order is fixed by the sort)
@@ -492,15 +497,21 @@ __global__ void __launch_bounds__(TX_THREADS) topx_cand_merge_kernel(const uint6
         __syncthreads();
         for (uint32_t t = warp; t < n_tiles; t += TX_THREADS / 32) {
             const uint32_t cnt = cnts[t];
-            if (cnt == 0) continue;
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_total, cnt);
-            base = __shfl_sync(0xffffffffu, base, 0);
             const uint64_t *src = cand + (q * n_tiles + t) * x;
-            for (uint32_t j = lane; j < cnt; j += 32) buf[base + j] = src[j];
+            for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const uint64_t c = j < cnt ? src[j] : 0ull;
+                const bool keep = j < cnt && (uint32_t)(c >> 32) >= thr;
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (m == 0) continue;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&s_total, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) buf[base + __popc(m & ((1u << lane) - 1u))] = c;
+            }
         }
         __syncthreads();
-        filled = total;
+        filled = s_total;
         uint32_t S = 2;
         while (S < filled) S <<= 1;
         for (uint32_t j = filled + tid; j < S; j += TX_THREADS) buf[j] = 0;
@@ -687,7 +698,8 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
             launch_score<true>(ctx, ix, a, sim);
         }
         MYRIO_LAUNCH(ctx, "k5_topx_merge_tiles", topx_cand_merge_kernel, (unsigned)qn, TX_THREADS, 0, cand.p,
-                     cand_cnt.p, (uint32_t)ix->tiles.size(), x, d_top_scores + q0 * x, d_top_ids + q0 * x);
+                     cand_cnt.p, gthr.p, (uint32_t)ix->tiles.size(), x, d_top_scores + q0 * x,
+                     d_top_ids + q0 * x);
         if (collect_stats) accumulate_stats(ctx);
     }
 }
