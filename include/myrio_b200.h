@@ -50,7 +50,8 @@ typedef enum {
     MYRIO_ERR_BAD_QUALITY = 5, /* Phred >= 128: table index out of bounds in the reference */
     MYRIO_ERR_UNSUPPORTED = 6,
     MYRIO_ERR_EMPTY = 7,       /* cluster(): no read survives t2 / no centroid (reference panics) */
-    MYRIO_ERR_NONFINITE = 8    /* SimScore::try_new(..).unwrap() would panic (clustering.rs:125) */
+    MYRIO_ERR_NONFINITE = 8,   /* SimScore::try_new(..).unwrap() would panic (clustering.rs:125) */
+    MYRIO_ERR_BAD_BASE = 9     /* a non-ACGT base: read_fastq fails the whole file (io/mod.rs:46-47) */
 } myrio_status;
 
 /* myrio-core/src/similarity.rs:26-33 */
@@ -87,6 +88,16 @@ int32_t myrio_prof_query(myrio_ctx *ctx, const char *prefix, double *ms_total, u
 int32_t myrio_reads_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t *word_off,
                            const uint64_t *base_off, const uint8_t *qual, uint64_t n_reads,
                            myrio_seqs **out);
+/* FASTQ ingestion on the device: the per-record conversion of io::read_fastq
+ * (myrio-core/src/io/mod.rs:46-48: Seq::<Dna>::from_str, quality = byte saturating_sub 33)
+ * followed by MyrSeq::pre_process (data/myrseq.rs:113-131).  seq_ascii / qual_ascii are the
+ * concatenated sequence and quality lines (no newlines), base_off[n+1] their prefix sums.
+ * A record is kept iff it is non-empty, len >= min_length, mean quality >= min_mean_qual and
+ * max quality <= max_qual; keep[n] (optional) receives 0/1 and *out holds the kept reads in
+ * input order.  Any base other than upper-case ACGT -> MYRIO_ERR_BAD_BASE. */
+int32_t myrio_reads_from_fastq(myrio_ctx *ctx, const uint8_t *seq_ascii, const uint8_t *qual_ascii,
+                               const uint64_t *base_off, uint64_t n_records, uint64_t min_length,
+                               float min_mean_qual, uint8_t max_qual, uint8_t *keep, myrio_seqs **out);
 /* The `seq: Seq<Iupac>` of every StorePayload (myrio-core/src/tax/store.rs:28-32)
  * in payload_id order. */
 int32_t myrio_leaves_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t *word_off,

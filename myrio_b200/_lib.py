@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmyrio_b200.so")
 
 OK = 0
-ERR_INVALID_K, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_BAD_QUALITY, ERR_UNSUPPORTED, ERR_EMPTY, ERR_NONFINITE = range(1, 9)
+ERR_INVALID_K, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_BAD_QUALITY, ERR_UNSUPPORTED, ERR_EMPTY, ERR_NONFINITE, ERR_BAD_BASE = range(1, 10)
 SIM_COSINE, SIM_JACARD_TANIMOTO, SIM_OVERLAP = 0, 1, 2
 VAL_F32, VAL_U16 = 0, 1
 
@@ -19,7 +19,7 @@ VAL_F32, VAL_U16 = 0, 1
 SYMBOLS = [
     "myrio_last_error", "myrio_version", "myrio_ctx_create", "myrio_ctx_destroy", "myrio_ctx_sync",
     "myrio_ctx_launch_count", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query",
-    "myrio_reads_upload", "myrio_leaves_upload", "myrio_seqs_free", "myrio_count_reads",
+    "myrio_reads_upload", "myrio_reads_from_fastq", "myrio_leaves_upload", "myrio_seqs_free", "myrio_count_reads",
     "myrio_count_leaves", "myrio_svecs_info", "myrio_svecs_download", "myrio_svecs_upload",
     "myrio_svecs_normalize", "myrio_svecs_free", "myrio_index_build", "myrio_index_info",
     "myrio_index_export_tile", "myrio_index_free", "myrio_score_all", "myrio_score_topx",
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
     L.myrio_prof_reset.argtypes = [vp]
     L.myrio_prof_query.argtypes = [vp, C.c_char_p, P(C.c_double), P(u64)]
     L.myrio_reads_upload.argtypes = [vp, vp, vp, vp, vp, u64, P(vp)]
+    L.myrio_reads_from_fastq.argtypes = [vp, vp, vp, vp, u64, u64, C.c_float, C.c_uint8, vp, P(vp)]
     L.myrio_leaves_upload.argtypes = [vp, vp, vp, vp, u64, P(vp)]
     L.myrio_seqs_free.argtypes = [vp]
     L.myrio_seqs_free.restype = None

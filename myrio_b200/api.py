@@ -153,6 +153,26 @@ class MyrSeqs:
         self._upload(words, word_off, base_off, qual)
         return self
 
+    @classmethod
+    def from_fastq_records(cls, ctx, seq_ascii, qual_ascii, base_off, min_length: int = 50,
+                           min_mean_qual: float = 12.0, max_qual: int = 255):
+        """io::read_fastq's record conversion (io/mod.rs:46-48) + MyrSeq::pre_process
+        (data/myrseq.rs:113-131, defaults of myrio-cli config.rs:24-26) on the device.
+        Returns (MyrSeqs of the kept reads, keep flags per record)."""
+        seq_ascii = np.ascontiguousarray(seq_ascii, np.uint8)
+        qual_ascii = np.ascontiguousarray(qual_ascii, np.uint8)
+        base_off = np.ascontiguousarray(base_off, np.uint64)
+        n = len(base_off) - 1
+        keep = np.zeros(max(1, n), np.uint8)
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        h = C.c_void_p()
+        _lib.check(ctx._L.myrio_reads_from_fastq(ctx.h, _p(seq_ascii), _p(qual_ascii), _p(base_off), n, min_length,
+                                                 min_mean_qual, max_qual, _p(keep), C.byref(h)))
+        self.h = h
+        self.n = int(keep[:n].sum())
+        return self, keep[:n].astype(bool)
+
     def __del__(self):
         try:
             if self.h and self.ctx.h:

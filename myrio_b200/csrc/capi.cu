@@ -190,6 +190,17 @@ int32_t myrio_reads_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t
     });
 }
 
+int32_t myrio_reads_from_fastq(myrio_ctx *ctx, const uint8_t *seq_ascii, const uint8_t *qual_ascii,
+                               const uint64_t *base_off, uint64_t n_records, uint64_t min_length,
+                               float min_mean_qual, uint8_t max_qual, uint8_t *keep, myrio_seqs **out) {
+    return guarded([&] {
+        if (!ctx || !out) fail(MYRIO_ERR_BAD_ARG, "NULL ctx/out");
+        ScopedCtx sc(ctx);
+        *out = reads_from_fastq(ctx, seq_ascii, qual_ascii, base_off, n_records, min_length, min_mean_qual,
+                                max_qual, keep);
+    });
+}
+
 int32_t myrio_leaves_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t *word_off,
                             const uint64_t *base_off, uint64_t n_leaves, myrio_seqs **out) {
     return guarded([&] {

@@ -12,6 +12,11 @@ myrio_svecs *count_reads(myrio_ctx *ctx, const myrio_seqs *reads, uint32_t k, fl
 myrio_svecs *count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k, uint32_t nb_resamples,
                           uint64_t seed, uint64_t leaf_id_base);
 
+// ingest.cu
+myrio_seqs *reads_from_fastq(myrio_ctx *ctx, const uint8_t *seq_ascii, const uint8_t *qual_ascii,
+                             const uint64_t *base_off, uint64_t n, uint64_t min_length, float min_mean_qual,
+                             uint8_t max_qual, uint8_t *keep_host);
+
 // svecs.cu
 myrio_svecs *svecs_normalize(myrio_ctx *ctx, const myrio_svecs *in);
 

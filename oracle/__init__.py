@@ -109,6 +109,9 @@ def lib():
         L.myo_pairwise.argtypes = [C.c_int, _u64p, _u64p, _f32p, C.c_size_t, _u64p, _u64p, _f32p,
                                    C.c_size_t, C.c_int, _f32p]
         L.myo_max_threads.restype = C.c_int
+        L.myo_fastq_preprocess.restype = C.c_longlong
+        L.myo_fastq_preprocess.argtypes = [_u8p, _u8p, _u64p, C.c_size_t, C.c_size_t, C.c_float, C.c_uint8,
+                                           _u8p, _u8p, _u8p, _u64p]
         _lib = L
     return _lib
 
@@ -157,6 +160,28 @@ def sort_reduce_u16(singles):
     v = np.zeros(max(1, len(s)), np.uint16)
     d = lib().myo_sort_reduce_u16(s, len(s), k, v)
     return k[:d], v[:d]
+
+
+def fastq_preprocess(seq_ascii: np.ndarray, qual_ascii: np.ndarray, base_off: np.ndarray,
+                     min_length: int = 50, min_mean_qual: float = 12.0, max_qual: int = 255):
+    """io/mod.rs:46-48 + data/myrseq.rs:113-131. Returns (codes, qual, kept_base_off, keep)."""
+    seq_ascii = np.ascontiguousarray(seq_ascii, np.uint8)
+    qual_ascii = np.ascontiguousarray(qual_ascii, np.uint8)
+    base_off = np.ascontiguousarray(base_off, np.uint64)
+    n = len(base_off) - 1
+    total = max(1, len(seq_ascii))
+    codes = np.zeros(total, np.uint8)
+    qual = np.zeros(total, np.uint8)
+    keep = np.zeros(max(1, n), np.uint8)
+    koff = np.zeros(n + 1, np.uint64)
+    sa = seq_ascii if len(seq_ascii) else np.zeros(1, np.uint8)
+    qa = qual_ascii if len(qual_ascii) else np.zeros(1, np.uint8)
+    k = lib().myo_fastq_preprocess(sa, qa, base_off, n, min_length, min_mean_qual, max_qual, codes, qual, keep,
+                                   koff)
+    if k < 0:
+        raise ValueError(f"non-ACGT base in record {-k - 1}")
+    koff = koff[:k + 1]
+    return codes[:int(koff[-1])], qual[:int(koff[-1])], koff, keep[:n]
 
 
 def count_reads(bases: np.ndarray, qual: np.ndarray, base_off: np.ndarray, k: int, cutoff: float,

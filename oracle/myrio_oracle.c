@@ -58,6 +58,50 @@ static int clamp_threads(int threads) {
     return threads;
 }
 
+/* ------------------------------------------------------- FASTQ ingestion */
+
+long long myo_fastq_preprocess(const uint8_t *seq_ascii, const uint8_t *qual_ascii, const uint64_t *base_off,
+                               size_t n, size_t min_length, float min_mean_qual, uint8_t max_qual,
+                               uint8_t *codes_out, uint8_t *qual_out, uint8_t *keep_out,
+                               uint64_t *kept_off_out) {
+    size_t kept = 0;
+    uint64_t w = 0;
+    kept_off_out[0] = 0;
+    for (size_t r = 0; r < n; ++r) {
+        size_t b = (size_t)base_off[r], len = (size_t)(base_off[r + 1] - base_off[r]);
+        /* io/mod.rs:46-47 Seq::from_str: only A, C, G, T */
+        for (size_t i = 0; i < len; ++i) {
+            uint8_t c = seq_ascii[b + i];
+            if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return -(long long)(r + 1);
+        }
+        /* data/myrseq.rs:119-128 */
+        int keep = len != 0;
+        if (keep) {
+            float sum = 0.0f;
+            uint8_t mx = 0;
+            for (size_t i = 0; i < len; ++i) {
+                uint8_t q = qual_ascii[b + i] >= 33 ? (uint8_t)(qual_ascii[b + i] - 33) : 0; /* io/mod.rs:48 */
+                sum = sum + (float)q;
+                if (q > mx) mx = q;
+            }
+            float mean = sum / (float)len;
+            keep = (len >= min_length) && (mean >= min_mean_qual) && (mx <= max_qual);
+        }
+        keep_out[r] = (uint8_t)keep;
+        if (keep) {
+            for (size_t i = 0; i < len; ++i) {
+                uint8_t c = seq_ascii[b + i];
+                codes_out[w + i] = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3;
+                qual_out[w + i] = qual_ascii[b + i] >= 33 ? (uint8_t)(qual_ascii[b + i] - 33) : 0;
+            }
+            w += len;
+            kept += 1;
+            kept_off_out[kept] = w;
+        }
+    }
+    return (long long)kept;
+}
+
 /* ------------------------------------------------------------ k-mer keys */
 
 /* bio-seq `usize::from(&Kmer<Dna,K>)`: A=0,C=1,G=2,T=3, base j of the window at

@@ -152,6 +152,16 @@ void myo_pairwise(int sim, const uint64_t *r_off, const uint64_t *r_keys, const 
                   size_t n_rows, const uint64_t *c_off, const uint64_t *c_keys, const float *c_vals,
                   size_t n_cols, int threads, float *out);
 
+/* io/mod.rs:46-48 (Seq::<Dna>::from_str + quality byte saturating_sub 33) followed by
+ * MyrSeq::pre_process (data/myrseq.rs:113-131).  codes_out/qual_out: capacity = total bases;
+ * keep_out[n]; kept_off_out[n+1] = prefix sums of the kept lengths (entries after the kept
+ * count are unused).  returns the number of kept records, or -(index+1) of the first record
+ * holding a non-ACGT base (the reference fails the whole file). */
+long long myo_fastq_preprocess(const uint8_t *seq_ascii, const uint8_t *qual_ascii, const uint64_t *base_off,
+                               size_t n, size_t min_length, float min_mean_qual, uint8_t max_qual,
+                               uint8_t *codes_out, uint8_t *qual_out, uint8_t *keep_out,
+                               uint64_t *kept_off_out);
+
 int myo_max_threads(void);
 
 #ifdef __cplusplus

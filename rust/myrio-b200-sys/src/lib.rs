@@ -16,6 +16,7 @@ pub const MYRIO_ERR_BAD_QUALITY: i32 = 5;
 pub const MYRIO_ERR_UNSUPPORTED: i32 = 6;
 pub const MYRIO_ERR_EMPTY: i32 = 7;
 pub const MYRIO_ERR_NONFINITE: i32 = 8;
+pub const MYRIO_ERR_BAD_BASE: i32 = 9;
 
 pub const MYRIO_SIM_COSINE: i32 = 0;
 pub const MYRIO_SIM_JACARD_TANIMOTO: i32 = 1;
@@ -52,6 +53,9 @@ unsafe extern "C" {
 
     pub fn myrio_reads_upload(ctx: *mut myrio_ctx, words: *const u64, word_off: *const u64, base_off: *const u64,
                               qual: *const u8, n_reads: u64, out: *mut *mut myrio_seqs) -> i32;
+    pub fn myrio_reads_from_fastq(ctx: *mut myrio_ctx, seq_ascii: *const u8, qual_ascii: *const u8, base_off: *const u64,
+                                  n_records: u64, min_length: u64, min_mean_qual: f32, max_qual: u8, keep: *mut u8,
+                                  out: *mut *mut myrio_seqs) -> i32;
     pub fn myrio_leaves_upload(ctx: *mut myrio_ctx, words: *const u64, word_off: *const u64, base_off: *const u64,
                                n_leaves: u64, out: *mut *mut myrio_seqs) -> i32;
     pub fn myrio_seqs_free(s: *mut myrio_seqs);

@@ -450,3 +450,32 @@ def test_topx_many_candidates_chunked_merge(api, ctx):
         assert (ti == res.top_ids[i]).all() and (bits(ts) == bits(res.top_scores[i])).all()
     with pytest.raises(api.MyrioError):
         api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 1025)
+
+
+# ------------------------------------------------------------- FASTQ ingestion
+
+def test_fastq_ingestion_matches_oracle_and_prepacked_path(api, ctx):
+    tree = synth.make_tree(40, 101)
+    reads = synth.make_reads(tree, 400, 102, min_length=1, min_mean_qual=0.0)  # unfiltered: the device filters
+    seq = synth.ASCII[reads.codes]
+    qual = (reads.qual + 33).astype(np.uint8)
+    m, keep = api.MyrSeqs.from_fastq_records(ctx, seq, qual, reads.base_off, 200, 17.0, 40)
+    ocodes, oqual, ooff, okeep = oracle.fastq_preprocess(seq, qual, reads.base_off, 200, 17.0, 40)
+    assert (keep == okeep.astype(bool)).all() and 0 < keep.sum() < reads.n
+    got = m.compute_kmer_counts(18, 0.1).download()
+    exp = oracle.count_reads(ocodes, oqual, ooff, 18, 0.1)
+    assert (got[0] == exp.row_off).all() and (got[1] == exp.keys).all()
+    assert (bits(got[2]) == bits(exp.vals)).all() and (got[3] == exp.aux).all()
+    # same result as packing on the host
+    sub = reads.subset(np.nonzero(keep)[0])
+    ref = api.MyrSeqs(ctx, sub).compute_kmer_counts(18, 0.1).download()
+    assert all((a == b).all() for a, b in zip(got[:2], ref[:2]))
+    # a non-ACGT base fails the whole batch like read_fastq
+    bad = seq.copy()
+    bad[int(reads.base_off[7]) + 3] = ord("N")
+    with pytest.raises(api.MyrioError) as e:
+        api.MyrSeqs.from_fastq_records(ctx, bad, qual, reads.base_off)
+    assert e.value.code == 9 and "record 7" in str(e.value)
+    # empty batch
+    m0, k0 = api.MyrSeqs.from_fastq_records(ctx, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert m0.n == 0 and len(k0) == 0

@@ -204,3 +204,25 @@ def test_score_and_cluster_recover_structure():
     assert (kept_a == kept_a[0]).mean() > 0.9 and (kept_b == kept_b[0]).mean() > 0.9
     assert kept_a[0] != kept_b[0]
     assert 1 <= iters <= 20
+
+
+def test_fastq_preprocess_restatement():
+    # io/mod.rs:46-48 + data/myrseq.rs:113-131
+    recs = [("ACGT" * 20, "I" * 80),            # Q40, len 80 -> kept
+            ("ACGT" * 5, "I" * 20),             # too short (min_length 50)
+            ("ACGT" * 20, "+" * 80),            # Q10 < 12 -> dropped
+            ("", ""),                           # empty -> dropped
+            ("TTGCA" * 12, "5" * 59 + " "),     # one byte below '!' saturates to Q0; mean still >= 12
+            ("ACGT" * 20, "I" * 79 + "~")]      # Q93 max > max_qual 60
+    seq = np.frombuffer("".join(r[0] for r in recs).encode(), np.uint8)
+    qual = np.frombuffer("".join(r[1] for r in recs).encode(), np.uint8)
+    off = np.zeros(len(recs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r[0]) for r in recs])
+    codes, q, koff, keep = oracle.fastq_preprocess(seq, qual, off, 50, 12.0, 60)
+    assert keep.tolist() == [1, 0, 0, 0, 1, 0]
+    assert koff.tolist() == [0, 80, 140]
+    assert codes[:4].tolist() == [0, 1, 2, 3] and q[:80].tolist() == [40] * 80
+    assert q[139] == 0 and q[138] == ord("5") - 33
+    with pytest.raises(ValueError):
+        oracle.fastq_preprocess(np.frombuffer(b"ACGN", np.uint8), np.frombuffer(b"IIII", np.uint8),
+                                np.array([0, 4], np.uint64), 1, 0.0, 255)
