@@ -41,6 +41,11 @@
 extern "C" {
 #endif
 
+/* the library is built with -fvisibility=hidden: only these entry points are exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
 typedef enum {
     MYRIO_OK = 0,
     MYRIO_ERR_INVALID_K = 1,   /* k outside 2..32: the reference panics (myrio-proc/src/lib.rs:70) */
@@ -218,6 +223,10 @@ int32_t myrio_pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svec
 /* device pointers of a batch, for zero-copy interop (torch / NCCL plumbing) */
 int32_t myrio_svecs_device_ptrs(const myrio_svecs *v, const uint64_t **row_off,
                                 const uint64_t **keys, const void **vals, const void **aux);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,8 @@
 
 namespace myrio {
 
-struct Error {
+// internal exception type (never crosses the ABI; NOT the myrio::Error of include/myrio_b200.hpp)
+struct Failure {
     int32_t code;
     std::string msg;
 };
@@ -29,7 +30,7 @@ void set_last_error(const std::string &msg);
     va_start(ap, fmt);
     vsnprintf(buf, sizeof(buf), fmt, ap);
     va_end(ap);
-    throw Error{code, std::string(buf)};
+    throw Failure{code, std::string(buf)};
 }
 
 #define MYRIO_CK(expr)                                                                          \
@@ -47,7 +48,7 @@ inline int32_t guarded(F &&f) {
     try {
         f();
         return MYRIO_OK;
-    } catch (const Error &e) {
+    } catch (const Failure &e) {
         set_last_error(e.msg);
         return e.code;
     } catch (const std::exception &e) {

@@ -39,6 +39,7 @@ static float dot(const SFVec &a, const SFVec &b) {  // data/sparse.rs:317-360 on
 int main() {
     Context ctx(0);
 
+    std::fprintf(stderr, "[1] simfunc_test\n");
     {  // similarity.rs:217-232 simfunc_test: ACTG vs ACTC, k=2, cutoff f32::MIN, Q=0
         MyrSeqs seqs(ctx, {"ACTG", "ACTC"}, {{0, 0, 0, 0}, {0, 0, 0, 0}});
         SFVecs counts = seqs.compute_kmer_counts(2, std::numeric_limits<float>::lowest());
@@ -54,12 +55,14 @@ int main() {
         auto norm = counts.into_normalized_l2().download();
         ASSERT_FLOAT_EQ(dot(norm[0], norm[1]), cosine);  // cosine_pre_normalized(normalised) == cosine
     }
+    std::fprintf(stderr, "[2] invalid k\n");
     {  // invalid k panics in the reference (myrio-proc/src/lib.rs:70)
         MyrSeqs seqs(ctx, {"ACGTACGT"}, {{40, 40, 40, 40, 40, 40, 40, 40}});
         bool panicked = false;
         try { seqs.compute_kmer_counts(33, 0.1f); } catch (const Panic &) { panicked = true; }
         ASSERT_TRUE(panicked);
     }
+    std::fprintf(stderr, "[3] tree new + run\n");
     {  // tree new + run on a tiny tree: from_store_tree -> from_compute_tree -> cut
         std::vector<std::string> leaves = {
             "ACGTTGCAAGCTTGCATGCAAGTCGATCGATTAGCTAGCTAGGATCGATCGGATTACGATCGAT",
@@ -84,6 +87,7 @@ int main() {
         }
         ASSERT_TRUE(unsupported);
     }
+    std::fprintf(stderr, "[4] cluster\n");
     {  // cluster(): two obviously different read families, no initial centroids
         std::vector<std::string> seqs;
         std::vector<std::vector<uint8_t>> quals;
@@ -115,7 +119,10 @@ int main() {
         try { cluster(reads, bad); } catch (const Error &) { threw = true; }
         ASSERT_TRUE(threw);
     }
-    std::printf(failures ? "%d FAILURES\n" : "host mirror ok (launches: %llu)\n",
-                failures ? failures : 0, (unsigned long long)ctx.launch_count());
+    std::fprintf(stderr, "[5] done\n");
+    if (failures)
+        std::printf("%d FAILURES\n", failures);
+    else
+        std::printf("host mirror ok (launches: %llu)\n", (unsigned long long)ctx.launch_count());
     return failures ? 1 : 0;
 }
