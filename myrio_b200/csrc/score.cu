@@ -232,38 +232,33 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
         // memory (bank == lane, conflict-free) -- keeping them in registers too costs a quarter
         // of the resident warps and measured slower (profiles/r01_k4_variants.md).
         const bool dense_tile = ti->n_dense != 0;  // implies tile_leaves <= DENSE_MAX_TILE
-        float racc[32];
-        bool in_regs = dense_tile;
         if (dense_tile) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
+            for (int r = 0; r < 32; ++r)
                 usm[32 * r + lane] = (32u * r + lane < nl) ? __ldg(ti->unit + 32 * r + lane) : 0.0f;
-                racc[r] = 0.0f;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 32; ++r) racc[r] = 0.0f;
-            for (uint32_t i = lane; i < nl; i += 32) acc[i] = 0.0f;
         }
-        if (lane == 0) acc[a.tile_leaves] = 0.0f;
+        for (uint32_t i = lane; i < a.tile_leaves + 32; i += 32) acc[i] = 0.0f;  // incl. the dummy slots
         __syncwarp();
-        auto flush_regs = [&]() {  // registers -> shared memory (slot 32*r + lane, bank == lane)
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-                if (32u * r < a.tile_leaves) acc[32 * r + lane] = racc[r];
-            in_regs = false;
-            __syncwarp();
-        };
-        auto reload_regs = [&]() {
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-                if (32u * r < a.tile_leaves) racc[r] = acc[32 * r + lane];
-            in_regs = true;
-        };
 
-        // ---- phase B: walk hits[0..n_hits) in order
+        // ---- phase B: walk hits[0..n_hits) in order.  The register accumulators are local to
+        // the walk (dead during the probe phase, which then has the registers for deep MLP);
+        // between walks the accumulators live in shared memory.
         auto process_hits = [&](uint32_t n_hits) {
+            float racc[32];
+            bool in_regs = false;
+            auto flush_regs = [&]() {  // registers -> shared memory (slot 32*r + lane, bank == lane)
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    if (32u * r < a.tile_leaves) acc[32 * r + lane] = racc[r];
+                in_regs = false;
+                __syncwarp();
+            };
+            auto reload_regs = [&]() {
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 32; ++r) racc[r] = (32u * r < a.tile_leaves) ? acc[32 * r + lane] : 0.0f;
+                in_regs = true;
+            };
             uint32_t hi = 0;  // next hit to open
             uint32_t cb = 0, cl = 0, coff = 0;
             float cv = 0.0f;
@@ -352,13 +347,14 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
                 have_a = fetch(pa, na, va);
                 process(pb, nb, vb);
             }
+            if (in_regs) flush_regs();
         };
 
         // ---- phase A: probe
         const uint64_t qb = a.q_row_off[a.q_first + ql], qe = a.q_row_off[a.q_first + ql + 1];
         st_keys += (lane == 0) ? (qe - qb) : 0;
         // Probe until the hit list is nearly full (or the keys are exhausted), then walk it.
-        // ONE textual call of process_hits keeps the lambda (and racc/unit) in registers.
+        // ONE textual call of process_hits keeps the lambda inlined (racc stays in registers).
         uint64_t base = qb;
         do {
             uint32_t n_hits = 0;
@@ -414,7 +410,6 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
             __syncwarp();
         } while (base < qe);
 
-        if (in_regs) flush_regs();
         if (FUSED) {
             const size_t slot = (size_t)ql * a.n_tiles + t;
             tile_topx<SIM>(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
