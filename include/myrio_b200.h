@@ -185,7 +185,7 @@ int32_t myrio_topx_merge_async(myrio_ctx *ctx, const float *d_scores_in, const u
                                uint32_t n_parts, uint64_t q_count, uint32_t x, float *d_scores_out,
                                uint32_t *d_ids_out);
 /* exact algorithmic work of the last myrio_score_* call: sum over queries of
- * query keys, of keys found in the index, and of postings touched (T_q) */
+ * query keys, of (query key, tile) hits, and of postings touched (T_q) */
 int32_t myrio_score_stats(myrio_ctx *ctx, uint64_t *n_query_keys, uint64_t *n_key_hits,
                           uint64_t *n_postings_touched);
 

@@ -70,6 +70,8 @@ void myrio_ctx_destroy(myrio_ctx *ctx) {
     ctx->topx_cand.release();
     ctx->topx_cand_cnt.release();
     ctx->topx_gthr.release();
+    if (ctx->plan) plan_scratch_free(ctx->plan);
+    ctx->plan = nullptr;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     alloc_stream() = nullptr;

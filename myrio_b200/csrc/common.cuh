@@ -136,6 +136,7 @@ struct myrio_ctx {
     myrio::DevBuf<unsigned long long> score_counters;
     myrio::DevBuf<uint64_t> topx_cand;
     myrio::DevBuf<uint32_t> topx_cand_cnt, topx_gthr;
+    void *plan = nullptr;  // myrio::Plan (score.cu): hit-list scratch, grow-only
     uint64_t last_stats[3] = {0, 0, 0};
     // pinned staging for small D2H reads
     void *pinned = nullptr;

@@ -14,7 +14,9 @@
 //   3. run heads -> unique (tile, key) entries + absolute posting offsets;
 //   4. unit[leaf] = smallest value of the leaf; a key that occurs in >= 1/4 of a tile's
 //      leaves, always with value == unit[leaf], is DENSE: one 128-byte bitmap;
-//   5. per-tile open-addressing dictionaries key -> (begin, len | DENSE_FLAG).
+//   5. the (tile, key) entries re-sorted by key + ONE open-addressing dictionary
+//      key -> [EntryRec{tile, begin, len | DENSE_FLAG}] (tiles ascending): a query key is looked
+//      up once per query, not once per tile.
 #include <algorithm>
 
 #include "index.cuh"
@@ -158,42 +160,57 @@ __global__ void __launch_bounds__(256) fill_bitmaps_kernel(const uint64_t *__res
     bitmaps[didx[u] * 32 + lane] = w;
 }
 
-struct TileBuildMeta {
-    uint64_t post_begin;   // first posting of the tile
-    uint64_t dict_begin;   // first slot of the tile's dictionary
-    uint64_t dense_begin;  // first bitmap of the tile
-    uint32_t dict_mask;
-    uint32_t pad_;
-};
-
-__global__ void __launch_bounds__(256) dict_insert_kernel(const uint64_t *__restrict__ ukeys,
-                                                          const uint32_t *__restrict__ ubegin,
-                                                          uint64_t n_unique, const uint32_t *__restrict__ flags,
-                                                          const uint64_t *__restrict__ didx,
-                                                          const uint64_t *__restrict__ ustart, uint32_t n_tiles,
-                                                          const TileBuildMeta *__restrict__ meta,
-                                                          DictSlot *dict_all) {
-    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_unique) return;
+// entry index u (tile-major, key ascending inside a tile) -> EntryRec
+__global__ void __launch_bounds__(256) make_entries_kernel(const uint64_t *__restrict__ ent_u, uint64_t n_unique,
+                                                           const uint32_t *__restrict__ ubegin,
+                                                           const uint32_t *__restrict__ dflags,
+                                                           const uint64_t *__restrict__ didx,
+                                                           const uint64_t *__restrict__ ustart,
+                                                           const uint64_t *__restrict__ bounds,
+                                                           const uint64_t *__restrict__ dstart, uint32_t n_tiles,
+                                                           EntryRec *__restrict__ entries) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_unique) return;
+    const uint64_t u = ent_u[j];
     const uint32_t t = tile_of(ustart, n_tiles, u);
-    const TileBuildMeta m = meta[t];
-    const uint64_t key = ukeys[u];
-    uint32_t begin = (uint32_t)(ubegin[u] - m.post_begin), len = ubegin[u + 1] - ubegin[u];
-    if (flags[u]) {
-        begin = (uint32_t)(didx[u] - m.dense_begin);
-        len |= DENSE_FLAG;
+    EntryRec e;
+    e.tile = t;
+    e.len = ubegin[u + 1] - ubegin[u];
+    if (dflags[u]) {
+        e.begin = (uint32_t)(didx[u] - dstart[t]);
+        e.len |= DENSE_FLAG;
+    } else {
+        e.begin = (uint32_t)(ubegin[u] - bounds[t]);
     }
-    DictSlot *dict = dict_all + m.dict_begin;
-    uint32_t h = dict_hash(key) & m.dict_mask;
+    entries[j] = e;
+}
+
+// heads of the key-sorted entry list -> dictionary slots key -> (first entry, number of tiles)
+__global__ void __launch_bounds__(256) gdict_insert_kernel(const uint64_t *__restrict__ ent_keys, uint64_t n_unique,
+                                                           const uint32_t *__restrict__ flags,
+                                                           const uint64_t *__restrict__ hidx,
+                                                           const uint32_t *__restrict__ hbegin, DictSlot *dict,
+                                                           uint32_t mask) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_unique || !flags[j]) return;
+    const uint64_t key = ent_keys[j];
+    const uint64_t h0 = hidx[j];
+    const uint32_t len = hbegin[h0 + 1] - hbegin[h0];
+    uint32_t h = dict_hash(key) & mask;
     for (;;) {
         // claim an empty slot through its `len` word (len != 0 for every real entry)
         if (atomicCAS(&dict[h].len, 0u, len) == 0u) {
             dict[h].key = key;
-            dict[h].begin = begin;
+            dict[h].begin = (uint32_t)j;
             return;
         }
-        h = (h + 1) & m.dict_mask;
+        h = (h + 1) & mask;
     }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint64_t *__restrict__ v, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
 }
 
 myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t leaf_id_base,
@@ -303,28 +320,46 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
     ix->n_unique_total = U;
     ix->n_dense_total = n_dense;
 
-    // 5. per-tile dictionaries in one slot array
-    std::vector<TileBuildMeta> meta(n_tiles);
-    uint64_t slots = 0;
-    for (uint64_t t = 0; t < n_tiles; ++t) {
-        const uint64_t ut = ustart[t + 1] - ustart[t];
-        uint32_t cap = 16;
-        while (cap < 8 * ut) cap <<= 1;  // load <= 0.25: a warp waits for its slowest lane, keep probe chains short
-        meta[t].post_begin = bounds[t];
-        meta[t].dict_begin = slots;
-        meta[t].dense_begin = dstart[t];
-        meta[t].dict_mask = cap - 1;
-        meta[t].pad_ = 0;
-        slots += cap;
-    }
-    ix->dicts.alloc(slots);
-    MYRIO_CK(cudaMemsetAsync(ix->dicts.p, 0, slots * sizeof(DictSlot), ctx->stream));
+    // 5. index-wide key map: entries re-sorted by key (stable: tiles stay ascending inside a key),
+    //    one EntryRec per (tile, key), and a dictionary key -> entry range
     if (U) {
-        DevBuf<TileBuildMeta> d_meta(n_tiles);
-        h2d(ctx, d_meta.p, meta.data(), n_tiles);
-        MYRIO_LAUNCH(ctx, "k3_dict_insert", dict_insert_kernel, (unsigned)((U + 255) / 256), 256, 0, ix->ukeys.p,
-                     ix->ubegin.p, U, dflags.p, didx.p, d_ustart.p, (uint32_t)n_tiles, d_meta.p, ix->dicts.p);
-        sync(ctx);  // meta (host vector) and d_meta stay alive until the kernel has run
+        DevBuf<uint64_t> ek(U), eu(U), ek2(U), eu2(U), d_dstart(n_tiles + 1);
+        h2d(ctx, d_dstart.p, dstart.data(), n_tiles + 1);
+        MYRIO_CK(cudaMemcpyAsync(ek.p, ix->ukeys.p, U * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        MYRIO_LAUNCH(ctx, "k3_iota", iota_kernel, (unsigned)((U + 255) / 256), 256, 0, eu.p, U);
+        DevBuf<uint32_t> hist2;
+        DevBuf<uint64_t> offs2;
+        const bool tmp2 = radix_sort_pairs_raw(ctx, ek.p, eu.p, ek2.p, eu2.p, U, key_bits, hist2, offs2);
+        const uint64_t *sk2 = tmp2 ? ek2.p : ek.p, *su2 = tmp2 ? eu2.p : eu.p;
+        ix->gentries.alloc(U);
+        MYRIO_LAUNCH(ctx, "k3_make_entries", make_entries_kernel, (unsigned)((U + 255) / 256), 256, 0, su2, U,
+                     ix->ubegin.p, dflags.p, didx.p, d_ustart.p, d_bounds.p, d_dstart.p, (uint32_t)n_tiles,
+                     ix->gentries.p);
+        DevBuf<uint32_t> hflags(U), hbegin;
+        DevBuf<uint64_t> hidx(U + 1), hkeys;
+        MYRIO_LAUNCH(ctx, "k3_mark_heads", mark_heads_kernel, (unsigned)((U + 255) / 256), 256, 0, sk2, U, hflags.p);
+        exclusive_scan_u32_to_u64(ctx, hflags.p, hidx.p, U);
+        uint64_t Ug = 0;
+        d2h(ctx, &Ug, hidx.p + U, 1);
+        sync(ctx);
+        hkeys.alloc(Ug);
+        hbegin.alloc(Ug + 1);
+        MYRIO_LAUNCH(ctx, "k3_emit_unique", emit_unique_kernel, (unsigned)((U + 255) / 256), 256, 0, sk2, U, hflags.p,
+                     hidx.p, hkeys.p, hbegin.p);
+        uint64_t cap = 16;
+        while (cap < 4 * Ug) cap <<= 1;
+        if (cap > 0x80000000ull) fail(MYRIO_ERR_UNSUPPORTED, "too many distinct keys for the index dictionary");
+        ix->gdict.alloc(cap);
+        ix->gdict_mask = (uint32_t)(cap - 1);
+        ix->n_unique_keys = Ug;
+        MYRIO_CK(cudaMemsetAsync(ix->gdict.p, 0, cap * sizeof(DictSlot), ctx->stream));
+        MYRIO_LAUNCH(ctx, "k3_gdict_insert", gdict_insert_kernel, (unsigned)((U + 255) / 256), 256, 0, sk2, U,
+                     hflags.p, hidx.p, hbegin.p, ix->gdict.p, ix->gdict_mask);
+        sync(ctx);
+    } else {
+        ix->gdict.alloc(16);
+        ix->gdict_mask = 15;
+        MYRIO_CK(cudaMemsetAsync(ix->gdict.p, 0, 16 * sizeof(DictSlot), ctx->stream));
     }
     for (uint64_t t = 0; t < n_tiles; ++t) {
         TileInfo &ti = ix->tiles[t];
@@ -333,9 +368,6 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         ti.n_unique = ustart[t + 1] - ustart[t];
         ti.leaf_begin = (uint32_t)(t * tile_leaves);
         ti.n_leaves = (uint32_t)(std::min<uint64_t>(L, (t + 1) * tile_leaves) - t * tile_leaves);
-        ti.dict = ix->dicts.p + meta[t].dict_begin;
-        ti.dict_mask = meta[t].dict_mask;
-        ti.pad_ = 0;
         ti.ukeys = ix->ukeys.p + ustart[t];
         ti.ubegin = ix->ubegin.p + ustart[t];
         ti.bitmaps = ix->bitmaps.p + dstart[t] * 32;

@@ -4,12 +4,18 @@
 
 namespace myrio {
 
-// Dictionary slot of a tile: open addressing, linear probing. len == 0 <=> empty.
-// Sparse key: begin = first posting (relative to the tile's posting range), len = df.
-// Dense key (DENSE_FLAG set in len): begin = index of the key's 32-word bitmap in the
-// tile's bitmap array, len & ~DENSE_FLAG = df.
+// Slot of the index-wide key dictionary: open addressing, linear probing, len == 0 <=> empty.
+// key -> entries[begin .. begin+len): one EntryRec per tile that holds the key, tiles ascending.
 struct __align__(16) DictSlot {
     uint64_t key;
+    uint32_t begin;
+    uint32_t len;
+};
+// One (tile, key) entry.  Sparse key: begin = first posting (relative to the tile's posting
+// range), len = df.  Dense key (DENSE_FLAG set in len): begin = index of the key's 32-word
+// bitmap in the tile's bitmap array, len & ~DENSE_FLAG = df.
+struct EntryRec {
+    uint32_t tile;
     uint32_t begin;
     uint32_t len;
 };
@@ -23,9 +29,6 @@ struct TileInfo {
     uint64_t n_unique;
     uint32_t leaf_begin;  // first leaf (shard-local payload index) of the tile
     uint32_t n_leaves;
-    const DictSlot *dict;
-    uint32_t dict_mask;  // table size - 1 (power of two)
-    uint32_t pad_;
     const uint64_t *ukeys;    // sorted unique keys of the tile        (export / tests)
     const uint32_t *ubegin;   // ABSOLUTE first posting of each unique key, +1 sentinel
     // dense keys: a posting whose value equals unit[leaf] (the leaf's smallest normalised
@@ -61,7 +64,10 @@ struct myrio_index {
     std::vector<myrio::TileInfo> tiles;
     myrio::DevBuf<myrio::TileInfo> d_tiles;
     // index-wide arrays; every TileInfo points at its slice
-    myrio::DevBuf<myrio::DictSlot> dicts;
+    myrio::DevBuf<myrio::DictSlot> gdict;     // key -> entry range
+    uint32_t gdict_mask = 0;
+    myrio::DevBuf<myrio::EntryRec> gentries;  // [n_unique_total], grouped by key, tiles ascending
+    uint64_t n_unique_keys = 0;
     myrio::DevBuf<uint64_t> ukeys;    // [n_unique_total]
     myrio::DevBuf<uint32_t> ubegin;   // [n_unique_total + 1], absolute posting offsets
     myrio::DevBuf<uint32_t> bitmaps;  // [n_dense_total][32]

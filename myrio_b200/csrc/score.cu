@@ -18,13 +18,17 @@
 
 namespace myrio {
 
+struct __align__(4) HitRec {  // one key of the query that occurs in the tile, in key order
+    uint32_t begin;
+    uint32_t len;  // DENSE_FLAG | df
+    float qv;
+};
+
 struct ScoreArgs {
     const TileInfo *tiles;
     const uint64_t *postings;
-    const uint64_t *q_row_off;
-    const uint64_t *q_keys;
-    const float *q_vals;
-    uint64_t q_first;
+    const HitRec *plan;         // hit lists of all (query, tile) tasks of the batch
+    const uint64_t *plan_off;   // [q_count * n_tiles + 1]
     uint32_t q_count;
     uint32_t tile_leaves;
     unsigned long long n_tasks;
@@ -174,24 +178,16 @@ __device__ __forceinline__ void tile_topx(float *acc, uint32_t *hist, uint32_t n
 
 // K4.  One warp owns one (query, tile) task.
 //
-// Phase A -- probe: the query's keys are looked up in the tile's dictionary, four
-// rounds of 32 keys at a time (four independent 16-byte loads per lane in flight),
-// and the hits are appended IN KEY ORDER to a per-warp list in shared memory.
-// Phase B -- accumulate: the hit list is walked in order.  A sparse key is streamed in
+// Phase A -- the task's hit list (the keys of the query that occur in the tile, IN KEY ORDER,
+// with where their postings are) was laid out by the plan kernels; it is staged in shared
+// memory.  Phase B -- accumulate: the hit list is walked in order.  A sparse key is streamed in
 // chunks of up to 32*SC_U postings (distinct leaves => independent updates, full ILP);
 // a dense key is one 128-byte bitmap applied to lane-owned accumulators that stay in
 // registers while dense keys follow one another.  Two chunks are kept in flight so the
 // load of chunk n+1 (possibly of the next key) hides behind the updates of chunk n.
 static constexpr int SC_U = 2;
 static constexpr int SC_MAX_WARPS = 20;  // 96 registers per thread (racc[32] in registers), ~11 KB of smem per warp
-static constexpr int SC_PROBE_ROUNDS = 2;
 static constexpr uint32_t SC_HITS = 160;  // hit-list capacity per warp (drained when nearly full)
-
-struct __align__(4) HitRec {
-    uint32_t begin;
-    uint32_t len;  // DENSE_FLAG | df
-    float qv;
-};
 
 __host__ __device__ inline size_t score_warp_smem_bytes(uint32_t tile_leaves, bool fused) {
     return ((size_t)tile_leaves + 32 + (fused ? 256 : 0) + DENSE_MAX_TILE) * sizeof(float) +
@@ -210,7 +206,7 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
     float *usm = acc + a.tile_leaves + 32 + (FUSED ? 256 : 0);  // unit values of the lane-owned leaves
     HitRec *hits = reinterpret_cast<HitRec *>(usm + DENSE_MAX_TILE);
     const uint64_t dummy_posting = (uint64_t)a.tile_leaves << 32;  // leaf = dummy slot, val = +0.0
-    unsigned long long st_keys = 0, st_hits = 0, st_post = 0;
+    unsigned long long st_post = 0;
 
     for (;;) {
         unsigned long long task = 0;
@@ -221,8 +217,6 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
         const uint32_t ql = (uint32_t)(task % a.q_count);
         const TileInfo *ti = a.tiles + t;
         const uint32_t nl = ti->n_leaves;
-        const uint32_t mask = ti->dict_mask;
-        const uint4 *dict = reinterpret_cast<const uint4 *>(ti->dict);
         const uint64_t *post = a.postings + ti->post_begin;
         const uint32_t *bitmaps = ti->bitmaps;
 
@@ -350,65 +344,20 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
             if (in_regs) flush_regs();
         };
 
-        // ---- phase A: probe
-        const uint64_t qb = a.q_row_off[a.q_first + ql], qe = a.q_row_off[a.q_first + ql + 1];
-        st_keys += (lane == 0) ? (qe - qb) : 0;
-        // Probe until the hit list is nearly full (or the keys are exhausted), then walk it.
-        // ONE textual call of process_hits keeps the lambda inlined (racc stays in registers).
-        uint64_t base = qb;
-        do {
-            uint32_t n_hits = 0;
-            while (base < qe && n_hits <= SC_HITS - 32 * SC_PROBE_ROUNDS) {
-                uint64_t key[SC_PROBE_ROUNDS];
-                float qv[SC_PROBE_ROUNDS];
-                uint32_t h[SC_PROBE_ROUNDS];
-                uint4 slot[SC_PROBE_ROUNDS];
-#pragma unroll
-                for (int j = 0; j < SC_PROBE_ROUNDS; ++j) {
-                    const uint64_t idx = base + 32 * j + lane;
-                    key[j] = 0;
-                    qv[j] = 0.0f;
-                    h[j] = 0;
-                    slot[j] = make_uint4(0, 0, 0, 0);
-                    if (idx < qe) {
-                        key[j] = a.q_keys[idx];
-                        qv[j] = a.q_vals[idx];
-                        h[j] = dict_hash(key[j]) & mask;
-                        slot[j] = __ldg(dict + h[j]);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < SC_PROBE_ROUNDS; ++j) {
-                    uint32_t begin = 0, len = 0;
-                    if (base + 32 * j + lane < qe) {
-                        for (;;) {
-                            if (slot[j].w == 0u) break;  // empty slot: key absent from this tile
-                            if ((((uint64_t)slot[j].y << 32) | slot[j].x) == key[j]) {
-                                begin = slot[j].z;
-                                len = slot[j].w;
-                                break;
-                            }
-                            h[j] = (h[j] + 1) & mask;
-                            slot[j] = __ldg(dict + h[j]);
-                        }
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, len != 0u);
-                    if (len != 0u) {  // lanes hold ascending keys: append in lane order
-                        HitRec r;
-                        r.begin = begin;
-                        r.len = len;
-                        r.qv = qv[j];
-                        hits[n_hits + __popc(m & lt)] = r;
-                    }
-                    n_hits += __popc(m);
-                }
-                base += 32 * SC_PROBE_ROUNDS;
+        // ---- phase A: the task's hit list comes from the plan (plan_* kernels below): stage it in
+        // shared memory SC_HITS records at a time (coalesced) and walk it.  ONE textual call of
+        // process_hits keeps the lambda inlined (racc stays in registers).
+        {
+            const size_t slot = (size_t)ql * a.n_tiles + t;
+            const uint64_t hb = a.plan_off[slot], he = a.plan_off[slot + 1];
+            for (uint64_t h0 = hb; h0 < he; h0 += SC_HITS) {
+                const uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
+                for (uint32_t i = lane; i < n_hits; i += 32) hits[i] = a.plan[h0 + i];
+                __syncwarp();
+                process_hits(n_hits);
+                __syncwarp();
             }
-            __syncwarp();
-            st_hits += (lane == 0) ? n_hits : 0;
-            process_hits(n_hits);
-            __syncwarp();
-        } while (base < qe);
+        }
 
         if (FUSED) {
             const size_t slot = (size_t)ql * a.n_tiles + t;
@@ -420,11 +369,7 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
         }
         __syncwarp();
     }
-    if (lane == 0) {
-        if (st_keys) atomicAdd(a.counters + 1, st_keys);
-        if (st_hits) atomicAdd(a.counters + 2, st_hits);
-        if (st_post) atomicAdd(a.counters + 3, st_post);
-    }
+    if (lane == 0 && st_post) atomicAdd(a.counters + 3, st_post);
 }
 
 // ------------------------------------------------------------------ K5: top-x
@@ -574,6 +519,132 @@ __global__ void __launch_bounds__(256) topx_merge_kernel(const float *__restrict
     }
 }
 
+// ------------------------------------------------------------------ plan
+
+// A query key is looked up ONCE per query in the index-wide dictionary (not once per tile);
+// the result is a short list of (tile, begin, len) entries.  plan_probe counts the hits of
+// every (query, tile) task, a prefix sum lays the hit lists out, plan_fill writes them in
+// ascending key order.  The scoring kernel then streams its hit list and never probes.
+static constexpr int PL_WARPS = 8;
+
+// one warp per query: dictionary lookups (lanes over keys) + per-tile hit counts
+__global__ void __launch_bounds__(PL_WARPS * 32) plan_probe_kernel(
+    const uint64_t *__restrict__ q_row_off, const uint64_t *__restrict__ q_keys, uint64_t q_first,
+    uint32_t q_count, const DictSlot *__restrict__ gdict, uint32_t gmask,
+    const EntryRec *__restrict__ entries, uint32_t n_tiles, uint2 *__restrict__ kref,
+    uint32_t *__restrict__ hitcnt) {
+    const uint32_t ql = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
+    if (ql >= q_count) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t kbase = q_row_off[q_first];
+    const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
+    const uint4 *dict = reinterpret_cast<const uint4 *>(gdict);
+    uint32_t *cnt = hitcnt + (size_t)ql * n_tiles;
+    for (uint64_t i = qb + lane; i < qe; i += 32) {
+        const uint64_t key = q_keys[i];
+        uint32_t h = dict_hash(key) & gmask;
+        uint32_t begin = 0, len = 0;
+        for (;;) {
+            const uint4 s = __ldg(dict + h);
+            if (s.w == 0u) break;  // empty slot: the key occurs nowhere in this index
+            if ((((uint64_t)s.y << 32) | s.x) == key) {
+                begin = s.z;
+                len = s.w;
+                break;
+            }
+            h = (h + 1) & gmask;
+        }
+        kref[i - kbase] = make_uint2(begin, len);
+        for (uint32_t e = 0; e < len; ++e) atomicAdd(&cnt[entries[begin + e].tile], 1u);
+    }
+}
+
+// one warp per query: keys in ascending order, the lanes fan out over ONE key's entries
+// (distinct tiles => no two lanes bump the same cursor)
+__global__ void __launch_bounds__(PL_WARPS * 32) plan_fill_kernel(
+    const uint64_t *__restrict__ q_row_off, const float *__restrict__ q_vals, uint64_t q_first,
+    uint32_t q_count, const EntryRec *__restrict__ entries, uint32_t n_tiles,
+    const uint2 *__restrict__ kref, const uint64_t *__restrict__ plan_off, HitRec *__restrict__ plan) {
+    extern __shared__ uint32_t pl_cursor[];  // [PL_WARPS][n_tiles], relative to the query's first hit
+    const uint32_t ql = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
+    if (ql >= q_count) return;
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t *cur = pl_cursor + (size_t)(threadIdx.x >> 5) * n_tiles;
+    const uint64_t *off = plan_off + (size_t)ql * n_tiles;
+    const uint64_t base = off[0];
+    for (uint32_t t = lane; t < n_tiles; t += 32) cur[t] = (uint32_t)(off[t] - base);
+    __syncwarp();
+    const uint64_t kbase = q_row_off[q_first];
+    const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
+    for (uint64_t r0 = qb; r0 < qe; r0 += 32) {
+        uint2 kr = make_uint2(0, 0);
+        float qv = 0.0f;
+        if (r0 + lane < qe) {
+            kr = kref[r0 + lane - kbase];
+            qv = q_vals[r0 + lane];
+        }
+        unsigned have = __ballot_sync(0xffffffffu, kr.y != 0u);
+        while (have) {
+            const int src = __ffs(have) - 1;
+            have &= have - 1;
+            const uint32_t eb = __shfl_sync(0xffffffffu, kr.x, src);
+            const uint32_t en = __shfl_sync(0xffffffffu, kr.y, src);
+            const float v = __shfl_sync(0xffffffffu, qv, src);
+            for (uint32_t e = lane; e < en; e += 32) {
+                const EntryRec er = entries[eb + e];
+                HitRec h;
+                h.begin = er.begin;
+                h.len = er.len;
+                h.qv = v;
+                plan[base + cur[er.tile]++] = h;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct Plan {
+    DevBuf<uint2> kref;
+    DevBuf<uint32_t> hitcnt;
+    DevBuf<uint64_t> off;
+    DevBuf<HitRec> hits;
+    uint64_t n_hits = 0;
+};
+
+// plan for queries [q0, q0+qn); returns false (nothing built) when the hit lists would not fit `budget`
+static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q0, uint64_t qn,
+                       uint64_t budget_bytes, Plan &pl) {
+    const uint64_t n_tiles = ix->tiles.size();
+    const uint64_t n_tasks = qn * n_tiles;
+    uint64_t kb[2];
+    d2h(ctx, &kb[0], queries->row_off.p + q0, 1);
+    d2h(ctx, &kb[1], queries->row_off.p + q0 + qn, 1);
+    sync(ctx);
+    const uint64_t nnz = kb[1] - kb[0];
+    pl.kref.reserve(std::max<uint64_t>(nnz, 1));
+    pl.hitcnt.reserve(std::max<uint64_t>(n_tasks, 1));
+    pl.off.reserve(n_tasks + 1);
+    MYRIO_CK(cudaMemsetAsync(pl.hitcnt.p, 0, std::max<uint64_t>(n_tasks, 1) * sizeof(uint32_t), ctx->stream));
+    const unsigned grid = (unsigned)((qn + PL_WARPS - 1) / PL_WARPS);
+    MYRIO_LAUNCH(ctx, "k4a_plan_probe", plan_probe_kernel, grid, PL_WARPS * 32, 0, queries->row_off.p,
+                 queries->keys.p, q0, (uint32_t)qn, ix->gdict.p, ix->gdict_mask, ix->gentries.p, (uint32_t)n_tiles,
+                 pl.kref.p, pl.hitcnt.p);
+    exclusive_scan_u32_to_u64(ctx, pl.hitcnt.p, pl.off.p, n_tasks);
+    d2h(ctx, &pl.n_hits, pl.off.p + n_tasks, 1);
+    sync(ctx);
+    if (pl.n_hits * sizeof(HitRec) > budget_bytes && qn > 1) return false;
+    ctx->last_stats[0] += nnz;
+    ctx->last_stats[1] += pl.n_hits;
+    pl.hits.reserve(std::max<uint64_t>(pl.n_hits, 1));
+    const size_t smem = (size_t)PL_WARPS * n_tiles * sizeof(uint32_t);
+    if (smem > ctx->smem_optin) fail(MYRIO_ERR_UNSUPPORTED, "too many tiles (%llu) for the plan kernel", (unsigned long long)n_tiles);
+    MYRIO_CK(cudaFuncSetAttribute(plan_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYRIO_LAUNCH(ctx, "k4a_plan_fill", plan_fill_kernel, grid, PL_WARPS * 32, smem, queries->row_off.p,
+                 queries->vals_f32.p, q0, (uint32_t)qn, ix->gentries.p, (uint32_t)n_tiles, pl.kref.p, pl.off.p,
+                 pl.hits.p);
+    return true;
+}
+
 // ------------------------------------------------------------------ host side
 
 static void check_queries(const myrio_svecs *q, uint64_t q_first, uint64_t q_count) {
@@ -605,15 +676,12 @@ static void launch_score(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a, in
     }
 }
 
-static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q0,
-                           uint64_t qn) {
+static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl, uint64_t qn) {
     ScoreArgs a{};
     a.tiles = ix->d_tiles.p;
     a.postings = ix->postings.p;
-    a.q_row_off = queries->row_off.p;
-    a.q_keys = queries->keys.p;
-    a.q_vals = queries->vals_f32.p;
-    a.q_first = q0;
+    a.plan = pl.hits.p;
+    a.plan_off = pl.off.p;
     a.q_count = (uint32_t)qn;
     a.tile_leaves = ix->tile_leaves;
     a.n_tiles = (uint32_t)ix->tiles.size();
@@ -634,11 +702,11 @@ static void accumulate_stats(myrio_ctx *ctx) {
     unsigned long long h[4] = {0, 0, 0, 0};
     d2h(ctx, h, ctx->score_counters.p, 4);
     sync(ctx);
-    ctx->last_stats[0] += h[1];
-    ctx->last_stats[1] += h[2];
     ctx->last_stats[2] += h[3];
     MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
 }
+
+static constexpr uint64_t PLAN_BUDGET = 12ull << 30;  // bytes of hit lists kept at once
 
 void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
                uint64_t q_count, int32_t sim, float *scores_host) {
@@ -648,16 +716,20 @@ void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries
     reset_stats(ctx);
     if (q_count == 0 || L == 0) return;
     const uint64_t budget = 1ull << 31;  // bytes of score rows kept on the device at once
-    const uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, budget / (L * 4)), q_count);
-    ctx->score_rows.reserve(per * L);
-    for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
-        const uint64_t qn = std::min(per, q_count - q0);
+    uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, budget / (L * 4)), q_count);
+    if (!ctx->plan) ctx->plan = plan_scratch_new();
+    Plan &pl = *static_cast<Plan *>(ctx->plan);
+    for (uint64_t q0 = 0; q0 < q_count;) {
+        uint64_t qn = std::min(per, q_count - q0);
+        while (!build_plan(ctx, ix, queries, q_first + q0, qn, PLAN_BUDGET, pl)) qn = (qn + 1) / 2;
+        ctx->score_rows.reserve(qn * L);
         MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
-        ScoreArgs a = base_args(ctx, ix, queries, q_first + q0, qn);
+        ScoreArgs a = base_args(ctx, ix, pl, qn);
         a.scores = ctx->score_rows.p;
         launch_score<false>(ctx, ix, a, sim);
         d2h(ctx, scores_host + q0 * L, ctx->score_rows.p, qn * L);
         accumulate_stats(ctx);
+        q0 += qn;
     }
     sync(ctx);
 }
@@ -676,16 +748,19 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     // grow-only scratch of the context: a steady-state step never goes back to the allocator
     DevBuf<uint64_t> &cand = ctx->topx_cand;
     DevBuf<uint32_t> &cand_cnt = ctx->topx_cand_cnt, &gthr = ctx->topx_gthr;
-    cand.reserve(per * n_tiles * x);
-    cand_cnt.reserve(per * n_tiles);
-    gthr.reserve(per);
-    for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
-        const uint64_t qn = std::min(per, q_count - q0);
+    if (!ctx->plan) ctx->plan = plan_scratch_new();
+    Plan &pl = *static_cast<Plan *>(ctx->plan);
+    for (uint64_t q0 = 0; q0 < q_count;) {
+        uint64_t qn = std::min(per, q_count - q0);
+        while (!build_plan(ctx, ix, queries, q_first + q0, qn, PLAN_BUDGET, pl)) qn = (qn + 1) / 2;
+        cand.reserve(qn * n_tiles * x);
+        cand_cnt.reserve(qn * n_tiles);
+        gthr.reserve(qn);
         MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
         MYRIO_CK(cudaMemsetAsync(gthr.p, 0, qn * sizeof(uint32_t), ctx->stream));
         MYRIO_CK(cudaMemsetAsync(cand_cnt.p, 0, qn * n_tiles * sizeof(uint32_t), ctx->stream));
         if (!ix->tiles.empty()) {
-            ScoreArgs a = base_args(ctx, ix, queries, q_first + q0, qn);
+            ScoreArgs a = base_args(ctx, ix, pl, qn);
             a.x = x;
             a.cand = cand.p;
             a.cand_cnt = cand_cnt.p;
@@ -696,6 +771,7 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
                      cand_cnt.p, gthr.p, (uint32_t)ix->tiles.size(), x, d_top_scores + q0 * x,
                      d_top_ids + q0 * x);
         if (collect_stats) accumulate_stats(ctx);
+        q0 += qn;
     }
 }
 
@@ -711,5 +787,9 @@ void topx_merge_device(myrio_ctx *ctx, const float *d_scores_in, const uint32_t 
     MYRIO_LAUNCH(ctx, "k7_topx_merge", topx_merge_kernel, (unsigned)q_count, 256, smem, d_scores_in, d_ids_in,
                  n_parts, q_count, x, d_scores_out, d_ids_out);
 }
+
+// the plan scratch of a context (allocated lazily, grow-only)
+void plan_scratch_free(void *p) { delete static_cast<Plan *>(p); }
+void *plan_scratch_new() { return new Plan(); }
 
 }  // namespace myrio

@@ -10,4 +10,6 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
                        uint32_t *d_top_ids, bool collect_stats);
 void topx_merge_device(myrio_ctx *ctx, const float *d_scores_in, const uint32_t *d_ids_in, uint32_t n_parts,
                        uint64_t q_count, uint32_t x, float *d_scores_out, uint32_t *d_ids_out);
+void *plan_scratch_new();
+void plan_scratch_free(void *p);
 }  // namespace myrio

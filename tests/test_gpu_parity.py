@@ -222,7 +222,8 @@ def test_score_all_and_topx_bit_exact(api, ctx, tile_leaves):
         assert (ti == res.top_ids[i]).all()
         assert (bits(ts) == bits(res.top_scores[i])).all()
     st = ctx.score_stats()
-    assert st["query_keys"] == int(oqn.row_off[-1]) * ttc.info()["n_tiles"]
+    assert st["query_keys"] == int(oqn.row_off[-1])
+    assert st["key_hits"] > 0 and st["postings_touched"] >= st["key_hits"]
 
 
 def test_score_jacard_tanimoto_and_k12(api, ctx):
