@@ -533,13 +533,16 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_probe_kernel(
     uint32_t q_count, const DictSlot *__restrict__ gdict, uint32_t gmask,
     const EntryRec *__restrict__ entries, uint32_t n_tiles, uint2 *__restrict__ kref,
     uint32_t *__restrict__ hitcnt) {
+    extern __shared__ uint32_t pl_count[];  // [PL_WARPS][n_tiles]: the warp's query owns one row of hitcnt
     const uint32_t ql = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
     if (ql >= q_count) return;
     const unsigned lane = threadIdx.x & 31;
+    uint32_t *cnt = pl_count + (size_t)(threadIdx.x >> 5) * n_tiles;
+    for (uint32_t t = lane; t < n_tiles; t += 32) cnt[t] = 0;
+    __syncwarp();
     const uint64_t kbase = q_row_off[q_first];
     const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
     const uint4 *dict = reinterpret_cast<const uint4 *>(gdict);
-    uint32_t *cnt = hitcnt + (size_t)ql * n_tiles;
     for (uint64_t i = qb + lane; i < qe; i += 32) {
         const uint64_t key = q_keys[i];
         uint32_t h = dict_hash(key) & gmask;
@@ -557,6 +560,9 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_probe_kernel(
         kref[i - kbase] = make_uint2(begin, len);
         for (uint32_t e = 0; e < len; ++e) atomicAdd(&cnt[entries[begin + e].tile], 1u);
     }
+    __syncwarp();
+    uint32_t *out = hitcnt + (size_t)ql * n_tiles;
+    for (uint32_t t = lane; t < n_tiles; t += 32) out[t] = cnt[t];
 }
 
 // one warp per query: keys in ascending order, the lanes fan out over ONE key's entries
@@ -564,10 +570,13 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_probe_kernel(
 __global__ void __launch_bounds__(PL_WARPS * 32) plan_fill_kernel(
     const uint64_t *__restrict__ q_row_off, const float *__restrict__ q_vals, uint64_t q_first,
     uint32_t q_count, const EntryRec *__restrict__ entries, uint32_t n_tiles,
-    const uint2 *__restrict__ kref, const uint64_t *__restrict__ plan_off, HitRec *__restrict__ plan) {
+    const uint2 *__restrict__ kref, const uint64_t *__restrict__ plan_off, HitRec *__restrict__ plan,
+    uint32_t skip_words) {
     extern __shared__ uint32_t pl_cursor[];  // [PL_WARPS][n_tiles], relative to the query's first hit
     const uint32_t ql = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
     if (ql >= q_count) return;
+    // queries of at most 32*skip_words keys were placed by plan_fill_ranked_kernel
+    if ((q_row_off[q_first + ql + 1] - q_row_off[q_first + ql] + 31) / 32 <= skip_words) return;
     const unsigned lane = threadIdx.x & 31;
     uint32_t *cur = pl_cursor + (size_t)(threadIdx.x >> 5) * n_tiles;
     const uint64_t *off = plan_off + (size_t)ql * n_tiles;
@@ -603,6 +612,112 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_fill_kernel(
     }
 }
 
+// Fast variant of plan_fill: one CTA per query.  present[tile][key/32] (shared memory) is the
+// bit-matrix "key i of the query occurs in tile t"; the place of a hit inside its (query, tile)
+// list is the number of earlier keys present in that tile = a prefix popcount, so all hits are
+// placed in parallel (no per-key serialisation).  Needs n_tiles * ceil(nq/32) words of shared
+// memory; plan_fill_kernel is the fallback for queries/tilings that do not fit.
+static constexpr int PF_THREADS = 256;
+__global__ void __launch_bounds__(PF_THREADS) plan_fill_ranked_kernel(
+    const uint64_t *__restrict__ q_row_off, const float *__restrict__ q_vals, uint64_t q_first,
+    const EntryRec *__restrict__ entries, uint32_t n_tiles, uint32_t words_cap,
+    const uint2 *__restrict__ kref, const uint64_t *__restrict__ plan_off, HitRec *__restrict__ plan) {
+    // shared: present[n_tiles][words] | hit_prefix[32*words_cap + 1] | ent_begin[32*words_cap]
+    // (staging the query's plan region in shared memory for coalesced stores was measured slower:
+    // the extra shared memory costs more occupancy than the scattered 12-byte stores cost)
+    extern __shared__ uint32_t pf_smem[];
+    __shared__ uint32_t s_warp[PF_THREADS / 32 + 1];
+    const uint32_t ql = blockIdx.x;
+    const uint64_t kbase = q_row_off[q_first];
+    const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
+    const uint32_t nq = (uint32_t)(qe - qb);
+    const uint32_t words = (nq + 31) >> 5;
+    if (words > words_cap || nq == 0) return;  // long queries: fallback kernel
+    uint32_t *present = pf_smem;
+    uint32_t *prefix = pf_smem + (size_t)n_tiles * words_cap;
+    uint32_t *ebegin = prefix + 32 * words_cap + 1;
+    const uint64_t *off = plan_off + (size_t)ql * n_tiles;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < n_tiles * words; i += PF_THREADS) present[i] = 0;
+    // exclusive prefix of the entry counts over the query's keys (chunks of PF_THREADS keys)
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nq; base += PF_THREADS) {
+        const uint32_t i = base + tid;
+        uint2 kr = make_uint2(0, 0);
+        if (i < nq) kr = kref[qb + i - kbase];
+        uint32_t inc = kr.y;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (unsigned)d) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (uint32_t w = 0; w < warp; ++w) wbase += s_warp[w];
+        if (i < nq) {
+            prefix[i] = carry + wbase + inc - kr.y;
+            ebegin[i] = kr.x;
+        }
+        uint32_t total = 0;
+        for (uint32_t w = 0; w < PF_THREADS / 32; ++w) total += s_warp[w];
+        carry += total;
+        __syncthreads();
+    }
+    if (tid == 0) prefix[nq] = carry;
+    __syncthreads();
+    const uint32_t H = carry;  // hits of this query over all tiles
+    auto key_of_hit = [&](uint32_t j) {  // last i with prefix[i] <= j
+        uint32_t lo = 0, hi = nq;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (prefix[mid] <= j) lo = mid; else hi = mid;
+        }
+        return lo;
+    };
+    // pass 1: one bit per (key, tile) hit -- one thread per hit
+    for (uint32_t j = tid; j < H; j += PF_THREADS) {
+        const uint32_t i = key_of_hit(j);
+        const uint32_t tile = entries[ebegin[i] + (j - prefix[i])].tile;
+        atomicOr(&present[tile * words + (i >> 5)], 1u << (i & 31));
+    }
+    __syncthreads();
+    // pass 2: rank of key i in tile t = popcount of present[t] below bit i
+    for (uint32_t j = tid; j < H; j += PF_THREADS) {
+        const uint32_t i = key_of_hit(j);
+        const EntryRec er = entries[ebegin[i] + (j - prefix[i])];
+        const uint32_t *row = present + er.tile * words;
+        uint32_t rank = __popc(row[i >> 5] & ((1u << (i & 31)) - 1u));
+        for (uint32_t w = 0; w < (i >> 5); ++w) rank += __popc(row[w]);
+        HitRec h;
+        h.begin = er.begin;
+        h.len = er.len;
+        h.qv = q_vals[qb + i];
+        plan[off[er.tile] + rank] = h;
+    }
+}
+
+__global__ void __launch_bounds__(256) max_row_len_kernel(const uint64_t *__restrict__ row_off, uint64_t n,
+                                                          unsigned long long *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = i < n ? row_off[i + 1] - row_off[i] : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+
+static uint64_t queries_max_keys(myrio_ctx *ctx, const myrio_svecs *q) {
+    if (q->n_rows == 0) return 0;
+    DevBuf<unsigned long long> d(1);
+    MYRIO_CK(cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+    MYRIO_LAUNCH(ctx, "max_row_len", max_row_len_kernel, (unsigned)((q->n_rows + 255) / 256), 256, 0, q->row_off.p,
+                 q->n_rows, d.p);
+    unsigned long long h = 0;
+    d2h(ctx, &h, d.p, 1);
+    sync(ctx);
+    return h;
+}
+
 struct Plan {
     DevBuf<uint2> kref;
     DevBuf<uint32_t> hitcnt;
@@ -624,9 +739,11 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     pl.kref.reserve(std::max<uint64_t>(nnz, 1));
     pl.hitcnt.reserve(std::max<uint64_t>(n_tasks, 1));
     pl.off.reserve(n_tasks + 1);
-    MYRIO_CK(cudaMemsetAsync(pl.hitcnt.p, 0, std::max<uint64_t>(n_tasks, 1) * sizeof(uint32_t), ctx->stream));
     const unsigned grid = (unsigned)((qn + PL_WARPS - 1) / PL_WARPS);
-    MYRIO_LAUNCH(ctx, "k4a_plan_probe", plan_probe_kernel, grid, PL_WARPS * 32, 0, queries->row_off.p,
+    const size_t smem = (size_t)PL_WARPS * n_tiles * sizeof(uint32_t);
+    if (smem > ctx->smem_optin) fail(MYRIO_ERR_UNSUPPORTED, "too many tiles (%llu) for the plan kernels", (unsigned long long)n_tiles);
+    MYRIO_CK(cudaFuncSetAttribute(plan_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYRIO_LAUNCH(ctx, "k4a_plan_probe", plan_probe_kernel, grid, PL_WARPS * 32, smem, queries->row_off.p,
                  queries->keys.p, q0, (uint32_t)qn, ix->gdict.p, ix->gdict_mask, ix->gentries.p, (uint32_t)n_tiles,
                  pl.kref.p, pl.hitcnt.p);
     exclusive_scan_u32_to_u64(ctx, pl.hitcnt.p, pl.off.p, n_tasks);
@@ -636,12 +753,26 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     ctx->last_stats[0] += nnz;
     ctx->last_stats[1] += pl.n_hits;
     pl.hits.reserve(std::max<uint64_t>(pl.n_hits, 1));
-    const size_t smem = (size_t)PL_WARPS * n_tiles * sizeof(uint32_t);
-    if (smem > ctx->smem_optin) fail(MYRIO_ERR_UNSUPPORTED, "too many tiles (%llu) for the plan kernel", (unsigned long long)n_tiles);
-    MYRIO_CK(cudaFuncSetAttribute(plan_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MYRIO_LAUNCH(ctx, "k4a_plan_fill", plan_fill_kernel, grid, PL_WARPS * 32, smem, queries->row_off.p,
-                 queries->vals_f32.p, q0, (uint32_t)qn, ix->gentries.p, (uint32_t)n_tiles, pl.kref.p, pl.off.p,
-                 pl.hits.p);
+    // queries whose presence bit-matrix fits in shared memory take the parallel kernel, the rest
+    // (very long queries on indexes with very many tiles) the per-key sequential one
+    const uint64_t max_q_keys = std::max<uint64_t>(queries_max_keys(ctx, queries), 1);
+    const size_t smem_budget = std::min<size_t>(ctx->smem_optin, 96 * 1024);
+    // shared memory per word of query keys: n_tiles presence words + 64 prefix/begin words
+    uint32_t words_cap = (uint32_t)std::min<uint64_t>((max_q_keys + 31) / 32,
+                                                      (smem_budget - 64) / ((n_tiles + 64) * sizeof(uint32_t)));
+    if (words_cap) {
+        const size_t psm = ((size_t)n_tiles * words_cap + 64 * words_cap + 1) * sizeof(uint32_t);
+        MYRIO_CK(cudaFuncSetAttribute(plan_fill_ranked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        MYRIO_LAUNCH(ctx, "k4a_plan_fill_ranked", plan_fill_ranked_kernel, (unsigned)qn, PF_THREADS, psm,
+                     queries->row_off.p, queries->vals_f32.p, q0, ix->gentries.p, (uint32_t)n_tiles, words_cap,
+                     pl.kref.p, pl.off.p, pl.hits.p);
+    }
+    if ((max_q_keys + 31) / 32 > words_cap) {
+        MYRIO_CK(cudaFuncSetAttribute(plan_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, "k4a_plan_fill", plan_fill_kernel, grid, PL_WARPS * 32, smem, queries->row_off.p,
+                     queries->vals_f32.p, q0, (uint32_t)qn, ix->gentries.p, (uint32_t)n_tiles, pl.kref.p, pl.off.p,
+                     pl.hits.p, words_cap);
+    }
     return true;
 }
 

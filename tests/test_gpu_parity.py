@@ -404,6 +404,11 @@ def test_cluster_centroid_query_against_tree(api, ctx):
     ts, ti = oracle.topx(s, 100)
     assert (ti == res.top_ids[0]).all() and (bits(ts) == bits(res.top_scores[0])).all()
     assert 600 <= ti[0] < 640
+    # many tiles x a long query: the presence bit-matrix of the parallel plan-fill kernel does not
+    # fit in shared memory, the per-key sequential plan-fill kernel takes over -- same bits
+    ttc4 = api.TaxTreeCompute.from_store_tree(st, 18, 32, tile_leaves=4)
+    res4 = api.TaxTreeResults.from_compute_tree(cen, ttc4, api.SIM_COSINE, 100, full_scores=True)
+    assert (bits(res4.scores) == bits(res.scores)).all() and (res4.top_ids == res.top_ids).all()
 
 
 def test_dense_and_sparse_tilings_agree(api, ctx):
