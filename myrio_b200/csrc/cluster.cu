@@ -19,26 +19,120 @@
 
 namespace myrio {
 
-static constexpr int PK_THREADS = 256;
-enum { PK_STORE = 0, PK_SILSUM = 1, PK_ARGMAX = 2 };
+// ------------------------------------------------------------------ K6 tile
+//
+// Rows: the sparse rows of a tile are re-packed once per call into a ROW SLAB: groups of 32
+// rows (one per lane), entries interleaved four at a time -- keys[(off + j/4) * 128 + lane * 4 +
+// j % 4] -- so that a warp reads 4 entries of each of its 32 rows with one coalesced 8-byte
+// (u16 keys) and one 16-byte (f32 values) load per lane.  Short rows are padded with
+// (key 0, +0.0): a +0.0 term leaves an f32 accumulator unchanged.
+// Columns: CB columns are dense in shared memory as [dim][4]-float planes (one LDS.128 per
+// plane and entry); a persistent grid of one 1024-thread CTA per SM walks (column chunk, row
+// slice) tasks, every thread accumulating CB scores of its row in ascending key order.
+// The tile is stored TRANSPOSED ([column][row], coalesced) for the order-preserving row
+// reductions below (silhouette sums, last-maximum argmax), or row-major for myrio_pairwise.
+static constexpr int PT_THREADS = 1024;
+static constexpr int PT_WARPS = PT_THREADS / 32;
+
+struct RowSlab {
+    DevBuf<uint16_t> keys;
+    DevBuf<float> vals;
+    DevBuf<uint32_t> grp_len;  // per group: entries per row / 4 (padded)
+    DevBuf<uint64_t> grp_off;  // per group: first quad of the group
+    uint32_t n_rows = 0, n_groups = 0;
+};
+
+__global__ void __launch_bounds__(256) slab_count_kernel(const uint64_t *__restrict__ r_off,
+                                                         const uint32_t *__restrict__ row_ids, uint32_t n_rows,
+                                                         uint32_t n_groups, uint32_t *__restrict__ grp_len) {
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t ri = g * 32 + lane;
+    uint32_t len = 0;
+    if (ri < n_rows) {
+        const uint32_t r = row_ids ? row_ids[ri] : ri;
+        len = (uint32_t)(r_off[r + 1] - r_off[r]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+    if (lane == 0) grp_len[g] = (len + 3) >> 2;
+}
+
+__global__ void __launch_bounds__(256) slab_fill_kernel(const uint64_t *__restrict__ r_off,
+                                                        const uint64_t *__restrict__ r_keys,
+                                                        const float *__restrict__ r_vals,
+                                                        const uint32_t *__restrict__ row_ids, uint32_t n_rows,
+                                                        uint32_t n_groups, const uint32_t *__restrict__ grp_len,
+                                                        const uint64_t *__restrict__ grp_off,
+                                                        uint16_t *__restrict__ keys, float *__restrict__ vals) {
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t ri = g * 32 + lane;
+    uint64_t b = 0;
+    uint32_t len = 0;
+    if (ri < n_rows) {
+        const uint32_t r = row_ids ? row_ids[ri] : ri;
+        b = r_off[r];
+        len = (uint32_t)(r_off[r + 1] - b);
+    }
+    const uint32_t quads = grp_len[g];
+    const uint64_t base = grp_off[g] * 128ull + lane * 4u;
+    for (uint32_t q = 0; q < quads; ++q) {
+        uint16_t k4[4];
+        float v4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t j = q * 4 + u;
+            k4[u] = j < len ? (uint16_t)r_keys[b + j] : (uint16_t)0;
+            v4[u] = j < len ? r_vals[b + j] : 0.0f;
+        }
+        *reinterpret_cast<uint2 *>(keys + base + (uint64_t)q * 128) =
+            make_uint2((uint32_t)k4[0] | ((uint32_t)k4[1] << 16), (uint32_t)k4[2] | ((uint32_t)k4[3] << 16));
+        *reinterpret_cast<float4 *>(vals + base + (uint64_t)q * 128) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+    }
+}
+
+static void build_row_slab(myrio_ctx *ctx, const uint64_t *r_off, const uint64_t *r_keys, const float *r_vals,
+                           const uint32_t *row_ids, uint32_t n_rows, RowSlab &s) {
+    s.n_rows = n_rows;
+    s.n_groups = (n_rows + 31) / 32;
+    if (s.n_groups == 0) return;
+    s.grp_len.alloc(s.n_groups);
+    s.grp_off.alloc(s.n_groups + 1);
+    const unsigned grid = (s.n_groups + 7) / 8;
+    MYRIO_LAUNCH(ctx, "k6_slab_count", slab_count_kernel, grid, 256, 0, r_off, row_ids, n_rows, s.n_groups,
+                 s.grp_len.p);
+    exclusive_scan_u32_to_u64(ctx, s.grp_len.p, s.grp_off.p, s.n_groups);
+    uint64_t quads = 0;
+    d2h(ctx, &quads, s.grp_off.p + s.n_groups, 1);
+    sync(ctx);
+    s.keys.alloc(std::max<uint64_t>(quads, 1) * 128);
+    s.vals.alloc(std::max<uint64_t>(quads, 1) * 128);
+    MYRIO_LAUNCH(ctx, "k6_slab_fill", slab_fill_kernel, grid, 256, 0, r_off, r_keys, r_vals, row_ids, n_rows,
+                 s.n_groups, s.grp_len.p, s.grp_off.p, s.keys.p, s.vals.p);
+}
 
 struct PairArgs {
-    const uint64_t *r_off;
-    const uint64_t *r_keys;
-    const float *r_vals;
-    const uint32_t *row_ids;  // rows of the CSR batch to use (NULL = identity)
-    uint32_t n_rows;
-    const uint64_t *c_off;  // sparse columns (CSR batch + id list) ...
+    // rows: slab
+    const uint16_t *s_keys;
+    const float *s_vals;
+    const uint32_t *grp_len;
+    const uint64_t *grp_off;
+    uint32_t n_rows, n_groups;
+    // columns [c_first, c_first + n_cols): sparse (CSR batch + optional id list) or dense [..][dim]
+    const uint64_t *c_off;
     const uint64_t *c_keys;
     const float *c_vals;
     const uint32_t *col_ids;
-    const float *c_dense;  // ... or dense columns [n_cols][dim]
-    uint32_t n_cols;
+    const float *c_dense;
+    uint32_t c_first, n_cols;
     uint32_t dim;
-    uint32_t split;  // PK_SILSUM: columns [0,split) feed sum a, the rest sum b
+    uint32_t n_slices;  // row slices per column chunk
     int sim;
-    float *out;         // STORE: [n_rows][n_cols]; SILSUM: [n_rows][2]; ARGMAX: best sim [n_rows]
-    uint32_t *out_idx;  // ARGMAX: best column (last maximum)
+    float *out;   // transposed: out[c * ld + row]; row-major: out[row * ld + c]   (c relative to c_first)
+    uint64_t ld;
 };
 
 __device__ __forceinline__ float pk_finite_or_zero(float x) { return (fabsf(x) <= 3.402823466e+38f) ? x : 0.0f; }
@@ -48,93 +142,166 @@ __device__ __forceinline__ float pk_sim(int sim, float dot) {
     return dot;
 }
 
-template <int MODE, int CB>
-__global__ void __launch_bounds__(PK_THREADS) pair_kernel(PairArgs a) {
-    extern __shared__ __align__(16) float colT[];  // [dim][CB]
-    const uint32_t tid = threadIdx.x;
-    const uint32_t ri = blockIdx.x * PK_THREADS + tid;
-    const bool row_ok = ri < a.n_rows;
-    uint64_t rb = 0, re = 0;
-    if (row_ok) {
-        const uint32_t r = a.row_ids ? a.row_ids[ri] : ri;
-        rb = a.r_off[r];
-        re = a.r_off[r + 1];
-    }
-    for (uint32_t i = tid; i < a.dim * CB; i += PK_THREADS) colT[i] = 0.0f;
-    __syncthreads();
+// CB = 8: two [dim][4] planes; CB = 2 (dim > 4096): one [dim][2] plane
+template <int CB, bool TRANSPOSED>
+__global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_kernel(PairArgs a) {
+    extern __shared__ __align__(16) float col_sm[];
+    constexpr int VW = CB >= 4 ? 4 : 2;        // floats per plane entry
+    constexpr int NP = CB / VW;                // planes
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_chunks = (a.n_cols + CB - 1) / CB;
+    const uint32_t n_tasks = n_chunks * a.n_slices;
+    const uint32_t plane = a.dim * VW;
+    for (uint32_t i = tid; i < plane * NP; i += PT_THREADS) col_sm[i] = 0.0f;
+    uint32_t staged = 0xFFFFFFFFu;
 
-    float sum_a = 0.0f, sum_b = 0.0f;  // SILSUM
-    float best = 0.0f;                  // ARGMAX
-    uint32_t best_idx = 0;
-
-    for (uint32_t c0 = 0; c0 < a.n_cols; c0 += CB) {
+    for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const uint32_t chunk = task / a.n_slices, slice = task % a.n_slices;
+        const uint32_t c0 = chunk * CB;
         const uint32_t nc = min((uint32_t)CB, a.n_cols - c0);
-        // stage the chunk's columns
-        if (a.c_dense) {
-            for (uint32_t i = tid; i < a.dim * nc; i += PK_THREADS) {
-                const uint32_t c = i / a.dim, key = i % a.dim;
-                colT[key * CB + c] = a.c_dense[(size_t)(c0 + c) * a.dim + key];
+        if (chunk != staged) {
+            __syncthreads();  // everyone is done with the previous chunk (and with the zero fill)
+            if (a.c_dense) {
+                for (uint32_t i = tid; i < a.dim * CB; i += PT_THREADS) {
+                    const uint32_t c = i / a.dim, key = i % a.dim;
+                    col_sm[(c / VW) * plane + key * VW + (c % VW)] =
+                        c < nc ? a.c_dense[(size_t)(a.c_first + c0 + c) * a.dim + key] : 0.0f;
+                }
+            } else {
+                if (staged != 0xFFFFFFFFu) {  // un-stage: sparse columns only touch their own entries
+                    const uint32_t p0 = staged * CB, pn = min((uint32_t)CB, a.n_cols - p0);
+                    for (uint32_t c = warp; c < pn; c += PT_WARPS) {
+                        const uint32_t cr = a.col_ids ? a.col_ids[a.c_first + p0 + c] : (a.c_first + p0 + c);
+                        const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
+                        for (uint64_t j = b + lane; j < e; j += 32)
+                            col_sm[(c / VW) * plane + (uint32_t)a.c_keys[j] * VW + (c % VW)] = 0.0f;
+                    }
+                    __syncthreads();
+                }
+                for (uint32_t c = warp; c < nc; c += PT_WARPS) {
+                    const uint32_t cr = a.col_ids ? a.col_ids[a.c_first + c0 + c] : (a.c_first + c0 + c);
+                    const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
+                    for (uint64_t j = b + lane; j < e; j += 32)
+                        col_sm[(c / VW) * plane + (uint32_t)a.c_keys[j] * VW + (c % VW)] = a.c_vals[j];
+                }
             }
-        } else {
-            for (uint32_t c = 0; c < nc; ++c) {
-                const uint32_t cr = a.col_ids ? a.col_ids[c0 + c] : (c0 + c);
-                const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
-                for (uint64_t j = b + tid; j < e; j += PK_THREADS) colT[(uint32_t)a.c_keys[j] * CB + c] = a.c_vals[j];
+            staged = chunk;
+            __syncthreads();
+        }
+        // row groups of this slice, one per warp at a time
+        const uint32_t g_lo = (uint32_t)((uint64_t)a.n_groups * slice / a.n_slices);
+        const uint32_t g_hi = (uint32_t)((uint64_t)a.n_groups * (slice + 1) / a.n_slices);
+        for (uint32_t g = g_lo + warp; g < g_hi; g += PT_WARPS) {
+            const uint32_t quads = a.grp_len[g];
+            const uint64_t base = a.grp_off[g] * 128ull + lane * 4u;
+            const uint2 *kp = reinterpret_cast<const uint2 *>(a.s_keys + base);
+            const float4 *vp = reinterpret_cast<const float4 *>(a.s_vals + base);
+            float acc[CB];
+#pragma unroll
+            for (int c = 0; c < CB; ++c) acc[c] = 0.0f;
+            uint2 kq = make_uint2(0, 0);
+            float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (quads) {
+                kq = __ldg(kp);
+                vq = __ldg(vp);
             }
-        }
-        __syncthreads();
-        float acc[CB];
+            for (uint32_t q = 0; q < quads; ++q) {
+                const uint2 kc = kq;
+                const float4 vc = vq;
+                if (q + 1 < quads) {  // next quad in flight while this one is applied (32 lanes x 8 / 16 B apart)
+                    kq = __ldg(kp + (size_t)(q + 1) * 32);
+                    vq = __ldg(vp + (size_t)(q + 1) * 32);
+                }
+                const uint32_t keys4[4] = {kc.x & 0xFFFFu, kc.x >> 16, kc.y & 0xFFFFu, kc.y >> 16};
+                const float vals4[4] = {vc.x, vc.y, vc.z, vc.w};
 #pragma unroll
-        for (int c = 0; c < CB; ++c) acc[c] = 0.0f;
-        for (uint64_t j = rb; j < re; ++j) {  // ascending key order
-            const uint32_t key = (uint32_t)a.r_keys[j];
-            const float v = a.r_vals[j];
-            const float *cp = colT + (size_t)key * CB;
+                for (int u = 0; u < 4; ++u) {  // ascending key order
+                    const float v = vals4[u];
 #pragma unroll
-            for (int c = 0; c < CB; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(v, cp[c]));
-        }
-        if (row_ok) {
-#pragma unroll
-            for (int c = 0; c < CB; ++c) {
-                if ((uint32_t)c < nc) {
-                    const float s = pk_sim(a.sim, acc[c]);
-                    if (MODE == PK_STORE) {
-                        a.out[(size_t)ri * a.n_cols + c0 + c] = s;
-                    } else if (MODE == PK_SILSUM) {
-                        const float d = __fsub_rn(1.0f, s);  // Similarity::dist, similarity.rs:53-56
-                        if (c0 + c < a.split)
-                            sum_a = __fadd_rn(sum_a, d);
-                        else
-                            sum_b = __fadd_rn(sum_b, d);
-                    } else {
-                        if ((c0 + c) == 0 || s >= best) {  // max_by_key keeps the LAST maximum
-                            best = s;
-                            best_idx = c0 + c;
+                    for (int p = 0; p < NP; ++p) {
+                        if (VW == 4) {
+                            const float4 x = *reinterpret_cast<const float4 *>(col_sm + p * plane + keys4[u] * 4);
+                            acc[p * 4 + 0] = __fadd_rn(acc[p * 4 + 0], __fmul_rn(v, x.x));
+                            acc[p * 4 + 1] = __fadd_rn(acc[p * 4 + 1], __fmul_rn(v, x.y));
+                            acc[p * 4 + 2] = __fadd_rn(acc[p * 4 + 2], __fmul_rn(v, x.z));
+                            acc[p * 4 + 3] = __fadd_rn(acc[p * 4 + 3], __fmul_rn(v, x.w));
+                        } else {
+                            const float2 x = *reinterpret_cast<const float2 *>(col_sm + p * plane + keys4[u] * 2);
+                            acc[p * 2 + 0] = __fadd_rn(acc[p * 2 + 0], __fmul_rn(v, x.x));
+                            acc[p * 2 + 1] = __fadd_rn(acc[p * 2 + 1], __fmul_rn(v, x.y));
                         }
                     }
                 }
             }
-        }
-        __syncthreads();
-        // un-stage (sparse columns only touch their own entries)
-        if (!a.c_dense) {
-            for (uint32_t c = 0; c < nc; ++c) {
-                const uint32_t cr = a.col_ids ? a.col_ids[c0 + c] : (c0 + c);
-                const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
-                for (uint64_t j = b + tid; j < e; j += PK_THREADS) colT[(uint32_t)a.c_keys[j] * CB + c] = 0.0f;
+            const uint32_t ri = g * 32 + lane;
+            if (ri < a.n_rows) {
+#pragma unroll
+                for (int c = 0; c < CB; ++c) {
+                    if ((uint32_t)c < nc) {
+                        const float s = pk_sim(a.sim, acc[c]);
+                        if (TRANSPOSED)
+                            a.out[(size_t)(c0 + c) * a.ld + ri] = s;
+                        else
+                            a.out[(size_t)ri * a.ld + c0 + c] = s;
+                    }
+                }
             }
-            __syncthreads();
         }
     }
-    if (row_ok) {
-        if (MODE == PK_SILSUM) {
-            a.out[(size_t)ri * 2] = sum_a;
-            a.out[(size_t)ri * 2 + 1] = sum_b;
-        } else if (MODE == PK_ARGMAX) {
-            a.out[ri] = best;
-            a.out_idx[ri] = best_idx;
+}
+
+// Silhouette sums (clustering.rs:323-336) over a transposed tile: one thread per row adds
+// dist = 1 - sim in COLUMN ORDER (the member order of the reference's iterators), continuing
+// the running sums of the previous column pass.
+__global__ void __launch_bounds__(128) silsum_rows_kernel(const float *__restrict__ tile, uint64_t ld,
+                                                          uint32_t n_rows, uint32_t c_first, uint32_t n_cols,
+                                                          uint32_t split, float *__restrict__ sums) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    float sa = sums[(size_t)r * 2], sb = sums[(size_t)r * 2 + 1];
+    uint32_t c = 0;
+    for (; c + 8 <= n_cols; c += 8) {
+        float s[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] = __ldg(tile + (size_t)(c + u) * ld + r);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float d = __fsub_rn(1.0f, s[u]);  // Similarity::dist, similarity.rs:53-56
+            if (c_first + c + u < split)
+                sa = __fadd_rn(sa, d);
+            else
+                sb = __fadd_rn(sb, d);
         }
     }
+    for (; c < n_cols; ++c) {
+        const float d = __fsub_rn(1.0f, __ldg(tile + (size_t)c * ld + r));
+        if (c_first + c < split)
+            sa = __fadd_rn(sa, d);
+        else
+            sb = __fadd_rn(sb, d);
+    }
+    sums[(size_t)r * 2] = sa;
+    sums[(size_t)r * 2 + 1] = sb;
+}
+
+// argmax over the columns of a transposed tile; max_by_key keeps the LAST maximum
+__global__ void __launch_bounds__(128) argmax_rows_kernel(const float *__restrict__ tile, uint64_t ld,
+                                                          uint32_t n_rows, uint32_t n_cols,
+                                                          float *__restrict__ best_out,
+                                                          uint32_t *__restrict__ idx_out) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    float best = 0.0f;
+    uint32_t best_idx = 0;
+    for (uint32_t c = 0; c < n_cols; ++c) {
+        const float s = __ldg(tile + (size_t)c * ld + r);
+        if (c == 0 || s >= best) {
+            best = s;
+            best_idx = c;
+        }
+    }
+    best_out[r] = best;
+    idx_out[r] = best_idx;
 }
 
 // generic fallback for myrio_pairwise at large k: one thread per pair, two-pointer merge
@@ -165,20 +332,37 @@ __global__ void __launch_bounds__(128) pair_merge_kernel(const uint64_t *__restr
     out[p] = pk_sim(sim, acc);
 }
 
-template <int MODE>
-static void launch_pair(myrio_ctx *ctx, const PairArgs &a, const char *name) {
-    if (a.n_rows == 0 || a.n_cols == 0) return;
-    const unsigned grid = (a.n_rows + PK_THREADS - 1) / PK_THREADS;
-    if (a.dim <= 4096) {
-        const size_t smem = (size_t)a.dim * 8 * sizeof(float);
-        MYRIO_CK(cudaFuncSetAttribute(pair_kernel<MODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MYRIO_LAUNCH(ctx, name, (pair_kernel<MODE, 8>), grid, PK_THREADS, smem, a);
+// rows x columns [c_first, c_first + n_cols) -> tile (transposed [col][ld] or row-major [row][ld])
+template <bool TRANSPOSED>
+static void launch_pair_tile(myrio_ctx *ctx, PairArgs a, const RowSlab &s, const char *name) {
+    if (s.n_rows == 0 || a.n_cols == 0) return;
+    a.s_keys = s.keys.p;
+    a.s_vals = s.vals.p;
+    a.grp_len = s.grp_len.p;
+    a.grp_off = s.grp_off.p;
+    a.n_rows = s.n_rows;
+    a.n_groups = s.n_groups;
+    const uint32_t cb = a.dim <= 4096 ? 8 : 2;
+    const uint32_t n_chunks = (a.n_cols + cb - 1) / cb;
+    // enough (chunk, slice) tasks for two rounds of the persistent grid, at least one warp-round per slice
+    const uint32_t want = 2u * (uint32_t)ctx->sm_count;
+    uint32_t n_slices = n_chunks >= want ? 1u : (want + n_chunks - 1) / n_chunks;
+    n_slices = std::max(1u, std::min(n_slices, (s.n_groups + PT_WARPS - 1) / PT_WARPS));
+    a.n_slices = n_slices;
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)n_chunks * n_slices, (uint64_t)ctx->sm_count);
+    const size_t smem = (size_t)a.dim * cb * sizeof(float);
+    if (cb == 8) {
+        auto kern = pair_tile_kernel<8, TRANSPOSED>;
+        MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, name, kern, grid, PT_THREADS, smem, a);
     } else {
-        const size_t smem = (size_t)a.dim * 2 * sizeof(float);
-        MYRIO_CK(cudaFuncSetAttribute(pair_kernel<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MYRIO_LAUNCH(ctx, name, (pair_kernel<MODE, 2>), grid, PK_THREADS, smem, a);
+        auto kern = pair_tile_kernel<2, TRANSPOSED>;
+        MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MYRIO_LAUNCH(ctx, name, kern, grid, PT_THREADS, smem, a);
     }
 }
+
+static constexpr uint64_t PT_TILE_BUDGET = 1ull << 30;  // bytes of similarity tile kept at once
 
 // ---------------------------------------------------------------- recentering
 
@@ -341,12 +525,9 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     const float max_nb_hck = (float)max_hck;
     if (nc == 0) push_centroid_from_read(kept[max_idx]);
 
+    RowSlab slab;  // the kept reads (normalised), packed once for every reads x centroids pass
+    build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_kept.p, nk, slab);
     PairArgs pa{};
-    pa.r_off = norm->row_off.p;
-    pa.r_keys = norm->keys.p;
-    pa.r_vals = norm->vals_f32.p;
-    pa.row_ids = d_kept.p;
-    pa.n_rows = nk;
     pa.c_dense = cen.p;
     pa.dim = dim;
     pa.sim = sim;
@@ -355,7 +536,8 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         DevBuf<float> d_dots((size_t)nk * nc);
         pa.n_cols = nc;
         pa.out = d_dots.p;
-        launch_pair<PK_STORE>(ctx, pa, "k6_pair_store");
+        pa.ld = nc;
+        launch_pair_tile<false>(ctx, pa, slab, "k6_pair_store");
         std::vector<float> dots((size_t)nk * nc);
         d2h(ctx, dots.data(), d_dots.p, dots.size());
         sync(ctx);
@@ -382,14 +564,20 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     DevBuf<uint32_t> d_target(nk), d_sums((size_t)nc * dim), d_members(nc);
     std::vector<float> best(nk);
     std::vector<uint32_t> target(nk);
+    DevBuf<float> d_tile((size_t)nc * nk);  // reads x centroids similarities, [centroid][read]
     pa.n_cols = nc;
-    pa.out = d_best.p;
-    pa.out_idx = d_target.p;
+    pa.out = d_tile.p;
+    pa.ld = nk;
+    auto assign_pass = [&]() {
+        launch_pair_tile<true>(ctx, pa, slab, "k6_pair_argmax");
+        MYRIO_LAUNCH(ctx, "k6_argmax_rows", argmax_rows_kernel, (nk + 127) / 128, 128, 0, d_tile.p, (uint64_t)nk, nk,
+                     nc, d_best.p, d_target.p);
+    };
     float previous_mean_wcsss = 1E-6f;
     float improvement_score = 3.40282347e+38f;
     uint64_t nb_iters = 0;
     while (improvement_score > p->eta_improvement && nb_iters < p->nb_iters_max) {
-        launch_pair<PK_ARGMAX>(ctx, pa, "k6_pair_argmax");
+        assign_pass();
         d2h(ctx, best.data(), d_best.p, nk);
         d2h(ctx, target.data(), d_target.p, nk);
         sync(ctx);
@@ -423,7 +611,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     if (n_iters) *n_iters = (uint32_t)nb_iters;
 
     // Step 5 / first half of step 4 (:200-233): final assignment
-    launch_pair<PK_ARGMAX>(ctx, pa, "k6_pair_argmax");
+    assign_pass();
     d2h(ctx, target.data(), d_target.p, nk);
     sync(ctx);
     for (uint32_t i = 0; i < nk; ++i) assign[kept[i]] = (int32_t)target[i];
@@ -457,22 +645,30 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         DevBuf<float> d_sums2((size_t)nm * 2);
         h2d(ctx, d_rows.p, members[c].data(), nm);
         h2d(ctx, d_cols.p, cols.data(), cols.size());
+        MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)nm * 2 * sizeof(float), ctx->stream));
+        RowSlab mslab;  // the cluster's members as rows
+        build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, mslab);
         PairArgs sa{};
-        sa.r_off = norm->row_off.p;
-        sa.r_keys = norm->keys.p;
-        sa.r_vals = norm->vals_f32.p;
-        sa.row_ids = d_rows.p;
-        sa.n_rows = nm;
         sa.c_off = norm->row_off.p;
         sa.c_keys = norm->keys.p;
         sa.c_vals = norm->vals_f32.p;
         sa.col_ids = d_cols.p;
-        sa.n_cols = (uint32_t)cols.size();
         sa.dim = dim;
-        sa.split = nm;
         sa.sim = sim;
-        sa.out = d_sums2.p;
-        launch_pair<PK_SILSUM>(ctx, sa, "k6_pair_silhouette");
+        sa.ld = nm;
+        // column passes of at most PT_TILE_BUDGET bytes of [column][member] similarities; the row
+        // sums continue from pass to pass, so the f32 addition order is the member order
+        const uint32_t n_cols_all = (uint32_t)cols.size();
+        uint32_t pass_cols = (uint32_t)std::min<uint64_t>(n_cols_all, std::max<uint64_t>(8, PT_TILE_BUDGET / (4ull * nm) / 8 * 8));
+        DevBuf<float> d_sil_tile((size_t)pass_cols * nm);
+        sa.out = d_sil_tile.p;
+        for (uint32_t cf = 0; cf < n_cols_all; cf += pass_cols) {
+            sa.c_first = cf;
+            sa.n_cols = std::min(pass_cols, n_cols_all - cf);
+            launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
+            MYRIO_LAUNCH(ctx, "k6_silsum_rows", silsum_rows_kernel, (nm + 127) / 128, 128, 0, d_sil_tile.p,
+                         (uint64_t)nm, nm, cf, sa.n_cols, nm, d_sums2.p);
+        }
         std::vector<float> sums((size_t)nm * 2);
         d2h(ctx, sums.data(), d_sums2.p, sums.size());
         sync(ctx);
@@ -644,11 +840,9 @@ void pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols, 
     if (mk < 16384) {
         uint32_t dim = 16;
         while (dim <= mk) dim <<= 2;
+        RowSlab slab;
+        build_row_slab(ctx, rows->row_off.p, rows->keys.p, rows->vals_f32.p, nullptr, (uint32_t)nr, slab);
         PairArgs a{};
-        a.r_off = rows->row_off.p;
-        a.r_keys = rows->keys.p;
-        a.r_vals = rows->vals_f32.p;
-        a.n_rows = (uint32_t)nr;
         a.c_off = cols->row_off.p;
         a.c_keys = cols->keys.p;
         a.c_vals = cols->vals_f32.p;
@@ -656,7 +850,8 @@ void pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols, 
         a.dim = dim;
         a.sim = sim;
         a.out = d_out.p;
-        launch_pair<PK_STORE>(ctx, a, "k6_pair_store");
+        a.ld = ncol;
+        launch_pair_tile<false>(ctx, a, slab, "k6_pair_store");
     } else {
         const uint64_t np = nr * ncol;
         MYRIO_LAUNCH(ctx, "k6_pair_merge", pair_merge_kernel, (unsigned)((np + 127) / 128), 128, 0,
