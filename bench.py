@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--tile-leaves", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clustering", action="store_true", help="skip the clustering stage (K6) measurement")
+    ap.add_argument("--clusters", type=int, default=4)
     return ap.parse_args()
 
 
@@ -148,6 +150,70 @@ def traffic_from_profiles():
                 except Exception:
                     pass
     return best
+
+
+# ------------------------------------------------------------- clustering stage (K6)
+
+SMEM_BYTES_PER_CLK_PER_SM = 128.0  # shared-memory bandwidth of one SM (32 banks x 4 B)
+
+
+def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu_seconds=0.0):
+    """Stage 3 of the hot path: clustering::cluster (clustering.rs:55-270) on the whole read batch at
+    the reference defaults (k=6, t1=0.2, t2=20), first without and then with silhouette trimming
+    (ssdcf 1.4, config_default.toml:30) -- the O(N^2) reads x reads similarity.  Kernel times are CUDA
+    events on the library's stream; the pair / term counts are exact (myrio_cluster_stats)."""
+    out = {"workload": f"cluster() k=6 t1=0.2 t2=20 on {resident.n} reads, {n_clusters} clusters "
+                       f"(farthest-point fill), cosine; then the same with silhouette trimming 1.4"}
+    for name, sil in (("assign_only", None), ("with_silhouette", 1.4)):
+        prm = api.ClusteringParameters(k=6, t1=0.2, t2=20, expected_nb_of_clusters=n_clusters,
+                                       silhouette_trimming=sil)
+        api.cluster(resident, prm)  # warm-up (allocator pool, kernel attributes)
+        ctx.prof_reset()
+        ctx.prof_enable(True)
+        t0 = time.perf_counter()
+        res = api.cluster(resident, prm)
+        call_s = time.perf_counter() - t0
+        st = ctx.cluster_stats()
+        tile_ms = sum(ctx.prof_query(p)[0] for p in ("k6_pair_", "k6_silsum", "k6_argmax"))
+        sil_ms = ctx.prof_query("k6_pair_silhouette")[0]
+        all_ms, n_launch = ctx.prof_query("")
+        ctx.prof_enable(False)
+        ctx.prof_reset()
+        d = {"call_ms": call_s * 1e3, "kernels_ms": all_ms, "k6_tile_kernels_ms": tile_ms, "gpu_launches": n_launch,
+             "iters": res.n_iters, "cluster_sizes": [int(len(c)) for c in res.clusters],
+             "rejected": int(len(res.rejected)), "pair_similarities": st["pair_similarities"],
+             "terms": st["terms"], "pair_similarities_per_s": st["pair_similarities"] / max(call_s, 1e-9)}
+        if sil is not None and sil_ms > 0:
+            # dominant kernel of the stage: pair_tile_kernel.  Every multiply-add term reads one f32 of a
+            # column from shared memory (4 B); the bound is the SMs' shared-memory bandwidth.
+            peak = 148 * SMEM_BYTES_PER_CLK_PER_SM * (sm_mhz or 1965.0) * 1e6 / 1e9
+            ach = 4.0 * st["terms"] / (sil_ms * 1e-3) / 1e9
+            d["roofline"] = {"bound": "shared-memory bandwidth", "kernel": "k6_pair_silhouette (pair_tile_kernel<8, transposed>)",
+                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                             "kernel_ms": sil_ms, "terms_per_s": st["terms"] / (sil_ms * 1e-3),
+                             "peak_source": "148 SMs x 128 B/clk x SM clock under load (nvidia-smi)",
+                             "note": "algorithmic bytes = 4 B (one column value) per multiply-add term; bank conflicts "
+                                     "of the per-thread random-key LDS.128 are the loss (profiles/r01_k6_tile_ncu_summary.json)"}
+        out[name] = d
+    if cpu_reads is not None and cpu_seconds > 0:
+        import oracle
+        threads = oracle.max_threads()
+        n = 256
+        oc = oracle.count_reads(cpu_reads.codes, cpu_reads.qual, cpu_reads.base_off, 6, 0.2)
+        on = oracle.normalize(oc, threads)
+        rows = oracle.Csr(on.row_off[:n + 1], on.keys[:int(on.row_off[n])], on.vals[:int(on.row_off[n])])
+        t0 = time.perf_counter()
+        oracle.pairwise(rows, on, threads=threads)
+        dt = max(time.perf_counter() - t0, 1e-9)
+        reps = int(max(1, min(20, cpu_seconds / dt)))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            oracle.pairwise(rows, on, threads=threads)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": reps * n * on.n_rows / dt, "unit": "pair similarities/s", "cores": threads,
+                               "kind": "port", "sample": f"{reps} x ({n} x {on.n_rows}) read x read merge-join dots at k=6, "
+                                                         f"{threads} OpenMP threads"}
+    return out
 
 
 # ------------------------------------------------------------- CPU arms
@@ -397,6 +463,14 @@ def run_ours(args, rank, local_rank, world):
                                "k4a_plan": k4a_ms / args.steps,
                                "k5_topx_merge_tiles": k5_ms / args.steps, "all_kernels": all_ms / args.steps},
     }
+
+    # ---- stage 3 (clustering), N=1 only: not part of `value`, reported beside it
+    if world == 1 and not args.no_clustering:
+        cpu_reads = None
+        if not args.no_cpu_baseline:
+            cpu_reads = reads.subset(np.arange(min(reads.n, 4096)))
+        line["clustering"] = bench_clustering(ctx, api, resident, args.clusters,
+                                              (clocks or {}).get("sm_mhz"), cpu_reads, min(args.cpu_seconds, 5.0))
 
     # ---- CPU baseline: the oracle on the host cores, rank 0, N=1 only, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

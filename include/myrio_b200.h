@@ -220,6 +220,10 @@ int32_t myrio_compute_cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts
 int32_t myrio_pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols,
                        int32_t similarity, float *out);
 
+/* exact algorithmic work of the last myrio_cluster / myrio_pairwise call: similarities
+ * computed (rows x columns over all K6 tiles) and multiply-add terms (row entries x columns) */
+int32_t myrio_cluster_stats(myrio_ctx *ctx, uint64_t *n_pair_similarities, uint64_t *n_terms);
+
 /* device pointers of a batch, for zero-copy interop (torch / NCCL plumbing) */
 int32_t myrio_svecs_device_ptrs(const myrio_svecs *v, const uint64_t **row_off,
                                 const uint64_t **keys, const void **vals, const void **aux);

@@ -24,7 +24,7 @@ SYMBOLS = [
     "myrio_svecs_normalize", "myrio_svecs_free", "myrio_index_build", "myrio_index_info",
     "myrio_index_export_tile", "myrio_index_free", "myrio_score_all", "myrio_score_topx",
     "myrio_score_topx_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
-    "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_svecs_device_ptrs",
+    "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_cluster_stats", "myrio_svecs_device_ptrs",
 ]
 
 
@@ -103,6 +103,7 @@ def load() -> C.CDLL:
     L.myrio_cluster.argtypes = [vp, vp, P(ClusterParams), vp, vp, P(u32), vp]
     L.myrio_compute_cluster_centroid.argtypes = [vp, vp, vp, u64, P(vp)]
     L.myrio_pairwise.argtypes = [vp, vp, vp, i32, vp]
+    L.myrio_cluster_stats.argtypes = [vp, P(u64), P(u64)]
     for name in SYMBOLS:
         f = getattr(L, name)
         if name not in ("myrio_last_error", "myrio_ctx_destroy", "myrio_ctx_launch_count", "myrio_seqs_free",

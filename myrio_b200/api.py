@@ -72,6 +72,12 @@ class Context:
         return {"query_keys": int(a.value), "key_hits": int(b.value), "postings_touched": int(c.value)}
 
 
+    def cluster_stats(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _lib.check(self._L.myrio_cluster_stats(self.h, C.byref(a), C.byref(b)))
+        return {"pair_similarities": int(a.value), "terms": int(b.value)}
+
+
 class SFVecs:
     """Device-resident batch of SparseVec<T> (myrio_svecs): row r is one sorted
     (usize key, value) vector -- SFVec for f32, SparseVec<u16> for leaf counts."""

@@ -440,4 +440,12 @@ int32_t myrio_pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svec
     });
 }
 
+int32_t myrio_cluster_stats(myrio_ctx *ctx, uint64_t *n_pair_similarities, uint64_t *n_terms) {
+    return guarded([&] {
+        if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
+        if (n_pair_similarities) *n_pair_similarities = ctx->cluster_stats[0];
+        if (n_terms) *n_terms = ctx->cluster_stats[1];
+    });
+}
+
 }  // extern "C"

@@ -39,12 +39,15 @@ struct RowSlab {
     DevBuf<float> vals;
     DevBuf<uint32_t> grp_len;  // per group: entries per row / 4 (padded)
     DevBuf<uint64_t> grp_off;  // per group: first quad of the group
+    DevBuf<unsigned long long> d_nnz;
     uint32_t n_rows = 0, n_groups = 0;
+    uint64_t nnz = 0;  // entries of the packed rows (without padding)
 };
 
 __global__ void __launch_bounds__(256) slab_count_kernel(const uint64_t *__restrict__ r_off,
                                                          const uint32_t *__restrict__ row_ids, uint32_t n_rows,
-                                                         uint32_t n_groups, uint32_t *__restrict__ grp_len) {
+                                                         uint32_t n_groups, uint32_t *__restrict__ grp_len,
+                                                         unsigned long long *__restrict__ nnz) {
     const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n_groups) return;
     const unsigned lane = threadIdx.x & 31;
@@ -54,9 +57,16 @@ __global__ void __launch_bounds__(256) slab_count_kernel(const uint64_t *__restr
         const uint32_t r = row_ids ? row_ids[ri] : ri;
         len = (uint32_t)(r_off[r + 1] - r_off[r]);
     }
+    uint32_t sum = len;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
-    if (lane == 0) grp_len[g] = (len + 3) >> 2;
+    for (int d = 16; d > 0; d >>= 1) {
+        len = max(len, __shfl_xor_sync(0xffffffffu, len, d));
+        sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    }
+    if (lane == 0) {
+        grp_len[g] = (len + 3) >> 2;
+        atomicAdd(nnz, (unsigned long long)sum);
+    }
 }
 
 __global__ void __launch_bounds__(256) slab_fill_kernel(const uint64_t *__restrict__ r_off,
@@ -101,13 +111,18 @@ static void build_row_slab(myrio_ctx *ctx, const uint64_t *r_off, const uint64_t
     if (s.n_groups == 0) return;
     s.grp_len.alloc(s.n_groups);
     s.grp_off.alloc(s.n_groups + 1);
+    s.d_nnz.alloc(1);
+    MYRIO_CK(cudaMemsetAsync(s.d_nnz.p, 0, sizeof(unsigned long long), ctx->stream));
     const unsigned grid = (s.n_groups + 7) / 8;
     MYRIO_LAUNCH(ctx, "k6_slab_count", slab_count_kernel, grid, 256, 0, r_off, row_ids, n_rows, s.n_groups,
-                 s.grp_len.p);
+                 s.grp_len.p, s.d_nnz.p);
     exclusive_scan_u32_to_u64(ctx, s.grp_len.p, s.grp_off.p, s.n_groups);
     uint64_t quads = 0;
+    unsigned long long h_nnz = 0;
     d2h(ctx, &quads, s.grp_off.p + s.n_groups, 1);
+    d2h(ctx, &h_nnz, s.d_nnz.p, 1);
     sync(ctx);
+    s.nnz = h_nnz;
     s.keys.alloc(std::max<uint64_t>(quads, 1) * 128);
     s.vals.alloc(std::max<uint64_t>(quads, 1) * 128);
     MYRIO_LAUNCH(ctx, "k6_slab_fill", slab_fill_kernel, grid, 256, 0, r_off, r_keys, r_vals, row_ids, n_rows,
@@ -155,8 +170,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_kernel(PairArgs a) {
     for (uint32_t i = tid; i < plane * NP; i += PT_THREADS) col_sm[i] = 0.0f;
     uint32_t staged = 0xFFFFFFFFu;
 
+    // slice-major task order: at any time all CTAs walk the SAME slice of the row slab (sized to stay
+    // L2-resident), each against its own column chunk
     for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
-        const uint32_t chunk = task / a.n_slices, slice = task % a.n_slices;
+        const uint32_t slice = task / n_chunks, chunk = task % n_chunks;
         const uint32_t c0 = chunk * CB;
         const uint32_t nc = min((uint32_t)CB, a.n_cols - c0);
         if (chunk != staged) {
@@ -168,21 +185,31 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_kernel(PairArgs a) {
                         c < nc ? a.c_dense[(size_t)(a.c_first + c0 + c) * a.dim + key] : 0.0f;
                 }
             } else {
-                if (staged != 0xFFFFFFFFu) {  // un-stage: sparse columns only touch their own entries
-                    const uint32_t p0 = staged * CB, pn = min((uint32_t)CB, a.n_cols - p0);
-                    for (uint32_t c = warp; c < pn; c += PT_WARPS) {
-                        const uint32_t cr = a.col_ids ? a.col_ids[a.c_first + p0 + c] : (a.c_first + p0 + c);
-                        const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
-                        for (uint64_t j = b + lane; j < e; j += 32)
-                            col_sm[(c / VW) * plane + (uint32_t)a.c_keys[j] * VW + (c % VW)] = 0.0f;
-                    }
+                if (staged != 0xFFFFFFFFu) {  // un-stage: zero the planes (16-byte stores, ~1k cycles)
+                    float4 *z = reinterpret_cast<float4 *>(col_sm);
+                    for (uint32_t i = tid; i < plane * NP / 4; i += PT_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     __syncthreads();
                 }
-                for (uint32_t c = warp; c < nc; c += PT_WARPS) {
+                // PT_WARPS / CB warps per column, four independent loads in flight per lane
+                constexpr uint32_t WPC = PT_WARPS / CB, LPC = WPC * 32;
+                const uint32_t c = warp / WPC, l = (warp % WPC) * 32 + lane;
+                if (c < nc) {
                     const uint32_t cr = a.col_ids ? a.col_ids[a.c_first + c0 + c] : (a.c_first + c0 + c);
                     const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
-                    for (uint64_t j = b + lane; j < e; j += 32)
-                        col_sm[(c / VW) * plane + (uint32_t)a.c_keys[j] * VW + (c % VW)] = a.c_vals[j];
+                    float *dst = col_sm + (c / VW) * plane + (c % VW);
+                    for (uint64_t j = b + l; j < e; j += 4 * LPC) {
+                        uint32_t kk[4];
+                        float vv[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint64_t jj = j + (uint64_t)u * LPC;
+                            kk[u] = jj < e ? (uint32_t)a.c_keys[jj] : 0xFFFFFFFFu;
+                            vv[u] = jj < e ? a.c_vals[jj] : 0.0f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (kk[u] != 0xFFFFFFFFu) dst[kk[u] * VW] = vv[u];
+                    }
                 }
             }
             staged = chunk;
@@ -332,6 +359,15 @@ __global__ void __launch_bounds__(128) pair_merge_kernel(const uint64_t *__restr
     out[p] = pk_sim(sim, acc);
 }
 
+static uint64_t pt_slice_bytes() {  // MYRIO_K6_SLICE_MB overrides (tuning)
+    static const uint64_t v = [] {
+        const char *e = getenv("MYRIO_K6_SLICE_MB");
+        const long mb = e ? atol(e) : 0;
+        return (uint64_t)(mb > 0 ? mb : 32) << 20;
+    }();
+    return v;
+}
+
 // rows x columns [c_first, c_first + n_cols) -> tile (transposed [col][ld] or row-major [row][ld])
 template <bool TRANSPOSED>
 static void launch_pair_tile(myrio_ctx *ctx, PairArgs a, const RowSlab &s, const char *name) {
@@ -342,11 +378,16 @@ static void launch_pair_tile(myrio_ctx *ctx, PairArgs a, const RowSlab &s, const
     a.grp_off = s.grp_off.p;
     a.n_rows = s.n_rows;
     a.n_groups = s.n_groups;
+    ctx->cluster_stats[0] += (uint64_t)s.n_rows * a.n_cols;  // pair similarities
+    ctx->cluster_stats[1] += s.nnz * a.n_cols;               // row entries x columns = multiply-add terms
     const uint32_t cb = a.dim <= 4096 ? 8 : 2;
     const uint32_t n_chunks = (a.n_cols + cb - 1) / cb;
-    // enough (chunk, slice) tasks for two rounds of the persistent grid, at least one warp-round per slice
+    // row slices: (a) small enough that a slice of the slab stays L2-resident while every CTA streams
+    // it once per column chunk, (b) enough (chunk, slice) tasks for two rounds of the persistent grid
+    const uint64_t slab_bytes = (uint64_t)s.keys.n * 2 + (uint64_t)s.vals.n * 4;
+    uint32_t n_slices = (uint32_t)((slab_bytes + pt_slice_bytes() - 1) / pt_slice_bytes());
     const uint32_t want = 2u * (uint32_t)ctx->sm_count;
-    uint32_t n_slices = n_chunks >= want ? 1u : (want + n_chunks - 1) / n_chunks;
+    if ((uint64_t)n_chunks * n_slices < want) n_slices = (want + n_chunks - 1) / n_chunks;
     n_slices = std::max(1u, std::min(n_slices, (s.n_groups + PT_WARPS - 1) / PT_WARPS));
     a.n_slices = n_slices;
     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)n_chunks * n_slices, (uint64_t)ctx->sm_count);
@@ -451,6 +492,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     const uint32_t dim = 1u << (2 * p->k);
     const int sim = p->similarity;
     if (n_iters) *n_iters = 0;
+    ctx->cluster_stats[0] = ctx->cluster_stats[1] = 0;
 
     // Step 1 (clustering.rs:78-90)
     std::unique_ptr<myrio_svecs> counts(count_reads(ctx, reads, p->k, p->t1));
@@ -833,6 +875,7 @@ void pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols, 
     if (sim != MYRIO_SIM_COSINE && sim != MYRIO_SIM_JACARD_TANIMOTO)
         fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path", sim);
     const uint64_t nr = rows->n_rows, ncol = cols->n_rows;
+    ctx->cluster_stats[0] = ctx->cluster_stats[1] = 0;
     if (nr == 0 || ncol == 0) return;
     if (nr > 0xFFFFFFFFull || ncol > 0xFFFFFFFFull) fail(MYRIO_ERR_BAD_ARG, "too many rows/cols");
     const uint64_t mk = std::max(max_key_of(ctx, rows), max_key_of(ctx, cols));

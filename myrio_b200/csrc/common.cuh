@@ -138,6 +138,7 @@ struct myrio_ctx {
     myrio::DevBuf<uint32_t> topx_cand_cnt, topx_gthr;
     void *plan = nullptr;  // myrio::Plan (score.cu): hit-list scratch, grow-only
     uint64_t last_stats[3] = {0, 0, 0};
+    uint64_t cluster_stats[2] = {0, 0};  // pair similarities, multiply-add terms of the last K6 call
     // pinned staging for small D2H reads
     void *pinned = nullptr;
     size_t pinned_bytes = 0;

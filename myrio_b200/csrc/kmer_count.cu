@@ -20,7 +20,8 @@
 
 namespace myrio {
 
-static constexpr int KC_THREADS = 256;
+static constexpr int KC_THREADS = 256;  // largest CTA; small size classes launch fewer threads (kc_threads_for)
+static constexpr int KC_BUCKETS = 256;
 
 static const uint32_t h_phred_bits[128] = {
 #include "phred_table.inc"
@@ -62,16 +63,17 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v) {
     return v;
 }
 
-// block-wide exclusive scan of one u32 per thread (KC_THREADS threads); wbuf: 33 u32
+// block-wide exclusive scan of one u32 per thread (blockDim.x threads, a multiple of 32); wbuf: 33 u32
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *wbuf, uint32_t *total) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inc = warp_incl_scan_u32(v);
     if (lane == 31) wbuf[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = lane < (KC_THREADS / 32) ? wbuf[lane] : 0;
+        const unsigned nw = blockDim.x >> 5;
+        uint32_t w = lane < nw ? wbuf[lane] : 0;
         uint32_t wi = warp_incl_scan_u32(w);
-        if (lane < (KC_THREADS / 32)) wbuf[lane] = wi - w;
+        if (lane < nw) wbuf[lane] = wi - w;
         if (lane == 31) wbuf[32] = wi;
     }
     __syncthreads();
@@ -87,7 +89,7 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *keys, uint16_t *w, uint32
     for (uint32_t size = 2; size <= S; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
-            for (uint32_t t = threadIdx.x; t < (S >> 1); t += KC_THREADS) {
+            for (uint32_t t = threadIdx.x; t < (S >> 1); t += blockDim.x) {
                 uint32_t lo = 2u * t - (t & (stride - 1u));
                 uint32_t hi = lo + stride;
                 bool asc = (lo & size) == 0u;
@@ -115,27 +117,43 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *keys, uint16_t *w, uint32
 // sequence); the caller then falls back to the bitonic network.
 __device__ __forceinline__ bool bucket_sort(uint64_t *keys, uint64_t *keys2, uint32_t E, uint32_t key_bits,
                                             uint32_t *s_hist, uint32_t *s_start, uint32_t *wbuf) {
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, T = blockDim.x;
+    const uint32_t BPT = KC_BUCKETS / T;  // buckets per thread (T is 64, 128 or 256)
     const uint32_t shift = key_bits > 8 ? key_bits - 8 : 0;
-    s_hist[tid] = 0;
+    for (uint32_t b = tid; b < KC_BUCKETS; b += T) s_hist[b] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < E; i += KC_THREADS) atomicAdd(&s_hist[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    for (uint32_t i = tid; i < E; i += T) atomicAdd(&s_hist[(uint32_t)(keys[i] >> shift) & 255u], 1u);
     __syncthreads();
-    const uint32_t c = s_hist[tid];
+    // thread t owns the contiguous buckets [t*BPT, (t+1)*BPT)
+    uint32_t c = 0, cmax = 0;
+    for (uint32_t j = 0; j < BPT; ++j) {
+        const uint32_t cj = s_hist[tid * BPT + j];
+        c += cj;
+        cmax = max(cmax, cj);
+    }
     uint32_t total;
     const uint32_t start = block_excl_scan_u32(c, wbuf, &total);
-    const int too_big = __syncthreads_or(c > 32u);
+    const int too_big = __syncthreads_or(cmax > 32u);
     if (too_big) return false;
-    s_start[tid] = start;
-    if (tid == KC_THREADS - 1) s_start[KC_THREADS] = E;
-    s_hist[tid] = 0;  // becomes the per-bucket cursor
+    {
+        uint32_t run = start;
+        for (uint32_t j = 0; j < BPT; ++j) {
+            const uint32_t cj = s_hist[tid * BPT + j];
+            s_start[tid * BPT + j] = run;
+            s_hist[tid * BPT + j] = 0;  // becomes the per-bucket cursor
+            run += cj;
+        }
+    }
+    if (tid == T - 1) s_start[KC_BUCKETS] = E;
     __syncthreads();
-    for (uint32_t i = tid; i < E; i += KC_THREADS) {
+    for (uint32_t i = tid; i < E; i += T) {
         const uint64_t key = keys[i];
         const uint32_t d = (uint32_t)(key >> shift) & 255u;
         keys2[s_start[d] + atomicAdd(&s_hist[d], 1u)] = key;
     }
     __syncthreads();
+    // insertion sort of the thread's own range: buckets are already in order, so an element never
+    // moves below the start of its bucket and one pass over [start, start + c) sorts them all
     {
         const uint32_t b = start, e = start + c;
         for (uint32_t i = b + 1; i < e; ++i) {
@@ -149,7 +167,7 @@ __device__ __forceinline__ bool bucket_sort(uint64_t *keys, uint64_t *keys2, uin
         }
     }
     __syncthreads();
-    for (uint32_t i = tid; i < E; i += KC_THREADS) keys[i] = keys2[i];
+    for (uint32_t i = tid; i < E; i += T) keys[i] = keys2[i];
     __syncthreads();
     return true;
 }
@@ -167,7 +185,7 @@ __device__ __forceinline__ uint32_t pow2_ceil(uint32_t v) {
 // Each thread owns a contiguous chunk so the scan keeps the order.
 __device__ __forceinline__ uint32_t find_run_heads(const uint64_t *keys, uint32_t E,
                                                    uint32_t *headpos, uint32_t *wbuf) {
-    const uint32_t C = (E + KC_THREADS - 1) / KC_THREADS;
+    const uint32_t C = (E + blockDim.x - 1) / blockDim.x;
     const uint32_t b = min(E, threadIdx.x * C), e = min(E, b + C);
     uint32_t cnt = 0;
     for (uint32_t i = b; i < e; ++i) cnt += (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
@@ -214,7 +232,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
     __shared__ float s_phred[128];
     __shared__ uint32_t s_wbuf[33];
     __shared__ uint32_t s_cnt;
-    __shared__ uint32_t s_hist[KC_THREADS], s_start[KC_THREADS + 1];
+    __shared__ uint32_t s_hist[KC_BUCKETS], s_start[KC_BUCKETS + 1];
 
     uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
     uint64_t *keys = reinterpret_cast<uint64_t *>(work);
@@ -229,7 +247,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
     const uint32_t n = (uint32_t)(a.base_off[r + 1] - b0);
     const uint32_t k = a.k;
 
-    if (tid < 128) s_phred[tid] = g_phred[tid];
+    for (uint32_t i = tid; i < 128; i += blockDim.x) s_phred[i] = g_phred[i];
     if (tid == 0) s_cnt = 0;
     if (n < k) {  // kmers::<K>() yields nothing
         if (tid == 0) {
@@ -246,7 +264,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
         const uint32_t nw = (n + 31) >> 5;
         const uint4 *src = reinterpret_cast<const uint4 *>(a.words + w0);
         uint4 *dst = reinterpret_cast<uint4 *>(words);
-        for (uint32_t i = tid; i < (nw + 1) / 2; i += KC_THREADS) dst[i] = __ldg(src + i);
+        for (uint32_t i = tid; i < (nw + 1) / 2; i += blockDim.x) dst[i] = __ldg(src + i);
         if (tid == 0) {  // window_key may touch one word past the end
             words[((nw + 1) / 2) * 2] = 0;
         }
@@ -259,7 +277,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
         const uint4 *q4 = reinterpret_cast<const uint4 *>(qp - mis);
         const uint32_t nchunks = (mis + n + 15) >> 4;
         bool bad = false;
-        for (uint32_t c = tid; c < nchunks; c += KC_THREADS) {
+        for (uint32_t c = tid; c < nchunks; c += blockDim.x) {
             uint4 v = __ldg(q4 + c);
             uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -278,7 +296,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
 
     // windows: confidence = product of k factors (sequential f32, as the reference);
     // every passing window emits its key and its reverse complement's key
-    for (uint32_t base = 0; base < nb; base += KC_THREADS) {
+    for (uint32_t base = 0; base < nb; base += blockDim.x) {
         const uint32_t i = base + tid;
         bool pass = false;
         uint64_t kf = 0, kr = 0;
@@ -316,14 +334,14 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
     }
     if (!(has_bucket_buffer(a.ecap) && bucket_sort(keys, keys2, E, 2u * k, s_hist, s_start, s_wbuf))) {
         const uint32_t S = pow2_ceil(E);
-        for (uint32_t i = E + tid; i < S; i += KC_THREADS) keys[i] = ~0ull;
+        for (uint32_t i = E + tid; i < S; i += blockDim.x) keys[i] = ~0ull;
         bitonic_sort<false>(keys, nullptr, S);
     }
 
     uint32_t *headpos = aux;  // conf factors are dead
     const uint32_t D = find_run_heads(keys, E, headpos, s_wbuf);
     const uint64_t o = a.eoff[r];
-    for (uint32_t idx = tid; idx < D; idx += KC_THREADS) {
+    for (uint32_t idx = tid; idx < D; idx += blockDim.x) {
         const uint32_t i = headpos[idx];
         const uint32_t nx = (idx + 1 < D) ? headpos[idx + 1] : E;
         a.skeys[o + idx] = keys[i];
@@ -399,7 +417,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     __shared__ uint32_t s_wbuf[33];
     __shared__ uint32_t s_cnt, s_namb, s_over;
     __shared__ uint32_t s_sum;
-    __shared__ uint32_t s_hist[KC_THREADS], s_start[KC_THREADS + 1];
+    __shared__ uint32_t s_hist[KC_BUCKETS], s_start[KC_BUCKETS + 1];
 
     uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
     size_t o_ = 0;
@@ -435,7 +453,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.words + a.word_off[r]);
         const uint32_t nchunks = (n_in + 31) >> 5;
-        for (uint32_t c = tid; c < nchunks; c += KC_THREADS) {
+        for (uint32_t c = tid; c < nchunks; c += blockDim.x) {
             uint4 v = __ldg(src + c);
             uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     // drop gaps (Iupac::X == 0), tax/mod.rs:98 -- ordered compaction
     uint32_t n;
     {
-        const uint32_t C = (n_in + KC_THREADS - 1) / KC_THREADS;
+        const uint32_t C = (n_in + blockDim.x - 1) / blockDim.x;
         const uint32_t b = min(n_in, tid * C), e = min(n_in, b + C);
         uint32_t cnt = 0, amb = 0;
         for (uint32_t i = b; i < e; ++i) {
@@ -479,7 +497,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
         // all resamples are identical: count once, scale by R (wrapping u16 like the
         // release-mode `+=` of from_unsorted_singles)
         const uint32_t nw = (n + 31) >> 5;
-        for (uint32_t wi = tid; wi <= nw; wi += KC_THREADS) {
+        for (uint32_t wi = tid; wi <= nw; wi += blockDim.x) {
             uint64_t w = 0;
             const uint32_t lim = min(32u, n > wi * 32 ? n - wi * 32 : 0u);
             for (uint32_t j = 0; j < lim; ++j)
@@ -487,7 +505,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
             words2[wi] = w;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < nb; i += KC_THREADS) {
+        for (uint32_t i = tid; i < nb; i += blockDim.x) {
             uint64_t kf = window_key(words2, i, k);
             keys[2 * i] = kf;
             keys[2 * i + 1] = revcomp_key(kf, k);
@@ -497,7 +515,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
         // prefix count of ambiguous symbols -> window i is ambiguous iff pre[i+k] > pre[i]
         uint32_t *pre = aux;
         {
-            const uint32_t C = (n + KC_THREADS - 1) / KC_THREADS;
+            const uint32_t C = (n + blockDim.x - 1) / blockDim.x;
             const uint32_t b = min(n, tid * C), e = min(n, b + C);
             uint32_t cnt = 0;
             for (uint32_t i = b; i < e; ++i) cnt += __popc((uint32_t)comp[i]) > 1;
@@ -507,10 +525,10 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
                 pre[i] = pos;
                 pos += __popc((uint32_t)comp[i]) > 1;
             }
-            if (tid == KC_THREADS - 1 || e == n) pre[n] = tot;
+            if (tid == blockDim.x - 1 || e == n) pre[n] = tot;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < nb; i += KC_THREADS) {
+        for (uint32_t i = tid; i < nb; i += blockDim.x) {
             const bool amb = pre[i + k] != pre[i];
             const uint32_t need = amb ? 2 * R : 2;
             const uint32_t slot = atomicAdd(&s_cnt, need);
@@ -549,7 +567,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     if (!(!ambiguous && has_bucket_buffer(a.ecap) &&
           bucket_sort(keys, keys2, E, 2u * k, s_hist, s_start, s_wbuf))) {
         const uint32_t S = pow2_ceil(E);
-        for (uint32_t i = E + tid; i < S; i += KC_THREADS) {
+        for (uint32_t i = E + tid; i < S; i += blockDim.x) {
             keys[i] = ~0ull;
             if (ambiguous) wts[i] = 0;
         }
@@ -563,7 +581,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     const uint32_t Dall = find_run_heads(keys, E, headpos, s_wbuf);
     // value per run, strip values <= cutoff (:130-134), ordered compaction of the survivors
     {
-        const uint32_t C = (Dall + KC_THREADS - 1) / KC_THREADS;
+        const uint32_t C = (Dall + blockDim.x - 1) / blockDim.x;
         const uint32_t b = min(Dall, tid * C), e = min(Dall, b + C);
         uint32_t kept = 0, sum = 0;
         // pass 1: count survivors of this thread's chunk
@@ -640,6 +658,18 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const uint64_t *__res
 
 static const uint32_t kSmemClasses[] = {1024, 2048, 4096, 8192, 16384};
 
+// threads per CTA for a sort capacity: the CTA's fixed costs (scans, barriers, idle lanes of short
+// loops) scale with its warps, so a ~500-key read gets 2-4 warps, not 8.  MYRIO_KC_THREADS=a,b
+// overrides the first two classes (tuning).
+static unsigned kc_threads_for(uint32_t ecap) {
+    static const int ov[2] = {[] { const char *e = getenv("MYRIO_KC_THREADS"); return e ? atoi(e) : 0; }(),
+                              [] { const char *e = getenv("MYRIO_KC_THREADS"); const char *c = e ? strchr(e, ',') : nullptr; return c ? atoi(c + 1) : 0; }()};
+    auto ok = [](int v) { return v == 64 || v == 128 || v == 256; };
+    if (ecap <= 1024) return ok(ov[0]) ? ov[0] : 128;  // measured: 64 / 128 / 256 threads = 1.23 / 1.02 / 1.07 ms (K1)
+    if (ecap <= 2048) return ok(ov[1]) ? ov[1] : 256;  // measured: 64 / 128 / 256 threads = 4.3 / 3.1 / 2.7 ms (K2)
+    return KC_THREADS;
+}
+
 template <typename KernelT>
 static void allow_smem(KernelT kernel, size_t bytes) {
     MYRIO_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -714,7 +744,7 @@ myrio_svecs *count_reads(myrio_ctx *ctx, const myrio_seqs *reads, uint32_t k, fl
             size_t smem = read_work_bytes(a.ecap);
             allow_smem(count_reads_kernel<false>, smem);
             MYRIO_LAUNCH(ctx, "k1_count_reads", count_reads_kernel<false>, (unsigned)cls[c].size(),
-                         KC_THREADS, smem, a);
+                         kc_threads_for(a.ecap), smem, a);
         } else {
             // sequences too long for shared memory: same algorithm on a global work area,
             // processed in waves to bound the scratch
@@ -820,7 +850,7 @@ myrio_svecs *count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k, 
             size_t smem = leaf_work_bytes(a.ecap);
             allow_smem(count_leaves_kernel<false>, smem);
             MYRIO_LAUNCH(ctx, "k2_count_leaves", count_leaves_kernel<false>, (unsigned)cls[c].size(),
-                         KC_THREADS, smem, a);
+                         kc_threads_for(a.ecap), smem, a);
         } else {
             a.ecap = host_pow2_ceil(max_cap);
             a.gstride = (leaf_work_bytes(a.ecap) + 255) / 256 * 256;

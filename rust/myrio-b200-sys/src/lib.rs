@@ -103,4 +103,5 @@ unsafe extern "C" {
                                           m: u64, out: *mut *mut myrio_svecs) -> i32;
     pub fn myrio_pairwise(ctx: *mut myrio_ctx, rows: *const myrio_svecs, cols: *const myrio_svecs, similarity: i32,
                           out: *mut f32) -> i32;
+    pub fn myrio_cluster_stats(ctx: *mut myrio_ctx, n_pair_similarities: *mut u64, n_terms: *mut u64) -> i32;
 }

@@ -13,6 +13,7 @@ ap.add_argument("--leaves", type=int, default=20_000)
 ap.add_argument("--clusters", type=int, default=4)
 ap.add_argument("--tile", type=int, default=8192)
 ap.add_argument("--only", default="tile,cluster,silhouette")
+ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 ctx = api.Context(0)
 tree = synth.make_tree(a.leaves, 1002, root_seed=1002)
@@ -22,7 +23,7 @@ only = a.only.split(",")
 if "tile" in only:
     sub = api.MyrSeqs(ctx, reads.subset(np.arange(min(a.tile, reads.n))))
     c6 = sub.compute_kmer_counts(6, 0.2).into_normalized_l2()
-    for rep in range(2):
+    for rep in range(a.reps):
         ctx.prof_reset(); ctx.prof_enable(True)
         t0 = time.perf_counter()
         out = api.pairwise(c6, c6)
@@ -34,7 +35,7 @@ if "tile" in only:
 for name, sil in (("cluster", None), ("silhouette", 1.4)):
     if name not in only:
         continue
-    for rep in range(2):
+    for rep in range(a.reps):
         ctx.prof_reset(); ctx.prof_enable(True)
         t0 = time.perf_counter()
         out = api.cluster(q, api.ClusteringParameters(k=6, t1=0.2, t2=20, expected_nb_of_clusters=a.clusters,
