@@ -184,6 +184,21 @@ int32_t myrio_score_topx_async(myrio_ctx *ctx, const myrio_index *ix, const myri
 int32_t myrio_topx_merge_async(myrio_ctx *ctx, const float *d_scores_in, const uint32_t *d_ids_in,
                                uint32_t n_parts, uint64_t q_count, uint32_t x, float *d_scores_out,
                                uint32_t *d_ids_out);
+/* Index-free scoring: the reference's own loop (tax/results.rs:82-93), one merge-join
+ * (data/sparse.rs:317-360, :143-221) per (leaf, query) pair over the normalised leaf vectors
+ * `leaf_vecs` (payload order).  Every Similarity is available here, including Overlap
+ * (similarity.rs:172-182), whose sum of maxima runs over the union of the keys and cannot be
+ * formed from an inverted index; Cosine / JacardTanimoto give the same bits as the index path.
+ * Outputs as myrio_score_all / myrio_score_topx(_async); ids are leaf_id_base + payload id. */
+int32_t myrio_score_all_direct(myrio_ctx *ctx, const myrio_svecs *leaf_vecs, const myrio_svecs *queries,
+                               uint64_t q_first, uint64_t q_count, int32_t similarity, float *scores);
+int32_t myrio_score_topx_direct(myrio_ctx *ctx, const myrio_svecs *leaf_vecs, uint32_t leaf_id_base,
+                                const myrio_svecs *queries, uint64_t q_first, uint64_t q_count, uint32_t x,
+                                int32_t similarity, float *top_scores, uint32_t *top_ids);
+int32_t myrio_score_topx_direct_async(myrio_ctx *ctx, const myrio_svecs *leaf_vecs, uint32_t leaf_id_base,
+                                      const myrio_svecs *queries, uint64_t q_first, uint64_t q_count,
+                                      uint32_t x, int32_t similarity, float *d_top_scores,
+                                      uint32_t *d_top_ids);
 /* exact algorithmic work of the last myrio_score_* call: sum over queries of
  * query keys, of (query key, tile) hits, and of postings touched (T_q) */
 int32_t myrio_score_stats(myrio_ctx *ctx, uint64_t *n_query_keys, uint64_t *n_key_hits,

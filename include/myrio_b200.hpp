@@ -250,11 +250,24 @@ class TaxTreeCompute {
         const int32_t rc = myrio_index_build(ttstore.ctx().get(), norm, 0, 0, &ix);
         myrio_svecs_free(norm);
         check(rc);
-        return TaxTreeCompute(ttstore.ctx(), ix, ttstore.n_leaves());
+        TaxTreeCompute out(ttstore.ctx(), ix, ttstore.n_leaves());
+        out.counts_ = ttstore.kmer_store_counts_vec[idx];
+        return out;
     }
-    TaxTreeCompute(TaxTreeCompute &&o) noexcept : ctx_(o.ctx_), h_(std::exchange(o.h_, nullptr)), n_(o.n_) {}
-    ~TaxTreeCompute() { myrio_index_free(h_); }
+    TaxTreeCompute(TaxTreeCompute &&o) noexcept
+        : ctx_(o.ctx_), h_(std::exchange(o.h_, nullptr)), n_(o.n_), counts_(o.counts_),
+          leaf_vecs_(std::exchange(o.leaf_vecs_, nullptr)) {}
+    ~TaxTreeCompute() {
+        myrio_index_free(h_);
+        if (leaf_vecs_) myrio_svecs_free(leaf_vecs_);
+    }
     myrio_index *get() const { return h_; }
+    // the reference's Box<[SFVec]> of normalised leaf vectors (tax/compute.rs:100-108), materialised
+    // only when a merge-join similarity (Overlap) needs them; the store must outlive this object
+    const myrio_svecs *leaf_vectors() const {
+        if (!leaf_vecs_) check(myrio_svecs_normalize(ctx_->get(), counts_, &leaf_vecs_));
+        return leaf_vecs_;
+    }
     size_t payloads_len() const { return n_; }
     const Context &ctx() const { return *ctx_; }
 
@@ -263,6 +276,8 @@ class TaxTreeCompute {
     const Context *ctx_;
     myrio_index *h_;
     size_t n_;
+    const myrio_svecs *counts_ = nullptr;
+    mutable myrio_svecs *leaf_vecs_ = nullptr;
 };
 
 // the scoring part of TaxTreeResults::from_compute_tree (tax/results.rs:82-93) and cut()
@@ -275,12 +290,23 @@ struct TaxTreeResults {
         SFVecs q = SFVecs::upload(ctx, {query});
         TaxTreeResults r;
         r.payloads.assign(ttcompute.payloads_len(), 0.0f);
-        check(myrio_score_all(ctx.get(), ttcompute.get(), q.get(), 0, 1, (int32_t)similarity, r.payloads.data()));
+        // Overlap sums maxima over the union of the keys (similarity.rs:172-182): merge-join over the
+        // leaf vectors like the reference; Cosine / JacardTanimoto run on the inverted index
+        const bool direct = similarity == Similarity::Overlap;
         std::vector<Float> ts(nb_best_analysis);
         std::vector<uint32_t> ti(nb_best_analysis);
-        if (nb_best_analysis)
-            check(myrio_score_topx(ctx.get(), ttcompute.get(), q.get(), 0, 1, (uint32_t)nb_best_analysis,
-                                   (int32_t)similarity, ts.data(), ti.data()));
+        if (direct) {
+            check(myrio_score_all_direct(ctx.get(), ttcompute.leaf_vectors(), q.get(), 0, 1, (int32_t)similarity,
+                                         r.payloads.data()));
+            if (nb_best_analysis)
+                check(myrio_score_topx_direct(ctx.get(), ttcompute.leaf_vectors(), 0, q.get(), 0, 1,
+                                              (uint32_t)nb_best_analysis, (int32_t)similarity, ts.data(), ti.data()));
+        } else {
+            check(myrio_score_all(ctx.get(), ttcompute.get(), q.get(), 0, 1, (int32_t)similarity, r.payloads.data()));
+            if (nb_best_analysis)
+                check(myrio_score_topx(ctx.get(), ttcompute.get(), q.get(), 0, 1, (uint32_t)nb_best_analysis,
+                                       (int32_t)similarity, ts.data(), ti.data()));
+        }
         for (size_t j = 0; j < nb_best_analysis; ++j)
             if (ti[j] != 0xFFFFFFFFu) r.best.emplace_back(ti[j], ts[j]);
         return r;

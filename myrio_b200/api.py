@@ -246,9 +246,20 @@ class TaxTreeStore:
 class TaxTreeCompute:
     """tax/compute.rs:13-20 -- the normalised leaf vectors, held as a tiled inverted index."""
 
-    def __init__(self, ctx, index_handle, n_leaves, leaf_id_base, leaf_vecs: SFVecs | None):
+    def __init__(self, ctx, index_handle, n_leaves, leaf_id_base, leaf_vecs: SFVecs | None,
+                 counts: SFVecs | None = None):
         self.ctx, self.h, self.n_leaves, self.leaf_id_base = ctx, index_handle, n_leaves, leaf_id_base
         self.leaf_vecs = leaf_vecs
+        self._counts = counts  # the store's cached counts: leaf vectors are re-derived on demand
+
+    def leaf_vectors(self) -> SFVecs:
+        """The reference's `Box<[SFVec]>` of L2-normalised leaf vectors (tax/compute.rs:100-108),
+        materialised only when a merge-join similarity (Overlap) needs them."""
+        if self.leaf_vecs is None:
+            if self._counts is None:
+                raise MyrioError(_lib.ERR_BAD_ARG, "this TaxTreeCompute was built without its leaf counts")
+            self.leaf_vecs = self._counts.into_normalized_l2()
+        return self.leaf_vecs
 
     def __del__(self):
         try:
@@ -283,7 +294,7 @@ class TaxTreeCompute:
         normalized = counts.into_normalized_l2()
         h = C.c_void_p()
         _lib.check(ctx._L.myrio_index_build(ctx.h, normalized.h, leaf_id_base, tile_leaves, C.byref(h)))
-        return cls(ctx, h, counts.n_rows, leaf_id_base, normalized if keep_leaf_vecs else None)
+        return cls(ctx, h, counts.n_rows, leaf_id_base, normalized if keep_leaf_vecs else None, counts)
 
     def info(self):
         a, b, c, d, e = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
@@ -316,19 +327,32 @@ class TaxTreeResults:
     @classmethod
     def from_compute_tree(cls, queries: SFVecs, ttcompute: TaxTreeCompute, similarity: int = SIM_COSINE,
                           nb_best_analysis: int = 100, *, q_first: int = 0, q_count: int | None = None,
-                          full_scores: bool = False) -> "TaxTreeResults":
+                          full_scores: bool = False, direct: bool = False) -> "TaxTreeResults":
         ctx = ttcompute.ctx
         q_count = queries.n_rows - q_first if q_count is None else q_count
         scores = ts = ti = None
+        # Overlap sums maxima over the UNION of the keys (similarity.rs:172-182): merge-join over the
+        # leaf vectors, like the reference; Cosine / JacardTanimoto run on the inverted index
+        direct = direct or similarity == SIM_OVERLAP
+        L = ctx._L
         if full_scores:
             scores = np.zeros((q_count, ttcompute.n_leaves), np.float32)
-            _lib.check(ctx._L.myrio_score_all(ctx.h, ttcompute.h, queries.h, q_first, q_count, similarity,
-                                              _p(scores)))
+            if direct:
+                _lib.check(L.myrio_score_all_direct(ctx.h, ttcompute.leaf_vectors().h, queries.h, q_first, q_count,
+                                                    similarity, _p(scores)))
+            else:
+                _lib.check(L.myrio_score_all(ctx.h, ttcompute.h, queries.h, q_first, q_count, similarity,
+                                             _p(scores)))
         if nb_best_analysis:
             ts = np.zeros((q_count, nb_best_analysis), np.float32)
             ti = np.zeros((q_count, nb_best_analysis), np.uint32)
-            _lib.check(ctx._L.myrio_score_topx(ctx.h, ttcompute.h, queries.h, q_first, q_count,
-                                               nb_best_analysis, similarity, _p(ts), _p(ti)))
+            if direct:
+                _lib.check(L.myrio_score_topx_direct(ctx.h, ttcompute.leaf_vectors().h, ttcompute.leaf_id_base,
+                                                     queries.h, q_first, q_count, nb_best_analysis, similarity,
+                                                     _p(ts), _p(ti)))
+            else:
+                _lib.check(L.myrio_score_topx(ctx.h, ttcompute.h, queries.h, q_first, q_count,
+                                              nb_best_analysis, similarity, _p(ts), _p(ti)))
         return cls(scores, ts, ti)
 
 

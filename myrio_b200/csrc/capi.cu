@@ -390,6 +390,43 @@ int32_t myrio_score_topx(myrio_ctx *ctx, const myrio_index *ix, const myrio_svec
     });
 }
 
+int32_t myrio_score_all_direct(myrio_ctx *ctx, const myrio_svecs *leaf_vecs, const myrio_svecs *queries,
+                               uint64_t q_first, uint64_t q_count, int32_t similarity, float *scores) {
+    return guarded([&] {
+        if (!ctx || !leaf_vecs || !queries || (!scores && q_count)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        score_all_direct(ctx, leaf_vecs, queries, q_first, q_count, similarity, scores);
+    });
+}
+
+int32_t myrio_score_topx_direct_async(myrio_ctx *ctx, const myrio_svecs *leaf_vecs, uint32_t leaf_id_base,
+                                      const myrio_svecs *queries, uint64_t q_first, uint64_t q_count,
+                                      uint32_t x, int32_t similarity, float *d_top_scores,
+                                      uint32_t *d_top_ids) {
+    return guarded([&] {
+        if (!ctx || !leaf_vecs || !queries || !d_top_scores || !d_top_ids) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        score_topx_direct_device(ctx, leaf_vecs, leaf_id_base, queries, q_first, q_count, x, similarity,
+                                 d_top_scores, d_top_ids);
+    });
+}
+
+int32_t myrio_score_topx_direct(myrio_ctx *ctx, const myrio_svecs *leaf_vecs, uint32_t leaf_id_base,
+                                const myrio_svecs *queries, uint64_t q_first, uint64_t q_count, uint32_t x,
+                                int32_t similarity, float *top_scores, uint32_t *top_ids) {
+    return guarded([&] {
+        if (!ctx || !leaf_vecs || !queries || !top_scores || !top_ids) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        DevBuf<float> ds(std::max<uint64_t>(q_count * x, 1));
+        DevBuf<uint32_t> di(std::max<uint64_t>(q_count * x, 1));
+        score_topx_direct_device(ctx, leaf_vecs, leaf_id_base, queries, q_first, q_count, x, similarity, ds.p,
+                                 di.p);
+        d2h(ctx, top_scores, ds.p, q_count * x);
+        d2h(ctx, top_ids, di.p, q_count * x);
+        sync(ctx);
+    });
+}
+
 int32_t myrio_topx_merge_async(myrio_ctx *ctx, const float *d_scores_in, const uint32_t *d_ids_in,
                                uint32_t n_parts, uint64_t q_count, uint32_t x, float *d_scores_out,
                                uint32_t *d_ids_out) {

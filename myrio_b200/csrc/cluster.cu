@@ -16,6 +16,7 @@
 #include "cluster.cuh"
 #include "index.cuh"
 #include "kmer_count.cuh"
+#include "merge.cuh"
 
 namespace myrio {
 
@@ -331,34 +332,6 @@ __global__ void __launch_bounds__(128) argmax_rows_kernel(const float *__restric
     idx_out[r] = best_idx;
 }
 
-// generic fallback for myrio_pairwise at large k: one thread per pair, two-pointer merge
-__global__ void __launch_bounds__(128) pair_merge_kernel(const uint64_t *__restrict__ r_off,
-                                                         const uint64_t *__restrict__ r_keys,
-                                                         const float *__restrict__ r_vals, uint32_t n_rows,
-                                                         const uint64_t *__restrict__ c_off,
-                                                         const uint64_t *__restrict__ c_keys,
-                                                         const float *__restrict__ c_vals, uint32_t n_cols,
-                                                         int sim, float *__restrict__ out) {
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= (uint64_t)n_rows * n_cols) return;
-    const uint32_t r = (uint32_t)(p / n_cols), c = (uint32_t)(p % n_cols);
-    uint64_t i = r_off[r], ie = r_off[r + 1], j = c_off[c], je = c_off[c + 1];
-    float acc = 0.0f;
-    while (i < ie && j < je) {
-        const uint64_t a = r_keys[i], b = c_keys[j];
-        if (a < b)
-            ++i;
-        else if (a > b)
-            ++j;
-        else {
-            acc = __fadd_rn(acc, __fmul_rn(r_vals[i], c_vals[j]));
-            ++i;
-            ++j;
-        }
-    }
-    out[p] = pk_sim(sim, acc);
-}
-
 static uint64_t pt_slice_bytes() {  // MYRIO_K6_SLICE_MB overrides (tuning)
     static const uint64_t v = [] {
         const char *e = getenv("MYRIO_K6_SLICE_MB");
@@ -475,6 +448,47 @@ static float host_sim(int sim, float dot) {
     return dot;
 }
 
+// similarity.rs:172-182 over dense vectors: a key absent from both contributes +0.0 to both sums
+static float host_dense_overlap(const float *a, const float *b, uint32_t dim) {
+    float sum_min = 0.0f, sum_max = 0.0f;
+    for (uint32_t k = 0; k < dim; ++k) {
+        sum_min = sum_min + fminf(a[k], b[k]);
+        sum_max = sum_max + fmaxf(a[k], b[k]);
+    }
+    const float s = sum_min / sum_max;
+    return std::isfinite(s) ? s : 0.0f;
+}
+
+static float host_dense_sim(int sim, const float *a, const float *b, uint32_t dim) {
+    if (sim == MYRIO_SIM_OVERLAP) return host_dense_overlap(a, b, dim);
+    return host_sim(sim, host_dense_dot(a, b, dim));
+}
+
+// dense centroid rows -> CSR with a fixed capacity of `dim` entries per row (one warp per row):
+// the merge-join kernel (Overlap) needs sparse columns
+__global__ void __launch_bounds__(32) dense_to_csr_kernel(const float *__restrict__ dense, uint32_t dim,
+                                                          uint64_t *__restrict__ off, uint64_t *__restrict__ end,
+                                                          uint64_t *__restrict__ keys, float *__restrict__ vals) {
+    const uint32_t c = blockIdx.x, lane = threadIdx.x;
+    const float *src = dense + (size_t)c * dim;
+    const uint64_t base = (uint64_t)c * dim;
+    uint32_t n = 0;
+    for (uint32_t k0 = 0; k0 < dim; k0 += 32) {
+        const float v = src[k0 + lane];
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0.0f);
+        if (v != 0.0f) {
+            const uint32_t pos = n + __popc(m & ((1u << lane) - 1u));
+            keys[base + pos] = k0 + lane;
+            vals[base + pos] = v;
+        }
+        n += __popc(m);
+    }
+    if (lane == 0) {
+        off[c] = base;
+        end[c] = base + n;
+    }
+}
+
 static uint64_t max_key_of(myrio_ctx *ctx, const myrio_svecs *v);
 
 void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *p,
@@ -485,8 +499,9 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     if (p->k < 2 || p->k > 32) fail(MYRIO_ERR_INVALID_K, "k=%u: only k in 2..32 is supported", p->k);
     if (p->k > 7)
         fail(MYRIO_ERR_UNSUPPORTED, "GPU clustering keeps 4^k dense columns in shared memory: k <= 7 (got %u)", p->k);
-    if (p->similarity != MYRIO_SIM_COSINE && p->similarity != MYRIO_SIM_JACARD_TANIMOTO)
-        fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path", p->similarity);
+    if (p->similarity != MYRIO_SIM_COSINE && p->similarity != MYRIO_SIM_JACARD_TANIMOTO &&
+        p->similarity != MYRIO_SIM_OVERLAP)
+        fail(MYRIO_ERR_BAD_ARG, "unknown similarity %d", p->similarity);
     if (init && init->vtype != MYRIO_VAL_F32) fail(MYRIO_ERR_BAD_ARG, "initial centroids must be f32");
     const uint64_t N = reads->n;
     const uint32_t dim = 1u << (2 * p->k);
@@ -567,19 +582,57 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     const float max_nb_hck = (float)max_hck;
     if (nc == 0) push_centroid_from_read(kept[max_idx]);
 
+    const bool merge_path = sim == MYRIO_SIM_OVERLAP;  // union-of-keys sums: merge-join kernel
     RowSlab slab;  // the kept reads (normalised), packed once for every reads x centroids pass
-    build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_kept.p, nk, slab);
+    if (!merge_path) build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_kept.p, nk, slab);
     PairArgs pa{};
     pa.c_dense = cen.p;
     pa.dim = dim;
     pa.sim = sim;
+    DevBuf<uint64_t> cs_off, cs_end, cs_keys;
+    DevBuf<float> cs_vals;
+    if (merge_path) {
+        cs_off.alloc(cmax);
+        cs_end.alloc(cmax);
+        cs_keys.alloc(cmax * dim);
+        cs_vals.alloc(cmax * dim);
+    }
+    // kept reads x current centroids -> tile (pa.out / pa.ld / pa.n_cols), transposed or row-major
+    auto centroid_tile = [&](bool transposed, const char *name) {
+        if (!merge_path) {
+            if (transposed)
+                launch_pair_tile<true>(ctx, pa, slab, name);
+            else
+                launch_pair_tile<false>(ctx, pa, slab, name);
+            return;
+        }
+        MYRIO_LAUNCH(ctx, "k6_dense_to_csr", dense_to_csr_kernel, pa.n_cols, 32, 0, cen.p, dim, cs_off.p, cs_end.p,
+                     cs_keys.p, cs_vals.p);
+        MergeArgs m{};
+        m.r_off = norm->row_off.p;
+        m.r_keys = norm->keys.p;
+        m.r_vals = norm->vals_f32.p;
+        m.row_ids = d_kept.p;
+        m.n_rows = nk;
+        m.c_off = cs_off.p;
+        m.c_end = cs_end.p;
+        m.c_keys = cs_keys.p;
+        m.c_vals = cs_vals.p;
+        m.n_cols = pa.n_cols;
+        m.sim = sim;
+        m.out = pa.out;
+        m.ld = pa.ld;
+        m.transposed = transposed;
+        ctx->cluster_stats[0] += (uint64_t)nk * pa.n_cols;
+        launch_merge_pairs(ctx, m, name);
+    };
 
     while (nc < p->expected_nb_of_clusters) {  // :114-129
         DevBuf<float> d_dots((size_t)nk * nc);
         pa.n_cols = nc;
         pa.out = d_dots.p;
         pa.ld = nc;
-        launch_pair_tile<false>(ctx, pa, slab, "k6_pair_store");
+        centroid_tile(false, "k6_pair_store");
         std::vector<float> dots((size_t)nk * nc);
         d2h(ctx, dots.data(), d_dots.p, dots.size());
         sync(ctx);
@@ -611,7 +664,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     pa.out = d_tile.p;
     pa.ld = nk;
     auto assign_pass = [&]() {
-        launch_pair_tile<true>(ctx, pa, slab, "k6_pair_argmax");
+        centroid_tile(true, "k6_pair_argmax");
         MYRIO_LAUNCH(ctx, "k6_argmax_rows", argmax_rows_kernel, (nk + 127) / 128, 128, 0, d_tile.p, (uint64_t)nk, nk,
                      nc, d_best.p, d_target.p);
     };
@@ -674,7 +727,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         float bs = 0.0f;
         for (uint32_t j = 0; j < nc; ++j) {
             if (j == c) continue;
-            const float s = host_sim(sim, host_dense_dot(&hcen[(size_t)c * dim], &hcen[(size_t)j * dim], dim));
+            const float s = host_dense_sim(sim, &hcen[(size_t)c * dim], &hcen[(size_t)j * dim], dim);
             if (nb == 0xFFFFFFFFu || s >= bs) {
                 bs = s;
                 nb = j;
@@ -689,7 +742,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         h2d(ctx, d_cols.p, cols.data(), cols.size());
         MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)nm * 2 * sizeof(float), ctx->stream));
         RowSlab mslab;  // the cluster's members as rows
-        build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, mslab);
+        if (!merge_path) build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, mslab);
         PairArgs sa{};
         sa.c_off = norm->row_off.p;
         sa.c_keys = norm->keys.p;
@@ -707,7 +760,28 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         for (uint32_t cf = 0; cf < n_cols_all; cf += pass_cols) {
             sa.c_first = cf;
             sa.n_cols = std::min(pass_cols, n_cols_all - cf);
-            launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
+            if (!merge_path) {
+                launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
+            } else {
+                MergeArgs m{};
+                m.r_off = norm->row_off.p;
+                m.r_keys = norm->keys.p;
+                m.r_vals = norm->vals_f32.p;
+                m.row_ids = d_rows.p;
+                m.n_rows = nm;
+                m.c_off = norm->row_off.p;
+                m.c_keys = norm->keys.p;
+                m.c_vals = norm->vals_f32.p;
+                m.col_ids = d_cols.p;
+                m.c_first = cf;
+                m.n_cols = sa.n_cols;
+                m.sim = sim;
+                m.out = d_sil_tile.p;
+                m.ld = nm;
+                m.transposed = true;
+                ctx->cluster_stats[0] += (uint64_t)nm * sa.n_cols;
+                launch_merge_pairs(ctx, m, "k6_pair_silhouette");
+            }
             MYRIO_LAUNCH(ctx, "k6_silsum_rows", silsum_rows_kernel, (nm + 127) / 128, 128, 0, d_sil_tile.p,
                          (uint64_t)nm, nm, cf, sa.n_cols, nm, d_sums2.p);
         }
@@ -872,15 +946,15 @@ static uint64_t max_key_of(myrio_ctx *ctx, const myrio_svecs *v) {
 void pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols, int32_t sim, float *out) {
     if (rows->vtype != MYRIO_VAL_F32 || cols->vtype != MYRIO_VAL_F32)
         fail(MYRIO_ERR_BAD_ARG, "pairwise needs f32 (pre-normalised) batches");
-    if (sim != MYRIO_SIM_COSINE && sim != MYRIO_SIM_JACARD_TANIMOTO)
-        fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path", sim);
+    if (sim != MYRIO_SIM_COSINE && sim != MYRIO_SIM_JACARD_TANIMOTO && sim != MYRIO_SIM_OVERLAP)
+        fail(MYRIO_ERR_BAD_ARG, "unknown similarity %d", sim);
     const uint64_t nr = rows->n_rows, ncol = cols->n_rows;
     ctx->cluster_stats[0] = ctx->cluster_stats[1] = 0;
     if (nr == 0 || ncol == 0) return;
     if (nr > 0xFFFFFFFFull || ncol > 0xFFFFFFFFull) fail(MYRIO_ERR_BAD_ARG, "too many rows/cols");
     const uint64_t mk = std::max(max_key_of(ctx, rows), max_key_of(ctx, cols));
     DevBuf<float> d_out(nr * ncol);
-    if (mk < 16384) {
+    if (mk < 16384 && sim != MYRIO_SIM_OVERLAP) {
         uint32_t dim = 16;
         while (dim <= mk) dim <<= 2;
         RowSlab slab;
@@ -896,10 +970,23 @@ void pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols, 
         a.ld = ncol;
         launch_pair_tile<false>(ctx, a, slab, "k6_pair_store");
     } else {
-        const uint64_t np = nr * ncol;
-        MYRIO_LAUNCH(ctx, "k6_pair_merge", pair_merge_kernel, (unsigned)((np + 127) / 128), 128, 0,
-                     rows->row_off.p, rows->keys.p, rows->vals_f32.p, (uint32_t)nr, cols->row_off.p,
-                     cols->keys.p, cols->vals_f32.p, (uint32_t)ncol, sim, d_out.p);
+        // Overlap (sum of maxima over the union of the keys) and key spaces too large for dense
+        // columns: the merge-join kernel
+        MergeArgs m{};
+        m.r_off = rows->row_off.p;
+        m.r_keys = rows->keys.p;
+        m.r_vals = rows->vals_f32.p;
+        m.n_rows = (uint32_t)nr;
+        m.c_off = cols->row_off.p;
+        m.c_keys = cols->keys.p;
+        m.c_vals = cols->vals_f32.p;
+        m.n_cols = (uint32_t)ncol;
+        m.sim = sim;
+        m.out = d_out.p;
+        m.ld = ncol;
+        m.transposed = false;
+        ctx->cluster_stats[0] += nr * ncol;
+        launch_merge_pairs(ctx, m, "k6_pair_merge");
     }
     d2h(ctx, out, d_out.p, nr * ncol);
     sync(ctx);

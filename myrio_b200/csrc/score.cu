@@ -14,6 +14,7 @@
 
 #include "index.cuh"
 #include "kmer_count.cuh"
+#include "merge.cuh"
 #include "score.cuh"
 
 namespace myrio {
@@ -917,6 +918,157 @@ void topx_merge_device(myrio_ctx *ctx, const float *d_scores_in, const uint32_t 
     MYRIO_CK(cudaFuncSetAttribute(topx_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MYRIO_LAUNCH(ctx, "k7_topx_merge", topx_merge_kernel, (unsigned)q_count, 256, smem, d_scores_in, d_ids_in,
                  n_parts, q_count, x, d_scores_out, d_ids_out);
+}
+
+// ------------------------------------------ direct (index-free) scoring
+
+// Exact top-x of one score row in global memory, one CTA per query: 4 x 8-bit radix select on the
+// f32 bit pattern (scores are >= +0), then the elements above the x-th best plus the first ties
+// by ascending id are gathered and sorted by the composite (score desc, payload_id asc) --
+// tax/results.rs:310-329.
+__global__ void __launch_bounds__(TX_THREADS) topx_rows_kernel(const float *__restrict__ rows, uint64_t L,
+                                                               uint32_t x, uint32_t id_base,
+                                                               float *__restrict__ out_s,
+                                                               uint32_t *__restrict__ out_i) {
+    __shared__ uint64_t buf[TX_MAX_X];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_warp[TX_THREADS / 32];
+    __shared__ uint32_t s_prefix, s_need, s_cursor, s_eq_base;
+    const size_t q = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t *row = reinterpret_cast<const uint32_t *>(rows + q * L);
+    const uint32_t take = (uint32_t)min((uint64_t)x, L);
+    uint32_t prefix = 0, need = take;
+    if (L > x) {
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            hist[tid] = 0;  // TX_THREADS == 256
+            __syncthreads();
+            for (uint64_t i = tid; i < L; i += TX_THREADS) {
+                const uint32_t b = row[i];
+                if (pass == 0 || (b >> (shift + 8)) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t run = 0, bin = 255;
+                for (;; --bin) {
+                    if (run + hist[bin] >= need || bin == 0) break;
+                    run += hist[bin];
+                }
+                s_prefix = (prefix << 8) | bin;
+                s_need = need - run;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            need = s_need;
+            __syncthreads();
+        }
+    }
+    const uint32_t T = prefix, need_eq = (L > x) ? need : 0xFFFFFFFFu;  // L <= x: everything is taken
+    if (tid == 0) {
+        s_cursor = 0;
+        s_eq_base = 0;
+    }
+    __syncthreads();
+    for (uint64_t base = 0; base < L; base += TX_THREADS) {
+        const uint64_t i = base + tid;
+        const bool valid = i < L;
+        const uint32_t b = valid ? row[i] : 0u;
+        const bool gt = valid && (L <= x || b > T);
+        const bool eq = valid && L > x && b == T;
+        // ties are taken in ascending id order: ordered block-wide count of the eq flags
+        const unsigned m_eq = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) s_warp[warp] = __popc(m_eq);
+        __syncthreads();
+        uint32_t before = s_eq_base;
+        for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+        const bool take_eq = eq && (before + __popc(m_eq & ((1u << lane) - 1u)) < need_eq);
+        if (gt || take_eq) buf[atomicAdd(&s_cursor, 1u)] = topx_composite(b, id_base + (uint32_t)i);
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t tot = 0;
+            for (uint32_t w = 0; w < TX_THREADS / 32; ++w) tot += s_warp[w];
+            s_eq_base += tot;
+        }
+        __syncthreads();
+    }
+    const uint32_t filled = s_cursor;  // == take
+    uint32_t S = 2;
+    while (S < filled) S <<= 1;
+    for (uint32_t j = filled + tid; j < S; j += TX_THREADS) buf[j] = 0;
+    bitonic_desc(buf, S);
+    for (uint32_t j = tid; j < x; j += TX_THREADS) {
+        if (j < filled) {
+            const uint64_t c = buf[j];
+            out_s[q * x + j] = __uint_as_float((uint32_t)(c >> 32));
+            out_i[q * x + j] = 0xFFFFFFFFu - (uint32_t)c;
+        } else {
+            out_s[q * x + j] = 0.0f;
+            out_i[q * x + j] = 0xFFFFFFFFu;
+        }
+    }
+}
+
+static void check_direct(const myrio_svecs *leaves, const myrio_svecs *queries, uint64_t q_first, uint64_t q_count,
+                         int32_t sim) {
+    check_queries(queries, q_first, q_count);
+    if (leaves->vtype != MYRIO_VAL_F32) fail(MYRIO_ERR_BAD_ARG, "leaf vectors must be f32 (pre-normalised)");
+    if (sim != MYRIO_SIM_COSINE && sim != MYRIO_SIM_JACARD_TANIMOTO && sim != MYRIO_SIM_OVERLAP)
+        fail(MYRIO_ERR_BAD_ARG, "unknown similarity %d", sim);
+    if (leaves->n_rows > 0xFFFFFFFFull) fail(MYRIO_ERR_BAD_ARG, "too many leaves");
+}
+
+// score rows of queries [q0, q0+qn) against all leaves into d_rows [qn][L]
+static void direct_rows(myrio_ctx *ctx, const myrio_svecs *leaves, const myrio_svecs *queries, uint64_t q0,
+                        uint64_t qn, int32_t sim, float *d_rows) {
+    // rows of the kernel = leaves (consecutive threads walk consecutive leaves against one query)
+    MergeArgs a{};
+    a.r_off = leaves->row_off.p;
+    a.r_keys = leaves->keys.p;
+    a.r_vals = leaves->vals_f32.p;
+    a.n_rows = (uint32_t)leaves->n_rows;
+    a.c_off = queries->row_off.p;
+    a.c_keys = queries->keys.p;
+    a.c_vals = queries->vals_f32.p;
+    a.c_first = (uint32_t)q0;
+    a.n_cols = (uint32_t)qn;
+    a.sim = sim;
+    a.out = d_rows;
+    a.ld = leaves->n_rows;
+    a.transposed = true;  // out[query][leaf]
+    launch_merge_pairs(ctx, a, "k4d_score_direct");
+}
+
+void score_all_direct(myrio_ctx *ctx, const myrio_svecs *leaves, const myrio_svecs *queries, uint64_t q_first,
+                      uint64_t q_count, int32_t sim, float *scores_host) {
+    check_direct(leaves, queries, q_first, q_count, sim);
+    const uint64_t L = leaves->n_rows;
+    if (q_count == 0 || L == 0) return;
+    const uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, (1ull << 31) / (L * 4)), q_count);
+    for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
+        const uint64_t qn = std::min(per, q_count - q0);
+        ctx->score_rows.reserve(qn * L);
+        direct_rows(ctx, leaves, queries, q_first + q0, qn, sim, ctx->score_rows.p);
+        d2h(ctx, scores_host + q0 * L, ctx->score_rows.p, qn * L);
+        sync(ctx);
+    }
+}
+
+void score_topx_direct_device(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t leaf_id_base,
+                              const myrio_svecs *queries, uint64_t q_first, uint64_t q_count, uint32_t x,
+                              int32_t sim, float *d_top_scores, uint32_t *d_top_ids) {
+    check_direct(leaves, queries, q_first, q_count, sim);
+    if (x == 0 || x > TX_MAX_X) fail(MYRIO_ERR_BAD_ARG, "x must be in 1..%d", TX_MAX_X);
+    const uint64_t L = leaves->n_rows;
+    if (q_count == 0) return;
+    const uint64_t per = std::min<uint64_t>(std::max<uint64_t>(1, (1ull << 31) / (std::max<uint64_t>(L, 1) * 4)), q_count);
+    for (uint64_t q0 = 0; q0 < q_count; q0 += per) {
+        const uint64_t qn = std::min(per, q_count - q0);
+        ctx->score_rows.reserve(std::max<uint64_t>(qn * L, 1));
+        if (L) direct_rows(ctx, leaves, queries, q_first + q0, qn, sim, ctx->score_rows.p);
+        MYRIO_LAUNCH(ctx, "k5_topx_rows", topx_rows_kernel, (unsigned)qn, TX_THREADS, 0, ctx->score_rows.p, L, x,
+                     leaf_id_base, d_top_scores + q0 * x, d_top_ids + q0 * x);
+    }
 }
 
 // the plan scratch of a context (allocated lazily, grow-only)

@@ -81,11 +81,11 @@ int main() {
         ASSERT_TRUE(std::fabs(res.best[0].second - 1.0f) < 1e-5f);
         ASSERT_TRUE(res.payloads[2] == 0.0f && res.payloads[3] == 0.0f);
         ASSERT_TRUE(res.best[0].second == res.payloads[1] && res.best[1].second == res.payloads[0]);
-        bool unsupported = false;
-        try { TaxTreeResults::from_compute_tree(q[0], ttc, Similarity::Overlap, 3); } catch (const Error &e) {
-            unsupported = e.code == MYRIO_ERR_UNSUPPORTED;
-        }
-        ASSERT_TRUE(unsupported);
+        // Overlap (similarity.rs:172-182) takes the merge-join path over the leaf vectors:
+        // a leaf scored against itself has sum_min == sum_max
+        TaxTreeResults ov = TaxTreeResults::from_compute_tree(q[0], ttc, Similarity::Overlap, 3);
+        ASSERT_TRUE(ov.best.size() == 3 && ov.best[0].first == 1 && ov.best[0].second == 1.0f);
+        ASSERT_TRUE(ov.payloads[2] == 0.0f && ov.best[0].second == ov.payloads[1]);
     }
     std::fprintf(stderr, "[4] cluster\n");
     {  // cluster(): two obviously different read families, no initial centroids

@@ -66,6 +66,9 @@ def test_reference_kat_simfunc(api, ctx):
     tile = api.pairwise(got.into_normalized_l2(), got.into_normalized_l2())
     assert abs(tile[0, 1] - cos) < np.finfo(np.float32).eps
     assert tile[0, 1] == tile[1, 0]
+    # overlap(kc1, kc2) == 0.5 on the raw counts (similarity.rs:226)
+    raw = api.SFVecs.upload(ctx, ro, keys, vals)
+    assert abs(api.pairwise(raw, raw, api.SIM_OVERLAP)[0, 1] - np.float32(0.5)) < np.finfo(np.float32).eps
 
 
 @pytest.mark.parametrize("k", [2, 6, 12, 18, 24, 31, 32])
@@ -235,9 +238,46 @@ def test_score_jacard_tanimoto_and_k12(api, ctx):
         assert (bits(s) == bits(res.scores[i])).all()
         ts, ti = oracle.topx(s, 7)
         assert (ti == res.top_ids[i]).all()
-    with pytest.raises(api.MyrioError) as e:
-        api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_OVERLAP, 7)
-    assert e.value.code == 6
+
+
+@pytest.mark.parametrize("k", [6, 18])
+def test_score_overlap_and_direct_path(api, ctx, k):
+    # Overlap (similarity.rs:172-182) runs as the reference's merge-join over the leaf vectors;
+    # the same kernel reproduces the inverted-index results for Cosine / JacardTanimoto
+    tree, reads, ttc, q, oln, oqn = build_case(api, ctx, 700, 24, 33, k=k, tile_leaves=128)
+    x = 9
+    res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_OVERLAP, x, full_scores=True)
+    for i in range(reads.n):
+        kk, vv = oqn.row(i)
+        s = oracle.score_all(oln, kk, vv, sim=oracle.SIM_OVERLAP)
+        assert (bits(s) == bits(res.scores[i])).all()
+        ts, ti = oracle.topx(s, x)
+        assert (ti == res.top_ids[i]).all() and (bits(ts) == bits(res.top_scores[i])).all()
+    for sim in (api.SIM_COSINE, api.SIM_JACARD_TANIMOTO):
+        a = api.TaxTreeResults.from_compute_tree(q, ttc, sim, x, full_scores=True)
+        b = api.TaxTreeResults.from_compute_tree(q, ttc, sim, x, full_scores=True, direct=True)
+        assert (bits(a.scores) == bits(b.scores)).all()
+        assert (a.top_ids == b.top_ids).all() and (bits(a.top_scores) == bits(b.top_scores)).all()
+
+
+def test_direct_topx_ties_and_short_rows(api, ctx):
+    # duplicates give exact ties (smallest payload id first); x larger than the leaf count pads
+    keys = [[1, 2, 3], [1, 2, 3], [7, 8], [1, 2, 3], [9], [2, 3, 4]]
+    row_off = np.zeros(len(keys) + 1, np.uint64)
+    row_off[1:] = np.cumsum([len(v) for v in keys])
+    kk = np.concatenate([np.array(v, np.uint64) for v in keys])
+    counts = api.SFVecs.upload(ctx, row_off, kk, np.ones(len(kk), np.uint16))
+    ttc = api.TaxTreeCompute.from_counts(counts, 100)
+    on = oracle.normalize(oracle.Csr(row_off, kk, np.ones(len(kk), np.float32)))
+    qv = api.SFVecs.upload(ctx, np.array([0, 3], np.uint64), np.array([1, 2, 3], np.uint64),
+                           np.ones(3, np.float32)).into_normalized_l2()
+    qro, qk, qvv, _ = qv.download(aux=False)
+    for sim, osim in ((api.SIM_OVERLAP, oracle.SIM_OVERLAP), (api.SIM_COSINE, oracle.SIM_COSINE)):
+        s = oracle.score_all(on, qk, qvv, sim=osim)
+        for x in (2, 4, 10):
+            r = api.TaxTreeResults.from_compute_tree(qv, ttc, sim, x, direct=True)
+            ts, ti = oracle.topx(s, x, id_base=100)
+            assert (r.top_ids[0] == ti).all() and (bits(r.top_scores[0]) == bits(ts)).all()
 
 
 def test_topx_ties_zero_rows_and_padding(api, ctx):
@@ -305,7 +345,7 @@ def test_pairwise_tile_bit_exact(api, ctx):
     reads = two_gene_reads(40, 51)
     oc = oracle.normalize(oracle.count_reads(reads.codes, reads.qual, reads.base_off, 6, 0.2))
     g = api.MyrSeqs(ctx, reads).compute_kmer_counts(6, 0.2).into_normalized_l2()
-    for sim in (api.SIM_COSINE, api.SIM_JACARD_TANIMOTO):
+    for sim in (api.SIM_COSINE, api.SIM_JACARD_TANIMOTO, api.SIM_OVERLAP):
         assert (bits(api.pairwise(g, g, sim)) == bits(oracle.pairwise(oc, oc, sim))).all()
     # large k takes the merge-join fallback
     oc18 = oracle.normalize(oracle.count_reads(reads.codes, reads.qual, reads.base_off, 18, 0.1))
@@ -337,6 +377,23 @@ def test_cluster_matches_oracle(api, ctx, silhouette, with_init):
         if silhouette is not None:
             both = ~np.isnan(osil)
             assert (np.isnan(out.silhouette) == np.isnan(osil)).all()
+            assert (bits(out.silhouette[both]) == bits(osil[both])).all()
+
+
+@pytest.mark.parametrize("sim", ["jacard", "overlap"])
+def test_cluster_other_similarities_match_oracle(api, ctx, sim):
+    gsim, osim = {"jacard": (api.SIM_JACARD_TANIMOTO, oracle.SIM_JACARD_TANIMOTO),
+                  "overlap": (api.SIM_OVERLAP, oracle.SIM_OVERLAP)}[sim]
+    reads = two_gene_reads(90, 67)
+    m = api.MyrSeqs(ctx, reads)
+    oc = oracle.count_reads(reads.codes, reads.qual, reads.base_off, 6, 0.2)
+    for silhouette in (None, 1.4):
+        oassign, oiters, osil = oracle.cluster(oc, 20, None, 2, silhouette=silhouette, sim=osim)
+        out = api.cluster(m, api.ClusteringParameters(k=6, t1=0.2, t2=20, similarity=gsim,
+                                                      expected_nb_of_clusters=2, silhouette_trimming=silhouette))
+        assert (out.assign == oassign).all() and out.n_iters == oiters
+        if silhouette is not None:
+            both = ~np.isnan(osil)
             assert (bits(out.silhouette[both]) == bits(osil[both])).all()
 
 
