@@ -378,6 +378,366 @@ static void launch_pair_tile(myrio_ctx *ctx, PairArgs a, const RowSlab &s, const
 
 static constexpr uint64_t PT_TILE_BUDGET = 1ull << 30;  // bytes of similarity tile kept at once
 
+// ------------------------------------------------ K6 tile, conflict-free variant
+//
+// pair_tile_kernel is bound by shared-memory wavefronts: every lane reads the 16-byte column
+// entry of ITS row's next key, and the 8 lanes of an LDS.128 phase collide in the 8 16-byte bank
+// groups about 2.1x (profiles/r01_k6_tile_ncu_summary.json).  For vectors that are symmetric
+// under reverse complement (every k-mer vector counted on both strands is: count(key) ==
+// count(revcomp key), data/myrseq.rs:96-103) the columns only need their CANONICAL keys --
+// 2080 of 4096 at k = 6 -- which leaves room for THREE replicas of the two [canonical key][4]
+// planes, the key's slot permuted so that its bank group is octal digit 0, digit 1 or
+// (digit 0 ^ digit 1) of the canonical index.  The row slab is then SCHEDULED: for every 8-lane
+// phase a greedy matcher (one level of augmentation) gives each lane's next entry a replica
+// whose bank group is still free in this slot; a lane that finds none waits (a +0.0 pad that
+// re-reads a placed lane's address, i.e. a broadcast).  Entries of a row stay in ascending key
+// order, so every accumulator sees the same f32 sequence as before.
+static constexpr uint32_t PC_REPLICAS = 3;
+
+struct CanonTable {
+    DevBuf<uint16_t> idx;  // [4^k]: canonical index | 0x8000 when key > revcomp(key)
+    uint32_t n_canon = 0;  // canonical keys
+    uint32_t plane_rows = 0;  // n_canon rounded up to a multiple of 64
+    uint32_t k = 0;
+};
+
+static uint64_t host_revcomp(uint64_t key, uint32_t k) {
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < k; ++i) {
+        r = (r << 2) | (3u - (key & 3u));
+        key >>= 2;
+    }
+    return r;
+}
+
+static void build_canon_table(myrio_ctx *ctx, uint32_t k, CanonTable &t) {
+    const uint32_t dim = 1u << (2 * k);
+    std::vector<uint16_t> h(dim);
+    uint32_t n = 0;
+    for (uint32_t key = 0; key < dim; ++key)
+        if (key <= host_revcomp(key, k)) h[key] = (uint16_t)n++;
+    for (uint32_t key = 0; key < dim; ++key) {
+        const uint32_t rc = (uint32_t)host_revcomp(key, k);
+        if (key > rc) h[key] = (uint16_t)(h[rc] | 0x8000u);
+    }
+    t.k = k;
+    t.n_canon = n;
+    t.plane_rows = (n + 63) / 64 * 64;
+    t.idx.alloc(dim);
+    h2d(ctx, t.idx.p, h.data(), dim);
+    sync(ctx);  // h goes out of scope
+}
+
+__device__ __forceinline__ uint32_t pc_slot(uint32_t ci, uint32_t r) {
+    const uint32_t d0 = ci & 7u, d1 = (ci >> 3) & 7u, hi = ci & ~63u;
+    if (r == 0) return ci;
+    if (r == 1) return hi | (d0 << 3) | d1;
+    return hi | (d1 << 3) | (d0 ^ d1);
+}
+
+// One thread per 8-lane phase.  WRITE == false: number of slots the phase needs.
+template <bool WRITE>
+__global__ void __launch_bounds__(128) slab_schedule_kernel(const uint64_t *__restrict__ r_off,
+                                                            const uint64_t *__restrict__ r_keys,
+                                                            const float *__restrict__ r_vals,
+                                                            const uint32_t *__restrict__ row_ids, uint32_t n_rows,
+                                                            uint32_t n_phases, const uint16_t *__restrict__ canon,
+                                                            uint32_t plane_rows, uint32_t *__restrict__ phase_len,
+                                                            const uint32_t *__restrict__ grp_len,
+                                                            const uint64_t *__restrict__ grp_off,
+                                                            uint16_t *__restrict__ keys, float *__restrict__ vals) {
+    const uint32_t ph = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ph >= n_phases) return;
+    uint64_t ptr[8], end[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        const uint32_t ri = ph * 8 + l;
+        ptr[l] = end[l] = 0;
+        if (ri < n_rows) {
+            const uint32_t r = row_ids ? row_ids[ri] : ri;
+            ptr[l] = r_off[r];
+            end[l] = r_off[r + 1];
+        }
+    }
+    const uint32_t g = ph >> 2, lane0 = (ph & 3u) * 8u;
+    uint64_t base = 0;
+    uint32_t total = 0;
+    if (WRITE) {
+        base = grp_off[g] * 128ull;
+        total = grp_len[g] * 4u;
+    }
+    uint32_t slot = 0;
+    for (;; ++slot) {
+        bool any = false;
+        uint32_t ci[8];
+        int choice[8];  // replica of the lane's entry in this slot, -1 = waits
+        int owner[8];   // bank group -> lane
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            choice[l] = -1;
+            owner[l] = -1;
+            ci[l] = 0xFFFFFFFFu;
+            if (ptr[l] < end[l]) {
+                ci[l] = canon[(uint32_t)r_keys[ptr[l]]] & 0x7FFFu;
+                any = true;
+            }
+        }
+        if (!any) break;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            if (ci[l] == 0xFFFFFFFFu) continue;
+            const uint32_t d0 = ci[l] & 7u, d1 = (ci[l] >> 3) & 7u;
+            const uint32_t grp[3] = {d0, d1, d0 ^ d1};
+            for (int r = 0; r < 3 && choice[l] < 0; ++r)
+                if (owner[grp[r]] < 0) {
+                    owner[grp[r]] = l;
+                    choice[l] = r;
+                }
+            // one level of augmentation: move the holder of one of our groups to another of its groups
+            for (int r = 0; r < 3 && choice[l] < 0; ++r) {
+                const int j = owner[grp[r]];
+                const uint32_t e0 = ci[j] & 7u, e1 = (ci[j] >> 3) & 7u;
+                const uint32_t gj[3] = {e0, e1, e0 ^ e1};
+                for (int r2 = 0; r2 < 3; ++r2)
+                    if (owner[gj[r2]] < 0) {
+                        owner[gj[r2]] = j;
+                        choice[j] = r2;
+                        owner[grp[r]] = l;
+                        choice[l] = r;
+                        break;
+                    }
+            }
+        }
+        if (WRITE) {
+            // waiting lanes re-read the address of a placed lane (broadcast) with value +0.0
+            uint32_t pad = 0;
+#pragma unroll
+            for (int l = 7; l >= 0; --l)
+                if (choice[l] >= 0) pad = (uint32_t)choice[l] * plane_rows + pc_slot(ci[l], (uint32_t)choice[l]);
+            const uint64_t at = base + (uint64_t)(slot >> 2) * 128 + (slot & 3u);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                uint32_t e = pad;
+                float v = 0.0f;
+                if (choice[l] >= 0) {
+                    e = (uint32_t)choice[l] * plane_rows + pc_slot(ci[l], (uint32_t)choice[l]);
+                    v = r_vals[ptr[l]];
+                }
+                keys[at + (lane0 + l) * 4] = (uint16_t)e;
+                vals[at + (lane0 + l) * 4] = v;
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 8; ++l)
+            if (choice[l] >= 0) ++ptr[l];
+    }
+    if (!WRITE) {
+        phase_len[ph] = slot;
+    } else {
+        for (; slot < total; ++slot) {  // the group is as long as its slowest phase
+            const uint64_t at = base + (uint64_t)(slot >> 2) * 128 + (slot & 3u);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                keys[at + (lane0 + l) * 4] = 0;
+                vals[at + (lane0 + l) * 4] = 0.0f;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) phase_to_group_len_kernel(const uint32_t *__restrict__ phase_len,
+                                                                 uint32_t n_phases, uint32_t n_groups,
+                                                                 uint32_t *__restrict__ grp_len) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    uint32_t m = 0;
+    for (uint32_t p = g * 4; p < min(n_phases, g * 4 + 4); ++p) m = max(m, phase_len[p]);
+    grp_len[g] = (m + 3) >> 2;
+}
+
+static void build_row_slab_scheduled(myrio_ctx *ctx, const uint64_t *r_off, const uint64_t *r_keys,
+                                     const float *r_vals, const uint32_t *row_ids, uint32_t n_rows,
+                                     const CanonTable &ct, RowSlab &s) {
+    s.n_rows = n_rows;
+    s.n_groups = (n_rows + 31) / 32;
+    if (s.n_groups == 0) return;
+    const uint32_t n_phases = s.n_groups * 4;  // every lane of every group gets written (rows past n_rows are empty)
+    s.grp_len.alloc(s.n_groups);
+    s.grp_off.alloc(s.n_groups + 1);
+    s.d_nnz.alloc(1);
+    DevBuf<uint32_t> phase_len(n_phases);
+    MYRIO_CK(cudaMemsetAsync(s.d_nnz.p, 0, sizeof(unsigned long long), ctx->stream));
+    // exact entry count (for the work statistics) with the plain counter kernel; its grp_len is replaced below
+    MYRIO_LAUNCH(ctx, "k6_slab_count", slab_count_kernel, (s.n_groups + 7) / 8, 256, 0, r_off, row_ids, n_rows,
+                 s.n_groups, s.grp_len.p, s.d_nnz.p);
+    MYRIO_LAUNCH(ctx, "k6_slab_schedule_count", slab_schedule_kernel<false>, (n_phases + 127) / 128, 128, 0, r_off,
+                 r_keys, r_vals, row_ids, n_rows, n_phases, ct.idx.p, ct.plane_rows, phase_len.p, nullptr, nullptr,
+                 nullptr, nullptr);
+    MYRIO_LAUNCH(ctx, "k6_slab_group_len", phase_to_group_len_kernel, (s.n_groups + 255) / 256, 256, 0, phase_len.p,
+                 n_phases, s.n_groups, s.grp_len.p);
+    exclusive_scan_u32_to_u64(ctx, s.grp_len.p, s.grp_off.p, s.n_groups);
+    uint64_t quads = 0;
+    unsigned long long h_nnz = 0;
+    d2h(ctx, &quads, s.grp_off.p + s.n_groups, 1);
+    d2h(ctx, &h_nnz, s.d_nnz.p, 1);
+    sync(ctx);
+    s.nnz = h_nnz;
+    s.keys.alloc(std::max<uint64_t>(quads, 1) * 128);
+    s.vals.alloc(std::max<uint64_t>(quads, 1) * 128);
+    MYRIO_LAUNCH(ctx, "k6_slab_schedule_fill", slab_schedule_kernel<true>, (n_phases + 127) / 128, 128, 0, r_off,
+                 r_keys, r_vals, row_ids, n_rows, n_phases, ct.idx.p, ct.plane_rows, nullptr, s.grp_len.p,
+                 s.grp_off.p, s.keys.p, s.vals.p);
+}
+
+struct CanonArgs {
+    const uint16_t *s_keys;  // scheduled slab: replica * plane_rows + permuted canonical index
+    const float *s_vals;
+    const uint32_t *grp_len;
+    const uint64_t *grp_off;
+    uint32_t n_rows, n_groups;
+    const uint64_t *c_off;  // sparse, reverse-complement-symmetric columns
+    const uint64_t *c_keys;
+    const float *c_vals;
+    const uint32_t *col_ids;
+    uint32_t c_first, n_cols;
+    const uint16_t *canon;
+    uint32_t plane_rows;
+    uint32_t n_slices;
+    int sim;
+    float *out;  // transposed: out[c * ld + row]
+    uint64_t ld;
+};
+
+// shared memory: plane A (columns 0-3) = PC_REPLICAS x plane_rows float4, then plane B (columns 4-7)
+__global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_canon_kernel(CanonArgs a) {
+    extern __shared__ __align__(16) float col_sm[];
+    constexpr int CB = 8;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_chunks = (a.n_cols + CB - 1) / CB;
+    const uint32_t n_tasks = n_chunks * a.n_slices;
+    const uint32_t plane_f4 = PC_REPLICAS * a.plane_rows;  // float4 entries per plane
+    float4 *sm4 = reinterpret_cast<float4 *>(col_sm);
+    const float4 *planeA = sm4, *planeB = sm4 + plane_f4;
+    uint32_t staged = 0xFFFFFFFFu;
+    for (uint32_t task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        const uint32_t slice = task / n_chunks, chunk = task % n_chunks;
+        const uint32_t c0 = chunk * CB;
+        const uint32_t nc = min((uint32_t)CB, a.n_cols - c0);
+        if (chunk != staged) {
+            __syncthreads();
+            for (uint32_t i = tid; i < 2 * plane_f4; i += PT_THREADS) sm4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+            constexpr uint32_t WPC = PT_WARPS / CB, LPC = WPC * 32;
+            const uint32_t c = warp / WPC, l = (warp % WPC) * 32 + lane;
+            if (c < nc) {
+                const uint32_t cr = a.col_ids ? a.col_ids[a.c_first + c0 + c] : (a.c_first + c0 + c);
+                const uint64_t b = a.c_off[cr], e = a.c_off[cr + 1];
+                float *dst = col_sm + (c / 4) * plane_f4 * 4 + (c % 4);
+                for (uint64_t j = b + l; j < e; j += 4 * LPC) {
+                    uint32_t kk[4];
+                    float vv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint64_t jj = j + (uint64_t)u * LPC;
+                        kk[u] = jj < e ? (uint32_t)a.canon[(uint32_t)a.c_keys[jj]] : 0x8000u;
+                        vv[u] = jj < e ? a.c_vals[jj] : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (!(kk[u] & 0x8000u)) {  // the canonical member of a (key, revcomp key) pair
+#pragma unroll
+                            for (uint32_t r = 0; r < PC_REPLICAS; ++r)
+                                dst[(r * a.plane_rows + pc_slot(kk[u], r)) * 4] = vv[u];
+                        }
+                }
+            }
+            staged = chunk;
+            __syncthreads();
+        }
+        const uint32_t g_lo = (uint32_t)((uint64_t)a.n_groups * slice / a.n_slices);
+        const uint32_t g_hi = (uint32_t)((uint64_t)a.n_groups * (slice + 1) / a.n_slices);
+        for (uint32_t g = g_lo + warp; g < g_hi; g += PT_WARPS) {
+            const uint32_t quads = a.grp_len[g];
+            const uint64_t base = a.grp_off[g] * 128ull + lane * 4u;
+            const uint2 *kp = reinterpret_cast<const uint2 *>(a.s_keys + base);
+            const float4 *vp = reinterpret_cast<const float4 *>(a.s_vals + base);
+            float acc[CB];
+#pragma unroll
+            for (int c = 0; c < CB; ++c) acc[c] = 0.0f;
+            uint2 kq = make_uint2(0, 0);
+            float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (quads) {
+                kq = __ldg(kp);
+                vq = __ldg(vp);
+            }
+            for (uint32_t q = 0; q < quads; ++q) {
+                const uint2 kc = kq;
+                const float4 vc = vq;
+                if (q + 1 < quads) {
+                    kq = __ldg(kp + (size_t)(q + 1) * 32);
+                    vq = __ldg(vp + (size_t)(q + 1) * 32);
+                }
+                const uint32_t e4[4] = {kc.x & 0xFFFFu, kc.x >> 16, kc.y & 0xFFFFu, kc.y >> 16};
+                const float v4[4] = {vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {  // ascending key order per row
+                    const float v = v4[u];
+                    const float4 x = planeA[e4[u]], y = planeB[e4[u]];
+                    acc[0] = __fadd_rn(acc[0], __fmul_rn(v, x.x));
+                    acc[1] = __fadd_rn(acc[1], __fmul_rn(v, x.y));
+                    acc[2] = __fadd_rn(acc[2], __fmul_rn(v, x.z));
+                    acc[3] = __fadd_rn(acc[3], __fmul_rn(v, x.w));
+                    acc[4] = __fadd_rn(acc[4], __fmul_rn(v, y.x));
+                    acc[5] = __fadd_rn(acc[5], __fmul_rn(v, y.y));
+                    acc[6] = __fadd_rn(acc[6], __fmul_rn(v, y.z));
+                    acc[7] = __fadd_rn(acc[7], __fmul_rn(v, y.w));
+                }
+            }
+            const uint32_t ri = g * 32 + lane;
+            if (ri < a.n_rows) {
+#pragma unroll
+                for (int c = 0; c < CB; ++c)
+                    if ((uint32_t)c < nc) a.out[(size_t)(c0 + c) * a.ld + ri] = pk_sim(a.sim, acc[c]);
+            }
+        }
+    }
+}
+
+static bool canon_path_enabled() {  // MYRIO_K6_CANON=0 keeps the plain tile kernel (comparison runs)
+    static const bool v = [] {
+        const char *e = getenv("MYRIO_K6_CANON");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
+static void launch_pair_tile_canon(myrio_ctx *ctx, CanonArgs a, const RowSlab &s, const CanonTable &ct,
+                                   const char *name) {
+    if (s.n_rows == 0 || a.n_cols == 0) return;
+    a.s_keys = s.keys.p;
+    a.s_vals = s.vals.p;
+    a.grp_len = s.grp_len.p;
+    a.grp_off = s.grp_off.p;
+    a.n_rows = s.n_rows;
+    a.n_groups = s.n_groups;
+    a.canon = ct.idx.p;
+    a.plane_rows = ct.plane_rows;
+    ctx->cluster_stats[0] += (uint64_t)s.n_rows * a.n_cols;
+    ctx->cluster_stats[1] += s.nnz * a.n_cols;
+    const uint32_t n_chunks = (a.n_cols + 7) / 8;
+    const uint64_t slab_bytes = (uint64_t)s.keys.n * 2 + (uint64_t)s.vals.n * 4;
+    uint32_t n_slices = (uint32_t)((slab_bytes + pt_slice_bytes() - 1) / pt_slice_bytes());
+    const uint32_t want = 2u * (uint32_t)ctx->sm_count;
+    if ((uint64_t)n_chunks * n_slices < want) n_slices = (want + n_chunks - 1) / n_chunks;
+    n_slices = std::max(1u, std::min(n_slices, (s.n_groups + PT_WARPS - 1) / PT_WARPS));
+    a.n_slices = n_slices;
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)n_chunks * n_slices, (uint64_t)ctx->sm_count);
+    const size_t smem = (size_t)2 * PC_REPLICAS * ct.plane_rows * 16;
+    MYRIO_CK(cudaFuncSetAttribute(pair_tile_canon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYRIO_LAUNCH(ctx, name, pair_tile_canon_kernel, grid, PT_THREADS, smem, a);
+}
+
+
 // ---------------------------------------------------------------- recentering
 
 // one warp per kept read: sums[c][key] += raw count (integer-valued, exact)
@@ -719,6 +1079,11 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     d2h(ctx, hcen.data(), cen.p, hcen.size());
     sync(ctx);
     const float ssdcf = p->silhouette_trimming;
+    // read vectors counted on both strands are reverse-complement symmetric: canonical-key columns,
+    // three bank-permuted replicas, scheduled row slabs (needs 6 * plane_rows * 16 B of shared memory)
+    CanonTable canon;
+    const bool canon_path = !merge_path && p->k <= 6 && canon_path_enabled();
+    if (canon_path) build_canon_table(ctx, p->k, canon);
     for (uint32_t c = 0; c < nc; ++c) {
         const uint32_t nm = (uint32_t)members[c].size();
         if (nm == 0) continue;
@@ -742,7 +1107,10 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         h2d(ctx, d_cols.p, cols.data(), cols.size());
         MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)nm * 2 * sizeof(float), ctx->stream));
         RowSlab mslab;  // the cluster's members as rows
-        if (!merge_path) build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, mslab);
+        if (canon_path)
+            build_row_slab_scheduled(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, canon, mslab);
+        else if (!merge_path)
+            build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, mslab);
         PairArgs sa{};
         sa.c_off = norm->row_off.p;
         sa.c_keys = norm->keys.p;
@@ -760,7 +1128,19 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         for (uint32_t cf = 0; cf < n_cols_all; cf += pass_cols) {
             sa.c_first = cf;
             sa.n_cols = std::min(pass_cols, n_cols_all - cf);
-            if (!merge_path) {
+            if (canon_path) {
+                CanonArgs ca{};
+                ca.c_off = sa.c_off;
+                ca.c_keys = sa.c_keys;
+                ca.c_vals = sa.c_vals;
+                ca.col_ids = sa.col_ids;
+                ca.c_first = cf;
+                ca.n_cols = sa.n_cols;
+                ca.sim = sim;
+                ca.out = d_sil_tile.p;
+                ca.ld = nm;
+                launch_pair_tile_canon(ctx, ca, mslab, canon, "k6_pair_silhouette");
+            } else if (!merge_path) {
                 launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
             } else {
                 MergeArgs m{};

@@ -41,7 +41,7 @@ for name, sil in (("cluster", None), ("silhouette", 1.4)):
         out = api.cluster(q, api.ClusteringParameters(k=6, t1=0.2, t2=20, expected_nb_of_clusters=a.clusters,
                                                       silhouette_trimming=sil))
         dt = time.perf_counter() - t0
-        res = {p: ctx.prof_query(p) for p in ("k6_pair_store", "k6_pair_argmax", "k6_pair_silhouette", "k6_recenter", "k1_", "")}
+        res = {p: ctx.prof_query(p) for p in ("k6_pair_store", "k6_pair_argmax", "k6_pair_silhouette", "k6_silsum", "k6_slab_schedule_count", "k6_slab_schedule_fill", "k6_slab", "k6_recenter", "k1_", "")}
         ctx.prof_enable(False)
     sizes = [int(len(c)) for c in out.clusters]
     print(json.dumps({"what": name, "reads": reads.n, "clusters": sizes, "rejected": int(len(out.rejected)),
