@@ -435,124 +435,109 @@ __device__ __forceinline__ uint32_t pc_slot(uint32_t ci, uint32_t r) {
     return hi | (d1 << 3) | (d0 ^ d1);
 }
 
-// One thread per 8-lane phase.  WRITE == false: number of slots the phase needs.
+// One warp per group of 32 rows (lane = row; the 8 lanes of an LDS.128 phase match among
+// themselves, the four phases advance in lockstep).  Per slot: three parallel rounds -- every
+// waiting lane proposes the bank group of replica 0, then 1, then 2 of its next entry, the
+// lowest lane wins a free group -- then one level of augmentation for the lanes still waiting
+// (a placed lane holding one of their groups moves to a free alternative).  ~1.12 slots per
+// entry of the longest row.  WRITE == false: only the number of slots (grp_len, in quads).
 template <bool WRITE>
 __global__ void __launch_bounds__(128) slab_schedule_kernel(const uint64_t *__restrict__ r_off,
                                                             const uint64_t *__restrict__ r_keys,
                                                             const float *__restrict__ r_vals,
                                                             const uint32_t *__restrict__ row_ids, uint32_t n_rows,
-                                                            uint32_t n_phases, const uint16_t *__restrict__ canon,
-                                                            uint32_t plane_rows, uint32_t *__restrict__ phase_len,
-                                                            const uint32_t *__restrict__ grp_len,
+                                                            uint32_t n_groups, const uint16_t *__restrict__ canon,
+                                                            uint32_t plane_rows, uint32_t *__restrict__ grp_len,
                                                             const uint64_t *__restrict__ grp_off,
                                                             uint16_t *__restrict__ keys, float *__restrict__ vals) {
-    const uint32_t ph = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ph >= n_phases) return;
-    uint64_t ptr[8], end[8];
-#pragma unroll
-    for (int l = 0; l < 8; ++l) {
-        const uint32_t ri = ph * 8 + l;
-        ptr[l] = end[l] = 0;
-        if (ri < n_rows) {
-            const uint32_t r = row_ids ? row_ids[ri] : ri;
-            ptr[l] = r_off[r];
-            end[l] = r_off[r + 1];
-        }
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    const uint32_t lane = threadIdx.x & 31, ph = lane >> 3;
+    const unsigned phase_mask = 0xFFu << (ph * 8);
+    const uint32_t ri = g * 32 + lane;
+    uint64_t ptr = 0, end = 0;
+    if (ri < n_rows) {
+        const uint32_t r = row_ids ? row_ids[ri] : ri;
+        ptr = r_off[r];
+        end = r_off[r + 1];
     }
-    const uint32_t g = ph >> 2, lane0 = (ph & 3u) * 8u;
     uint64_t base = 0;
     uint32_t total = 0;
     if (WRITE) {
-        base = grp_off[g] * 128ull;
+        base = grp_off[g] * 128ull + lane * 4u;
         total = grp_len[g] * 4u;
     }
+    auto phase_or = [&](uint32_t v) {  // OR over the 8 lanes of the phase
+        v |= __shfl_xor_sync(FULL, v, 1);
+        v |= __shfl_xor_sync(FULL, v, 2);
+        v |= __shfl_xor_sync(FULL, v, 4);
+        return v;
+    };
     uint32_t slot = 0;
     for (;; ++slot) {
-        bool any = false;
-        uint32_t ci[8];
-        int choice[8];  // replica of the lane's entry in this slot, -1 = waits
-        int owner[8];   // bank group -> lane
+        const bool has = ptr < end;
+        if (!__any_sync(FULL, has)) break;
+        const uint32_t ci = has ? (uint32_t)(canon[(uint32_t)r_keys[ptr]] & 0x7FFFu) : 0u;
+        const uint32_t g0 = ci & 7u, g1 = (ci >> 3) & 7u, g2 = g0 ^ g1;
+        uint32_t taken = 0;  // bank groups in use in my phase
+        int choice = -1;
 #pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            choice[l] = -1;
-            owner[l] = -1;
-            ci[l] = 0xFFFFFFFFu;
-            if (ptr[l] < end[l]) {
-                ci[l] = canon[(uint32_t)r_keys[ptr[l]]] & 0x7FFFu;
-                any = true;
-            }
+        for (int r = 0; r < 3; ++r) {
+            const uint32_t gr = r == 0 ? g0 : (r == 1 ? g1 : g2);
+            const bool want = has && choice < 0 && !((taken >> gr) & 1u);
+            const unsigned peers = __match_any_sync(FULL, want ? (ph * 8u + gr) : (64u + lane));
+            const bool win = want && ((uint32_t)(__ffs(peers) - 1) == lane);
+            if (win) choice = r;
+            taken |= phase_or(win ? (1u << gr) : 0u);
         }
-        if (!any) break;
+        // augmentation, one waiting lane of every phase at a time
+        unsigned um = __ballot_sync(FULL, has && choice < 0) & phase_mask;
+        while (__any_sync(FULL, um != 0u)) {
+            const bool active = um != 0u;
+            const uint32_t i = active ? (uint32_t)(__ffs(um) - 1) : lane;
+            um &= um - 1u;
+            const uint32_t i0 = __shfl_sync(FULL, g0, i), i1 = __shfl_sync(FULL, g1, i), i2 = __shfl_sync(FULL, g2, i);
+            const uint32_t mine = choice == 0 ? g0 : (choice == 1 ? g1 : g2);
+            int alt = -1;
 #pragma unroll
-        for (int l = 0; l < 8; ++l) {
-            if (ci[l] == 0xFFFFFFFFu) continue;
-            const uint32_t d0 = ci[l] & 7u, d1 = (ci[l] >> 3) & 7u;
-            const uint32_t grp[3] = {d0, d1, d0 ^ d1};
-            for (int r = 0; r < 3 && choice[l] < 0; ++r)
-                if (owner[grp[r]] < 0) {
-                    owner[grp[r]] = l;
-                    choice[l] = r;
-                }
-            // one level of augmentation: move the holder of one of our groups to another of its groups
-            for (int r = 0; r < 3 && choice[l] < 0; ++r) {
-                const int j = owner[grp[r]];
-                const uint32_t e0 = ci[j] & 7u, e1 = (ci[j] >> 3) & 7u;
-                const uint32_t gj[3] = {e0, e1, e0 ^ e1};
-                for (int r2 = 0; r2 < 3; ++r2)
-                    if (owner[gj[r2]] < 0) {
-                        owner[gj[r2]] = j;
-                        choice[j] = r2;
-                        owner[grp[r]] = l;
-                        choice[l] = r;
-                        break;
-                    }
+            for (int r2 = 2; r2 >= 0; --r2) {
+                const uint32_t gr2 = r2 == 0 ? g0 : (r2 == 1 ? g1 : g2);
+                if (r2 != choice && !((taken >> gr2) & 1u)) alt = r2;
+            }
+            const bool cand = active && choice >= 0 && alt >= 0 && (mine == i0 || mine == i1 || mine == i2);
+            const unsigned cm = __ballot_sync(FULL, cand) & phase_mask;
+            const uint32_t j = cm ? (uint32_t)(__ffs(cm) - 1) : lane;
+            const uint32_t jold = __shfl_sync(FULL, mine, j);
+            const uint32_t altg = alt == 0 ? g0 : (alt == 1 ? g1 : g2);
+            const uint32_t jnew = __shfl_sync(FULL, altg, j);
+            if (cm) {
+                if (lane == j) choice = alt;
+                if (lane == i) choice = (jold == g0) ? 0 : ((jold == g1) ? 1 : 2);
+                taken |= 1u << jnew;
             }
         }
         if (WRITE) {
-            // waiting lanes re-read the address of a placed lane (broadcast) with value +0.0
-            uint32_t pad = 0;
-#pragma unroll
-            for (int l = 7; l >= 0; --l)
-                if (choice[l] >= 0) pad = (uint32_t)choice[l] * plane_rows + pc_slot(ci[l], (uint32_t)choice[l]);
+            const uint32_t mine_e = choice >= 0 ? (uint32_t)choice * plane_rows + pc_slot(ci, (uint32_t)choice) : 0u;
+            // waiting lanes re-read the address of a placed lane of their phase (broadcast), value +0.0
+            const unsigned pm = __ballot_sync(FULL, choice >= 0) & phase_mask;
+            const uint32_t src = pm ? (uint32_t)(__ffs(pm) - 1) : lane;
+            const uint32_t pad_e = __shfl_sync(FULL, mine_e, src);
             const uint64_t at = base + (uint64_t)(slot >> 2) * 128 + (slot & 3u);
-#pragma unroll
-            for (int l = 0; l < 8; ++l) {
-                uint32_t e = pad;
-                float v = 0.0f;
-                if (choice[l] >= 0) {
-                    e = (uint32_t)choice[l] * plane_rows + pc_slot(ci[l], (uint32_t)choice[l]);
-                    v = r_vals[ptr[l]];
-                }
-                keys[at + (lane0 + l) * 4] = (uint16_t)e;
-                vals[at + (lane0 + l) * 4] = v;
-            }
+            keys[at] = (uint16_t)(choice >= 0 ? mine_e : pad_e);
+            vals[at] = choice >= 0 ? r_vals[ptr] : 0.0f;
         }
-#pragma unroll
-        for (int l = 0; l < 8; ++l)
-            if (choice[l] >= 0) ++ptr[l];
+        if (choice >= 0) ++ptr;
     }
     if (!WRITE) {
-        phase_len[ph] = slot;
+        if (lane == 0) grp_len[g] = (slot + 3) >> 2;
     } else {
-        for (; slot < total; ++slot) {  // the group is as long as its slowest phase
+        for (; slot < total; ++slot) {  // round the group up to whole quads
             const uint64_t at = base + (uint64_t)(slot >> 2) * 128 + (slot & 3u);
-#pragma unroll
-            for (int l = 0; l < 8; ++l) {
-                keys[at + (lane0 + l) * 4] = 0;
-                vals[at + (lane0 + l) * 4] = 0.0f;
-            }
+            keys[at] = 0;
+            vals[at] = 0.0f;
         }
     }
-}
-
-__global__ void __launch_bounds__(256) phase_to_group_len_kernel(const uint32_t *__restrict__ phase_len,
-                                                                 uint32_t n_phases, uint32_t n_groups,
-                                                                 uint32_t *__restrict__ grp_len) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_groups) return;
-    uint32_t m = 0;
-    for (uint32_t p = g * 4; p < min(n_phases, g * 4 + 4); ++p) m = max(m, phase_len[p]);
-    grp_len[g] = (m + 3) >> 2;
 }
 
 static void build_row_slab_scheduled(myrio_ctx *ctx, const uint64_t *r_off, const uint64_t *r_keys,
@@ -561,20 +546,16 @@ static void build_row_slab_scheduled(myrio_ctx *ctx, const uint64_t *r_off, cons
     s.n_rows = n_rows;
     s.n_groups = (n_rows + 31) / 32;
     if (s.n_groups == 0) return;
-    const uint32_t n_phases = s.n_groups * 4;  // every lane of every group gets written (rows past n_rows are empty)
     s.grp_len.alloc(s.n_groups);
     s.grp_off.alloc(s.n_groups + 1);
     s.d_nnz.alloc(1);
-    DevBuf<uint32_t> phase_len(n_phases);
     MYRIO_CK(cudaMemsetAsync(s.d_nnz.p, 0, sizeof(unsigned long long), ctx->stream));
     // exact entry count (for the work statistics) with the plain counter kernel; its grp_len is replaced below
     MYRIO_LAUNCH(ctx, "k6_slab_count", slab_count_kernel, (s.n_groups + 7) / 8, 256, 0, r_off, row_ids, n_rows,
                  s.n_groups, s.grp_len.p, s.d_nnz.p);
-    MYRIO_LAUNCH(ctx, "k6_slab_schedule_count", slab_schedule_kernel<false>, (n_phases + 127) / 128, 128, 0, r_off,
-                 r_keys, r_vals, row_ids, n_rows, n_phases, ct.idx.p, ct.plane_rows, phase_len.p, nullptr, nullptr,
-                 nullptr, nullptr);
-    MYRIO_LAUNCH(ctx, "k6_slab_group_len", phase_to_group_len_kernel, (s.n_groups + 255) / 256, 256, 0, phase_len.p,
-                 n_phases, s.n_groups, s.grp_len.p);
+    const unsigned grid = (s.n_groups + 3) / 4;
+    MYRIO_LAUNCH(ctx, "k6_slab_schedule_count", slab_schedule_kernel<false>, grid, 128, 0, r_off, r_keys, r_vals,
+                 row_ids, n_rows, s.n_groups, ct.idx.p, ct.plane_rows, s.grp_len.p, nullptr, nullptr, nullptr);
     exclusive_scan_u32_to_u64(ctx, s.grp_len.p, s.grp_off.p, s.n_groups);
     uint64_t quads = 0;
     unsigned long long h_nnz = 0;
@@ -584,9 +565,9 @@ static void build_row_slab_scheduled(myrio_ctx *ctx, const uint64_t *r_off, cons
     s.nnz = h_nnz;
     s.keys.alloc(std::max<uint64_t>(quads, 1) * 128);
     s.vals.alloc(std::max<uint64_t>(quads, 1) * 128);
-    MYRIO_LAUNCH(ctx, "k6_slab_schedule_fill", slab_schedule_kernel<true>, (n_phases + 127) / 128, 128, 0, r_off,
-                 r_keys, r_vals, row_ids, n_rows, n_phases, ct.idx.p, ct.plane_rows, nullptr, s.grp_len.p,
-                 s.grp_off.p, s.keys.p, s.vals.p);
+    MYRIO_LAUNCH(ctx, "k6_slab_schedule_fill", slab_schedule_kernel<true>, grid, 128, 0, r_off, r_keys, r_vals,
+                 row_ids, n_rows, s.n_groups, ct.idx.p, ct.plane_rows, s.grp_len.p, s.grp_off.p, s.keys.p,
+                 s.vals.p);
 }
 
 struct CanonArgs {
