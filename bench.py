@@ -188,12 +188,13 @@ def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu
             # column from shared memory (4 B); the bound is the SMs' shared-memory bandwidth.
             peak = 148 * SMEM_BYTES_PER_CLK_PER_SM * (sm_mhz or 1965.0) * 1e6 / 1e9
             ach = 4.0 * st["terms"] / (sil_ms * 1e-3) / 1e9
-            d["roofline"] = {"bound": "shared-memory bandwidth", "kernel": "k6_pair_silhouette (pair_tile_kernel<8, transposed>)",
+            d["roofline"] = {"bound": "shared-memory bandwidth", "kernel": "k6_pair_silhouette (pair_tile_canon_kernel)",
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "kernel_ms": sil_ms, "terms_per_s": st["terms"] / (sil_ms * 1e-3),
                              "peak_source": "148 SMs x 128 B/clk x SM clock under load (nvidia-smi)",
-                             "note": "algorithmic bytes = 4 B (one column value) per multiply-add term; bank conflicts "
-                                     "of the per-thread random-key LDS.128 are the loss (profiles/r01_k6_tile_ncu_summary.json)"}
+                             "note": "algorithmic bytes = 4 B (one column value read from shared memory) per multiply-add "
+                                     "term; the scheduled slab is conflict-free, the loss is its ~1.12x waiting slots, "
+                                     "column staging and the row-slab stream (profiles/r01_k6_canon_ncu_summary.json)"}
         out[name] = d
     if cpu_reads is not None and cpu_seconds > 0:
         import oracle
