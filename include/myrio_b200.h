@@ -226,6 +226,22 @@ typedef struct {
 int32_t myrio_cluster(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *params,
                       const myrio_svecs *initial_centroids, int32_t *assign, uint32_t *n_iters,
                       float *silhouette);
+/* Row-sharded clustering over `world` GPUs (one process per GPU).  Every rank passes the SAME reads
+ * and parameters; the reads x centroids tiles of every iteration and the members x (members +
+ * neighbours) silhouette tiles are computed for the rank's contiguous share of the rows and the
+ * per-row results are exchanged through `allgather`: host_buf holds `world` chunks of
+ * bytes_per_rank, chunk `rank` is filled on entry, all chunks on return (0 = ok).  A binding
+ * implements it with ncclAllGather (or any collective it already has).  Results are identical on
+ * every rank and identical to myrio_cluster. */
+typedef int32_t (*myrio_allgather_fn)(void *user, void *host_buf, uint64_t bytes_per_rank);
+typedef struct {
+    uint32_t rank, world;
+    myrio_allgather_fn allgather;
+    void *user;
+} myrio_shard;
+int32_t myrio_cluster_sharded(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *params,
+                              const myrio_svecs *initial_centroids, const myrio_shard *shard,
+                              int32_t *assign, uint32_t *n_iters, float *silhouette);
 /* compute_cluster_centroid (clustering.rs:44-53) over rows member_ids[0..m) of
  * `counts` (raw, un-normalised); out is a 1-row normalised batch. */
 int32_t myrio_compute_cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts,

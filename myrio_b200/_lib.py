@@ -25,8 +25,18 @@ SYMBOLS = [
     "myrio_index_export_tile", "myrio_index_free", "myrio_score_all", "myrio_score_topx",
     "myrio_score_topx_async", "myrio_score_all_direct", "myrio_score_topx_direct",
     "myrio_score_topx_direct_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
+    "myrio_cluster_sharded",
     "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_cluster_stats", "myrio_svecs_device_ptrs",
 ]
+
+
+# int32_t (*myrio_allgather_fn)(void *user, void *host_buf, uint64_t bytes_per_rank)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+class Shard(C.Structure):
+    """myrio_shard: this rank's place in a row-sharded myrio_cluster_sharded call"""
+    _fields_ = [("rank", C.c_uint32), ("world", C.c_uint32), ("allgather", ALLGATHER_FN), ("user", C.c_void_p)]
 
 
 class MyrioError(RuntimeError):
@@ -105,6 +115,7 @@ def load() -> C.CDLL:
     L.myrio_topx_merge_async.argtypes = [vp, vp, vp, u32, u64, u32, vp, vp]
     L.myrio_score_stats.argtypes = [vp, P(u64), P(u64), P(u64)]
     L.myrio_cluster.argtypes = [vp, vp, P(ClusterParams), vp, vp, P(u32), vp]
+    L.myrio_cluster_sharded.argtypes = [vp, vp, P(ClusterParams), vp, P(Shard), vp, P(u32), vp]
     L.myrio_compute_cluster_centroid.argtypes = [vp, vp, vp, u64, P(vp)]
     L.myrio_pairwise.argtypes = [vp, vp, vp, i32, vp]
     L.myrio_cluster_stats.argtypes = [vp, P(u64), P(u64)]

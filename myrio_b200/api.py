@@ -381,8 +381,10 @@ class ClusteringOutput:
     silhouette: np.ndarray = field(default=None)
 
 
-def cluster(myrseqs: MyrSeqs, params: ClusteringParameters) -> ClusteringOutput:
-    """clustering::cluster (myrio-core/src/clustering.rs:55-270)."""
+def cluster(myrseqs: MyrSeqs, params: ClusteringParameters, shard=None) -> ClusteringOutput:
+    """clustering::cluster (myrio-core/src/clustering.rs:55-270).  `shard` = (rank, world, allgather)
+    runs the row-sharded variant (myrio_cluster_sharded; see myrio_b200.dist.cluster_sharded): every
+    rank passes the same reads and gets the same result."""
     ctx = myrseqs.ctx
     p = _lib.ClusterParams()
     p.k, p.t1, p.t2, p.similarity = params.k, params.t1, params.t2, params.similarity
@@ -394,7 +396,14 @@ def cluster(myrseqs: MyrSeqs, params: ClusteringParameters) -> ClusteringOutput:
     sil = np.zeros(max(1, myrseqs.n), np.float32)
     iters = C.c_uint32(0)
     init = params.intial_centroids.h if params.intial_centroids is not None else None
-    _lib.check(ctx._L.myrio_cluster(ctx.h, myrseqs.h, C.byref(p), init, _p(assign), C.byref(iters), _p(sil)))
+    if shard is None:
+        _lib.check(ctx._L.myrio_cluster(ctx.h, myrseqs.h, C.byref(p), init, _p(assign), C.byref(iters), _p(sil)))
+    else:
+        rank, world, allgather = shard
+        cb = allgather if isinstance(allgather, _lib.ALLGATHER_FN) else _lib.ALLGATHER_FN(allgather)
+        sh = _lib.Shard(rank, world, cb, None)
+        _lib.check(ctx._L.myrio_cluster_sharded(ctx.h, myrseqs.h, C.byref(p), init, C.byref(sh), _p(assign),
+                                                C.byref(iters), _p(sil)))
     assign, sil = assign[:myrseqs.n], sil[:myrseqs.n]
     nc = int(assign.max()) + 1 if (assign >= 0).any() else 0
     nc = max(nc, params.expected_nb_of_clusters,

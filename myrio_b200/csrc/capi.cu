@@ -455,7 +455,17 @@ int32_t myrio_cluster(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_clust
     return guarded([&] {
         if (!ctx || !reads || !params || (!assign && reads->n)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
         ScopedCtx sc(ctx);
-        cluster_reads(ctx, reads, params, initial_centroids, assign, n_iters, silhouette);
+        cluster_reads(ctx, reads, params, initial_centroids, nullptr, assign, n_iters, silhouette);
+    });
+}
+
+int32_t myrio_cluster_sharded(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *params,
+                              const myrio_svecs *initial_centroids, const myrio_shard *shard, int32_t *assign,
+                              uint32_t *n_iters, float *silhouette) {
+    return guarded([&] {
+        if (!ctx || !reads || !params || !shard || (!assign && reads->n)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        cluster_reads(ctx, reads, params, initial_centroids, shard, assign, n_iters, silhouette);
     });
 }
 

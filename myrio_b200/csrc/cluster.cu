@@ -832,8 +832,28 @@ __global__ void __launch_bounds__(32) dense_to_csr_kernel(const float *__restric
 
 static uint64_t max_key_of(myrio_ctx *ctx, const myrio_svecs *v);
 
+// `sh` (optional): row-sharded run.  Every rank holds ALL reads and runs the same host
+// loop; the similarity tiles -- reads x centroids per iteration, members x (members + neighbours) for
+// the silhouette -- are computed for the rank's contiguous share of the ROWS only and the per-row
+// results (best similarity + target, dots, silhouette sums) are all-gathered through sh->allgather,
+// after which every rank continues with identical data.  Recentering is replicated (cheap, exact).
 void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *p,
-                   const myrio_svecs *init, int32_t *assign, uint32_t *n_iters, float *silhouette) {
+                   const myrio_svecs *init, const myrio_shard *sh, int32_t *assign, uint32_t *n_iters,
+                   float *silhouette) {
+    const uint32_t W = sh ? sh->world : 1, R = sh ? sh->rank : 0;
+    if (W == 0 || R >= W || (W > 1 && !sh->allgather)) fail(MYRIO_ERR_BAD_ARG, "bad shard description");
+    // contiguous share of n rows: rank r owns [r * chunk, min(n, (r + 1) * chunk))
+    auto share = [&](uint32_t n, uint32_t &lo, uint32_t &cnt, uint32_t &chunk) {
+        chunk = (n + W - 1) / W;
+        lo = std::min(n, R * chunk);
+        cnt = std::min(n, lo + chunk) - lo;
+    };
+    // buf holds W chunks of bytes_per_rank; this rank's chunk is filled, the others arrive
+    auto exchange = [&](void *buf, uint64_t bytes_per_rank) {
+        if (W == 1 || bytes_per_rank == 0) return;
+        const int32_t rc = sh->allgather(sh->user, buf, bytes_per_rank);
+        if (rc != 0) fail(MYRIO_ERR_BAD_ARG, "allgather callback failed (%d)", rc);
+    };
     const uint64_t n_init = init ? init->n_rows : 0;
     if (n_init == 0 && p->expected_nb_of_clusters == 0)
         fail(MYRIO_ERR_BAD_ARG, "Ensure `initial_centroids` is not empty or `expected_nb_of_clusters` > 0");
@@ -924,8 +944,10 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     if (nc == 0) push_centroid_from_read(kept[max_idx]);
 
     const bool merge_path = sim == MYRIO_SIM_OVERLAP;  // union-of-keys sums: merge-join kernel
-    RowSlab slab;  // the kept reads (normalised), packed once for every reads x centroids pass
-    if (!merge_path) build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_kept.p, nk, slab);
+    uint32_t klo, kcnt, kchunk;  // this rank's share of the kept reads
+    share(nk, klo, kcnt, kchunk);
+    RowSlab slab;  // this rank's kept reads (normalised), packed once for every reads x centroids pass
+    if (!merge_path) build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_kept.p + klo, kcnt, slab);
     PairArgs pa{};
     pa.c_dense = cen.p;
     pa.dim = dim;
@@ -953,8 +975,8 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         m.r_off = norm->row_off.p;
         m.r_keys = norm->keys.p;
         m.r_vals = norm->vals_f32.p;
-        m.row_ids = d_kept.p;
-        m.n_rows = nk;
+        m.row_ids = d_kept.p + klo;
+        m.n_rows = kcnt;
         m.c_off = cs_off.p;
         m.c_end = cs_end.p;
         m.c_keys = cs_keys.p;
@@ -964,19 +986,20 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         m.out = pa.out;
         m.ld = pa.ld;
         m.transposed = transposed;
-        ctx->cluster_stats[0] += (uint64_t)nk * pa.n_cols;
+        ctx->cluster_stats[0] += (uint64_t)kcnt * pa.n_cols;
         launch_merge_pairs(ctx, m, name);
     };
 
     while (nc < p->expected_nb_of_clusters) {  // :114-129
-        DevBuf<float> d_dots((size_t)nk * nc);
+        DevBuf<float> d_dots(std::max<size_t>((size_t)kcnt * nc, 1));
         pa.n_cols = nc;
         pa.out = d_dots.p;
         pa.ld = nc;
         centroid_tile(false, "k6_pair_store");
-        std::vector<float> dots((size_t)nk * nc);
-        d2h(ctx, dots.data(), d_dots.p, dots.size());
+        std::vector<float> dots((size_t)W * kchunk * nc);
+        d2h(ctx, dots.data() + (size_t)klo * nc, d_dots.p, (size_t)kcnt * nc);
         sync(ctx);
+        exchange(dots.data(), (uint64_t)kchunk * nc * sizeof(float));
         uint32_t best = 0;
         float best_score = 0.0f;
         for (uint32_t i = 0; i < nk; ++i) {
@@ -996,27 +1019,33 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     }
 
     // Step 3 (:132-169)
-    DevBuf<float> d_best(nk);
-    DevBuf<uint32_t> d_target(nk), d_sums((size_t)nc * dim), d_members(nc);
-    std::vector<float> best(nk);
-    std::vector<uint32_t> target(nk);
-    DevBuf<float> d_tile((size_t)nc * nk);  // reads x centroids similarities, [centroid][read]
+    DevBuf<float> d_best(std::max<uint32_t>(kcnt, 1));
+    DevBuf<uint32_t> d_target_loc(std::max<uint32_t>(kcnt, 1)), d_target(nk), d_sums((size_t)nc * dim), d_members(nc);
+    std::vector<float> best((size_t)W * kchunk);
+    std::vector<uint32_t> target((size_t)W * kchunk);
+    DevBuf<float> d_tile(std::max<size_t>((size_t)nc * kcnt, 1));  // reads x centroids similarities, [centroid][read]
     pa.n_cols = nc;
     pa.out = d_tile.p;
-    pa.ld = nk;
+    pa.ld = kcnt;
+    // best similarity + target of every kept read (host), target also on the device for the recentering
     auto assign_pass = [&]() {
-        centroid_tile(true, "k6_pair_argmax");
-        MYRIO_LAUNCH(ctx, "k6_argmax_rows", argmax_rows_kernel, (nk + 127) / 128, 128, 0, d_tile.p, (uint64_t)nk, nk,
-                     nc, d_best.p, d_target.p);
+        if (kcnt) {
+            centroid_tile(true, "k6_pair_argmax");
+            MYRIO_LAUNCH(ctx, "k6_argmax_rows", argmax_rows_kernel, (kcnt + 127) / 128, 128, 0, d_tile.p,
+                         (uint64_t)kcnt, kcnt, nc, d_best.p, d_target_loc.p);
+            d2h(ctx, best.data() + klo, d_best.p, kcnt);
+            d2h(ctx, target.data() + klo, d_target_loc.p, kcnt);
+        }
+        sync(ctx);
+        exchange(best.data(), (uint64_t)kchunk * sizeof(float));
+        exchange(target.data(), (uint64_t)kchunk * sizeof(uint32_t));
+        h2d(ctx, d_target.p, target.data(), nk);
     };
     float previous_mean_wcsss = 1E-6f;
     float improvement_score = 3.40282347e+38f;
     uint64_t nb_iters = 0;
     while (improvement_score > p->eta_improvement && nb_iters < p->nb_iters_max) {
         assign_pass();
-        d2h(ctx, best.data(), d_best.p, nk);
-        d2h(ctx, target.data(), d_target.p, nk);
-        sync(ctx);
         // wcsss (:307-316): sum1 over members (push order = read order)
         std::vector<float> w(nc, 0.0f);
         std::vector<uint8_t> seen(nc, 0);
@@ -1048,7 +1077,6 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
 
     // Step 5 / first half of step 4 (:200-233): final assignment
     assign_pass();
-    d2h(ctx, target.data(), d_target.p, nk);
     sync(ctx);
     for (uint32_t i = 0; i < nk; ++i) assign[kept[i]] = (int32_t)target[i];
     if (!p->has_silhouette_trimming || nc == 1) return;
@@ -1082,73 +1110,81 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         const uint32_t nn = (uint32_t)members[nb].size();
         std::vector<uint32_t> cols(members[c]);
         cols.insert(cols.end(), members[nb].begin(), members[nb].end());
-        DevBuf<uint32_t> d_rows(nm), d_cols(cols.size());
-        DevBuf<float> d_sums2((size_t)nm * 2);
-        h2d(ctx, d_rows.p, members[c].data(), nm);
-        h2d(ctx, d_cols.p, cols.data(), cols.size());
-        MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)nm * 2 * sizeof(float), ctx->stream));
-        RowSlab mslab;  // the cluster's members as rows
-        if (canon_path)
-            build_row_slab_scheduled(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, canon, mslab);
-        else if (!merge_path)
-            build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, nm, mslab);
-        PairArgs sa{};
-        sa.c_off = norm->row_off.p;
-        sa.c_keys = norm->keys.p;
-        sa.c_vals = norm->vals_f32.p;
-        sa.col_ids = d_cols.p;
-        sa.dim = dim;
-        sa.sim = sim;
-        sa.ld = nm;
-        // column passes of at most PT_TILE_BUDGET bytes of [column][member] similarities; the row
-        // sums continue from pass to pass, so the f32 addition order is the member order
-        const uint32_t n_cols_all = (uint32_t)cols.size();
-        uint32_t pass_cols = (uint32_t)std::min<uint64_t>(n_cols_all, std::max<uint64_t>(8, PT_TILE_BUDGET / (4ull * nm) / 8 * 8));
-        DevBuf<float> d_sil_tile((size_t)pass_cols * nm);
-        sa.out = d_sil_tile.p;
-        for (uint32_t cf = 0; cf < n_cols_all; cf += pass_cols) {
-            sa.c_first = cf;
-            sa.n_cols = std::min(pass_cols, n_cols_all - cf);
-            if (canon_path) {
-                CanonArgs ca{};
-                ca.c_off = sa.c_off;
-                ca.c_keys = sa.c_keys;
-                ca.c_vals = sa.c_vals;
-                ca.col_ids = sa.col_ids;
-                ca.c_first = cf;
-                ca.n_cols = sa.n_cols;
-                ca.sim = sim;
-                ca.out = d_sil_tile.p;
-                ca.ld = nm;
-                launch_pair_tile_canon(ctx, ca, mslab, canon, "k6_pair_silhouette");
-            } else if (!merge_path) {
-                launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
-            } else {
-                MergeArgs m{};
-                m.r_off = norm->row_off.p;
-                m.r_keys = norm->keys.p;
-                m.r_vals = norm->vals_f32.p;
-                m.row_ids = d_rows.p;
-                m.n_rows = nm;
-                m.c_off = norm->row_off.p;
-                m.c_keys = norm->keys.p;
-                m.c_vals = norm->vals_f32.p;
-                m.col_ids = d_cols.p;
-                m.c_first = cf;
-                m.n_cols = sa.n_cols;
-                m.sim = sim;
-                m.out = d_sil_tile.p;
-                m.ld = nm;
-                m.transposed = true;
-                ctx->cluster_stats[0] += (uint64_t)nm * sa.n_cols;
-                launch_merge_pairs(ctx, m, "k6_pair_silhouette");
+        uint32_t mlo, mcnt, mchunk;  // this rank's share of the cluster's members (rows of the tile)
+        share(nm, mlo, mcnt, mchunk);
+        std::vector<float> sums((size_t)W * mchunk * 2);
+        if (mcnt) {
+            DevBuf<uint32_t> d_rows(mcnt), d_cols(cols.size());
+            DevBuf<float> d_sums2((size_t)mcnt * 2);
+            h2d(ctx, d_rows.p, members[c].data() + mlo, mcnt);
+            h2d(ctx, d_cols.p, cols.data(), cols.size());
+            MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)mcnt * 2 * sizeof(float), ctx->stream));
+            RowSlab mslab;  // the rank's members as rows
+            if (canon_path)
+                build_row_slab_scheduled(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, mcnt, canon,
+                                         mslab);
+            else if (!merge_path)
+                build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, mcnt, mslab);
+            PairArgs sa{};
+            sa.c_off = norm->row_off.p;
+            sa.c_keys = norm->keys.p;
+            sa.c_vals = norm->vals_f32.p;
+            sa.col_ids = d_cols.p;
+            sa.dim = dim;
+            sa.sim = sim;
+            sa.ld = mcnt;
+            // column passes of at most PT_TILE_BUDGET bytes of [column][member] similarities; the row
+            // sums continue from pass to pass, so the f32 addition order is the member order
+            const uint32_t n_cols_all = (uint32_t)cols.size();
+            uint32_t pass_cols = (uint32_t)std::min<uint64_t>(
+                n_cols_all, std::max<uint64_t>(8, PT_TILE_BUDGET / (4ull * mcnt) / 8 * 8));
+            DevBuf<float> d_sil_tile((size_t)pass_cols * mcnt);
+            sa.out = d_sil_tile.p;
+            for (uint32_t cf = 0; cf < n_cols_all; cf += pass_cols) {
+                sa.c_first = cf;
+                sa.n_cols = std::min(pass_cols, n_cols_all - cf);
+                if (canon_path) {
+                    CanonArgs ca{};
+                    ca.c_off = sa.c_off;
+                    ca.c_keys = sa.c_keys;
+                    ca.c_vals = sa.c_vals;
+                    ca.col_ids = sa.col_ids;
+                    ca.c_first = cf;
+                    ca.n_cols = sa.n_cols;
+                    ca.sim = sim;
+                    ca.out = d_sil_tile.p;
+                    ca.ld = mcnt;
+                    launch_pair_tile_canon(ctx, ca, mslab, canon, "k6_pair_silhouette");
+                } else if (!merge_path) {
+                    launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
+                } else {
+                    MergeArgs m{};
+                    m.r_off = norm->row_off.p;
+                    m.r_keys = norm->keys.p;
+                    m.r_vals = norm->vals_f32.p;
+                    m.row_ids = d_rows.p;
+                    m.n_rows = mcnt;
+                    m.c_off = norm->row_off.p;
+                    m.c_keys = norm->keys.p;
+                    m.c_vals = norm->vals_f32.p;
+                    m.col_ids = d_cols.p;
+                    m.c_first = cf;
+                    m.n_cols = sa.n_cols;
+                    m.sim = sim;
+                    m.out = d_sil_tile.p;
+                    m.ld = mcnt;
+                    m.transposed = true;
+                    ctx->cluster_stats[0] += (uint64_t)mcnt * sa.n_cols;
+                    launch_merge_pairs(ctx, m, "k6_pair_silhouette");
+                }
+                // columns [0, nm) are the cluster's own members (sum a), the rest the neighbour's (sum b)
+                MYRIO_LAUNCH(ctx, "k6_silsum_rows", silsum_rows_kernel, (mcnt + 127) / 128, 128, 0, d_sil_tile.p,
+                             (uint64_t)mcnt, mcnt, cf, sa.n_cols, nm, d_sums2.p);
             }
-            MYRIO_LAUNCH(ctx, "k6_silsum_rows", silsum_rows_kernel, (nm + 127) / 128, 128, 0, d_sil_tile.p,
-                         (uint64_t)nm, nm, cf, sa.n_cols, nm, d_sums2.p);
+            d2h(ctx, sums.data() + (size_t)mlo * 2, d_sums2.p, (size_t)mcnt * 2);
+            sync(ctx);
         }
-        std::vector<float> sums((size_t)nm * 2);
-        d2h(ctx, sums.data(), d_sums2.p, sums.size());
-        sync(ctx);
+        exchange(sums.data(), (uint64_t)mchunk * 2 * sizeof(float));
         std::vector<float> sil(nm);
         for (uint32_t t = 0; t < nm; ++t) {  // inner() :323-336
             const float a = sums[(size_t)t * 2] / (float)(nm - 1);

@@ -93,3 +93,44 @@ def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=Non
                                              C.c_void_p(out_i.data_ptr())))
     ctx.sync()
     return out_s, out_i
+
+
+def make_allgather_callback(group=None):
+    """The `myrio_allgather_fn` of a row-sharded clustering call over torch.distributed: host_buf
+    holds `world` chunks of nbytes, this rank's chunk is filled; all chunks are filled on return.
+    (NCCL: staged through a device tensor; the exchanged arrays are a few bytes per read.)"""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = _device_for_backend()
+
+    def allgather(user, host_buf, nbytes):
+        try:
+            nbytes = int(nbytes)
+            arr = np.ctypeslib.as_array(C.cast(host_buf, C.POINTER(C.c_uint8)), shape=(world * nbytes,))
+            mine = torch.from_numpy(arr[rank * nbytes:(rank + 1) * nbytes].copy()).to(dev)
+            if dist.get_backend(group) == "nccl":
+                out = torch.empty(world * nbytes, dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(out, mine, group=group)
+                arr[:] = out.cpu().numpy()
+            else:
+                bufs = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(bufs, mine, group=group)
+                for r, b in enumerate(bufs):
+                    arr[r * nbytes:(r + 1) * nbytes] = b.numpy()
+            return 0
+        except Exception:  # never unwind through the C ABI
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    return allgather
+
+
+def cluster_sharded(myrseqs, params, group=None):
+    """clustering::cluster over all ranks of `group` (SURVEY §8e-3): the reads are replicated, the rows of
+    every similarity tile are split across the ranks, per-row results are all-gathered.  Same result on
+    every rank as api.cluster on one GPU."""
+    from . import api
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return api.cluster(myrseqs, params)
+    return api.cluster(myrseqs, params,
+                       shard=(dist.get_rank(group), dist.get_world_size(group), make_allgather_callback(group)))

@@ -39,6 +39,20 @@ pub struct myrio_cluster_params {
     pub silhouette_trimming: f32,
 }
 
+/// all-gather of `world` host chunks of `bytes_per_rank` (chunk `rank` filled on entry); 0 = ok
+pub type myrio_allgather_fn =
+    Option<unsafe extern "C" fn(user: *mut c_void, host_buf: *mut c_void, bytes_per_rank: u64) -> i32>;
+
+/// this rank's place in a row-sharded `myrio_cluster_sharded` call
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct myrio_shard {
+    pub rank: u32,
+    pub world: u32,
+    pub allgather: myrio_allgather_fn,
+    pub user: *mut c_void,
+}
+
 unsafe extern "C" {
     pub fn myrio_last_error() -> *const c_char;
     pub fn myrio_version() -> i32;
@@ -107,6 +121,9 @@ unsafe extern "C" {
     pub fn myrio_cluster(ctx: *mut myrio_ctx, reads: *const myrio_seqs, params: *const myrio_cluster_params,
                          initial_centroids: *const myrio_svecs, assign: *mut i32, n_iters: *mut u32,
                          silhouette: *mut f32) -> i32;
+    pub fn myrio_cluster_sharded(ctx: *mut myrio_ctx, reads: *const myrio_seqs, params: *const myrio_cluster_params,
+                                 initial_centroids: *const myrio_svecs, shard: *const myrio_shard, assign: *mut i32,
+                                 n_iters: *mut u32, silhouette: *mut f32) -> i32;
     pub fn myrio_compute_cluster_centroid(ctx: *mut myrio_ctx, counts: *const myrio_svecs, member_ids: *const u64,
                                           m: u64, out: *mut *mut myrio_svecs) -> i32;
     pub fn myrio_pairwise(ctx: *mut myrio_ctx, rows: *const myrio_svecs, cols: *const myrio_svecs, similarity: i32,

@@ -89,3 +89,34 @@ def test_shard_bounds_cover_everything():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _cb_worker(rank, world, port, tmp):
+    """The exchange of the row-sharded clustering (myrio_shard.allgather) over gloo: called through the
+    C function-pointer type exactly as libmyrio_b200.so calls it."""
+    import ctypes as C
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from myrio_b200 import _lib
+    from myrio_b200 import dist as mdist
+    cb = _lib.ALLGATHER_FN(mdist.make_allgather_callback())
+    for chunk in (1, 7, 4096):
+        # float payload like (best similarity | silhouette sums), chunk elements per rank
+        buf = np.full(world * chunk, -1.0, np.float32)
+        buf[rank * chunk:(rank + 1) * chunk] = np.arange(chunk, dtype=np.float32) + 1000 * rank
+        rc = cb(None, buf.ctypes.data_as(C.c_void_p), chunk * 4)
+        assert rc == 0
+        for r in range(world):
+            assert (buf[r * chunk:(r + 1) * chunk] == np.arange(chunk, dtype=np.float32) + 1000 * r).all()
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, f"cb{rank}"), "w").write("ok")
+
+
+def test_cluster_shard_allgather_callback_world2(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_cb_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "cb0").exists() and (tmp_path / "cb1").exists()

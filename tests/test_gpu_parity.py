@@ -397,6 +397,53 @@ def test_cluster_other_similarities_match_oracle(api, ctx, sim):
             assert (bits(out.silhouette[both]) == bits(osil[both])).all()
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_cluster_row_sharded_ranks_agree_with_oracle(api, world):
+    # myrio_cluster_sharded with `world` ranks emulated as threads on ONE GPU (a context each); the
+    # all-gather callback is a barrier-synchronised copy between the ranks' host buffers
+    import ctypes as C
+    import threading
+    reads = two_gene_reads(101, 91)
+    oc = oracle.count_reads(reads.codes, reads.qual, reads.base_off, 6, 0.2)
+    oassign, oiters, osil = oracle.cluster(oc, 20, None, 3, silhouette=1.4)
+    barrier = threading.Barrier(world)
+    stage = {}
+    results, errors = [None] * world, []
+
+    def make_cb(rank):
+        def cb(user, host_buf, nbytes):
+            nbytes = int(nbytes)
+            arr = np.ctypeslib.as_array(C.cast(host_buf, C.POINTER(C.c_uint8)), shape=(world * nbytes,))
+            stage[rank] = arr[rank * nbytes:(rank + 1) * nbytes].copy()
+            barrier.wait(timeout=120)
+            for r in range(world):
+                arr[r * nbytes:(r + 1) * nbytes] = stage[r]
+            barrier.wait(timeout=120)
+            return 0
+        return cb
+
+    def run(rank):
+        try:
+            c = api.Context(0)
+            m = api.MyrSeqs(c, reads)
+            prm = api.ClusteringParameters(k=6, t1=0.2, t2=20, expected_nb_of_clusters=3, silhouette_trimming=1.4)
+            results[rank] = api.cluster(m, prm, shard=(rank, world, make_cb(rank)))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    both = ~np.isnan(osil)
+    for out in results:
+        assert (out.assign == oassign).all() and out.n_iters == oiters
+        assert (bits(out.silhouette[both]) == bits(osil[both])).all()
+
+
 def test_cluster_errors(api, ctx):
     reads = two_gene_reads(10, 71)
     m = api.MyrSeqs(ctx, reads)
