@@ -157,32 +157,49 @@ def traffic_from_profiles():
 SMEM_BYTES_PER_CLK_PER_SM = 128.0  # shared-memory bandwidth of one SM (32 banks x 4 B)
 
 
-def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu_seconds=0.0):
+def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu_seconds=0.0, world=1,
+                     cluster_fn=None, reduce_max=None, reduce_sum=None):
     """Stage 3 of the hot path: clustering::cluster (clustering.rs:55-270) on the whole read batch at
     the reference defaults (k=6, t1=0.2, t2=20), first without and then with silhouette trimming
     (ssdcf 1.4, config_default.toml:30) -- the O(N^2) reads x reads similarity.  Kernel times are CUDA
     events on the library's stream; the pair / term counts are exact (myrio_cluster_stats)."""
+    cluster_fn = cluster_fn or api.cluster
+    reduce_max = reduce_max or (lambda v: v)
+    reduce_sum = reduce_sum or (lambda v: v)
     out = {"workload": f"cluster() k=6 t1=0.2 t2=20 on {resident.n} reads, {n_clusters} clusters "
-                       f"(farthest-point fill), cosine; then the same with silhouette trimming 1.4"}
+                       f"(farthest-point fill), cosine; then the same with silhouette trimming 1.4",
+           "parallelism": "single GPU" if world == 1 else
+                          f"reads replicated, rows of every similarity tile split over {world} GPUs, per-row results "
+                          f"all-gathered (myrio_cluster_sharded)",
+           "scaling": "strong"}
     for name, sil in (("assign_only", None), ("with_silhouette", 1.4)):
         prm = api.ClusteringParameters(k=6, t1=0.2, t2=20, expected_nb_of_clusters=n_clusters,
                                        silhouette_trimming=sil)
-        api.cluster(resident, prm)  # warm-up (allocator pool, kernel attributes)
-        ctx.prof_reset()
-        ctx.prof_enable(True)
-        t0 = time.perf_counter()
-        res = api.cluster(resident, prm)
-        call_s = time.perf_counter() - t0
-        st = ctx.cluster_stats()
+        cluster_fn(resident, prm)  # warm-up (allocator pool, kernel attributes)
+        calls = []
+        for _ in range(3):  # median of three timed calls (the stream-ordered allocator adds run-to-run noise)
+            ctx.prof_reset()
+            ctx.prof_enable(True)
+            reduce_max(0.0)  # barrier
+            t0 = time.perf_counter()
+            res = cluster_fn(resident, prm)
+            calls.append(reduce_max(time.perf_counter() - t0))  # max over ranks
+        call_s = sorted(calls)[1]
+        st = ctx.cluster_stats()  # this rank's share of the tiles
+        pairs_all = int(reduce_sum(float(st["pair_similarities"])))
         tile_ms = sum(ctx.prof_query(p)[0] for p in ("k6_pair_", "k6_silsum", "k6_argmax"))
         sil_ms = ctx.prof_query("k6_pair_silhouette")[0]
         all_ms, n_launch = ctx.prof_query("")
         ctx.prof_enable(False)
         ctx.prof_reset()
-        d = {"call_ms": call_s * 1e3, "kernels_ms": all_ms, "k6_tile_kernels_ms": tile_ms, "gpu_launches": n_launch,
+        d = {"call_ms": call_s * 1e3, "calls_ms": [c * 1e3 for c in calls], "kernels_ms": all_ms, "k6_tile_kernels_ms": tile_ms, "gpu_launches": n_launch,
              "iters": res.n_iters, "cluster_sizes": [int(len(c)) for c in res.clusters],
-             "rejected": int(len(res.rejected)), "pair_similarities": st["pair_similarities"],
-             "terms": st["terms"], "pair_similarities_per_s": st["pair_similarities"] / max(call_s, 1e-9)}
+             "rejected": int(len(res.rejected)), "pair_similarities": pairs_all,
+             "pair_similarities_rank0": st["pair_similarities"],
+             "terms_rank0": st["terms"], "pair_similarities_per_s": pairs_all / max(call_s, 1e-9)}
+        if getattr(res, "exchange", None):
+            d["exchange"] = {"calls": res.exchange["calls"], "ms_incl_waiting_for_peers": res.exchange["seconds"] * 1e3,
+                             "bytes": res.exchange["bytes"]}
         if sil is not None and sil_ms > 0:
             # dominant kernel of the stage: pair_tile_kernel.  Every multiply-add term reads one f32 of a
             # column from shared memory (4 B); the bound is the SMs' shared-memory bandwidth.
@@ -465,13 +482,30 @@ def run_ours(args, rank, local_rank, world):
                                "k5_topx_merge_tiles": k5_ms / args.steps, "all_kernels": all_ms / args.steps},
     }
 
-    # ---- stage 3 (clustering), N=1 only: not part of `value`, reported beside it
-    if world == 1 and not args.no_clustering:
+    # ---- stage 3 (clustering): not part of `value`, reported beside it; N > 1 shards the rows
+    if not args.no_clustering:
         cpu_reads = None
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:
             cpu_reads = reads.subset(np.arange(min(reads.n, 4096)))
-        line["clustering"] = bench_clustering(ctx, api, resident, args.clusters,
-                                              (clocks or {}).get("sm_mhz"), cpu_reads, min(args.cpu_seconds, 5.0))
+
+        def _reduce(v, op):
+            if world == 1:
+                return v
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=op)
+            return float(t.item())
+
+        def reduce_max(v):
+            return _reduce(v, dist.ReduceOp.MAX)
+
+        def reduce_sum(v):
+            return _reduce(v, dist.ReduceOp.SUM)
+
+        cl = bench_clustering(ctx, api, resident, args.clusters, (clocks or {}).get("sm_mhz") if clocks else None,
+                              cpu_reads, min(args.cpu_seconds, 5.0), world,
+                              (lambda m, prm: mdist.cluster_sharded(m, prm)) if world > 1 else None, reduce_max,
+                              reduce_sum)
+        line["clustering"] = cl
 
     # ---- CPU baseline: the oracle on the host cores, rank 0, N=1 only, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

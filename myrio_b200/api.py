@@ -379,6 +379,7 @@ class ClusteringOutput:
     assign: np.ndarray
     n_iters: int
     silhouette: np.ndarray = field(default=None)
+    exchange: dict = field(default=None)  # row-sharded runs: all-gather statistics
 
 
 def cluster(myrseqs: MyrSeqs, params: ClusteringParameters, shard=None) -> ClusteringOutput:

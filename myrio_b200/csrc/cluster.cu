@@ -10,6 +10,7 @@
 // sparse merge-join (data/sparse.rs:317-360).  No tensor cores: the sum order is
 // part of the result.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <numeric>
 
@@ -849,10 +850,35 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         cnt = std::min(n, lo + chunk) - lo;
     };
     // buf holds W chunks of bytes_per_rank; this rank's chunk is filled, the others arrive
+    const bool timing = getenv("MYRIO_CLUSTER_TIMING") != nullptr;
+    double t_exchange = 0.0;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto seconds_since = [](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count();
+    };
     auto exchange = [&](void *buf, uint64_t bytes_per_rank) {
         if (W == 1 || bytes_per_rank == 0) return;
+        const auto t0 = std::chrono::steady_clock::now();
         const int32_t rc = sh->allgather(sh->user, buf, bytes_per_rank);
+        t_exchange += seconds_since(t0);
         if (rc != 0) fail(MYRIO_ERR_BAD_ARG, "allgather callback failed (%d)", rc);
+    };
+    struct TimingReport {
+        bool on;
+        uint32_t rank;
+        const double &ex;
+        std::chrono::steady_clock::time_point t0;
+        std::vector<std::pair<const char *, double>> marks;
+        ~TimingReport() {
+            if (!on) return;
+            std::fprintf(stderr, "[myrio_cluster rank %u] total %.1f ms, exchange %.1f ms", rank,
+                         std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3, ex * 1e3);
+            for (auto &m : marks) std::fprintf(stderr, ", %s @%.1f", m.first, m.second * 1e3);
+            std::fprintf(stderr, "\n");
+        }
+    } report{timing, R, t_exchange, t_begin, {}};
+    auto mark = [&](const char *what) {
+        if (timing) report.marks.emplace_back(what, seconds_since(t_begin));
     };
     const uint64_t n_init = init ? init->n_rows : 0;
     if (n_init == 0 && p->expected_nb_of_clusters == 0)
@@ -943,6 +969,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     const float max_nb_hck = (float)max_hck;
     if (nc == 0) push_centroid_from_read(kept[max_idx]);
 
+    mark("counted+init");
     const bool merge_path = sim == MYRIO_SIM_OVERLAP;  // union-of-keys sums: merge-join kernel
     uint32_t klo, kcnt, kchunk;  // this rank's share of the kept reads
     share(nk, klo, kcnt, kchunk);
@@ -1018,6 +1045,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         push_centroid_from_read(kept[best]);
     }
 
+    mark("centroids filled");
     // Step 3 (:132-169)
     DevBuf<float> d_best(std::max<uint32_t>(kcnt, 1));
     DevBuf<uint32_t> d_target_loc(std::max<uint32_t>(kcnt, 1)), d_target(nk), d_sums((size_t)nc * dim), d_members(nc);
@@ -1075,6 +1103,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     }
     if (n_iters) *n_iters = (uint32_t)nb_iters;
 
+    mark("iterations done");
     // Step 5 / first half of step 4 (:200-233): final assignment
     assign_pass();
     sync(ctx);
@@ -1110,6 +1139,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         const uint32_t nn = (uint32_t)members[nb].size();
         std::vector<uint32_t> cols(members[c]);
         cols.insert(cols.end(), members[nb].begin(), members[nb].end());
+        mark("silhouette cluster");
         uint32_t mlo, mcnt, mchunk;  // this rank's share of the cluster's members (rows of the tile)
         share(nm, mlo, mcnt, mchunk);
         std::vector<float> sums((size_t)W * mchunk * 2);

@@ -102,9 +102,15 @@ def make_allgather_callback(group=None):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = _device_for_backend()
 
+    import time
+    stats = {"calls": 0, "seconds": 0.0, "bytes": 0}
+
     def allgather(user, host_buf, nbytes):
+        t0 = time.perf_counter()
         try:
             nbytes = int(nbytes)
+            stats["calls"] += 1
+            stats["bytes"] += nbytes * world
             arr = np.ctypeslib.as_array(C.cast(host_buf, C.POINTER(C.c_uint8)), shape=(world * nbytes,))
             mine = torch.from_numpy(arr[rank * nbytes:(rank + 1) * nbytes].copy()).to(dev)
             if dist.get_backend(group) == "nccl":
@@ -121,7 +127,10 @@ def make_allgather_callback(group=None):
             import traceback
             traceback.print_exc()
             return 1
+        finally:
+            stats["seconds"] += time.perf_counter() - t0
 
+    allgather.stats = stats
     return allgather
 
 
@@ -132,5 +141,7 @@ def cluster_sharded(myrseqs, params, group=None):
     from . import api
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return api.cluster(myrseqs, params)
-    return api.cluster(myrseqs, params,
-                       shard=(dist.get_rank(group), dist.get_world_size(group), make_allgather_callback(group)))
+    cb = make_allgather_callback(group)
+    out = api.cluster(myrseqs, params, shard=(dist.get_rank(group), dist.get_world_size(group), cb))
+    out.exchange = dict(cb.stats)  # calls / seconds / bytes spent in the all-gathers (includes waiting for peers)
+    return out
