@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clustering", action="store_true", help="skip the clustering stage (K6) measurement")
     ap.add_argument("--clusters", type=int, default=4)
+    ap.add_argument("--cluster-reps", type=int, default=3, help="timed cluster() calls per variant (median reported)")
+    ap.add_argument("--cluster-warmup", type=int, default=1)
     return ap.parse_args()
 
 
@@ -158,7 +160,7 @@ SMEM_BYTES_PER_CLK_PER_SM = 128.0  # shared-memory bandwidth of one SM (32 banks
 
 
 def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu_seconds=0.0, world=1,
-                     cluster_fn=None, reduce_max=None, reduce_sum=None):
+                     cluster_fn=None, reduce_max=None, reduce_sum=None, reps=3, warmup=1):
     """Stage 3 of the hot path: clustering::cluster (clustering.rs:55-270) on the whole read batch at
     the reference defaults (k=6, t1=0.2, t2=20), first without and then with silhouette trimming
     (ssdcf 1.4, config_default.toml:30) -- the O(N^2) reads x reads similarity.  Kernel times are CUDA
@@ -175,16 +177,17 @@ def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu
     for name, sil in (("assign_only", None), ("with_silhouette", 1.4)):
         prm = api.ClusteringParameters(k=6, t1=0.2, t2=20, expected_nb_of_clusters=n_clusters,
                                        silhouette_trimming=sil)
-        cluster_fn(resident, prm)  # warm-up (allocator pool, kernel attributes)
+        for _ in range(warmup):
+            cluster_fn(resident, prm)  # warm-up (allocator pool, kernel attributes)
         calls = []
-        for _ in range(3):  # median of three timed calls (the stream-ordered allocator adds run-to-run noise)
+        for _ in range(max(1, reps)):  # median of the timed calls (the stream-ordered allocator adds run-to-run noise)
             ctx.prof_reset()
             ctx.prof_enable(True)
             reduce_max(0.0)  # barrier
             t0 = time.perf_counter()
             res = cluster_fn(resident, prm)
             calls.append(reduce_max(time.perf_counter() - t0))  # max over ranks
-        call_s = sorted(calls)[1]
+        call_s = sorted(calls)[len(calls) // 2]
         st = ctx.cluster_stats()  # this rank's share of the tiles
         pairs_all = int(reduce_sum(float(st["pair_similarities"])))
         tile_ms = sum(ctx.prof_query(p)[0] for p in ("k6_pair_", "k6_silsum", "k6_argmax"))
@@ -504,7 +507,7 @@ def run_ours(args, rank, local_rank, world):
         cl = bench_clustering(ctx, api, resident, args.clusters, (clocks or {}).get("sm_mhz") if clocks else None,
                               cpu_reads, min(args.cpu_seconds, 5.0), world,
                               (lambda m, prm: mdist.cluster_sharded(m, prm)) if world > 1 else None, reduce_max,
-                              reduce_sum)
+                              reduce_sum, args.cluster_reps, args.cluster_warmup)
         line["clustering"] = cl
 
     # ---- CPU baseline: the oracle on the host cores, rank 0, N=1 only, bounded sample

@@ -195,8 +195,12 @@ __host__ __device__ inline size_t score_warp_smem_bytes(uint32_t tile_leaves, bo
            SC_HITS * sizeof(HitRec);
 }
 
-template <int SIM, bool FUSED>
-__global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArgs a) {
+// STATS: count the postings touched (bench / tests; the timed path leaves it out).
+// UREG: the unit values of the lane-owned leaves live in registers (3 instead of 4 instructions per
+// dense slot, 128 registers -> 16 warps) instead of shared memory (96 registers -> 20 warps).
+static constexpr int SC_UREG_WARPS = 16;
+template <int SIM, bool FUSED, bool STATS, bool UREG>
+__global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) score_tiles_kernel(ScoreArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
@@ -227,10 +231,19 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
         // memory (bank == lane, conflict-free) -- keeping them in registers too costs a quarter
         // of the resident warps and measured slower (profiles/r01_k4_variants.md).
         const bool dense_tile = ti->n_dense != 0;  // implies tile_leaves <= DENSE_MAX_TILE
+        float ureg[UREG ? 32 : 1];
         if (dense_tile) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r)
-                usm[32 * r + lane] = (32u * r + lane < nl) ? __ldg(ti->unit + 32 * r + lane) : 0.0f;
+            for (int r = 0; r < 32; ++r) {
+                const float u = (32u * r + lane < nl) ? __ldg(ti->unit + 32 * r + lane) : 0.0f;
+                if (UREG)
+                    ureg[UREG ? r : 0] = u;
+                else
+                    usm[32 * r + lane] = u;
+            }
+        } else if (UREG) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r) ureg[UREG ? r : 0] = 0.0f;
         }
         for (uint32_t i = lane; i < a.tile_leaves + 32; i += 32) acc[i] = 0.0f;  // incl. the dummy slots
         __syncwarp();
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
                 cv = h.qv;
                 coff = 0;
                 open = true;
-                st_post += (lane == 0) ? cl : 0;
+                if (STATS) st_post += (lane == 0) ? cl : 0;
             };
             constexpr uint32_t DENSE_CHUNK = 0xFFFFFFFFu;  // chunk-size marker of a dense key
             auto fetch = [&](uint64_t(&p)[SC_U], uint32_t &n, float &v) -> bool {
@@ -304,7 +317,7 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
                     const uint32_t w = (uint32_t)p[0];
 #pragma unroll
                     for (int r = 0; r < 32; ++r) {
-                        const float s2 = __fadd_rn(racc[r], __fmul_rn(v, usm[32 * r + lane]));
+                        const float s2 = __fadd_rn(racc[r], __fmul_rn(v, UREG ? ureg[UREG ? r : 0] : usm[32 * r + lane]));
                         racc[r] = (w & (1u << r)) ? s2 : racc[r];
                     }
                     return;
@@ -370,7 +383,7 @@ __global__ void __launch_bounds__(SC_MAX_WARPS * 32) score_tiles_kernel(ScoreArg
         }
         __syncwarp();
     }
-    if (lane == 0 && st_post) atomicAdd(a.counters + 3, st_post);
+    if (STATS && lane == 0 && st_post) atomicAdd(a.counters + 3, st_post);
 }
 
 // ------------------------------------------------------------------ K5: top-x
@@ -789,23 +802,45 @@ static void check_sim(int32_t sim) {
         fail(MYRIO_ERR_UNSUPPORTED, "similarity %d is not implemented on the GPU path (Cosine, JacardTanimoto are)", sim);
 }
 
-template <bool FUSED>
-static void launch_score(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a, int32_t sim) {
+static bool k4_unit_in_registers() {  // MYRIO_K4_UREG=1/0 (tuning)
+    static const bool v = [] {
+        const char *e = getenv("MYRIO_K4_UREG");
+        return e ? e[0] == '1' : false;
+    }();
+    return v;
+}
+
+template <int SIM, bool FUSED, bool STATS, bool UREG>
+static void launch_score_variant(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a) {
     const size_t per_warp = score_warp_smem_bytes(ix->tile_leaves, FUSED);
-    int warps = (int)std::min<size_t>(SC_MAX_WARPS, (ctx->smem_optin - 1024) / per_warp);
+    int warps = (int)std::min<size_t>(UREG ? SC_UREG_WARPS : SC_MAX_WARPS, (ctx->smem_optin - 1024) / per_warp);
     if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
     const size_t smem = per_warp * warps;
     const unsigned grid = (unsigned)std::min<unsigned long long>(a.n_tasks, (unsigned long long)ctx->sm_count);
     const char *name = FUSED ? "k4_score_tiles_topx" : "k4_score_tiles_rows";
-    if (sim == MYRIO_SIM_COSINE) {
-        auto kern = score_tiles_kernel<MYRIO_SIM_COSINE, FUSED>;
-        MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MYRIO_LAUNCH(ctx, name, kern, grid, warps * 32, smem, a);
-    } else {
-        auto kern = score_tiles_kernel<MYRIO_SIM_JACARD_TANIMOTO, FUSED>;
-        MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MYRIO_LAUNCH(ctx, name, kern, grid, warps * 32, smem, a);
-    }
+    auto kern = score_tiles_kernel<SIM, FUSED, STATS, UREG>;
+    MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYRIO_LAUNCH(ctx, name, kern, grid, warps * 32, smem, a);
+}
+
+template <bool FUSED>
+static void launch_score(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a, int32_t sim, bool stats) {
+    const bool ureg = k4_unit_in_registers();
+#define MYRIO_K4_DISPATCH(SIMV)                                                         \
+    do {                                                                                \
+        if (stats) {                                                                    \
+            if (ureg) launch_score_variant<SIMV, FUSED, true, true>(ctx, ix, a);        \
+            else launch_score_variant<SIMV, FUSED, true, false>(ctx, ix, a);            \
+        } else {                                                                        \
+            if (ureg) launch_score_variant<SIMV, FUSED, false, true>(ctx, ix, a);       \
+            else launch_score_variant<SIMV, FUSED, false, false>(ctx, ix, a);           \
+        }                                                                               \
+    } while (0)
+    if (sim == MYRIO_SIM_COSINE)
+        MYRIO_K4_DISPATCH(MYRIO_SIM_COSINE);
+    else
+        MYRIO_K4_DISPATCH(MYRIO_SIM_JACARD_TANIMOTO);
+#undef MYRIO_K4_DISPATCH
 }
 
 static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl, uint64_t qn) {
@@ -858,7 +893,7 @@ void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries
         MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
         ScoreArgs a = base_args(ctx, ix, pl, qn);
         a.scores = ctx->score_rows.p;
-        launch_score<false>(ctx, ix, a, sim);
+        launch_score<false>(ctx, ix, a, sim, true);
         d2h(ctx, scores_host + q0 * L, ctx->score_rows.p, qn * L);
         accumulate_stats(ctx);
         q0 += qn;
@@ -897,7 +932,7 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
             a.cand = cand.p;
             a.cand_cnt = cand_cnt.p;
             a.gthr = gthr.p;
-            launch_score<true>(ctx, ix, a, sim);
+            launch_score<true>(ctx, ix, a, sim, collect_stats);
         }
         MYRIO_LAUNCH(ctx, "k5_topx_merge_tiles", topx_cand_merge_kernel, (unsigned)qn, TX_THREADS, 0, cand.p,
                      cand_cnt.p, gthr.p, (uint32_t)ix->tiles.size(), x, d_top_scores + q0 * x,
