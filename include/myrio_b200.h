@@ -242,8 +242,14 @@ typedef struct {
 int32_t myrio_cluster_sharded(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_params *params,
                               const myrio_svecs *initial_centroids, const myrio_shard *shard,
                               int32_t *assign, uint32_t *n_iters, float *silhouette);
-/* compute_cluster_centroid (clustering.rs:44-53) over rows member_ids[0..m) of
- * `counts` (raw, un-normalised); out is a 1-row normalised batch. */
+/* compute_cluster_centroid (clustering.rs:44-53) over rows member_ids[0..m) of `counts`
+ * (raw, un-normalised f32 counts): out = normalize_l2(sum of the members), a 1-row batch.
+ * The per-key sums are sequential f32 additions in member order, which is also
+ * `iter.sum::<SFVec>().into_normalized_l2()` -- so the same call builds the FINGERPRINTS of
+ * TaxTreeCompute::from_store_tree (tax/compute.rs:51-77): with `counts` = a u16 batch of
+ * myrio_count_leaves at cluster_k (converted like kmer_store_counts_to_kmer_counts, tax/mod.rs:55-58:
+ * count as f32 * rescale) and member_ids = the leaves sampled from one branch it returns the local
+ * fingerprint; over the f32 batch of local fingerprints it returns the global one. */
 int32_t myrio_compute_cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts,
                                        const uint64_t *member_ids, uint64_t m, myrio_svecs **out);
 /* the reads x reads (or reads x centroids) similarity tile used by the clustering

@@ -415,7 +415,9 @@ def cluster(myrseqs: MyrSeqs, params: ClusteringParameters, shard=None) -> Clust
 
 
 def compute_cluster_centroid(counts: SFVecs, member_ids) -> SFVecs:
-    """clustering::compute_cluster_centroid (clustering.rs:44-53) over rows of a raw count batch."""
+    """clustering::compute_cluster_centroid (clustering.rs:44-53) over rows of a raw count batch.
+    Also `rows.sum::<SFVec>().into_normalized_l2()` for any f32 batch, and -- for a u16 batch of
+    cached leaf counts -- the sum of kmer_store_counts_to_kmer_counts(row) (tax/mod.rs:55-58)."""
     ids = np.ascontiguousarray(member_ids, np.uint64)
     h = C.c_void_p()
     _lib.check(counts.ctx._L.myrio_compute_cluster_centroid(counts.ctx.h, counts.h, _p(ids), len(ids),
@@ -429,3 +431,21 @@ def pairwise(rows: SFVecs, cols: SFVecs, similarity: int = SIM_COSINE) -> np.nda
     if out.size:
         _lib.check(rows.ctx._L.myrio_pairwise(rows.ctx.h, rows.h, cols.h, similarity, _p(out)))
     return out
+
+
+def fingerprints(ttstore: TaxTreeStore, cluster_k: int, branch_leaf_samples, fasta_nb_resamples: int = 32,
+                 seed: int = 0):
+    """The fingerprints of TaxTreeCompute::from_store_tree (tax/compute.rs:51-77) at `cluster_k`:
+    one local fingerprint per entry of `branch_leaf_samples` (the leaves drawn from one branch at
+    the fingerprint rank -- the reference draws them with an OS-seeded RNG, `choose_multiple`, so
+    the caller supplies the sample) and the global fingerprint (the normalised sum of the local
+    ones).  Returns (local: list[SFVecs], global: SFVecs)."""
+    counts = ttstore._count(cluster_k, fasta_nb_resamples, seed)
+    local = [compute_cluster_centroid(counts, ids) for ids in branch_leaf_samples]
+    rows = [fp.download(aux=False) for fp in local]
+    ro = np.zeros(len(rows) + 1, np.uint64)
+    ro[1:] = np.cumsum([len(r[1]) for r in rows])
+    keys = np.concatenate([r[1] for r in rows]) if rows else np.zeros(0, np.uint64)
+    vals = np.concatenate([r[2] for r in rows]) if rows else np.zeros(0, np.float32)
+    batch = SFVecs.upload(ttstore.ctx, ro, keys, vals)
+    return local, compute_cluster_centroid(batch, np.arange(len(rows)))

@@ -1242,9 +1242,13 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
 
 // ------------------------------------------------ compute_cluster_centroid
 
+// VT = float: rows of an f32 batch (read counts, fingerprints).  VT = uint16_t: cached leaf counts,
+// converted like kmer_store_counts_to_kmer_counts (tax/mod.rs:55-58): val as f32 * rescale_factor.
+template <typename VT>
 __global__ void __launch_bounds__(256) gather_members_kernel(const uint64_t *__restrict__ r_off,
                                                              const uint64_t *__restrict__ r_keys,
-                                                             const float *__restrict__ r_vals,
+                                                             const VT *__restrict__ r_vals,
+                                                             const float *__restrict__ rescale,
                                                              const uint64_t *__restrict__ ids,
                                                              const uint64_t *__restrict__ dst_off, uint64_t m,
                                                              uint64_t *__restrict__ okeys,
@@ -1253,9 +1257,11 @@ __global__ void __launch_bounds__(256) gather_members_kernel(const uint64_t *__r
     if (i >= m) return;
     const unsigned lane = threadIdx.x & 31;
     const uint64_t r = ids[i], b = r_off[r], n = r_off[r + 1] - b, d = dst_off[i];
+    const float f = rescale ? rescale[r] : 1.0f;
     for (uint64_t j = lane; j < n; j += 32) {
         okeys[d + j] = r_keys[b + j];
-        ovals[d + j] = (uint64_t)r_vals[b + j];  // raw counts are integer-valued
+        const float v = rescale ? __fmul_rn((float)r_vals[b + j], f) : (float)r_vals[b + j];
+        ovals[d + j] = (uint64_t)__float_as_uint(v);
     }
 }
 
@@ -1273,12 +1279,14 @@ __global__ void __launch_bounds__(256) cc_reduce_runs_kernel(const uint64_t *__r
                                                              float *__restrict__ usum) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !flags[i]) return;
+    // iter.sum::<SFVec>() (data/sparse.rs:521-528): a fold of `acc + x` from the empty vector, i.e. per
+    // key a sequential f32 sum in member order (the stable sort kept it); exact for integer counts
     const uint64_t key = keys[i];
-    uint64_t s = 0;
-    for (uint64_t j = i; j < n && keys[j] == key; ++j) s += vals[j];
+    float s = __uint_as_float((uint32_t)vals[i]);
+    for (uint64_t j = i + 1; j < n && keys[j] == key; ++j) s = __fadd_rn(s, __uint_as_float((uint32_t)vals[j]));
     const uint64_t u = uidx[i];
     ukeys[u] = key;
-    usum[u] = (float)s;
+    usum[u] = s;
 }
 
 __global__ void cc_norm_kernel(const float *__restrict__ v, uint64_t n, float *__restrict__ magn) {
@@ -1297,7 +1305,9 @@ __global__ void __launch_bounds__(256) cc_scale_kernel(float *__restrict__ v, ui
 
 myrio_svecs *cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts, const uint64_t *member_ids,
                               uint64_t m) {
-    if (counts->vtype != MYRIO_VAL_F32) fail(MYRIO_ERR_BAD_ARG, "counts must be an f32 batch");
+    const bool leaf_counts = counts->vtype == MYRIO_VAL_U16;
+    if (leaf_counts && counts->aux_kind != 2)
+        fail(MYRIO_ERR_BAD_ARG, "u16 counts need their rescale factors (a myrio_count_leaves batch)");
     for (uint64_t i = 0; i < m; ++i)
         if (member_ids[i] >= counts->n_rows) fail(MYRIO_ERR_BAD_ARG, "member id out of range");
     auto out = std::make_unique<myrio_svecs>();
@@ -1317,8 +1327,14 @@ myrio_svecs *cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts, const u
         DevBuf<uint64_t> offs;
         h2d(ctx, d_ids.p, member_ids, m);
         h2d(ctx, d_dst.p, dst.data(), m + 1);
-        MYRIO_LAUNCH(ctx, "cc_gather", gather_members_kernel, (unsigned)((m + 7) / 8), 256, 0, counts->row_off.p,
-                     counts->keys.p, counts->vals_f32.p, d_ids.p, d_dst.p, m, k1.p, v1.p);
+        if (leaf_counts)
+            MYRIO_LAUNCH(ctx, "cc_gather", gather_members_kernel<uint16_t>, (unsigned)((m + 7) / 8), 256, 0,
+                         counts->row_off.p, counts->keys.p, counts->vals_u16.p, counts->aux_f32.p, d_ids.p, d_dst.p, m,
+                         k1.p, v1.p);
+        else
+            MYRIO_LAUNCH(ctx, "cc_gather", gather_members_kernel<float>, (unsigned)((m + 7) / 8), 256, 0,
+                         counts->row_off.p, counts->keys.p, counts->vals_f32.p, (const float *)nullptr, d_ids.p,
+                         d_dst.p, m, k1.p, v1.p);
         const bool in_tmp = radix_sort_pairs_raw(ctx, k1.p, v1.p, k2.p, v2.p, total, 64, hist, offs);
         const uint64_t *sk = in_tmp ? k2.p : k1.p, *sv = in_tmp ? v2.p : v1.p;
         const unsigned g = (unsigned)((total + 255) / 256);

@@ -468,6 +468,36 @@ def test_compute_cluster_centroid_search_k(api, ctx):
 
 # ------------------------------------------- long queries, dense keys, properties
 
+def test_fingerprints_match_oracle(api, ctx):
+    # tax/compute.rs:51-77 with explicit leaf samples: local fingerprint = normalize(sum over the sampled
+    # leaves of count * rescale) at cluster_k, global = normalize(sum of the local ones).  Leaves with
+    # ambiguity codes make the rescale factors (and the summed values) non-integer f32.
+    rng = np.random.default_rng(17)
+    tree = synth.make_tree(120, 41)
+    iupac = synth.tree_to_iupac(tree).copy()
+    amb = rng.choice(len(iupac), 60, replace=False)
+    iupac[amb] = rng.choice(np.array([3, 5, 6, 9, 10, 12, 7, 15], np.uint8), 60)  # R Y S W K M ... N
+    store = api.TaxTreeStore(ctx, iupac=iupac, base_off=tree.base_off)
+    samples = [rng.choice(120, 16, replace=False) for _ in range(5)] + [np.array([7], np.int64)]
+    local, glob = api.fingerprints(store, 6, samples, 32, seed=3)
+    oc = oracle.count_leaves(iupac, tree.base_off, 6, 32, seed=3)
+    scaled = oracle.Csr(oc.row_off, oc.keys, (oc.vals.astype(np.float32) *
+                                              np.repeat(oc.aux, np.diff(oc.row_off).astype(np.int64))).astype(np.float32))
+    assert (np.abs(oc.aux - 1 / 32) > 1e-9).any()  # at least one non-trivial rescale factor
+    rows = []
+    for ids, fp in zip(samples, local):
+        ek, ev = oracle.centroid(scaled, ids)
+        _, gk, gv, _ = fp.download(aux=False)
+        assert (gk == ek).all() and (bits(gv) == bits(ev)).all()
+        rows.append((ek, ev))
+    ro = np.zeros(len(rows) + 1, np.uint64)
+    ro[1:] = np.cumsum([len(r[0]) for r in rows])
+    lb = oracle.Csr(ro, np.concatenate([r[0] for r in rows]), np.concatenate([r[1] for r in rows]))
+    ek, ev = oracle.centroid(lb, np.arange(len(rows)))
+    _, gk, gv, _ = glob.download(aux=False)
+    assert (gk == ek).all() and (bits(gv) == bits(ev)).all()
+
+
 def test_leaves_as_queries_self_score_and_long_hit_lists(api, ctx):
     # every leaf vector scored against the tree: ~1266 keys per query, all present in the
     # query's own tile (hit list drained several times), top-1 must be the leaf itself
