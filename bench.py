@@ -459,6 +459,20 @@ def run_ours(args, rank, local_rank, world):
     }
     if tr:
         roofline["traffic_source"] = tr.get("source")
+    # the kernel's actual limiter, from the committed ncu capture (not measured in this run)
+    k4_ncu = os.path.join(ROOT, "profiles", "r01_final_k4_full_ncu_summary.json")
+    if os.path.exists(k4_ncu):
+        try:
+            n = json.load(open(k4_ncu))["launches"][0]
+            roofline["limiter"] = {"bound": "warp-instruction issue (postings are re-used from L2, DRAM ~1 % busy)",
+                                   "sm_throughput_pct_of_peak": n.get("sm_throughput_pct"),
+                                   "l1tex_throughput_pct_of_peak": n.get("l1tex_throughput_pct"),
+                                   "dram_pct_of_peak": n.get("dram_pct_of_peak"),
+                                   "l2_hit_rate_pct": n.get("l2_hit_rate_pct"),
+                                   "warp_instructions_per_launch": n.get("warp_instructions"),
+                                   "source": "profiles/r01_final_k4_full_ncu_summary.json (ncu --set full, same workload)"}
+        except Exception:
+            pass
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
