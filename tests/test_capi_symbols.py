@@ -46,3 +46,16 @@ def test_product_never_references_the_oracle():
                 assert not re.search(r"^\s*(import|from)\s+oracle", text, re.M), f
                 assert "libmyrio_oracle" not in text, f
                 assert "myrio_oracle.h" not in text, f
+
+
+def test_header_is_plain_c99():
+    """The boundary is a C ABI: include/myrio_b200.h must compile as C (what cgo / bindgen / ctypes
+    authors read), with no C++ or CUDA types in any signature."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                        os.path.join(ROOT, "include", "myrio_b200.h")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
