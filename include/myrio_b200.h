@@ -79,6 +79,12 @@ int32_t myrio_ctx_sync(myrio_ctx *ctx);
 void *myrio_ctx_stream(const myrio_ctx *ctx);
 /* number of kernels this library has launched on the context so far */
 uint64_t myrio_ctx_launch_count(const myrio_ctx *ctx);
+/* Integer value of a k-mer key (`usize::from(&Kmer<Dna, K>)` of the pinned bio-seq fork, Cargo.toml:23):
+ * 0 (default) = base j of the window at bits 2j..2j+1 (Seq is a BitVec<usize, Lsb0>); 1 = base j at bits
+ * 2(k-1-j).  The dependency is not vendored in the reference tree, so the order is an option rather than a
+ * constant; it decides the stored .myrtree keys and, through the sort order, the f32 summation order.
+ * Applies to the myrio_count_* calls made on this context afterwards. */
+int32_t myrio_ctx_set_kmer_bit_order(myrio_ctx *ctx, int32_t msb_first);
 /* optional per-kernel CUDA-event timing (events on the context's stream) */
 int32_t myrio_prof_enable(myrio_ctx *ctx, int32_t on);
 int32_t myrio_prof_reset(myrio_ctx *ctx);

@@ -46,6 +46,10 @@ class Context:
     def sync(self):
         _lib.check(self._L.myrio_ctx_sync(self.h))
 
+    def set_kmer_bit_order(self, msb_first: bool):
+        """Integer value of a k-mer key: False (default) = bio-seq's LSB-first packing, True = MSB-first."""
+        _lib.check(self._L.myrio_ctx_set_kmer_bit_order(self.h, int(bool(msb_first))))
+
     @property
     def stream(self) -> int:
         """cudaStream_t of the context as an integer (torch.cuda.ExternalStream(ctx.stream))."""

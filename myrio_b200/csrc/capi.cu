@@ -87,6 +87,13 @@ int32_t myrio_ctx_sync(myrio_ctx *ctx) {
 
 uint64_t myrio_ctx_launch_count(const myrio_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int32_t myrio_ctx_set_kmer_bit_order(myrio_ctx *ctx, int32_t msb_first) {
+    return guarded([&] {
+        if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
+        ctx->kmer_msb_first = msb_first ? 1u : 0u;
+    });
+}
+
 void *myrio_ctx_stream(const myrio_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int32_t myrio_prof_enable(myrio_ctx *ctx, int32_t on) {

@@ -129,6 +129,7 @@ struct myrio_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     uint64_t launches = 0;
+    uint32_t kmer_msb_first = 0;  // key bit order of K1/K2 (0 = bio-seq's LSB-first)
     bool prof_on = false;
     std::vector<myrio::ProfEntry> prof;
     // scoring scratch (grow-only)

@@ -53,6 +53,19 @@ __device__ __forceinline__ uint64_t revcomp_key(uint64_t key, uint32_t k) {
     return x >> (64u - 2u * k);
 }
 
+// The (forward, reverse-complement) key pair of a window in the configured bit order.  LSB-first
+// (base j at bits 2j, bio-seq's BitVec<usize, Lsb0>) is the default; MSB-first (base j at bits
+// 2(k-1-j)) is the same pair with its 2-bit groups reversed: reversing the groups of kf is
+// revcomp_key(~kf), and reversing those of kr = revcomp_key(kf) leaves ~kf.
+__device__ __forceinline__ void order_key_pair(uint64_t &kf, uint64_t &kr, uint32_t k, uint32_t msb_first) {
+    if (msb_first) {
+        const uint64_t mask = k < 32 ? (1ull << (2u * k)) - 1ull : ~0ull;
+        const uint64_t f = kf;
+        kf = revcomp_key(~f, k);
+        kr = ~f & mask;
+    }
+}
+
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v) {
     const unsigned lane = threadIdx.x & 31;
 #pragma unroll
@@ -206,6 +219,7 @@ struct ReadCountArgs {
     const uint8_t *qual;
     const uint32_t *ids;  // rows handled by this launch
     uint32_t k;
+    uint32_t msb_first;    // key bit order (myrio_ctx_set_kmer_bit_order)
     float cutoff;
     uint32_t ecap;         // sort capacity (power of two) >= 2*(n-k+1) for every row of the launch
     const uint64_t *eoff;  // scratch offset of every row
@@ -307,6 +321,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
             if (pass) {
                 kf = window_key(words, i, k);
                 kr = revcomp_key(kf, k);
+                order_key_pair(kf, kr, k, a.msb_first);
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, pass);
@@ -390,6 +405,7 @@ struct LeafCountArgs {
     const uint64_t *base_off;
     const uint32_t *ids;
     uint32_t k;
+    uint32_t msb_first;  // key bit order (myrio_ctx_set_kmer_bit_order)
     uint32_t nb_resamples;
     uint64_t seed;
     uint64_t leaf_id_base;
@@ -506,9 +522,10 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
         }
         __syncthreads();
         for (uint32_t i = tid; i < nb; i += blockDim.x) {
-            uint64_t kf = window_key(words2, i, k);
+            uint64_t kf = window_key(words2, i, k), kr = revcomp_key(kf, k);
+            order_key_pair(kf, kr, k, a.msb_first);
             keys[2 * i] = kf;
-            keys[2 * i + 1] = revcomp_key(kf, k);
+            keys[2 * i + 1] = kr;
         }
         E = 2 * nb;
     } else {
@@ -540,18 +557,22 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
                 uint64_t kf = 0;
                 for (uint32_t j = 0; j < k; ++j)
                     kf |= (uint64_t)((uint32_t)__clz((uint32_t)comp[i + j]) - 28u) << (2 * j);
+                uint64_t kr = revcomp_key(kf, k);
+                order_key_pair(kf, kr, k, a.msb_first);
                 keys[slot] = kf;
                 wts[slot] = (uint16_t)R;
-                keys[slot + 1] = revcomp_key(kf, k);
+                keys[slot + 1] = kr;
                 wts[slot + 1] = (uint16_t)R;
             } else {
                 for (uint32_t rs = 0; rs < R; ++rs) {
                     uint64_t kf = 0;
                     for (uint32_t j = 0; j < k; ++j)
                         kf |= (uint64_t)resolve_iupac(comp[i + j], a.seed, leaf, rs, i + j) << (2 * j);
+                    uint64_t kr = revcomp_key(kf, k);
+                    order_key_pair(kf, kr, k, a.msb_first);
                     keys[slot + 2 * rs] = kf;
                     wts[slot + 2 * rs] = 1;
-                    keys[slot + 2 * rs + 1] = revcomp_key(kf, k);
+                    keys[slot + 2 * rs + 1] = kr;
                     wts[slot + 2 * rs + 1] = 1;
                 }
             }
@@ -732,6 +753,7 @@ myrio_svecs *count_reads(myrio_ctx *ctx, const myrio_seqs *reads, uint32_t k, fl
         a.qual = reads->qual.p;
         a.ids = id_bufs.back().p;
         a.k = k;
+        a.msb_first = ctx->kmer_msb_first;
         a.cutoff = cutoff;
         a.eoff = d_eoff.p;
         a.skeys = skeys.p;
@@ -836,6 +858,7 @@ myrio_svecs *count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k, 
         a.base_off = leaves->base_off.p;
         a.ids = id_bufs.back().p;
         a.k = k;
+        a.msb_first = ctx->kmer_msb_first;
         a.nb_resamples = nb_resamples;
         a.seed = seed;
         a.leaf_id_base = leaf_id_base;

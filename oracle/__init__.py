@@ -67,6 +67,8 @@ def lib():
         L.myo_phred_correct_table.restype = C.POINTER(C.c_float)
         L.myo_kmer_key.restype = C.c_uint64
         L.myo_kmer_key.argtypes = [_u8p, C.c_int]
+        L.myo_set_kmer_msb_first.restype = None
+        L.myo_set_kmer_msb_first.argtypes = [C.c_int]
         L.myo_sort_reduce_f32.restype = C.c_size_t
         L.myo_sort_reduce_f32.argtypes = [_u64p, C.c_size_t, _u64p, _f32p]
         L.myo_sort_reduce_u16.restype = C.c_size_t
@@ -140,6 +142,11 @@ class Csr:
 def phred_correct_table() -> np.ndarray:
     p = lib().myo_phred_correct_table()
     return np.ctypeslib.as_array(p, shape=(128,)).copy()
+
+
+def set_kmer_msb_first(on: bool) -> None:
+    """The alternative key packing (base j at bits 2(k-1-j)); mirrors Context.set_kmer_bit_order."""
+    lib().myo_set_kmer_msb_first(int(bool(on)))
 
 
 def kmer_key(bases: np.ndarray, k: int) -> int:

@@ -107,8 +107,18 @@ long long myo_fastq_preprocess(const uint8_t *seq_ascii, const uint8_t *qual_asc
 /* bio-seq `usize::from(&Kmer<Dna,K>)`: A=0,C=1,G=2,T=3, base j of the window at
  * bits 2j..2j+1 (Seq is a BitVec<usize,Lsb0>).  ASSUMED -- bio-seq is not
  * vendored; see header. */
+static int g_kmer_msb_first = 0;
+
+/* the alternative packing (base j at bits 2(k-1-j)), for the case the assumption above is wrong:
+ * mirrors myrio_ctx_set_kmer_bit_order of the product */
+void myo_set_kmer_msb_first(int on) { g_kmer_msb_first = on ? 1 : 0; }
+
 uint64_t myo_kmer_key(const uint8_t *bases, int k) {
     uint64_t key = 0;
+    if (g_kmer_msb_first) {
+        for (int j = 0; j < k; ++j) key |= (uint64_t)(bases[j] & 3u) << (2 * (k - 1 - j));
+        return key;
+    }
     for (int j = 0; j < k; ++j) key |= (uint64_t)(bases[j] & 3u) << (2 * j);
     return key;
 }

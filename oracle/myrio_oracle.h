@@ -41,6 +41,7 @@ const float *myo_phred_correct_table(void);
 
 /* bio-seq Kmer -> usize (assumed, see header): base j at bits 2j */
 uint64_t myo_kmer_key(const uint8_t *bases, int k);
+void myo_set_kmer_msb_first(int on);
 
 /* data/sparse.rs:229-272 from_unsorted_singles with value=1.0f (f32 "+=").
  * keys_out/vals_out capacity n. returns number of distinct keys. */

@@ -79,6 +79,41 @@ def test_count_reads_k_sweep(api, ctx, k):
     assert_reads_parity(api, ctx, reads, k, cutoff)
 
 
+def test_msb_first_key_order_matches_oracle(api):
+    # the alternative packing of a k-mer key (myrio_ctx_set_kmer_bit_order): reads, ACGT and ambiguous leaves,
+    # and scores on top of them, against the oracle in the same mode
+    c = api.Context(0)
+    c.set_kmer_bit_order(True)
+    oracle.set_kmer_msb_first(True)
+    try:
+        tree = synth.make_tree(90, 19)
+        reads = synth.make_reads(tree, 40, 23)
+        for k, cut in ((6, 0.2), (18, 0.1), (32, 0.05)):
+            got = api.MyrSeqs(c, reads).compute_kmer_counts(k, cut)
+            ro, keys, vals, hck = got.download()
+            oc = oracle.count_reads(reads.codes, reads.qual, reads.base_off, k, cut)
+            assert (ro == oc.row_off).all() and (keys == oc.keys).all() and (vals == oc.vals).all()
+            assert (hck == oc.aux).all()
+        iupac = synth.tree_to_iupac(tree).copy()
+        rng = np.random.default_rng(3)
+        iupac[rng.choice(len(iupac), 40, replace=False)] = 15  # N
+        store = api.TaxTreeStore(c, iupac=iupac, base_off=tree.base_off)
+        store.compute_and_append_kmer_counts(18, 32, seed=9)
+        lro, lk, lv, resc = store.kmer_store_counts_vec[0].download()
+        ol = oracle.count_leaves(iupac, tree.base_off, 18, 32, seed=9)
+        assert (lro == ol.row_off).all() and (lk == ol.keys).all() and (lv == ol.vals).all() and (resc == ol.aux).all()
+        ttc = api.TaxTreeCompute.from_store_tree(store, 18, 32, tile_leaves=32)
+        q = api.MyrSeqs(c, reads).compute_kmer_counts(18, 0.1).into_normalized_l2()
+        res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 5, full_scores=True)
+        oln = oracle.normalize(ol)
+        oqn = oracle.normalize(oracle.count_reads(reads.codes, reads.qual, reads.base_off, 18, 0.1))
+        for i in range(reads.n):
+            kk, vv = oqn.row(i)
+            assert (bits(oracle.score_all(oln, kk, vv)) == bits(res.scores[i])).all()
+    finally:
+        oracle.set_kmer_msb_first(False)
+
+
 def test_count_reads_edge_cases(api, ctx):
     rng = np.random.default_rng(1)
 

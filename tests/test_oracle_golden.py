@@ -226,3 +226,33 @@ def test_fastq_preprocess_restatement():
     with pytest.raises(ValueError):
         oracle.fastq_preprocess(np.frombuffer(b"ACGN", np.uint8), np.frombuffer(b"IIII", np.uint8),
                                 np.array([0, 4], np.uint64), 1, 0.0, 255)
+
+
+def test_kmer_key_bit_orders():
+    """The key packing is an assumption about the un-vendored bio-seq fork: both orders are
+    implemented; MSB-first is LSB-first with its 2-bit groups reversed, and counts do not depend on it."""
+    bases = np.array([0, 0, 1, 3, 3], np.uint8)  # AACTT
+    try:
+        assert [oracle.kmer_key(bases[i:i + 2], 2) for i in range(4)] == [0, 4, 13, 15]   # upstream bio-seq's own example
+        oracle.set_kmer_msb_first(True)
+        assert [oracle.kmer_key(bases[i:i + 2], 2) for i in range(4)] == [0, 1, 7, 15]
+        rng = np.random.default_rng(5)
+        seq = rng.integers(0, 4, 300).astype(np.uint8)
+        qual = np.full(300, 30, np.uint8)
+        off = np.array([0, 300], np.uint64)
+        for k in (5, 18, 32):
+            oracle.set_kmer_msb_first(False)
+            a = oracle.count_reads(seq, qual, off, k, 0.1)
+            oracle.set_kmer_msb_first(True)
+            b = oracle.count_reads(seq, qual, off, k, 0.1)
+
+            def rev_groups(key):
+                out = 0
+                for j in range(k):
+                    out |= ((int(key) >> (2 * j)) & 3) << (2 * (k - 1 - j))
+                return out
+            ma = {rev_groups(x): float(v) for x, v in zip(a.keys, a.vals)}
+            mb = {int(x): float(v) for x, v in zip(b.keys, b.vals)}
+            assert ma == mb and (np.diff(b.keys.astype(object)) > 0).all()
+    finally:
+        oracle.set_kmer_msb_first(False)
