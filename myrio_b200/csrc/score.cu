@@ -212,27 +212,42 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
     HitRec *hits = reinterpret_cast<HitRec *>(usm + DENSE_MAX_TILE);
     const uint64_t dummy_posting = (uint64_t)a.tile_leaves << 32;  // leaf = dummy slot, val = +0.0
     unsigned long long st_post = 0;
+    uint32_t cached_tile = 0xFFFFFFFFu;  // tile whose unit values sit in usm (and whose TileInfo is in registers)
+    uint32_t nl = 0;
+    const uint64_t *post = nullptr;
+    const uint32_t *bitmaps = nullptr;
+    const TileInfo *ti = a.tiles;
+    bool dense_tile = false;
 
+    // task ids are handed out by an atomic counter; the id of the NEXT task is requested at the top of
+    // the current one, so its round trip to L2 is off the critical path (a batch has < 2^32 tasks)
+    uint32_t next_task = 0;
+    if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
     for (;;) {
-        unsigned long long task = 0;
-        if (lane == 0) task = atomicAdd(a.counters, 1ull);
-        task = __shfl_sync(0xffffffffu, task, 0);
+        const uint32_t task = __shfl_sync(0xffffffffu, next_task, 0);
         if (task >= a.n_tasks) break;
-        const uint32_t t = (uint32_t)(task / a.q_count);  // tile-major: a tile's index stays hot in L2
-        const uint32_t ql = (uint32_t)(task % a.q_count);
-        const TileInfo *ti = a.tiles + t;
-        const uint32_t nl = ti->n_leaves;
-        const uint64_t *post = a.postings + ti->post_begin;
-        const uint32_t *bitmaps = ti->bitmaps;
+        if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
+        const uint32_t t = task / a.q_count;  // tile-major: a tile's index stays hot in L2
+        const uint32_t ql = task - t * a.q_count;
+        if (t != cached_tile) {
+            ti = a.tiles + t;
+            nl = ti->n_leaves;
+            post = a.postings + ti->post_begin;
+            bitmaps = ti->bitmaps;
+            dense_tile = ti->n_dense != 0;  // implies tile_leaves <= DENSE_MAX_TILE
+        }
 
         // Dense keys (tiles of <= 1024 leaves): this lane owns leaves 32*r + lane.  Their
         // accumulators live in registers while dense keys follow one another (flushed to /
         // reloaded from shared memory around sparse chunks); their unit values sit in shared
         // memory (bank == lane, conflict-free) -- keeping them in registers too costs a quarter
         // of the resident warps and measured slower (profiles/r01_k4_variants.md).
-        const bool dense_tile = ti->n_dense != 0;  // implies tile_leaves <= DENSE_MAX_TILE
         float ureg[UREG ? 32 : 1];
-        if (dense_tile) {
+        // tile-major task order: a warp's consecutive tasks are mostly in the same tile, whose unit
+        // values are still in its shared-memory slice
+        const bool unit_cached = !UREG && t == cached_tile;
+        cached_tile = t;
+        if (dense_tile && !unit_cached) {
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const float u = (32u * r + lane < nl) ? __ldg(ti->unit + 32 * r + lane) : 0.0f;
@@ -816,6 +831,7 @@ static void launch_score_variant(myrio_ctx *ctx, const myrio_index *ix, ScoreArg
     int warps = (int)std::min<size_t>(UREG ? SC_UREG_WARPS : SC_MAX_WARPS, (ctx->smem_optin - 1024) / per_warp);
     if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
     const size_t smem = per_warp * warps;
+    if (a.n_tasks >= 0xFFF00000ull) fail(MYRIO_ERR_BAD_ARG, "too many (query, tile) tasks in one batch");
     const unsigned grid = (unsigned)std::min<unsigned long long>(a.n_tasks, (unsigned long long)ctx->sm_count);
     const char *name = FUSED ? "k4_score_tiles_topx" : "k4_score_tiles_rows";
     auto kern = score_tiles_kernel<SIM, FUSED, STATS, UREG>;
