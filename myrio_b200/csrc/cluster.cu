@@ -9,6 +9,13 @@
 // accumulator unchanged, so the result is bit-identical to the reference's
 // sparse merge-join (data/sparse.rs:317-360).  No tensor cores: the sum order is
 // part of the result.
+//
+// File map: row slabs (coalesced interleaved rows) and pair_tile_kernel (plain tile: centroid
+// columns, myrio_pairwise); the conflict-free silhouette tile (canonical-key planes, three
+// bank-permuted replicas, slab_schedule_kernel, pair_tile_canon_kernel); the order-preserving row
+// reductions (silsum_rows / argmax_rows); recentering; cluster_reads = the host loop of cluster(),
+// optionally row-sharded over ranks; compute_cluster_centroid / fingerprints; myrio_pairwise.
+// Similarity::Overlap takes the merge-join kernel of merge.cu everywhere.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
