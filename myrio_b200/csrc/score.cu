@@ -43,7 +43,12 @@ struct ScoreArgs {
     uint64_t *cand;      // composites [q_count][n_tiles][x]
     uint32_t *cand_cnt;  // [q_count][n_tiles]
     uint32_t *gthr;      // [q_count] running lower bound (score bits) of the query's x-th best score
+    // seeding of the bound: pass 1 scores every query against its SEED tile only (the tile holding most of
+    // its keys, i.e. its closest relatives), pass 2 sweeps all other tasks tile-major with the bound already high
+    const uint32_t *seed;  // [q_count] seed tile (pass 1); its plan_off entry carries PLAN_SEED_FLAG (pass 2 skips it)
+    uint32_t seed_mode;    // 0 = no seeding, 1 = seed pass (task == query), 2 = sweep
 };
+static constexpr uint64_t PLAN_SEED_FLAG = 1ull << 63;
 
 __device__ __forceinline__ float finite_or_zero(float x) {
     return (fabsf(x) <= 3.402823466e+38f) ? x : 0.0f;  // false for NaN and inf
@@ -227,8 +232,19 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
         const uint32_t task = __shfl_sync(0xffffffffu, next_task, 0);
         if (task >= a.n_tasks) break;
         if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
-        const uint32_t t = task / a.q_count;  // tile-major: a tile's index stays hot in L2
-        const uint32_t ql = task - t * a.q_count;
+        uint32_t t, ql;
+        if (a.seed_mode == 1) {
+            ql = task;
+            t = __ldg(a.seed + ql);
+        } else {
+            t = task / a.q_count;  // tile-major: a tile's index stays hot in L2
+            ql = task - t * a.q_count;
+        }
+        // the task's slice of the plan (requested first: everything below overlaps its latency)
+        const size_t slot = (size_t)ql * a.n_tiles + t;
+        const uint64_t hb_raw = a.plan_off[slot];
+        const uint64_t hb = hb_raw & ~PLAN_SEED_FLAG, he = a.plan_off[slot + 1] & ~PLAN_SEED_FLAG;
+        if (a.seed_mode == 2 && (hb_raw & PLAN_SEED_FLAG)) continue;  // scored by the seed pass
         if (t != cached_tile) {
             ti = a.tiles + t;
             nl = ti->n_leaves;
@@ -377,8 +393,6 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
         // shared memory SC_HITS records at a time (coalesced) and walk it.  ONE textual call of
         // process_hits keeps the lambda inlined (racc stays in registers).
         {
-            const size_t slot = (size_t)ql * a.n_tiles + t;
-            const uint64_t hb = a.plan_off[slot], he = a.plan_off[slot + 1];
             for (uint64_t h0 = hb; h0 < he; h0 += SC_HITS) {
                 const uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
                 for (uint32_t i = lane; i < n_hits; i += 32) hits[i] = a.plan[h0 + i];
@@ -389,7 +403,6 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
         }
 
         if (FUSED) {
-            const size_t slot = (size_t)ql * a.n_tiles + t;
             tile_topx<SIM>(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
                            a.cand + slot * a.x, a.cand_cnt + slot, lane);
         } else {
@@ -726,6 +739,28 @@ __global__ void __launch_bounds__(PF_THREADS) plan_fill_ranked_kernel(
     }
 }
 
+// one warp per query: its seed tile = the tile that holds most of its keys (ties: the lowest tile); the
+// tile's plan_off entry is flagged so that the sweep skips the (query, seed tile) task
+__global__ void __launch_bounds__(256) seed_tile_kernel(const uint32_t *__restrict__ hitcnt, uint32_t q_count,
+                                                        uint32_t n_tiles, uint64_t *__restrict__ plan_off,
+                                                        uint32_t *__restrict__ seed) {
+    const uint32_t ql = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ql >= q_count) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t *row = hitcnt + (size_t)ql * n_tiles;
+    // composite (count, ~tile): max = most hits, lowest tile on ties
+    unsigned long long best = 0;
+    for (uint32_t t = lane; t < n_tiles; t += 32)
+        best = max(best, ((unsigned long long)row[t] << 32) | (unsigned long long)(0xFFFFFFFFu - t));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (lane == 0) {
+        const uint32_t t = 0xFFFFFFFFu - (uint32_t)best;
+        seed[ql] = t;
+        plan_off[(size_t)ql * n_tiles + t] |= PLAN_SEED_FLAG;
+    }
+}
+
 __global__ void __launch_bounds__(256) max_row_len_kernel(const uint64_t *__restrict__ row_off, uint64_t n,
                                                           unsigned long long *__restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,6 +787,7 @@ struct Plan {
     DevBuf<uint32_t> hitcnt;
     DevBuf<uint64_t> off;
     DevBuf<HitRec> hits;
+    DevBuf<uint32_t> seed;
     uint64_t n_hits = 0;
 };
 
@@ -891,6 +927,14 @@ static void accumulate_stats(myrio_ctx *ctx) {
 
 static constexpr uint64_t PLAN_BUDGET = 12ull << 30;  // bytes of hit lists kept at once
 
+static bool topx_seeding() {  // MYRIO_K4_SEED=0 disables the seed pass (comparison runs)
+    static const bool v = [] {
+        const char *e = getenv("MYRIO_K4_SEED");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
 void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
                uint64_t q_count, int32_t sim, float *scores_host) {
     check_queries(queries, q_first, q_count);
@@ -948,6 +992,20 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
             a.cand = cand.p;
             a.cand_cnt = cand_cnt.p;
             a.gthr = gthr.p;
+            if (ix->tiles.size() > 1 && topx_seeding()) {
+                // pass 1: every query against its seed tile; pass 2: everything else, tile-major
+                pl.seed.reserve(qn);
+                MYRIO_LAUNCH(ctx, "k4a_seed_tiles", seed_tile_kernel, (unsigned)((qn + 7) / 8), 256, 0, pl.hitcnt.p,
+                             (uint32_t)qn, (uint32_t)ix->tiles.size(), pl.off.p, pl.seed.p);
+                ScoreArgs s1 = a;
+                s1.seed = pl.seed.p;
+                s1.seed_mode = 1;
+                s1.n_tasks = qn;
+                launch_score<true>(ctx, ix, s1, sim, collect_stats);
+                MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+                a.seed = pl.seed.p;
+                a.seed_mode = 2;
+            }
             launch_score<true>(ctx, ix, a, sim, collect_stats);
         }
         MYRIO_LAUNCH(ctx, "k5_topx_merge_tiles", topx_cand_merge_kernel, (unsigned)qn, TX_THREADS, 0, cand.p,
