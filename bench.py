@@ -500,6 +500,15 @@ def run_ours(args, rank, local_rank, world):
                                "k5_topx_merge_tiles": k5_ms / args.steps, "all_kernels": all_ms / args.steps},
     }
 
+    # ---- N > 1: the two exchange paths must give the same merged top-x (untimed)
+    if world > 1:
+        s1, i1 = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE)
+        s2, i2 = mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE)
+        torch.cuda.synchronize(dev)
+        bad = int((~((s1.view(torch.int32) == s2.view(torch.int32)).all(dim=1) & (i1 == i2).all(dim=1))).sum().item())
+        line["parity_in_bench"] = {"queries_checked": int(Q), "two_phase_vs_allgather_topx_mismatches": bad}
+        line["config"]["parallelism"] += "; seed pass, all-reduce(MAX) of the per-query bounds, sweep, all-gather of 8-byte composites"
+
     # ---- stage 3 (clustering): not part of `value`, reported beside it; N > 1 shards the rows
     if not args.no_clustering:
         cpu_reads = None

@@ -205,6 +205,25 @@ int32_t myrio_score_topx_direct_async(myrio_ctx *ctx, const myrio_svecs *leaf_ve
                                       const myrio_svecs *queries, uint64_t q_first, uint64_t q_count,
                                       uint32_t x, int32_t similarity, float *d_top_scores,
                                       uint32_t *d_top_ids);
+/* Two-phase shard-local top-x for the multi-GPU path (one process per GPU, leaves sharded):
+ *   1. myrio_score_topx_seed_async : plan + every query against its seed tile on this shard;
+ *      d_bound[q] = running lower bound of the query's x-th best score (f32 bits, scores >= +0).
+ *   2. the caller all-reduces d_bound with MAX over the ranks (Q x 4 bytes; the maximum is still a
+ *      lower bound of the GLOBAL x-th best score: x leaves of one tile of one rank reach it).
+ *   3. myrio_score_topx_sweep_async: all remaining (query, tile) tasks with the exchanged bounds, then
+ *      the shard's list as composites d_top[q][x] = score bits << 32 | (0xFFFFFFFF - payload id), best
+ *      first, 0 = padding.  Entries below the global bound are dropped, so the shard-local list may be
+ *      shorter than x: only the merge over all ranks (myrio_topx_merge_composites_async after ONE
+ *      all-gather of Q*x*8 bytes per rank) is the exact global top-x.
+ * The queries must fit one batch (MYRIO_ERR_UNSUPPORTED otherwise: use myrio_score_topx_async). */
+int32_t myrio_score_topx_seed_async(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                                    uint64_t q_first, uint64_t q_count, uint32_t x, int32_t similarity,
+                                    uint32_t *d_bound);
+int32_t myrio_score_topx_sweep_async(myrio_ctx *ctx, const myrio_index *ix, uint64_t q_count, uint32_t x,
+                                     int32_t similarity, const uint32_t *d_bound, uint64_t *d_top);
+int32_t myrio_topx_merge_composites_async(myrio_ctx *ctx, const uint64_t *d_in, uint32_t n_parts,
+                                          uint64_t q_count, uint32_t x, float *d_scores_out,
+                                          uint32_t *d_ids_out);
 /* exact algorithmic work of the last myrio_score_* call: sum over queries of
  * query keys, of (query key, tile) hits, and of postings touched (T_q) */
 int32_t myrio_score_stats(myrio_ctx *ctx, uint64_t *n_query_keys, uint64_t *n_key_hits,

@@ -24,7 +24,8 @@ SYMBOLS = [
     "myrio_svecs_normalize", "myrio_svecs_free", "myrio_index_build", "myrio_index_info",
     "myrio_index_export_tile", "myrio_index_free", "myrio_score_all", "myrio_score_topx",
     "myrio_score_topx_async", "myrio_score_all_direct", "myrio_score_topx_direct",
-    "myrio_score_topx_direct_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
+    "myrio_score_topx_direct_async", "myrio_score_topx_seed_async", "myrio_score_topx_sweep_async",
+    "myrio_topx_merge_composites_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
     "myrio_cluster_sharded",
     "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_cluster_stats", "myrio_svecs_device_ptrs",
 ]
@@ -113,6 +114,9 @@ def load() -> C.CDLL:
     L.myrio_score_all_direct.argtypes = [vp, vp, vp, u64, u64, i32, vp]
     L.myrio_score_topx_direct.argtypes = [vp, vp, u32, vp, u64, u64, u32, i32, vp, vp]
     L.myrio_score_topx_direct_async.argtypes = [vp, vp, u32, vp, u64, u64, u32, i32, vp, vp]
+    L.myrio_score_topx_seed_async.argtypes = [vp, vp, vp, u64, u64, u32, i32, vp]
+    L.myrio_score_topx_sweep_async.argtypes = [vp, vp, u64, u32, i32, vp, vp]
+    L.myrio_topx_merge_composites_async.argtypes = [vp, vp, u32, u64, u32, vp, vp]
     L.myrio_topx_merge_async.argtypes = [vp, vp, vp, u32, u64, u32, vp, vp]
     L.myrio_score_stats.argtypes = [vp, P(u64), P(u64), P(u64)]
     L.myrio_cluster.argtypes = [vp, vp, P(ClusterParams), vp, vp, P(u32), vp]

@@ -444,6 +444,35 @@ int32_t myrio_topx_merge_async(myrio_ctx *ctx, const float *d_scores_in, const u
     });
 }
 
+int32_t myrio_score_topx_seed_async(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                                    uint64_t q_first, uint64_t q_count, uint32_t x, int32_t similarity,
+                                    uint32_t *d_bound) {
+    return guarded([&] {
+        if (!ctx || !ix || !queries || !d_bound) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        score_topx_seed_device(ctx, ix, queries, q_first, q_count, x, similarity, d_bound);
+    });
+}
+
+int32_t myrio_score_topx_sweep_async(myrio_ctx *ctx, const myrio_index *ix, uint64_t q_count, uint32_t x,
+                                     int32_t similarity, const uint32_t *d_bound, uint64_t *d_top) {
+    return guarded([&] {
+        if (!ctx || !ix || !d_top) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        score_topx_sweep_device(ctx, ix, q_count, x, similarity, d_bound, d_top);
+    });
+}
+
+int32_t myrio_topx_merge_composites_async(myrio_ctx *ctx, const uint64_t *d_in, uint32_t n_parts,
+                                          uint64_t q_count, uint32_t x, float *d_scores_out,
+                                          uint32_t *d_ids_out) {
+    return guarded([&] {
+        if (!ctx || !d_in || !d_scores_out || !d_ids_out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        topx_merge_composites_device(ctx, d_in, n_parts, q_count, x, d_scores_out, d_ids_out);
+    });
+}
+
 int32_t myrio_score_stats(myrio_ctx *ctx, uint64_t *n_query_keys, uint64_t *n_key_hits,
                           uint64_t *n_postings_touched) {
     return guarded([&] {

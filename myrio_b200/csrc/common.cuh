@@ -138,6 +138,10 @@ struct myrio_ctx {
     myrio::DevBuf<uint64_t> topx_cand;
     myrio::DevBuf<uint32_t> topx_cand_cnt, topx_gthr;
     void *plan = nullptr;  // myrio::Plan (score.cu): hit-list scratch, grow-only
+    // state between myrio_score_topx_seed_async and myrio_score_topx_sweep_async
+    bool twophase_ready = false, twophase_seeded = false;
+    uint64_t twophase_q = 0;
+    uint32_t twophase_x = 0;
     uint64_t last_stats[3] = {0, 0, 0};
     uint64_t cluster_stats[2] = {0, 0};  // pair similarities, multiply-add terms of the last K6 call
     // pinned staging for small D2H reads

@@ -447,7 +447,8 @@ __global__ void __launch_bounds__(TX_THREADS) topx_cand_merge_kernel(const uint6
                                                                      const uint32_t *__restrict__ gthr,
                                                                      uint32_t n_tiles, uint32_t x,
                                                                      float *__restrict__ out_s,
-                                                                     uint32_t *__restrict__ out_i) {
+                                                                     uint32_t *__restrict__ out_i,
+                                                                     uint64_t *__restrict__ out_c) {
     __shared__ uint64_t buf[TX_SORT_CAP];
     __shared__ uint32_t s_warp[TX_THREADS / 32 + 1];
     __shared__ uint32_t s_total;
@@ -518,13 +519,12 @@ __global__ void __launch_bounds__(TX_THREADS) topx_cand_merge_kernel(const uint6
         }
     }
     for (uint32_t j = tid; j < x; j += TX_THREADS) {
-        if (j < filled) {
-            const uint64_t c = buf[j];
+        const uint64_t c = j < filled ? buf[j] : 0ull;  // padding = (score 0, id 0xFFFFFFFF) = composite 0
+        if (out_c) {
+            out_c[q * x + j] = c;
+        } else {
             out_s[q * x + j] = __uint_as_float((uint32_t)(c >> 32));
             out_i[q * x + j] = 0xFFFFFFFFu - (uint32_t)c;
-        } else {
-            out_s[q * x + j] = 0.0f;
-            out_i[q * x + j] = 0xFFFFFFFFu;
         }
     }
 }
@@ -550,6 +550,32 @@ __global__ void __launch_bounds__(256) topx_merge_kernel(const float *__restrict
             const uint32_t id = in_i[src];
             // padding (id 0xFFFFFFFF, score 0) maps to composite 0 = worst
             c = ((uint64_t)__float_as_uint(in_s[src]) << 32) | (uint64_t)(0xFFFFFFFFu - id);
+        }
+        mk[j] = c;
+    }
+    bitonic_desc(mk, S);
+    for (uint32_t j = threadIdx.x; j < x; j += blockDim.x) {
+        const uint64_t c = mk[j];
+        out_s[q * x + j] = __uint_as_float((uint32_t)(c >> 32));
+        out_i[q * x + j] = 0xFFFFFFFFu - (uint32_t)c;
+    }
+}
+
+// K7 on composites: in_c = [n_parts][q][x] of (score bits << 32 | ~payload id), padding = 0
+__global__ void __launch_bounds__(256) topx_merge_composites_kernel(const uint64_t *__restrict__ in_c,
+                                                                    uint32_t n_parts, uint64_t q_count, uint32_t x,
+                                                                    float *__restrict__ out_s,
+                                                                    uint32_t *__restrict__ out_i) {
+    extern __shared__ uint64_t mk[];
+    const uint64_t q = blockIdx.x;
+    const uint32_t total = n_parts * x;
+    uint32_t S = 2;
+    while (S < total) S <<= 1;
+    for (uint32_t j = threadIdx.x; j < S; j += blockDim.x) {
+        uint64_t c = 0;
+        if (j < total) {
+            const uint32_t p = j / x, e = j % x;
+            c = in_c[((size_t)p * q_count + q) * x + e];
         }
         mk[j] = c;
     }
@@ -1010,10 +1036,106 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
         }
         MYRIO_LAUNCH(ctx, "k5_topx_merge_tiles", topx_cand_merge_kernel, (unsigned)qn, TX_THREADS, 0, cand.p,
                      cand_cnt.p, gthr.p, (uint32_t)ix->tiles.size(), x, d_top_scores + q0 * x,
-                     d_top_ids + q0 * x);
+                     d_top_ids + q0 * x, (uint64_t *)nullptr);
         if (collect_stats) accumulate_stats(ctx);
         q0 += qn;
     }
+}
+
+// ---- two-phase sharded top-x: seed pass | exchange of the bounds between ranks | sweep + merge
+//
+// A shard that does not hold a query's clade seeds a weak bound from its own tiles; the maximum of the
+// ranks' bounds is still a lower bound of the query's GLOBAL x-th best score (x leaves of some tile of some
+// rank reach it), so after an all-reduce(MAX) of Q x 4 bytes every rank sweeps with the strongest bound.
+// The shard-local result may then hold fewer than x entries (padded): only the merged list is exact.
+static uint64_t topx_batch_capacity(const myrio_index *ix, uint32_t x) {
+    const uint64_t n_tiles = std::max<uint64_t>(ix->tiles.size(), 1);
+    return std::max<uint64_t>(1, (8ull << 30) / (n_tiles * x * 8));
+}
+
+void score_topx_seed_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
+                            uint64_t q_count, uint32_t x, int32_t sim, uint32_t *d_bound) {
+    check_queries(queries, q_first, q_count);
+    check_sim(sim);
+    if (x == 0 || x > TX_MAX_X) fail(MYRIO_ERR_BAD_ARG, "x must be in 1..%d", TX_MAX_X);
+    if (q_count > topx_batch_capacity(ix, x))
+        fail(MYRIO_ERR_UNSUPPORTED, "two-phase top-x needs the queries in one batch (%llu > %llu)",
+             (unsigned long long)q_count, (unsigned long long)topx_batch_capacity(ix, x));
+    reset_stats(ctx);
+    ctx->twophase_ready = false;
+    if (q_count == 0) return;
+    const uint64_t n_tiles = std::max<uint64_t>(ix->tiles.size(), 1);
+    if (!ctx->plan) ctx->plan = plan_scratch_new();
+    Plan &pl = *static_cast<Plan *>(ctx->plan);
+    if (!build_plan(ctx, ix, queries, q_first, q_count, ~0ull, pl))
+        fail(MYRIO_ERR_UNSUPPORTED, "two-phase top-x: the hit lists do not fit");
+    ctx->topx_cand.reserve(q_count * n_tiles * x);
+    ctx->topx_cand_cnt.reserve(q_count * n_tiles);
+    ctx->topx_gthr.reserve(q_count);
+    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+    MYRIO_CK(cudaMemsetAsync(ctx->topx_gthr.p, 0, q_count * sizeof(uint32_t), ctx->stream));
+    MYRIO_CK(cudaMemsetAsync(ctx->topx_cand_cnt.p, 0, q_count * n_tiles * sizeof(uint32_t), ctx->stream));
+    ctx->twophase_seeded = false;
+    if (ix->tiles.size() > 1) {
+        pl.seed.reserve(q_count);
+        MYRIO_LAUNCH(ctx, "k4a_seed_tiles", seed_tile_kernel, (unsigned)((q_count + 7) / 8), 256, 0, pl.hitcnt.p,
+                     (uint32_t)q_count, (uint32_t)ix->tiles.size(), pl.off.p, pl.seed.p);
+        ScoreArgs s1 = base_args(ctx, ix, pl, q_count);
+        s1.x = x;
+        s1.cand = ctx->topx_cand.p;
+        s1.cand_cnt = ctx->topx_cand_cnt.p;
+        s1.gthr = ctx->topx_gthr.p;
+        s1.seed = pl.seed.p;
+        s1.seed_mode = 1;
+        s1.n_tasks = q_count;
+        launch_score<true>(ctx, ix, s1, sim, false);
+        ctx->twophase_seeded = true;
+    }
+    MYRIO_CK(cudaMemcpyAsync(d_bound, ctx->topx_gthr.p, q_count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->twophase_ready = true;
+    ctx->twophase_q = q_count;
+    ctx->twophase_x = x;
+}
+
+void score_topx_sweep_device(myrio_ctx *ctx, const myrio_index *ix, uint64_t q_count, uint32_t x, int32_t sim,
+                             const uint32_t *d_bound, uint64_t *d_top) {
+    check_sim(sim);
+    if (!ctx->twophase_ready || ctx->twophase_q != q_count || ctx->twophase_x != x)
+        fail(MYRIO_ERR_BAD_ARG, "myrio_score_topx_sweep_async must follow myrio_score_topx_seed_async with the same queries");
+    ctx->twophase_ready = false;
+    if (q_count == 0) return;
+    Plan &pl = *static_cast<Plan *>(ctx->plan);
+    if (d_bound)  // the exchanged (raised) bounds; also the final filter of the merge
+        MYRIO_CK(cudaMemcpyAsync(ctx->topx_gthr.p, d_bound, q_count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (!ix->tiles.empty()) {
+        MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+        ScoreArgs a = base_args(ctx, ix, pl, q_count);
+        a.x = x;
+        a.cand = ctx->topx_cand.p;
+        a.cand_cnt = ctx->topx_cand_cnt.p;
+        a.gthr = ctx->topx_gthr.p;
+        if (ctx->twophase_seeded) {
+            a.seed = pl.seed.p;
+            a.seed_mode = 2;
+        }
+        launch_score<true>(ctx, ix, a, sim, false);
+    }
+    MYRIO_LAUNCH(ctx, "k5_topx_merge_tiles", topx_cand_merge_kernel, (unsigned)q_count, TX_THREADS, 0,
+                 ctx->topx_cand.p, ctx->topx_cand_cnt.p, ctx->topx_gthr.p, (uint32_t)ix->tiles.size(), x,
+                 (float *)nullptr, (uint32_t *)nullptr, d_top);
+}
+
+void topx_merge_composites_device(myrio_ctx *ctx, const uint64_t *d_in, uint32_t n_parts, uint64_t q_count,
+                                  uint32_t x, float *d_scores_out, uint32_t *d_ids_out) {
+    if (x == 0 || n_parts == 0) fail(MYRIO_ERR_BAD_ARG, "x and n_parts must be > 0");
+    uint64_t total = (uint64_t)n_parts * x, S = 2;
+    while (S < total) S <<= 1;
+    const size_t smem = S * sizeof(uint64_t);
+    if (smem > ctx->smem_optin) fail(MYRIO_ERR_UNSUPPORTED, "n_parts*x=%llu too large to merge", (unsigned long long)total);
+    if (q_count == 0) return;
+    MYRIO_CK(cudaFuncSetAttribute(topx_merge_composites_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYRIO_LAUNCH(ctx, "k7_topx_merge", topx_merge_composites_kernel, (unsigned)q_count, 256, smem, d_in, n_parts,
+                 q_count, x, d_scores_out, d_ids_out);
 }
 
 void topx_merge_device(myrio_ctx *ctx, const float *d_scores_in, const uint32_t *d_ids_in, uint32_t n_parts,

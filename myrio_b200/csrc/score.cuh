@@ -16,6 +16,13 @@ void score_all_direct(myrio_ctx *ctx, const myrio_svecs *leaves, const myrio_sve
 void score_topx_direct_device(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t leaf_id_base,
                               const myrio_svecs *queries, uint64_t q_first, uint64_t q_count, uint32_t x,
                               int32_t sim, float *d_top_scores, uint32_t *d_top_ids);
+// two-phase sharded top-x (seed pass | exchange of bounds | sweep) and the merge of composite lists
+void score_topx_seed_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
+                            uint64_t q_count, uint32_t x, int32_t sim, uint32_t *d_bound);
+void score_topx_sweep_device(myrio_ctx *ctx, const myrio_index *ix, uint64_t q_count, uint32_t x, int32_t sim,
+                             const uint32_t *d_bound, uint64_t *d_top);
+void topx_merge_composites_device(myrio_ctx *ctx, const uint64_t *d_in, uint32_t n_parts, uint64_t q_count,
+                                  uint32_t x, float *d_scores_out, uint32_t *d_ids_out);
 void *plan_scratch_new();
 void plan_scratch_free(void *p);
 }  // namespace myrio

@@ -70,10 +70,64 @@ def allgather_topx(scores: torch.Tensor, ids: torch.Tensor, group=None):
     return gs, gi
 
 
+_TWO_PHASE_OK: dict = {}
+
+
+def _two_phase_fits_everywhere(ctx, ttcompute, Q: int, x: int, group=None) -> bool:
+    """The two-phase path needs all queries in one batch on EVERY rank (the batch capacity depends on the
+    shard's tile count): decided once per (index, Q, x) with an all-reduce(MIN) so all ranks agree."""
+    key = (id(ttcompute), Q, x)
+    if key not in _TWO_PHASE_OK:
+        n_tiles = max(1, ttcompute.info()["n_tiles"])
+        fits = 1 if Q <= max(1, (8 << 30) // (n_tiles * x * 8)) else 0
+        t = torch.tensor([fits], dtype=torch.int32, device=torch.device("cuda", ctx.device))
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+        _TWO_PHASE_OK[key] = bool(int(t.item()))
+    return _TWO_PHASE_OK[key]
+
+
+def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None):
+    """The multi-GPU step with the bound exchange: seed pass on this rank's leaves, all-reduce(MAX) of
+    the per-query bounds (Q x 4 bytes), sweep with the global bound, ONE all-gather of the shard lists as
+    8-byte composites, merge (K7).  Everything is enqueued on the library's stream (torch's collectives
+    order themselves after it), no host synchronisation in between.  Raises MyrioError(UNSUPPORTED) when
+    the queries do not fit one batch."""
+    from . import _lib
+    Q = queries.n_rows
+    dev = torch.device("cuda", ctx.device)
+    L = ctx._L
+    world = dist.get_world_size(group)
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=dev)):
+        bound = torch.empty(max(Q, 1), dtype=torch.int32, device=dev)
+        _lib.check(L.myrio_score_topx_seed_async(ctx.h, ttcompute.h, queries.h, 0, Q, x, similarity,
+                                                 C.c_void_p(bound.data_ptr())))
+        dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=group)  # scores are >= +0: int order == float order
+        top = torch.empty((Q, x), dtype=torch.int64, device=dev)
+        _lib.check(L.myrio_score_topx_sweep_async(ctx.h, ttcompute.h, Q, x, similarity,
+                                                  C.c_void_p(bound.data_ptr()), C.c_void_p(top.data_ptr())))
+        g = torch.empty((world, Q, x), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(g.view(-1), top.view(-1), group=group)
+        out_s = torch.empty((Q, x), dtype=torch.float32, device=dev)
+        out_i = torch.empty((Q, x), dtype=torch.int32, device=dev)
+        _lib.check(L.myrio_topx_merge_composites_async(ctx.h, C.c_void_p(g.data_ptr()), world, Q, x,
+                                                       C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr())))
+    ctx.sync()
+    return out_s, out_i
+
+
 def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None):
-    """Shard-local top-x on this rank's leaves (K4+K5), NCCL all-gather, merge (K7).
-    Returns device tensors (scores [Q,x] f32, ids [Q,x] i32 holding u32 payload ids),
-    identical on every rank and identical to the single-GPU result."""
+    """The multi-GPU scoring step: shard-local top-x on this rank's leaves, exchange, merge (K7).
+    Returns device tensors (scores [Q,x] f32, ids [Q,x] i32 holding u32 payload ids), identical on every
+    rank and identical to the single-GPU result.  Two-phase with the bound exchange when the queries fit
+    one batch on every rank, otherwise exact shard lists + all-gather."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
+        if _two_phase_fits_everywhere(ctx, ttcompute, queries.n_rows, x, group):
+            return sharded_topx_two_phase(ctx, ttcompute, queries, x, similarity, group)
+    return sharded_topx_allgather(ctx, ttcompute, queries, x, similarity, group)
+
+
+def sharded_topx_allgather(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None):
+    """Exact shard-local top-x (K4+K5), all-gather of Q x x (score, id) pairs, merge (K7)."""
     from . import _lib
     Q = queries.n_rows
     dev = torch.device("cuda", ctx.device)

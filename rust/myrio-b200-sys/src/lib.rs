@@ -114,6 +114,12 @@ unsafe extern "C" {
     pub fn myrio_score_topx_direct_async(ctx: *mut myrio_ctx, leaf_vecs: *const myrio_svecs, leaf_id_base: u32,
                                          queries: *const myrio_svecs, q_first: u64, q_count: u64, x: u32,
                                          similarity: i32, d_top_scores: *mut f32, d_top_ids: *mut u32) -> i32;
+    pub fn myrio_score_topx_seed_async(ctx: *mut myrio_ctx, ix: *const myrio_index, queries: *const myrio_svecs,
+                                       q_first: u64, q_count: u64, x: u32, similarity: i32, d_bound: *mut u32) -> i32;
+    pub fn myrio_score_topx_sweep_async(ctx: *mut myrio_ctx, ix: *const myrio_index, q_count: u64, x: u32,
+                                        similarity: i32, d_bound: *const u32, d_top: *mut u64) -> i32;
+    pub fn myrio_topx_merge_composites_async(ctx: *mut myrio_ctx, d_in: *const u64, n_parts: u32, q_count: u64,
+                                             x: u32, d_scores_out: *mut f32, d_ids_out: *mut u32) -> i32;
     pub fn myrio_topx_merge_async(ctx: *mut myrio_ctx, d_scores_in: *const f32, d_ids_in: *const u32, n_parts: u32,
                                   q_count: u64, x: u32, d_scores_out: *mut f32, d_ids_out: *mut u32) -> i32;
     pub fn myrio_score_stats(ctx: *mut myrio_ctx, n_query_keys: *mut u64, n_key_hits: *mut u64,

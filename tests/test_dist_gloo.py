@@ -68,6 +68,20 @@ def _worker(rank, world, port, tmp):
         k, v = oq.row(q)
         es, ei = oracle.topx(oracle.score_all(full, k, v), X)
         assert (ei == mi[q]).all() and (es.view(np.uint32) == ms[q].view(np.uint32)).all()
+
+    # the two-phase exchange (dist.sharded_topx_two_phase): every rank's bound = its own X-th best score,
+    # all-reduce(MAX), shard lists pruned to the global bound (padding = score 0 / id 0xFFFFFFFF) -- the
+    # merged list is unchanged although the shard lists got shorter
+    bound = torch.from_numpy(ls[:, X - 1].copy().view(np.int32))
+    dist.all_reduce(bound, op=dist.ReduceOp.MAX)
+    gb = bound.numpy().view(np.float32)
+    ps, pi = ls.copy(), li.copy()
+    drop = ps < gb[:, None]
+    ps[drop], pi[drop] = 0.0, 0xFFFFFFFF
+    gs2, gi2 = mdist.allgather_topx(torch.from_numpy(ps), torch.from_numpy(pi.view(np.int32)))
+    ms2, mi2 = merge_rule(gs2.numpy(), gi2.numpy().view(np.uint32), X)
+    assert (mi2 == mi).all() and (ms2.view(np.uint32) == ms.view(np.uint32)).all()
+    assert drop.any()
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")

@@ -365,6 +365,48 @@ def test_topx_merge_matches_single_shard(api, ctx):
     assert (bits(out_s.cpu().numpy()) == bits(full.top_scores)).all()
 
 
+def test_two_phase_sharded_topx_with_bound_exchange(api):
+    # three shards (a context each, as three ranks would have): seed pass on every shard, the bounds are
+    # maxed like the all-reduce does, sweep with the global bound, merge of the composite lists ==
+    # the unsharded top-x, although a shard's own list may now be shorter than x
+    import ctypes as C
+    import torch
+    from myrio_b200 import _lib
+    base = api.Context(0)
+    tree, reads, ttc, q, oln, oqn = build_case(api, base, 1200, 24, 43, tile_leaves=64)
+    x, Q = 20, reads.n
+    full = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, x)
+    qro, qk, qv, _ = q.download(aux=False)
+    shards = []
+    for lo, hi in ((0, 400), (400, 800), (800, 1200)):
+        c = api.Context(0)
+        st = api.TaxTreeStore(c, tree.subset(np.arange(lo, hi)), leaf_id_base=lo)
+        shards.append((c, st, api.TaxTreeCompute.from_store_tree(st, 18, 32, tile_leaves=64),
+                       api.SFVecs.upload(c, qro, qk, qv)))
+    bounds = torch.zeros((3, Q), dtype=torch.int32, device="cuda")
+    for r, (c, st, sh, qq) in enumerate(shards):
+        _lib.check(c._L.myrio_score_topx_seed_async(c.h, sh.h, qq.h, 0, Q, x, 0, C.c_void_p(bounds[r].data_ptr())))
+        c.sync()
+    gbound = bounds.max(dim=0).values.contiguous()
+    assert (gbound > bounds).any()  # the exchange raises some shard's bound
+    tops = torch.zeros((3, Q, x), dtype=torch.int64, device="cuda")
+    for r, (c, st, sh, qq) in enumerate(shards):
+        _lib.check(c._L.myrio_score_topx_sweep_async(c.h, sh.h, Q, x, 0, C.c_void_p(gbound.data_ptr()),
+                                                     C.c_void_p(tops[r].data_ptr())))
+        c.sync()
+    assert (tops == 0).any()  # pruned by another shard's bound: shorter than x somewhere
+    out_s = torch.zeros((Q, x), dtype=torch.float32, device="cuda")
+    out_i = torch.zeros((Q, x), dtype=torch.int32, device="cuda")
+    _lib.check(base._L.myrio_topx_merge_composites_async(base.h, C.c_void_p(tops.data_ptr()), 3, Q, x,
+                                                         C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr())))
+    base.sync()
+    assert (out_i.cpu().numpy().view(np.uint32) == full.top_ids).all()
+    assert (bits(out_s.cpu().numpy()) == bits(full.top_scores)).all()
+    # protocol errors: sweep without seed, seed that does not fit one batch is reported, not silently wrong
+    c0, _, sh0, _ = shards[0]
+    assert c0._L.myrio_score_topx_sweep_async(c0.h, sh0.h, Q, x, 0, None, C.c_void_p(tops[0].data_ptr())) == _lib.ERR_BAD_ARG
+
+
 # ------------------------------------------------------------ K6 cluster
 
 def two_gene_reads(n_each, seed):
