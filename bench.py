@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--k", type=int, default=18)
     ap.add_argument("--x", type=int, default=100)
     ap.add_argument("--tile-leaves", type=int, default=0)
+    ap.add_argument("--topx-batch", type=int, default=0, help="N > 1: cap the queries per two-phase exchange batch (tests)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clustering", action="store_true", help="skip the clustering stage (K6) measurement")
@@ -360,14 +361,14 @@ def run_ours(args, rank, local_rank, world):
     def step_resident():
         counts = resident.compute_kmer_counts(k, 0.1)
         qn = counts.into_normalized_l2()
-        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE)
+        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
         return counts, s, i
 
     def step_e2e():
         m = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)      # H2D from pinned memory
         counts = m.compute_kmer_counts(k, 0.1)
         qn = counts.into_normalized_l2()
-        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE)
+        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
         out_s_t.copy_(s, non_blocking=True)                                    # D2H of the step's result
         out_i_t.copy_(i, non_blocking=True)
         torch.cuda.synchronize(dev)
@@ -502,7 +503,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- N > 1: the two exchange paths must give the same merged top-x (untimed)
     if world > 1:
-        s1, i1 = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE)
+        s1, i1 = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
         s2, i2 = mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE)
         torch.cuda.synchronize(dev)
         bad = int((~((s1.view(torch.int32) == s2.view(torch.int32)).all(dim=1) & (i1 == i2).all(dim=1))).sum().item())

@@ -70,59 +70,64 @@ def allgather_topx(scores: torch.Tensor, ids: torch.Tensor, group=None):
     return gs, gi
 
 
-_TWO_PHASE_OK: dict = {}
+_TWO_PHASE_CAP: dict = {}
 
 
-def _two_phase_fits_everywhere(ctx, ttcompute, Q: int, x: int, group=None) -> bool:
-    """The two-phase path needs all queries in one batch on EVERY rank (the batch capacity depends on the
-    shard's tile count): decided once per (index, Q, x) with an all-reduce(MIN) so all ranks agree."""
-    key = (id(ttcompute), Q, x)
-    if key not in _TWO_PHASE_OK:
+def _two_phase_batch(ctx, ttcompute, x: int, group=None) -> int:
+    """Queries per two-phase batch: the library needs a batch's per-tile candidates in 8 GB (the capacity
+    depends on the shard's tile count), and every rank must cut the queries at the same places: the minimum
+    over the ranks, decided once per (index, x) with an all-reduce(MIN)."""
+    key = (id(ttcompute), x)
+    if key not in _TWO_PHASE_CAP:
         n_tiles = max(1, ttcompute.info()["n_tiles"])
-        fits = 1 if Q <= max(1, (8 << 30) // (n_tiles * x * 8)) else 0
-        t = torch.tensor([fits], dtype=torch.int32, device=torch.device("cuda", ctx.device))
+        cap = max(1, (8 << 30) // (n_tiles * x * 8))
+        t = torch.tensor([cap], dtype=torch.int64, device=torch.device("cuda", ctx.device))
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
-        _TWO_PHASE_OK[key] = bool(int(t.item()))
-    return _TWO_PHASE_OK[key]
+        _TWO_PHASE_CAP[key] = int(t.item())
+    return _TWO_PHASE_CAP[key]
 
 
-def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None):
-    """The multi-GPU step with the bound exchange: seed pass on this rank's leaves, all-reduce(MAX) of
-    the per-query bounds (Q x 4 bytes), sweep with the global bound, ONE all-gather of the shard lists as
-    8-byte composites, merge (K7).  Everything is enqueued on the library's stream (torch's collectives
-    order themselves after it), no host synchronisation in between.  Raises MyrioError(UNSUPPORTED) when
-    the queries do not fit one batch."""
+def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0):
+    """The multi-GPU step with the bound exchange, per batch of queries: seed pass on this rank's leaves,
+    all-reduce(MAX) of the per-query bounds (4 bytes each), sweep with the global bound, ONE all-gather of
+    the shard lists as 8-byte composites, merge (K7).  Everything is enqueued on the library's stream
+    (torch's collectives order themselves after it), no host synchronisation in between."""
     from . import _lib
     Q = queries.n_rows
     dev = torch.device("cuda", ctx.device)
     L = ctx._L
     world = dist.get_world_size(group)
+    batch = _two_phase_batch(ctx, ttcompute, x, group)
+    if max_batch:
+        batch = min(batch, max_batch)
     with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=dev)):
-        bound = torch.empty(max(Q, 1), dtype=torch.int32, device=dev)
-        _lib.check(L.myrio_score_topx_seed_async(ctx.h, ttcompute.h, queries.h, 0, Q, x, similarity,
-                                                 C.c_void_p(bound.data_ptr())))
-        dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=group)  # scores are >= +0: int order == float order
-        top = torch.empty((Q, x), dtype=torch.int64, device=dev)
-        _lib.check(L.myrio_score_topx_sweep_async(ctx.h, ttcompute.h, Q, x, similarity,
-                                                  C.c_void_p(bound.data_ptr()), C.c_void_p(top.data_ptr())))
-        g = torch.empty((world, Q, x), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(g.view(-1), top.view(-1), group=group)
         out_s = torch.empty((Q, x), dtype=torch.float32, device=dev)
         out_i = torch.empty((Q, x), dtype=torch.int32, device=dev)
-        _lib.check(L.myrio_topx_merge_composites_async(ctx.h, C.c_void_p(g.data_ptr()), world, Q, x,
-                                                       C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr())))
+        for q0 in range(0, Q, batch):
+            qc = min(batch, Q - q0)
+            bound = torch.empty(qc, dtype=torch.int32, device=dev)
+            _lib.check(L.myrio_score_topx_seed_async(ctx.h, ttcompute.h, queries.h, q0, qc, x, similarity,
+                                                     C.c_void_p(bound.data_ptr())))
+            dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=group)  # scores are >= +0: int order == float order
+            top = torch.empty((qc, x), dtype=torch.int64, device=dev)
+            _lib.check(L.myrio_score_topx_sweep_async(ctx.h, ttcompute.h, qc, x, similarity,
+                                                      C.c_void_p(bound.data_ptr()), C.c_void_p(top.data_ptr())))
+            g = torch.empty((world, qc, x), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(g.view(-1), top.view(-1), group=group)
+            _lib.check(L.myrio_topx_merge_composites_async(ctx.h, C.c_void_p(g.data_ptr()), world, qc, x,
+                                                           C.c_void_p(out_s[q0:q0 + qc].data_ptr()),
+                                                           C.c_void_p(out_i[q0:q0 + qc].data_ptr())))
     ctx.sync()
     return out_s, out_i
 
 
-def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None):
+def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0):
     """The multi-GPU scoring step: shard-local top-x on this rank's leaves, exchange, merge (K7).
     Returns device tensors (scores [Q,x] f32, ids [Q,x] i32 holding u32 payload ids), identical on every
-    rank and identical to the single-GPU result.  Two-phase with the bound exchange when the queries fit
-    one batch on every rank, otherwise exact shard lists + all-gather."""
+    rank and identical to the single-GPU result: two-phase with the bound exchange over NCCL
+    (`sharded_topx_two_phase`); `sharded_topx_allgather` is the plain exchange of exact shard lists."""
     if dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
-        if _two_phase_fits_everywhere(ctx, ttcompute, queries.n_rows, x, group):
-            return sharded_topx_two_phase(ctx, ttcompute, queries, x, similarity, group)
+        return sharded_topx_two_phase(ctx, ttcompute, queries, x, similarity, group, max_batch)
     return sharded_topx_allgather(ctx, ttcompute, queries, x, similarity, group)
 
 
