@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- the Myrio hot path on N B200s (BASELINE.json: query x reference-leaf
-similarity scores/s and k-mers counted/s).
+similarity scores/s and k-mers counted/s at 1/2/4/8 B200).
 
   python bench.py --gpus N --steps K --warmup W            # the CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference
 
-Workload (BASELINE.json configs[1]): a synthetic BOLD-scale ITS tree of 100 000
-leaves per GPU x 100 000 simulated reads, k = 18.  One STEP = one pass of the hot
-path over the read batch: 2-bit k-mer counting of every read (K1), L2
-normalisation, scoring of every read against every leaf of the rank's shard over
-the inverted index (K4), top-100 per read (K5) and -- for N > 1 -- the NCCL
-all-gather of the shard-local top-x plus the merge kernel (K7).  The reference
-tree is counted (K2) and indexed (K3) once before the timed region; both are
-timed separately and reported in the same JSON line.
+Headline workload (BASELINE.json configs[1]): a synthetic BOLD-scale ITS tree of 100 000
+leaves per GPU x 100 000 simulated reads, k = 18.  One STEP = one pass of the hot path over
+the read batch: 2-bit k-mer counting of every read (K1), L2 normalisation, scoring of every
+read against every leaf of the rank's shard over the inverted index (K4), top-100 per read
+(K5) and -- for N > 1 -- the bound all-reduce, the all-gather of the shard lists and the merge
+(K7), all inside libmyrio_b200.so (myrio_score_topx_sharded).  The reference tree is counted
+(K2) and indexed (K3) once before the timed region; both are timed separately and reported.
 
-`value` has the reads resident in HBM; `e2e` goes through the public API with
-pinned host buffers (H2D of the packed reads and D2H of the top-x inside the
-timed region).  Inputs (index ~1 GB/GPU) are larger than the 126 MB L2.
+Data are independent of N: rank r holds sub-tree r of one global tree (same root, payload ids
+r*L .. (r+1)*L), and the ONE read batch is simulated from sub-tree 0, so N = 1 is exactly
+configs[1] and larger N add sister clades to the reference ("weak": leaves per GPU fixed).
+`strong` (BASELINE.json configs[4]) is the 1 M-leaf tree -- 8 fixed sub-trees of 125 000
+leaves -- sharded over the N ranks against one fixed read batch drawn from all of it.
+
+`value` has the reads resident in HBM; `e2e` goes through the public API with pinned host
+buffers (H2D of the packed reads on every rank, D2H of each rank's 1/N of the merged top-x
+inside the timed region).  Inputs (index >= 1 GB per GPU) are larger than the 126 MB L2.
+
+stdout carries exactly one JSON line; everything else any library prints (NCCL_DEBUG output
+included -- the caller's NCCL_DEBUG setting is left alone) goes to stderr.
 """
 from __future__ import annotations
 
@@ -37,6 +45,7 @@ if ROOT not in sys.path:
 
 METRIC = "query_x_leaf_similarity_scores_per_s"
 UNIT = "scores/s"
+N_STRONG_SUBTREES = 8
 
 
 def parse():
@@ -45,18 +54,25 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--leaves", type=int, default=100_000, help="reference leaves per GPU")
+    ap.add_argument("--leaves", type=int, default=100_000, help="reference leaves per GPU (weak scaling)")
     ap.add_argument("--reads", type=int, default=100_000, help="reads (queries), total")
     ap.add_argument("--k", type=int, default=18)
     ap.add_argument("--x", type=int, default=100)
     ap.add_argument("--tile-leaves", type=int, default=0)
-    ap.add_argument("--topx-batch", type=int, default=0, help="N > 1: cap the queries per two-phase exchange batch (tests)")
+    ap.add_argument("--topx-batch", type=int, default=0, help="N > 1: cap the queries per exchange batch (tests)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clustering", action="store_true", help="skip the clustering stage (K6) measurement")
     ap.add_argument("--clusters", type=int, default=4)
     ap.add_argument("--cluster-reps", type=int, default=3, help="timed cluster() calls per variant (median reported)")
     ap.add_argument("--cluster-warmup", type=int, default=1)
+    ap.add_argument("--strong-leaves", type=int, default=1_000_000,
+                    help="total leaves of the strong-scaling tree (configs[4]); 0 skips the block")
+    ap.add_argument("--strong-reads", type=int, default=100_000)
+    ap.add_argument("--strong-steps", type=int, default=2)
+    ap.add_argument("--no-variants", action="store_true",
+                    help="skip the sparse-path variants (tree without conserved block, 1 %% ambiguity codes, k=12)")
+    ap.add_argument("--variant-reads", type=int, default=50_000)
     return ap.parse_args()
 
 
@@ -66,10 +82,35 @@ def config_dict(args, world):
                     f"{args.reads} reads, k={args.k}, top-{args.x}, cosine",
         "leaves_per_gpu": args.leaves, "leaves_total": args.leaves * world, "reads": args.reads,
         "k": args.k, "x": args.x, "read_cutoff_t1": 0.1, "nb_resamples": 32,
-        "parallelism": f"leaf-shard x{world}, queries replicated, NCCL all-gather of top-x",
+        "parallelism": f"leaf-shard x{world} (contiguous payload-id blocks), queries replicated; seed pass, "
+                       f"ncclAllReduce(MAX) of the per-query bounds, sweep, ncclAllGather of 8-byte composites, merge "
+                       f"-- all inside myrio_score_topx_sharded" if world > 1 else "single GPU",
+        "data_independent_of_n": "rank r indexes sub-tree r (seed 1002, shard r) of one global tree; the read batch "
+                                 "(seed 2002) is simulated from sub-tree 0 at every N",
         "l2_policy": "inputs larger than L2 (index >= 1 GB per GPU vs 126 MB L2); no explicit flush",
         "seeds": {"tree": 1002, "reads": 2002},
     }
+
+
+# ------------------------------------------------------------------ stdout discipline
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """fd 1 -> stderr for the rest of the process (NCCL's C-level logging follows), the JSON line goes to
+    the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 # ------------------------------------------------------------------ clocks
@@ -122,13 +163,27 @@ class ClockSampler:
 
 # ------------------------------------------------------------- data
 
-def make_data(args, rank, world):
+def weak_tree(args, shard):
     from myrio_b200 import synth
-    tree = synth.make_tree(args.leaves, 1002, root_seed=1002, shard=rank)
-    lo = rank * args.reads // world
-    hi = (rank + 1) * args.reads // world
-    reads_local = synth.make_reads(tree, hi - lo, 2002 + rank)
-    return tree, reads_local
+    return synth.make_tree(args.leaves, 1002, root_seed=1002, shard=shard)
+
+
+def weak_reads(args, tree0):
+    from myrio_b200 import synth
+    return synth.make_reads(tree0, args.reads, 2002)
+
+
+def strong_subtree(args, j):
+    """Sub-tree j of the configs[4] tree: fixed for every N (the tree is ALWAYS cut into 8 sub-trees, a rank
+    holds 8/N consecutive ones)."""
+    from myrio_b200 import synth
+    per = args.strong_leaves // N_STRONG_SUBTREES
+    return synth.make_tree(per, 1005, root_seed=1005, shard=j)
+
+
+def strong_reads_of(args, sub, j):
+    from myrio_b200 import synth
+    return synth.make_reads(sub, args.strong_reads // N_STRONG_SUBTREES, 2005 + j)
 
 
 def peaks():
@@ -141,23 +196,45 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profiles():
-    """dram bytes per K4 launch from the committed ncu capture, if any (profiles/*k4*traffic*.json)."""
+def latest_profile(pattern: str):
+    """Newest committed profiles/*<pattern>*.json (files are named per round: r01_, r02_, ...)."""
     d = os.path.join(ROOT, "profiles")
     best = None
     if os.path.isdir(d):
         for f in sorted(os.listdir(d)):
-            if f.endswith(".json") and "traffic" in f:
+            if f.endswith(".json") and pattern in f:
                 try:
-                    best = json.load(open(os.path.join(d, f)))
+                    best = (f, json.load(open(os.path.join(d, f))))
                 except Exception:
                     pass
     return best
 
 
+def ascii_leaves(tree):
+    """FASTA sequence text of an ACGT tree (what load_from_fasta_string reads), for the device ingestion."""
+    from myrio_b200 import synth
+    return synth.ASCII[tree.codes & 3], np.ascontiguousarray(tree.base_off, np.uint64)
+
+
+def logical_leaf_kmers(tree, k):
+    return float(2 * (tree.lengths() - k + 1).clip(0).sum())
+
+
+def k1_algorithmic_bytes(reads, nnz):
+    """ceil(n/4) + n in, 12*D + 16 out per read."""
+    n = reads.lengths()
+    return float(((n + 3) // 4).sum() + n.sum() + 12 * nnz + 16 * reads.n)
+
+
+def k2_algorithmic_bytes(tree, nnz):
+    """ceil(n/2) in, 10*D + 12 out per leaf."""
+    n = tree.lengths()
+    return float(((n + 1) // 2).sum() + 10 * nnz + 12 * tree.n)
+
+
 # ------------------------------------------------------------- clustering stage (K6)
 
-SMEM_BYTES_PER_CLK_PER_SM = 128.0  # shared-memory bandwidth of one SM (32 banks x 4 B)
+SMEM_BYTES_PER_CLK_PER_SM = 128.0  # nominal shared-memory bandwidth of one SM (32 banks x 4 B)
 
 
 def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu_seconds=0.0, world=1,
@@ -169,12 +246,14 @@ def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu
     cluster_fn = cluster_fn or api.cluster
     reduce_max = reduce_max or (lambda v: v)
     reduce_sum = reduce_sum or (lambda v: v)
-    out = {"workload": f"cluster() k=6 t1=0.2 t2=20 on {resident.n} reads, {n_clusters} clusters "
-                       f"(farthest-point fill), cosine; then the same with silhouette trimming 1.4",
+    out = {"workload": f"cluster() k=6 t1=0.2 t2=20 on {resident.n} reads (the same batch at every N), {n_clusters} "
+                       f"clusters (farthest-point fill), cosine; then the same with silhouette trimming 1.4",
            "parallelism": "single GPU" if world == 1 else
                           f"reads replicated, rows of every similarity tile split over {world} GPUs, per-row results "
-                          f"all-gathered (myrio_cluster_sharded)",
+                          f"exchanged with ncclAllGather inside the library (myrio_cluster_sharded, no callback)",
            "scaling": "strong"}
+    # measured shared-memory bandwidth (a conflict-free LDS.128 read kernel of the library), the K6 denominator
+    smem_meas = ctx.bench_smem_bandwidth()
     for name, sil in (("assign_only", None), ("with_silhouette", 1.4)):
         prm = api.ClusteringParameters(k=6, t1=0.2, t2=20, expected_nb_of_clusters=n_clusters,
                                        silhouette_trimming=sil)
@@ -202,17 +281,19 @@ def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu
              "pair_similarities_rank0": st["pair_similarities"],
              "terms_rank0": st["terms"], "pair_similarities_per_s": pairs_all / max(call_s, 1e-9)}
         if getattr(res, "exchange", None):
-            d["exchange"] = {"calls": res.exchange["calls"], "ms_incl_waiting_for_peers": res.exchange["seconds"] * 1e3,
-                             "bytes": res.exchange["bytes"]}
+            d["exchange"] = res.exchange
         if sil is not None and sil_ms > 0:
-            # dominant kernel of the stage: pair_tile_kernel.  Every multiply-add term reads one f32 of a
+            # dominant kernel of the stage: pair_tile_canon_kernel.  Every multiply-add term reads one f32 of a
             # column from shared memory (4 B); the bound is the SMs' shared-memory bandwidth.
-            peak = 148 * SMEM_BYTES_PER_CLK_PER_SM * (sm_mhz or 1965.0) * 1e6 / 1e9
+            nominal = 148 * SMEM_BYTES_PER_CLK_PER_SM * (sm_mhz or 1965.0) * 1e6 / 1e9
+            peak = smem_meas["gbps"] if smem_meas["gbps"] > 0 else nominal
             ach = 4.0 * st["terms"] / (sil_ms * 1e-3) / 1e9
             d["roofline"] = {"bound": "shared-memory bandwidth", "kernel": "k6_pair_silhouette (pair_tile_canon_kernel)",
                              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "kernel_ms": sil_ms, "terms_per_s": st["terms"] / (sil_ms * 1e-3),
-                             "peak_source": "148 SMs x 128 B/clk x SM clock under load (nvidia-smi)",
+                             "peak_source": "measured in this run: myrio_bench_smem_bandwidth (conflict-free LDS.128 reads "
+                                            f"on every SM, {smem_meas['ms']:.2f} ms)",
+                             "peak_nominal": nominal,
                              "note": "algorithmic bytes = 4 B (one column value read from shared memory) per multiply-add "
                                      "term; the scheduled slab is conflict-free, the loss is its ~1.12x waiting slots, "
                                      "column staging and the row-slab stream (profiles/r01_k6_canon_ncu_summary.json)"}
@@ -240,25 +321,39 @@ def bench_clustering(ctx, api, resident, n_clusters, sm_mhz, cpu_reads=None, cpu
 
 # ------------------------------------------------------------- CPU arms
 
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port) on ALL host cores, rank 0 only; the same
+    config (tree seed 1002 shard 0 = the per-GPU shard, reads seed 2002) at every N."""
     if rank != 0:
         return
+    claim_stdout()
     import oracle
     from myrio_b200 import synth
+    oracle.set_num_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1
     threads = oracle.max_threads()
-    tree, reads_local = make_data(args, 0, 1 if world == 1 else world)
+    tree = weak_tree(args, 0)
+    reads = weak_reads(args, tree)
     # leaf vectors (the reference's "index" is the list of normalised leaf vectors)
     t0 = time.perf_counter()
     lc = oracle.count_leaves(synth.tree_to_iupac(tree), tree.base_off, args.k, 32, threads=threads)
     t_leaves = time.perf_counter() - t0
     ln = oracle.normalize(lc, threads)
     # queries
-    nq_probe = min(reads_local.n, 8)
-    sub = reads_local.subset(np.arange(min(reads_local.n, 4096)))
+    nq_probe = min(reads.n, 8)
+    sub = reads.subset(np.arange(min(reads.n, 4096)))
     t0 = time.perf_counter()
     rc = oracle.count_reads(sub.codes, sub.qual, sub.base_off, args.k, 0.1, threads=1)  # serial like the reference
     t_reads = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle.count_reads(sub.codes, sub.qual, sub.base_off, args.k, 0.1, threads=threads)
+    t_reads_par = time.perf_counter() - t0
     qn = oracle.normalize(rc, threads)
 
     def score_n(n):
@@ -278,9 +373,12 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         score_n(n_step)
     dt = time.perf_counter() - t0
+    # the work a rank-count of N asks for is Q x (N x L) scores; the CPU arm scores against one L-leaf shard
+    # per step sample, so its rate is per (query, leaf) pair either way
     value = n_step * args.steps * tree.n / dt
     sample = (f"{n_step} queries x {tree.n} leaves per step (first reads of the seed-2002 batch), "
               f"{threads} OpenMP threads over leaves like rayon (tax/results.rs:89-93)")
+    leaf_kmers = logical_leaf_kmers(tree, args.k)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -289,19 +387,21 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "kmers_counted_per_s": {
-            "reads_serial": float(rc.aux.sum()) / t_reads,
-            "leaves_reference_equivalent_x32": float(2 * (tree.lengths() - args.k + 1).clip(0).sum() * 32) / t_leaves,
-            "leaves_logical": float(2 * (tree.lengths() - args.k + 1).clip(0).sum()) / t_leaves,
-            "cores": threads,
+            "reads_serial_like_the_reference": float(rc.aux.sum()) / t_reads,
+            "reads_all_threads": float(rc.aux.sum()) / t_reads_par,
+            "leaves_reference_equivalent_x32": leaf_kmers * 32 / t_leaves,
+            "leaves_logical": leaf_kmers / t_leaves,
+            "cores": threads, "sample": f"{sub.n} reads; all {tree.n} leaves x 32 resamples",
         },
         "note": "CPU restatement of the reference algorithm (the Rust binary cannot be built: no cargo/rustc)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------- GPU arm
 
 def run_ours(args, rank, local_rank, world):
+    claim_stdout()
     import torch
     import torch.distributed as dist
     from myrio_b200 import _lib, api, synth
@@ -311,68 +411,12 @@ def run_ours(args, rank, local_rank, world):
         raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        os.environ["NCCL_DEBUG"] = os.environ.get("MYRIO_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = api.Context(local_rank)
     L = ctx._L
     dev = torch.device("cuda", local_rank)
     ext = torch.cuda.ExternalStream(ctx.stream, device=dev)
-
-    tree, reads_local = make_data(args, rank, world)
-    reads = mdist.allgather_reads(reads_local) if world > 1 else reads_local
-    Q, x, k = reads.n, args.x, args.k
-
-    # ---- setup (timed separately): K2 leaf counting, normalise, K3 index build
-    ctx.prof_enable(True)
-    t0 = time.perf_counter()
-    store = api.TaxTreeStore(ctx, tree, leaf_id_base=rank * args.leaves)
-    t_upload_leaves = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    store.compute_and_append_kmer_counts(k, 32)
-    ctx.sync()
-    t_count_leaves = time.perf_counter() - t0
-    k2_ms, _ = ctx.prof_query("k2_")
-    t0 = time.perf_counter()
-    ttc = api.TaxTreeCompute.from_store_tree(store, k, 32, tile_leaves=args.tile_leaves)
-    ctx.sync()
-    t_index = time.perf_counter() - t0
-    info = ttc.info()
-    leaf_kmers = float(2 * (tree.lengths() - k + 1).clip(0).sum())
-    ctx.prof_enable(False)
-    ctx.prof_reset()
-
-    # ---- pinned host copies of the packed reads (e2e path) and resident reads (value path)
-    words, word_off = synth.pack_dna2(reads)
-    base_off = np.ascontiguousarray(reads.base_off, np.uint64)
-
-    def pinned(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t, t.numpy()
-
-    keep = [pinned(words), pinned(word_off), pinned(base_off), pinned(reads.qual)]
-    p_words, p_woff, p_boff, p_qual = (kp[1] for kp in keep)
-    h2d_bytes = int(p_words.nbytes + p_woff.nbytes + p_boff.nbytes + p_qual.nbytes)
-    out_s_t = torch.empty((Q, x), dtype=torch.float32).pin_memory()
-    out_i_t = torch.empty((Q, x), dtype=torch.int32).pin_memory()
-    d2h_bytes = int(out_s_t.numel() * 4 + out_i_t.numel() * 4)
-    resident = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)
-
-    def step_resident():
-        counts = resident.compute_kmer_counts(k, 0.1)
-        qn = counts.into_normalized_l2()
-        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
-        return counts, s, i
-
-    def step_e2e():
-        m = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)      # H2D from pinned memory
-        counts = m.compute_kmer_counts(k, 0.1)
-        qn = counts.into_normalized_l2()
-        s, i = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
-        out_s_t.copy_(s, non_blocking=True)                                    # D2H of the step's result
-        out_i_t.copy_(i, non_blocking=True)
-        torch.cuda.synchronize(dev)
-        return counts
+    comm_info = mdist.init_library_comm(ctx) if world > 1 else ctx.comm_info()
 
     def barrier():
         if world > 1:
@@ -380,7 +424,22 @@ def run_ours(args, rank, local_rank, world):
         ctx.sync()
         torch.cuda.synchronize(dev)
 
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     def timed(fn, steps):
+        """`steps` calls bracketed by barrier + synchronize, CUDA events on the library's stream, max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
@@ -390,13 +449,79 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
         e1.record(ext)
         e1.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = allmax(e0.elapsed_time(e1))
         barrier()
         return ms
+
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+
+    tree0 = weak_tree(args, 0)
+    tree = tree0 if rank == 0 else weak_tree(args, rank)
+    reads = weak_reads(args, tree0)
+    Q, x, k = reads.n, args.x, args.k
+
+    # ---- setup (timed separately): FASTA text -> packed leaves on the device (K0), K2 leaf counting,
+    # normalise, K3 index build
+    ctx.prof_enable(True)
+    text, text_off = ascii_leaves(tree)
+    t0 = time.perf_counter()
+    store, _ = api.TaxTreeStore.from_fasta_records(ctx, text, text_off, leaf_id_base=rank * args.leaves)
+    t_upload_leaves = time.perf_counter() - t0
+    store.compute_and_append_kmer_counts(k, 32)  # first call: kernel attributes, pool growth
+    ctx.sync()
+    store.kmer_store_counts_vec, store.k_precomputed = [], []
+    ctx.prof_reset()
+    t0 = time.perf_counter()
+    store.compute_and_append_kmer_counts(k, 32)
+    ctx.sync()
+    t_count_leaves = time.perf_counter() - t0
+    k2_ms, _ = ctx.prof_query("k2_")
+    leaf_nnz = store.kmer_store_counts_vec[0].nnz
+    t0 = time.perf_counter()
+    ttc = api.TaxTreeCompute.from_store_tree(store, k, 32, tile_leaves=args.tile_leaves)
+    ctx.sync()
+    t_index = time.perf_counter() - t0
+    info = ttc.info()
+    leaf_kmers = logical_leaf_kmers(tree, k)
+    ctx.prof_enable(False)
+    ctx.prof_reset()
+
+    # ---- pinned host copies of the packed reads (e2e path) and resident reads (value path)
+    words, word_off = synth.pack_dna2(reads)
+    base_off = np.ascontiguousarray(reads.base_off, np.uint64)
+    keep = [pinned(words), pinned(word_off), pinned(base_off), pinned(reads.qual)]
+    p_words, p_woff, p_boff, p_qual = (kp[1] for kp in keep)
+    h2d_rank = int(p_words.nbytes + p_woff.nbytes + p_boff.nbytes + p_qual.nbytes)
+    # every rank brings back its 1/N of the merged result: together the host holds all of it once
+    q_lo, q_hi = mdist.shard_bounds(Q, rank, world)
+    out_s_t = torch.empty((max(q_hi - q_lo, 1), x), dtype=torch.float32).pin_memory()
+    out_i_t = torch.empty((max(q_hi - q_lo, 1), x), dtype=torch.int32).pin_memory()
+    d2h_total = int(Q * x * 8)
+    resident = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)
+
+    def topx(qn):
+        if world > 1:
+            return mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
+        return mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE)  # one rank: K4 + K5, no exchange
+
+    def step_resident():
+        counts = resident.compute_kmer_counts(k, 0.1)
+        qn = counts.into_normalized_l2()
+        s, i = topx(qn)
+        return counts, s, i
+
+    def step_e2e():
+        m = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)      # H2D from pinned memory
+        counts = m.compute_kmer_counts(k, 0.1)
+        qn = counts.into_normalized_l2()
+        s, i = topx(qn)
+        if q_hi > q_lo:                                                        # D2H of this rank's share
+            out_s_t[:q_hi - q_lo].copy_(s[q_lo:q_hi], non_blocking=True)
+            out_i_t[:q_hi - q_lo].copy_(i[q_lo:q_hi], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return counts
 
     # ---- warm-up, then the timed region of the resident path; the e2e path is warmed up right
     # before its own timed region (switching paths reshuffles the memory pool once)
@@ -415,6 +540,7 @@ def run_ours(args, rank, local_rank, world):
     k1_ms, k1_n = ctx.prof_query("k1_")
     k5_ms, k5_n = ctx.prof_query("k5_")
     k4a_ms, _ = ctx.prof_query("k4a_")
+    k7_ms, _ = ctx.prof_query("k7_")
     all_ms, all_n = ctx.prof_query("")
     ctx.prof_enable(False)
     ctx.prof_reset()
@@ -423,7 +549,18 @@ def run_ours(args, rank, local_rank, world):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- exact algorithmic work of one step (one untimed pass with the counters on)
+    # ---- k-mer counting THROUGH THE CALL (reads): myrio_count_reads + sync, wall clock, max over ranks
+    n_cr = max(3, args.steps)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_cr):
+        c_tmp = resident.compute_kmer_counts(k, 0.1)
+    ctx.sync()
+    t_count_reads_call = allmax((time.perf_counter() - t0) / n_cr)
+    read_nnz = c_tmp.nnz
+    del c_tmp
+
+    # ---- exact algorithmic work of one step on this rank's shard (one untimed pass with the counters on)
     counts = resident.compute_kmer_counts(k, 0.1)
     qn = counts.into_normalized_l2()
     ts = np.zeros((Q, x), np.float32)
@@ -440,110 +577,142 @@ def run_ours(args, rank, local_rank, world):
     value = n_gpu_scores * args.steps / (ms_value * 1e-3)
     e2e_value = n_gpu_scores * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel (K4), per launch, SURVEY §8d bytes
+    # ---- roofline of the dominant kernel (K4).  The kernel is bound by warp-instruction ISSUE, not by HBM:
+    # 98 % of the postings a query touches are bits of 128-byte dense-key bitmaps that stay in L2, so DRAM
+    # moves a few % of its peak (ncu: `traffic`), while the SM sub-partitions issue near their limit.
     peak, peak_src = peaks()
     alg_bytes_step = 12 * nq_sum + 16 * nq_sum + 8 * t_q + 8 * x * Q
     k4_per_step = max(k4_n // max(args.steps, 1), 1)
-    alg_bytes_launch = alg_bytes_step / k4_per_step
     k4_avg_ms = k4_ms / max(k4_n, 1)
-    achieved = alg_bytes_launch / (k4_avg_ms * 1e-3) / 1e9 if k4_avg_ms > 0 else 0.0
-    tr = traffic_from_profiles()
+    k4_step_ms = k4_ms / max(args.steps, 1)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    prof = latest_profile("r02_k4_ncu_summary") or latest_profile("r01_k4_v14_ncu_summary")
+    issue_peak = 148 * 4 * sm_mhz * 1e6  # warp instructions / s: 148 SMs x 4 schedulers x 1 issue / clk
     roofline = {
-        "bound": "hbm", "kernel": "k4_score_tiles_topx (score_tiles_kernel<COSINE, fused top-x>)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": (tr or {}).get("dram_bytes_per_launch"),
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
-        "launch_ms_avg": k4_avg_ms, "launches_per_step": k4_per_step,
-        "launches": "per step: seed pass (every query against its best tile) + tile-major sweep of all other (query, tile) tasks",
-        "postings_touched_per_step": t_q, "query_keys_per_step": nq_sum,
+        "bound": "issue",
+        "kernel": "k4_score_tiles_topx (score_tiles_kernel<COSINE, fused top-x>), seed pass + tile-major sweep",
+        "unit": "Gwarp-inst/s", "peak": issue_peak / 1e9,
+        "peak_source": f"148 SMs x 4 warp schedulers x SM clock under load ({sm_mhz:.0f} MHz, nvidia-smi during the timed region)",
+        "launch_ms_avg": k4_avg_ms, "launches_per_step": k4_per_step, "kernel_ms_per_step": k4_step_ms,
         "kernel_share_of_step": k4_ms / max(all_ms, 1e-9),
-        "note": "achieved counts every posting a query touches (8 B each); posting lists are re-used across "
-                "queries from L2, so achieved can exceed the HBM peak -- `traffic` is the measured DRAM bytes",
+        "postings_touched_per_step": t_q, "query_keys_per_step": nq_sum,
+        "algorithmic_bytes_per_step_survey_8d": alg_bytes_step,
     }
-    if tr:
-        roofline["traffic_source"] = tr.get("source")
-    # the kernel's actual limiter, from the committed ncu capture (not measured in this run)
-    k4_ncu = os.path.join(ROOT, "profiles", "r01_k4_v14_ncu_summary.json")
-    if os.path.exists(k4_ncu):
-        try:
-            n = json.load(open(k4_ncu))["launches"][-1]  # the tile-major sweep (93 % of the two launches' time)
-            roofline["limiter"] = {"bound": "warp-instruction issue (postings are re-used from L2, DRAM ~1 % busy)",
-                                   "sm_throughput_pct_of_peak": n.get("sm_throughput_pct"),
-                                   "l1tex_throughput_pct_of_peak": n.get("l1tex_throughput_pct"),
-                                   "dram_pct_of_peak": n.get("dram_pct_of_peak"),
-                                   "l2_hit_rate_pct": n.get("l2_hit_rate_pct"),
-                                   "warp_instructions_per_launch": n.get("warp_instructions"),
-                                   "source": "profiles/r01_k4_v14_ncu_summary.json (ncu --set full, same workload; sweep launch)"}
-        except Exception:
-            pass
+    if prof:
+        pname, pj = prof
+        pl = pj.get("launches", [])
+        wi = float(sum(l.get("warp_instructions", 0.0) for l in pl))
+        dram = float(sum(l.get("dram_bytes", 0.0) for l in pl))
+        # the round-1 capture predates the field: its workload touched 2.4347e11 postings per step (BENCH_r01)
+        post_prof = float(pj.get("postings_touched_per_step") or (2.4347e11 if pname.startswith("r01_k4_v14") else 0.0))
+        # warp instructions of THIS run = instructions per posting of the committed capture (same code, same
+        # workload) x the postings counted in this run; / measured kernel time / issue peak
+        if wi > 0:
+            wi_run = wi * (t_q / post_prof) if post_prof > 0 else wi
+            roofline.update({
+                "achieved": wi_run / (k4_step_ms * 1e-3) / 1e9,
+                "frac": wi_run / (k4_step_ms * 1e-3) / issue_peak,
+                "warp_instructions_per_step": wi_run,
+                "thread_instructions_per_posting": 32.0 * wi / post_prof if post_prof > 0 else None,
+                "instruction_count_source": f"profiles/{pname} (ncu smsp__inst_executed.sum of the K4 launches of one step"
+                                            + (", scaled by postings touched" if post_prof > 0 else "") + ")",
+            })
+        if dram > 0:
+            roofline["traffic"] = dram / max(len(pl), 1)
+            roofline["traffic_source"] = f"profiles/{pname}: dram__bytes_read.sum + dram__bytes_write.sum per launch"
+            roofline["hbm"] = {"achieved": dram / (k4_step_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": dram / (k4_step_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                               "note": "measured DRAM bytes of the K4 launches of one step / measured kernel time"}
+            roofline["l2_reuse_ratio"] = alg_bytes_step / dram
+            roofline["l2_reuse_note"] = ("SURVEY §8d algorithmic bytes (8 B per posting touched) / DRAM bytes moved: posting "
+                                         "lists and bitmaps are served from L2 and as bits, not as 8-byte postings")
+    roofline.setdefault("achieved", None)
+    roofline.setdefault("frac", None)
+    roofline.setdefault("traffic", None)
+
+    k1_bytes = k1_algorithmic_bytes(reads, read_nnz)
+    k2_bytes = k2_algorithmic_bytes(tree, leaf_nnz)
+    k1_step_ms = k1_ms / max(args.steps, 1)
+    kmers = {
+        "unit": "k-mers/s", "n_gpus": world,
+        "reads": {
+            "kmers_per_step": read_kmers,
+            "k1_kernel": read_kmers / (k1_step_ms * 1e-3) if k1_ms > 0 else None,
+            "count_call": read_kmers / t_count_reads_call,
+            "count_call_ms": t_count_reads_call * 1e3, "k1_kernel_ms": k1_step_ms,
+            "whole_job": read_kmers * world / t_count_reads_call,
+            "note": "reads are replicated: every rank counts the whole batch (whole_job = N x count_call)",
+            "roofline": {"bound": "hbm", "algorithmic_bytes": k1_bytes, "achieved": k1_bytes / (k1_step_ms * 1e-3) / 1e9 if k1_ms > 0 else None,
+                         "peak": peak, "unit": "GB/s", "frac": k1_bytes / (k1_step_ms * 1e-3) / 1e9 / peak if k1_ms > 0 else None,
+                         "bytes_rule": "SURVEY §8d K1: ceil(n/4) + n in, 12 D + 16 out per read"},
+        },
+        "leaves": {
+            "kmers_logical": leaf_kmers,
+            "k2_kernel_logical": leaf_kmers / (k2_ms * 1e-3) if k2_ms > 0 else None,
+            "k2_kernel_reference_equivalent_x32": leaf_kmers * 32 / (k2_ms * 1e-3) if k2_ms > 0 else None,
+            "count_call_logical": leaf_kmers / t_count_leaves,
+            "count_call_ms": t_count_leaves * 1e3, "k2_kernel_ms": k2_ms,
+            "whole_job_logical": allsum(leaf_kmers) / allmax(t_count_leaves),
+            "note": "leaves are sharded: whole_job = all ranks' leaf k-mers / slowest rank's call",
+            "roofline": {"bound": "hbm", "algorithmic_bytes": k2_bytes, "achieved": k2_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
+                         "peak": peak, "unit": "GB/s", "frac": k2_bytes / (k2_ms * 1e-3) / 1e9 / peak if k2_ms > 0 else None,
+                         "bytes_rule": "SURVEY §8d K2: ceil(n/2) in, 10 D + 12 out per leaf"},
+        },
+    }
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, world),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_rank * world,
+                "d2h_bytes_per_step": d2h_total, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step_per_rank": h2d_rank,
+                "note": "every rank uploads the read batch (queries are replicated) and downloads its 1/N of the merged top-x"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks,
-        "kmers_counted_per_s": {
-            "reads_k1_kernel": read_kmers * args.steps / (k1_ms * 1e-3) if k1_ms > 0 else None,
-            "reads_count_call": None,
-            "leaves_k2_kernel_logical": leaf_kmers / (k2_ms * 1e-3) if k2_ms > 0 else None,
-            "leaves_k2_kernel_reference_equivalent_x32": leaf_kmers * 32 / (k2_ms * 1e-3) if k2_ms > 0 else None,
-            "leaves_count_call_logical": leaf_kmers / t_count_leaves,
-            "read_kmers_per_step": read_kmers, "leaf_kmers_logical": leaf_kmers,
-        },
-        "setup_s": {"leaves_upload": t_upload_leaves, "k2_count_leaves": t_count_leaves, "k3_index_build": t_index},
+        "kmers": kmers,
+        "comm": comm_info,
+        "setup_s": {"leaves_fasta_ingest": t_upload_leaves, "k2_count_leaves": t_count_leaves, "k3_index_build": t_index},
         "index": info,
         "kernel_ms_per_step": {"k1_count_reads": k1_ms / args.steps, "k4_score_tiles_topx": k4_ms / args.steps,
-                               "k4a_plan": k4a_ms / args.steps,
-                               "k5_topx_merge_tiles": k5_ms / args.steps, "all_kernels": all_ms / args.steps},
+                               "k4a_plan": k4a_ms / args.steps, "k5_topx_merge_tiles": k5_ms / args.steps,
+                               "k7_merge": k7_ms / args.steps, "all_kernels": all_ms / args.steps},
     }
 
-    # ---- N > 1: the two exchange paths must give the same merged top-x (untimed)
+    # ---- N > 1: the in-library exchange and the plain torch.distributed exchange must agree (untimed)
     if world > 1:
         s1, i1 = mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
         s2, i2 = mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE)
         torch.cuda.synchronize(dev)
         bad = int((~((s1.view(torch.int32) == s2.view(torch.int32)).all(dim=1) & (i1 == i2).all(dim=1))).sum().item())
         line["parity_in_bench"] = {"queries_checked": int(Q), "two_phase_vs_allgather_topx_mismatches": bad}
-        line["config"]["parallelism"] += "; seed pass, all-reduce(MAX) of the per-query bounds, sweep, all-gather of 8-byte composites"
 
     # ---- stage 3 (clustering): not part of `value`, reported beside it; N > 1 shards the rows
     if not args.no_clustering:
         cpu_reads = None
         if world == 1 and not args.no_cpu_baseline:
             cpu_reads = reads.subset(np.arange(min(reads.n, 4096)))
-
-        def _reduce(v, op):
-            if world == 1:
-                return v
-            t = torch.tensor([v], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=op)
-            return float(t.item())
-
-        def reduce_max(v):
-            return _reduce(v, dist.ReduceOp.MAX)
-
-        def reduce_sum(v):
-            return _reduce(v, dist.ReduceOp.SUM)
-
-        cl = bench_clustering(ctx, api, resident, args.clusters, (clocks or {}).get("sm_mhz") if clocks else None,
-                              cpu_reads, min(args.cpu_seconds, 5.0), world,
-                              (lambda m, prm: mdist.cluster_sharded(m, prm)) if world > 1 else None, reduce_max,
-                              reduce_sum, args.cluster_reps, args.cluster_warmup)
-        line["clustering"] = cl
+        line["clustering"] = bench_clustering(
+            ctx, api, resident, args.clusters, (clocks or {}).get("sm_mhz") if clocks else None, cpu_reads,
+            min(args.cpu_seconds, 5.0), world, (lambda m, prm: mdist.cluster_sharded(m, prm)) if world > 1 else None,
+            allmax, allsum, args.cluster_reps, args.cluster_warmup)
 
     # ---- CPU baseline: the oracle on the host cores, rank 0, N=1 only, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
+        oracle.set_num_threads(host_threads())
         threads = oracle.max_threads()
         nleaf = min(tree.n, 2048)
         sub_tree = tree.subset(np.arange(nleaf))
         t0 = time.perf_counter()
         oracle.count_leaves(synth.tree_to_iupac(sub_tree), sub_tree.base_off, k, 32, threads=threads)
         t_cl = time.perf_counter() - t0
+        sub_reads = reads.subset(np.arange(min(reads.n, 8192)))
+        t0 = time.perf_counter()
+        orc = oracle.count_reads(sub_reads.codes, sub_reads.qual, sub_reads.base_off, k, 0.1, threads=1)
+        t_cr = time.perf_counter() - t0
         # leaf vectors for the score sample come from the GPU counts (already parity-checked in tests/)
         lro, lkeys, lvals, _ = store.kmer_store_counts_vec[0].download(aux=False)
         oln = oracle.normalize(oracle.Csr(lro, lkeys, lvals), threads)
@@ -566,15 +735,140 @@ def run_ours(args, rank, local_rank, world):
             "value": n_s * tree.n / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"first {n_s} of {Q} queries x all {tree.n} leaves (merge-join dots + top-{x}), "
                       f"{threads} OpenMP threads over leaves like rayon",
-            "leaf_kmers_per_s_reference_equivalent_x32": float(2 * (sub_tree.lengths() - k + 1).clip(0).sum() * 32) / t_cl,
-            "leaf_count_sample": f"{nleaf} leaves, {threads} threads",
+            "kmers": {"leaves_reference_equivalent_x32": logical_leaf_kmers(sub_tree, k) * 32 / t_cl,
+                      "leaves_logical": logical_leaf_kmers(sub_tree, k) / t_cl,
+                      "reads_serial_like_the_reference": float(orc.aux.sum()) / t_cr,
+                      "sample": f"{nleaf} leaves x 32 resamples on {threads} threads; {sub_reads.n} reads on 1 thread "
+                                f"(clustering.rs:78-90 and run.rs:301-309 count reads sequentially)"},
         }
         line["parity_in_bench"] = {"queries_checked": n_s, "topx_mismatches": mism}
+    del ttc, store, qn, counts
+
+    # ---- strong scaling (configs[4]): the 1 M-leaf tree sharded over the ranks x one fixed read batch
+    if args.strong_leaves > 0:
+        line["strong"] = bench_strong(args, ctx, api, mdist, synth, rank, world, timed, allmax, dev)
+
+    # ---- the sparse path (N = 1): where the dense-key bitmaps thin out
+    if world == 1 and not args.no_variants:
+        line["variants"] = bench_variants(args, ctx, api, synth, timed, tree0)
+
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
+        ctx.comm_destroy()
         dist.destroy_process_group()
+
+
+def bench_strong(args, ctx, api, mdist, synth, rank, world, timed, allmax, dev):
+    """BASELINE.json configs[4] as a strong-scaling point: total work fixed (strong_reads x strong_leaves
+    scores per step), the tree ALWAYS the same 8 sub-trees, rank r holding sub-trees [8r/N, 8(r+1)/N); reads
+    drawn from every sub-tree (12.5 k each), the same batch at every N."""
+    if N_STRONG_SUBTREES % world != 0:
+        return {"skipped": f"{N_STRONG_SUBTREES} sub-trees do not split over {world} ranks"}
+    per_rank = N_STRONG_SUBTREES // world
+    per_sub = args.strong_leaves // N_STRONG_SUBTREES
+    t0 = time.perf_counter()
+    subs, read_parts = [], []
+    for j in range(rank * per_rank, (rank + 1) * per_rank):
+        sub = strong_subtree(args, j)
+        subs.append(sub)
+        read_parts.append(strong_reads_of(args, sub, j))
+    tree = synth.concat(subs)
+    local_reads = synth.concat(read_parts)
+    reads = mdist.allgather_reads(local_reads) if world > 1 else local_reads  # rank order == sub-tree order
+    t_gen = time.perf_counter() - t0
+    k, x = args.k, args.x
+    text, text_off = ascii_leaves(tree)
+    t0 = time.perf_counter()
+    store, _ = api.TaxTreeStore.from_fasta_records(ctx, text, text_off, leaf_id_base=rank * per_rank * per_sub)
+    store.compute_and_append_kmer_counts(k, 32)
+    ttc = api.TaxTreeCompute.from_store_tree(store, k, 32, tile_leaves=args.tile_leaves)
+    store.kmer_store_counts_vec, store.k_precomputed = [], []
+    ctx.sync()
+    t_build = allmax(time.perf_counter() - t0)
+    resident = api.MyrSeqs(ctx, reads)
+    Q = reads.n
+
+    def step():
+        qn = resident.compute_kmer_counts(k, 0.1).into_normalized_l2()
+        if world > 1:
+            return mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
+        return mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE)
+
+    step()
+    ms = timed(step, args.strong_steps)
+    scores = float(Q) * float(per_sub * N_STRONG_SUBTREES)
+    out = {"workload": f"configs[4]: 1 tree of {per_sub * N_STRONG_SUBTREES} leaves ({N_STRONG_SUBTREES} fixed sub-trees, seed 1005) "
+                       f"sharded over {world} GPU(s) x {Q} reads (seed 2005+j per sub-tree), k={k}, top-{x}",
+           "scaling": "strong", "leaves_total": per_sub * N_STRONG_SUBTREES, "reads": Q, "n_gpus": world,
+           "steps": args.strong_steps, "ms_per_step": ms / args.strong_steps,
+           "value": scores * args.strong_steps / (ms * 1e-3), "unit": UNIT,
+           "index": ttc.info(), "setup_s": {"generate": t_gen, "ingest_count_index_max_over_ranks": t_build}}
+    del ttc, store, resident
+    return out
+
+
+def bench_variants(args, ctx, api, synth, timed, tree0):
+    """Scoring throughput where the conserved-block bitmaps do not carry the load (extra keys, not the headline):
+    (a) the same tree generator WITHOUT the 160-bp conserved block; (b) the headline tree with 1 % of the bases
+    replaced by ambiguity codes (resampled counts are no longer the common count -> dense keys demoted to sparse
+    postings); (c) the headline tree at k = 12 (short k-mers: long sparse posting lists)."""
+    out = {}
+    nq = min(args.variant_reads, args.reads)
+
+    def run(tag, store, reads, k, desc):
+        ttc = api.TaxTreeCompute.from_store_tree(store, k, 32, tile_leaves=args.tile_leaves)
+        store.kmer_store_counts_vec, store.k_precomputed = [], []
+        resident = api.MyrSeqs(ctx, reads)
+        qn = resident.compute_kmer_counts(k, 0.1).into_normalized_l2()
+        ts = np.zeros((reads.n, args.x), np.float32)
+        ti = np.zeros((reads.n, args.x), np.uint32)
+        from myrio_b200 import _lib
+        _lib.check(ctx._L.myrio_score_topx(ctx.h, ttc.h, qn.h, 0, reads.n, args.x, api.SIM_COSINE,
+                                           ts.ctypes.data_as(C.c_void_p), ti.ctypes.data_as(C.c_void_p)))
+        st = ctx.score_stats()
+
+        def step():
+            q2 = resident.compute_kmer_counts(k, 0.1).into_normalized_l2()
+            api.TaxTreeResults.from_compute_tree(q2, ttc, api.SIM_COSINE, args.x)
+
+        step()
+        ctx.prof_reset()
+        ctx.prof_enable(True)
+        ms = timed(step, 2)
+        k4_ms, _ = ctx.prof_query("k4_score")
+        ctx.prof_enable(False)
+        ctx.prof_reset()
+        info = ttc.info()
+        out[tag] = {"workload": desc, "leaves": info["n_leaves"], "reads": reads.n, "k": k,
+                    "ms_per_step": ms / 2, "value": reads.n * info["n_leaves"] * 2 / (ms * 1e-3), "unit": UNIT,
+                    "k4_kernel_ms_per_step": k4_ms / 2, "postings_touched_per_step": st["postings_touched"],
+                    "postings_per_score": st["postings_touched"] / max(1.0, float(reads.n) * info["n_leaves"]),
+                    "index": info, "note": "value includes the D2H of the top-x (public call); 2 timed steps"}
+
+    # (a) no conserved block
+    t_a = synth.make_tree(args.leaves, 1012, root_seed=1012, conserved_len=0)
+    r_a = synth.make_reads(t_a, nq, 2012)
+    text, off = ascii_leaves(t_a)
+    st_a, _ = api.TaxTreeStore.from_fasta_records(ctx, text, off)
+    run("no_conserved_block", st_a, r_a, args.k, f"tree seed 1012 without the 160-bp conserved block, {nq} of its reads")
+    del st_a, t_a
+    # (b) 1 % ambiguity codes in the headline tree
+    rng = np.random.default_rng(77)
+    iupac = synth.tree_to_iupac(tree0).copy()
+    pos = rng.choice(len(iupac), len(iupac) // 100, replace=False)
+    iupac[pos] = rng.choice(np.array([3, 5, 6, 9, 10, 12, 7, 11, 13, 14, 15], np.uint8), len(pos))
+    st_b, _ = api.TaxTreeStore.from_fasta_records(ctx, synth.iupac_to_ascii(iupac), np.ascontiguousarray(tree0.base_off, np.uint64))
+    r_b = synth.make_reads(tree0, nq, 2002)
+    run("ambiguity_1pct", st_b, r_b, args.k, f"headline tree with 1 % of the bases replaced by IUPAC ambiguity codes "
+                                             f"(32 resamples on the device), {nq} reads")
+    del st_b
+    # (c) k = 12
+    text, off = ascii_leaves(tree0)
+    st_c, _ = api.TaxTreeStore.from_fasta_records(ctx, text, off)
+    run("k12", st_c, r_b, 12, f"headline tree at k = 12, {nq} reads")
+    return out
 
 
 def main():

@@ -56,7 +56,9 @@ typedef enum {
     MYRIO_ERR_UNSUPPORTED = 6,
     MYRIO_ERR_EMPTY = 7,       /* cluster(): no read survives t2 / no centroid (reference panics) */
     MYRIO_ERR_NONFINITE = 8,   /* SimScore::try_new(..).unwrap() would panic (clustering.rs:125) */
-    MYRIO_ERR_BAD_BASE = 9     /* a non-ACGT base: read_fastq fails the whole file (io/mod.rs:46-47) */
+    MYRIO_ERR_BAD_BASE = 9,    /* a non-ACGT base: read_fastq fails the whole file (io/mod.rs:46-47) */
+    MYRIO_ERR_COMM = 10,       /* NCCL failure, or another rank of a sharded call failed */
+    MYRIO_ERR_FORMAT = 11      /* malformed .myrtree bytes (tax/store.rs:408-454 returns Error) */
 } myrio_status;
 
 /* myrio-core/src/similarity.rs:26-33 */
@@ -91,6 +93,10 @@ int32_t myrio_prof_reset(myrio_ctx *ctx);
 /* accumulated device time and launch count of the kernels whose name starts with `prefix` */
 int32_t myrio_prof_query(myrio_ctx *ctx, const char *prefix, double *ms_total, uint64_t *launches);
 
+/* measured aggregate shared-memory read bandwidth (GB/s; conflict-free 16-byte loads, one 1024-thread CTA
+ * per SM) -- the denominator of the roofline fraction of the clustering tile kernels (bench.py) */
+int32_t myrio_bench_smem_bandwidth(myrio_ctx *ctx, double *gbps, double *ms);
+
 /* ---- sequences ---------------------------------------------------------- */
 
 /* A batch of MyrSeq (myrio-core/src/data/myrseq.rs:21-33): `sequence` as packed
@@ -113,6 +119,16 @@ int32_t myrio_reads_from_fastq(myrio_ctx *ctx, const uint8_t *seq_ascii, const u
  * in payload_id order. */
 int32_t myrio_leaves_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_t *word_off,
                             const uint64_t *base_off, uint64_t n_leaves, myrio_seqs **out);
+/* FASTA ingestion on the device: the `Seq::<Iupac>::from_str(&string_seq)` of every record in
+ * TaxTreeStore::load_from_fasta_string (myrio-core/src/tax/store.rs:166-195).  seq_ascii = the
+ * concatenated sequence lines of all records (headers and newlines removed), base_off[n+1] their
+ * prefix sums.  Upper-case IUPAC nucleotide codes and '-' (gap, Iupac::X) are valid; a record holding
+ * any other byte is skipped like the reference does (store.rs:181-187: reported, no payload), so
+ * keep[n] (optional) receives 0/1 and *out holds the kept records in input order = payload_id order. */
+int32_t myrio_leaves_from_fasta(myrio_ctx *ctx, const uint8_t *seq_ascii, const uint64_t *base_off,
+                                uint64_t n_records, uint8_t *keep, myrio_seqs **out);
+/* number of sequences held by a batch */
+int32_t myrio_seqs_count(const myrio_seqs *s, uint64_t *n_seqs);
 void myrio_seqs_free(myrio_seqs *s);
 
 /* ---- k-mer counting ----------------------------------------------------- */
@@ -224,6 +240,30 @@ int32_t myrio_score_topx_sweep_async(myrio_ctx *ctx, const myrio_index *ix, uint
 int32_t myrio_topx_merge_composites_async(myrio_ctx *ctx, const uint64_t *d_in, uint32_t n_parts,
                                           uint64_t q_count, uint32_t x, float *d_scores_out,
                                           uint32_t *d_ids_out);
+/* ---- multi-GPU: one process per GPU, reference leaves sharded, queries replicated -------------
+ * The reference is a single-process rayon program; these calls are what a multi-GPU binding of
+ * TaxTreeResults::from_compute_tree (tax/results.rs:82-93 + cut(), :310-329) uses.
+ * NCCL is bound at run time (dlopen libnccl.so.2); single-GPU users never load it.
+ *   rank 0: myrio_comm_unique_id(id) -> ship the 128 bytes to every rank (any channel) ->
+ *   every rank: myrio_comm_init(ctx, nranks, rank, id) (collective: ncclCommInitRank).
+ * The communicator belongs to the context and runs its collectives on the context's stream. */
+#define MYRIO_UNIQUE_ID_BYTES 128
+int32_t myrio_comm_unique_id(uint8_t id[MYRIO_UNIQUE_ID_BYTES]);
+int32_t myrio_comm_init(myrio_ctx *ctx, uint32_t nranks, uint32_t rank, const uint8_t id[MYRIO_UNIQUE_ID_BYTES]);
+int32_t myrio_comm_destroy(myrio_ctx *ctx);
+/* rank / world of the context's communicator (0 / 1 without one) and the NCCL version bound */
+int32_t myrio_comm_info(const myrio_ctx *ctx, uint32_t *rank, uint32_t *nranks, int32_t *nccl_version);
+/* The sharded scoring step (collective: every rank calls it with the same queries and x, each with the
+ * index of ITS leaf shard, built with leaf_id_base = first payload id of the shard).  Per batch of queries:
+ * seed pass -> ncclAllReduce(MAX) of the per-query bounds -> sweep with the exchanged bound ->
+ * ONE ncclAllGather of the shard lists (8-byte composites) -> merge (K7), all on the context's stream.
+ * d_top_*[q*x + j] (device pointers, every rank receives the full merged result) equal what
+ * myrio_score_topx gives on one GPU holding all leaves.  max_batch = 0 lets the library pick.
+ * Without a communicator (or nranks == 1) it is myrio_score_topx_async. */
+int32_t myrio_score_topx_sharded(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                                 uint64_t q_first, uint64_t q_count, uint32_t x, int32_t similarity,
+                                 float *d_top_scores, uint32_t *d_top_ids, uint64_t max_batch);
+
 /* exact algorithmic work of the last myrio_score_* call: sum over queries of
  * query keys, of (query key, tile) hits, and of postings touched (T_q) */
 int32_t myrio_score_stats(myrio_ctx *ctx, uint64_t *n_query_keys, uint64_t *n_key_hits,
@@ -255,9 +295,11 @@ int32_t myrio_cluster(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_clust
  * and parameters; the reads x centroids tiles of every iteration and the members x (members +
  * neighbours) silhouette tiles are computed for the rank's contiguous share of the rows and the
  * per-row results are exchanged through `allgather`: host_buf holds `world` chunks of
- * bytes_per_rank, chunk `rank` is filled on entry, all chunks on return (0 = ok).  A binding
- * implements it with ncclAllGather (or any collective it already has).  Results are identical on
- * every rank and identical to myrio_cluster. */
+ * bytes_per_rank, chunk `rank` is filled on entry, all chunks on return (0 = ok).  With
+ * allgather == NULL the exchange runs inside the library: ncclAllGather on the context's own
+ * communicator (myrio_comm_init with the same rank / world), device to device on the context's
+ * stream; the callback remains for callers that bring their own collective.  Results are identical
+ * on every rank and identical to myrio_cluster. */
 typedef int32_t (*myrio_allgather_fn)(void *user, void *host_buf, uint64_t bytes_per_rank);
 typedef struct {
     uint32_t rank, world;

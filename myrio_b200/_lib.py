@@ -11,15 +11,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmyrio_b200.so")
 
 OK = 0
-ERR_INVALID_K, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_BAD_QUALITY, ERR_UNSUPPORTED, ERR_EMPTY, ERR_NONFINITE, ERR_BAD_BASE = range(1, 10)
+(ERR_INVALID_K, ERR_BAD_ARG, ERR_CUDA, ERR_OOM, ERR_BAD_QUALITY, ERR_UNSUPPORTED, ERR_EMPTY, ERR_NONFINITE, ERR_BAD_BASE,
+ ERR_COMM, ERR_FORMAT) = range(1, 12)
+UNIQUE_ID_BYTES = 128
 SIM_COSINE, SIM_JACARD_TANIMOTO, SIM_OVERLAP = 0, 1, 2
 VAL_F32, VAL_U16 = 0, 1
 
 # every symbol include/myrio_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
     "myrio_last_error", "myrio_version", "myrio_ctx_create", "myrio_ctx_destroy", "myrio_ctx_sync",
-    "myrio_ctx_launch_count", "myrio_ctx_set_kmer_bit_order", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query",
-    "myrio_reads_upload", "myrio_reads_from_fastq", "myrio_leaves_upload", "myrio_seqs_free", "myrio_count_reads",
+    "myrio_ctx_launch_count", "myrio_ctx_set_kmer_bit_order", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query", "myrio_bench_smem_bandwidth",
+    "myrio_reads_upload", "myrio_reads_from_fastq", "myrio_leaves_upload", "myrio_leaves_from_fasta", "myrio_seqs_count", "myrio_seqs_free", "myrio_count_reads",
     "myrio_count_leaves", "myrio_svecs_info", "myrio_svecs_download", "myrio_svecs_upload",
     "myrio_svecs_normalize", "myrio_svecs_free", "myrio_index_build", "myrio_index_info",
     "myrio_index_export_tile", "myrio_index_free", "myrio_score_all", "myrio_score_topx",
@@ -28,6 +30,7 @@ SYMBOLS = [
     "myrio_topx_merge_composites_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
     "myrio_cluster_sharded",
     "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_cluster_stats", "myrio_svecs_device_ptrs",
+    "myrio_comm_unique_id", "myrio_comm_init", "myrio_comm_destroy", "myrio_comm_info", "myrio_score_topx_sharded",
 ]
 
 
@@ -88,9 +91,12 @@ def load() -> C.CDLL:
     L.myrio_prof_enable.argtypes = [vp, i32]
     L.myrio_prof_reset.argtypes = [vp]
     L.myrio_prof_query.argtypes = [vp, C.c_char_p, P(C.c_double), P(u64)]
+    L.myrio_bench_smem_bandwidth.argtypes = [vp, P(C.c_double), P(C.c_double)]
     L.myrio_reads_upload.argtypes = [vp, vp, vp, vp, vp, u64, P(vp)]
     L.myrio_reads_from_fastq.argtypes = [vp, vp, vp, vp, u64, u64, C.c_float, C.c_uint8, vp, P(vp)]
     L.myrio_leaves_upload.argtypes = [vp, vp, vp, vp, u64, P(vp)]
+    L.myrio_leaves_from_fasta.argtypes = [vp, vp, vp, u64, vp, P(vp)]
+    L.myrio_seqs_count.argtypes = [vp, P(u64)]
     L.myrio_seqs_free.argtypes = [vp]
     L.myrio_seqs_free.restype = None
     L.myrio_count_reads.argtypes = [vp, vp, u32, C.c_float, P(vp)]
@@ -119,6 +125,11 @@ def load() -> C.CDLL:
     L.myrio_topx_merge_composites_async.argtypes = [vp, vp, u32, u64, u32, vp, vp]
     L.myrio_topx_merge_async.argtypes = [vp, vp, vp, u32, u64, u32, vp, vp]
     L.myrio_score_stats.argtypes = [vp, P(u64), P(u64), P(u64)]
+    L.myrio_comm_unique_id.argtypes = [vp]
+    L.myrio_comm_init.argtypes = [vp, u32, u32, vp]
+    L.myrio_comm_destroy.argtypes = [vp]
+    L.myrio_comm_info.argtypes = [vp, P(u32), P(u32), P(i32)]
+    L.myrio_score_topx_sharded.argtypes = [vp, vp, vp, u64, u64, u32, i32, vp, vp, u64]
     L.myrio_cluster.argtypes = [vp, vp, P(ClusterParams), vp, vp, P(u32), vp]
     L.myrio_cluster_sharded.argtypes = [vp, vp, P(ClusterParams), vp, P(Shard), vp, P(u32), vp]
     L.myrio_compute_cluster_centroid.argtypes = [vp, vp, vp, u64, P(vp)]

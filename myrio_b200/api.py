@@ -70,6 +70,34 @@ class Context:
         _lib.check(self._L.myrio_prof_query(self.h, prefix.encode(), C.byref(ms), C.byref(n)))
         return ms.value, int(n.value)
 
+    # ---- multi-GPU (include/myrio_b200.h "multi-GPU"): the library owns its NCCL communicator
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """ncclGetUniqueId through the library (rank 0; ship the 128 bytes to every rank)."""
+        buf = (C.c_uint8 * _lib.UNIQUE_ID_BYTES)()
+        _lib.check(_lib.load().myrio_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        """Collective: every rank calls it with rank 0's id (ncclCommInitRank on this context's GPU)."""
+        assert len(unique_id) == _lib.UNIQUE_ID_BYTES
+        buf = (C.c_uint8 * _lib.UNIQUE_ID_BYTES).from_buffer_copy(unique_id)
+        _lib.check(self._L.myrio_comm_init(self.h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        _lib.check(self._L.myrio_comm_destroy(self.h))
+
+    def comm_info(self):
+        r, w, v = C.c_uint32(0), C.c_uint32(1), C.c_int32(0)
+        _lib.check(self._L.myrio_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
+        return {"rank": int(r.value), "nranks": int(w.value), "nccl_version": int(v.value)}
+
+    def bench_smem_bandwidth(self):
+        """Measured shared-memory read bandwidth of this GPU (the K6 roofline denominator)."""
+        g, ms = C.c_double(0), C.c_double(0)
+        _lib.check(self._L.myrio_bench_smem_bandwidth(self.h, C.byref(g), C.byref(ms)))
+        return {"gbps": g.value, "ms": ms.value}
+
     def score_stats(self):
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         _lib.check(self._L.myrio_score_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
@@ -219,6 +247,24 @@ class TaxTreeStore:
         self.h = h
         self.k_precomputed: list[int] = []
         self.kmer_store_counts_vec: list[SFVecs] = []
+
+    @classmethod
+    def from_fasta_records(cls, ctx: Context, seq_ascii, base_off, *, gene: str = "", leaf_id_base: int = 0):
+        """The sequence half of TaxTreeStore::load_from_fasta_string (tax/store.rs:166-195) on the device:
+        `Seq::<Iupac>::from_str` of every record's concatenated sequence lines; records with an invalid
+        byte are skipped (store.rs:181-187).  Returns (store of the kept records, keep flags)."""
+        seq_ascii = np.ascontiguousarray(seq_ascii, np.uint8)
+        base_off = np.ascontiguousarray(base_off, np.uint64)
+        n = len(base_off) - 1
+        keep = np.zeros(max(1, n), np.uint8)
+        self = cls.__new__(cls)
+        self.ctx, self.gene, self.leaf_id_base = ctx, gene, leaf_id_base
+        h = C.c_void_p()
+        _lib.check(ctx._L.myrio_leaves_from_fasta(ctx.h, _p(seq_ascii), _p(base_off), n, _p(keep), C.byref(h)))
+        self.h = h
+        self.n_leaves = int(keep[:n].sum())
+        self.k_precomputed, self.kmer_store_counts_vec = [], []
+        return self, keep[:n].astype(bool)
 
     def __del__(self):
         try:
@@ -405,7 +451,10 @@ def cluster(myrseqs: MyrSeqs, params: ClusteringParameters, shard=None) -> Clust
         _lib.check(ctx._L.myrio_cluster(ctx.h, myrseqs.h, C.byref(p), init, _p(assign), C.byref(iters), _p(sil)))
     else:
         rank, world, allgather = shard
-        cb = allgather if isinstance(allgather, _lib.ALLGATHER_FN) else _lib.ALLGATHER_FN(allgather)
+        if allgather is None:  # the library's own communicator (Context.comm_init): device-side exchange
+            cb = _lib.ALLGATHER_FN()
+        else:
+            cb = allgather if isinstance(allgather, _lib.ALLGATHER_FN) else _lib.ALLGATHER_FN(allgather)
         sh = _lib.Shard(rank, world, cb, None)
         _lib.check(ctx._L.myrio_cluster_sharded(ctx.h, myrseqs.h, C.byref(p), init, C.byref(sh), _p(assign),
                                                 C.byref(iters), _p(sil)))

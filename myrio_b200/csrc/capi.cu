@@ -3,6 +3,7 @@
 #include <mutex>
 
 #include "cluster.cuh"
+#include "comm.cuh"
 #include "index.cuh"
 #include "kmer_count.cuh"
 #include "score.cuh"
@@ -70,6 +71,7 @@ void myrio_ctx_destroy(myrio_ctx *ctx) {
     ctx->topx_cand.release();
     ctx->topx_cand_cnt.release();
     ctx->topx_gthr.release();
+    comm_destroy(ctx);
     if (ctx->plan) plan_scratch_free(ctx->plan);
     ctx->plan = nullptr;
     cudaStreamSynchronize(ctx->stream);
@@ -128,6 +130,14 @@ int32_t myrio_prof_query(myrio_ctx *ctx, const char *prefix, double *ms_total, u
         }
         if (ms_total) *ms_total = ms;
         if (launches) *launches = n;
+    });
+}
+
+int32_t myrio_bench_smem_bandwidth(myrio_ctx *ctx, double *gbps, double *ms) {
+    return guarded([&] {
+        if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
+        ScopedCtx sc(ctx);
+        bench_smem_bandwidth(ctx, gbps, ms);
     });
 }
 
@@ -216,6 +226,22 @@ int32_t myrio_leaves_upload(myrio_ctx *ctx, const uint64_t *words, const uint64_
         if (!ctx || !out) fail(MYRIO_ERR_BAD_ARG, "NULL ctx/out");
         ScopedCtx sc(ctx);
         *out = upload_seqs(ctx, 1, words, word_off, base_off, nullptr, n_leaves);
+    });
+}
+
+int32_t myrio_leaves_from_fasta(myrio_ctx *ctx, const uint8_t *seq_ascii, const uint64_t *base_off,
+                                uint64_t n_records, uint8_t *keep, myrio_seqs **out) {
+    return guarded([&] {
+        if (!ctx || !out) fail(MYRIO_ERR_BAD_ARG, "NULL ctx/out");
+        ScopedCtx sc(ctx);
+        *out = leaves_from_fasta(ctx, seq_ascii, base_off, n_records, keep);
+    });
+}
+
+int32_t myrio_seqs_count(const myrio_seqs *s, uint64_t *n_seqs) {
+    return guarded([&] {
+        if (!s || !n_seqs) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        *n_seqs = s->n;
     });
 }
 
@@ -470,6 +496,50 @@ int32_t myrio_topx_merge_composites_async(myrio_ctx *ctx, const uint64_t *d_in, 
         if (!ctx || !d_in || !d_scores_out || !d_ids_out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
         ScopedCtx sc(ctx);
         topx_merge_composites_device(ctx, d_in, n_parts, q_count, x, d_scores_out, d_ids_out);
+    });
+}
+
+// ------------------------------------------------------------- multi-GPU
+
+int32_t myrio_comm_unique_id(uint8_t id[MYRIO_UNIQUE_ID_BYTES]) {
+    return guarded([&] {
+        if (!id) fail(MYRIO_ERR_BAD_ARG, "NULL id");
+        comm_unique_id(id);
+    });
+}
+
+int32_t myrio_comm_init(myrio_ctx *ctx, uint32_t nranks, uint32_t rank, const uint8_t id[MYRIO_UNIQUE_ID_BYTES]) {
+    return guarded([&] {
+        if (!ctx || !id) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        comm_init(ctx, nranks, rank, id);
+    });
+}
+
+int32_t myrio_comm_destroy(myrio_ctx *ctx) {
+    return guarded([&] {
+        if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
+        ScopedCtx sc(ctx);
+        comm_destroy(ctx);
+    });
+}
+
+int32_t myrio_comm_info(const myrio_ctx *ctx, uint32_t *rank, uint32_t *nranks, int32_t *nccl_version) {
+    return guarded([&] {
+        if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
+        if (rank) *rank = ctx->comm_rank;
+        if (nranks) *nranks = ctx->comm_world;
+        if (nccl_version) *nccl_version = ctx->comm ? comm_nccl_version() : 0;
+    });
+}
+
+int32_t myrio_score_topx_sharded(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
+                                 uint64_t q_first, uint64_t q_count, uint32_t x, int32_t similarity,
+                                 float *d_top_scores, uint32_t *d_top_ids, uint64_t max_batch) {
+    return guarded([&] {
+        if (!ctx || !ix || !queries || !d_top_scores || !d_top_ids) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        score_topx_sharded(ctx, ix, queries, q_first, q_count, x, similarity, d_top_scores, d_top_ids, max_batch);
     });
 }
 

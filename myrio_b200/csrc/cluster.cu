@@ -22,6 +22,7 @@
 #include <numeric>
 
 #include "cluster.cuh"
+#include "comm.cuh"
 #include "index.cuh"
 #include "kmer_count.cuh"
 #include "merge.cuh"
@@ -849,7 +850,12 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
                    const myrio_svecs *init, const myrio_shard *sh, int32_t *assign, uint32_t *n_iters,
                    float *silhouette) {
     const uint32_t W = sh ? sh->world : 1, R = sh ? sh->rank : 0;
-    if (W == 0 || R >= W || (W > 1 && !sh->allgather)) fail(MYRIO_ERR_BAD_ARG, "bad shard description");
+    // exchange of the per-row results: the caller's callback (host buffers), or -- allgather == NULL -- the
+    // context's own NCCL communicator (myrio_comm_init), device to device on the context's stream
+    const bool use_nccl = sh && W > 1 && !sh->allgather;
+    if (W == 0 || R >= W) fail(MYRIO_ERR_BAD_ARG, "bad shard description");
+    if (use_nccl && (!ctx->comm || ctx->comm_world != W || ctx->comm_rank != R))
+        fail(MYRIO_ERR_BAD_ARG, "myrio_cluster_sharded without a callback needs myrio_comm_init with the same rank/world");
     // contiguous share of n rows: rank r owns [r * chunk, min(n, (r + 1) * chunk))
     auto share = [&](uint32_t n, uint32_t &lo, uint32_t &cnt, uint32_t &chunk) {
         chunk = (n + W - 1) / W;
@@ -869,6 +875,26 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         const int32_t rc = sh->allgather(sh->user, buf, bytes_per_rank);
         t_exchange += seconds_since(t0);
         if (rc != 0) fail(MYRIO_ERR_BAD_ARG, "allgather callback failed (%d)", rc);
+    };
+    // per-row results of all ranks: this rank's `cnt` elements (device) -> W chunks of `chunk` elements (host)
+    DevBuf<uint8_t> gbuf;
+    auto gather_rows = [&](const void *d_local, size_t elem, uint32_t lo, uint32_t cnt, uint32_t chunk, void *host) {
+        uint8_t *h = static_cast<uint8_t *>(host);
+        if (use_nccl) {
+            const auto t0 = std::chrono::steady_clock::now();
+            gbuf.reserve((size_t)W * chunk * elem);
+            if (cnt)
+                MYRIO_CK(cudaMemcpyAsync(gbuf.p + (size_t)R * chunk * elem, d_local, (size_t)cnt * elem,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+            comm_allgather_inplace(ctx, gbuf.p, (uint64_t)chunk * elem);
+            d2h(ctx, h, gbuf.p, (size_t)W * chunk * elem);
+            sync(ctx);
+            t_exchange += seconds_since(t0);
+            return;
+        }
+        if (cnt) d2h(ctx, h + (size_t)lo * elem, static_cast<const uint8_t *>(d_local), (size_t)cnt * elem);
+        sync(ctx);
+        exchange(h, (uint64_t)chunk * elem);
     };
     struct TimingReport {
         bool on;
@@ -1031,9 +1057,7 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         pa.ld = nc;
         centroid_tile(false, "k6_pair_store");
         std::vector<float> dots((size_t)W * kchunk * nc);
-        d2h(ctx, dots.data() + (size_t)klo * nc, d_dots.p, (size_t)kcnt * nc);
-        sync(ctx);
-        exchange(dots.data(), (uint64_t)kchunk * nc * sizeof(float));
+        gather_rows(d_dots.p, nc * sizeof(float), klo, kcnt, kchunk, dots.data());
         uint32_t best = 0;
         float best_score = 0.0f;
         for (uint32_t i = 0; i < nk; ++i) {
@@ -1068,12 +1092,9 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
             centroid_tile(true, "k6_pair_argmax");
             MYRIO_LAUNCH(ctx, "k6_argmax_rows", argmax_rows_kernel, (kcnt + 127) / 128, 128, 0, d_tile.p,
                          (uint64_t)kcnt, kcnt, nc, d_best.p, d_target_loc.p);
-            d2h(ctx, best.data() + klo, d_best.p, kcnt);
-            d2h(ctx, target.data() + klo, d_target_loc.p, kcnt);
         }
-        sync(ctx);
-        exchange(best.data(), (uint64_t)kchunk * sizeof(float));
-        exchange(target.data(), (uint64_t)kchunk * sizeof(uint32_t));
+        gather_rows(d_best.p, sizeof(float), klo, kcnt, kchunk, best.data());
+        gather_rows(d_target_loc.p, sizeof(uint32_t), klo, kcnt, kchunk, target.data());
         h2d(ctx, d_target.p, target.data(), nk);
     };
     float previous_mean_wcsss = 1E-6f;
@@ -1150,9 +1171,9 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         uint32_t mlo, mcnt, mchunk;  // this rank's share of the cluster's members (rows of the tile)
         share(nm, mlo, mcnt, mchunk);
         std::vector<float> sums((size_t)W * mchunk * 2);
+        DevBuf<float> d_sums2(std::max<size_t>((size_t)mcnt * 2, 1));
         if (mcnt) {
             DevBuf<uint32_t> d_rows(mcnt), d_cols(cols.size());
-            DevBuf<float> d_sums2((size_t)mcnt * 2);
             h2d(ctx, d_rows.p, members[c].data() + mlo, mcnt);
             h2d(ctx, d_cols.p, cols.data(), cols.size());
             MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)mcnt * 2 * sizeof(float), ctx->stream));
@@ -1218,10 +1239,8 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
                 MYRIO_LAUNCH(ctx, "k6_silsum_rows", silsum_rows_kernel, (mcnt + 127) / 128, 128, 0, d_sil_tile.p,
                              (uint64_t)mcnt, mcnt, cf, sa.n_cols, nm, d_sums2.p);
             }
-            d2h(ctx, sums.data() + (size_t)mlo * 2, d_sums2.p, (size_t)mcnt * 2);
-            sync(ctx);
         }
-        exchange(sums.data(), (uint64_t)mchunk * 2 * sizeof(float));
+        gather_rows(d_sums2.p, 2 * sizeof(float), mlo, mcnt, mchunk, sums.data());
         std::vector<float> sil(nm);
         for (uint32_t t = 0; t < nm; ++t) {  // inner() :323-336
             const float a = sums[(size_t)t * 2] / (float)(nm - 1);

@@ -142,6 +142,11 @@ struct myrio_ctx {
     bool twophase_ready = false, twophase_seeded = false;
     uint64_t twophase_q = 0;
     uint32_t twophase_x = 0;
+    const void *twophase_ix = nullptr;  // the index the seed pass planned against
+    int32_t twophase_sim = 0;
+    // multi-GPU (comm.cu): ncclComm_t of this rank, bound by myrio_comm_init
+    void *comm = nullptr;
+    uint32_t comm_rank = 0, comm_world = 1;
     uint64_t last_stats[3] = {0, 0, 0};
     uint64_t cluster_stats[2] = {0, 0};  // pair similarities, multiply-add terms of the last K6 call
     // pinned staging for small D2H reads

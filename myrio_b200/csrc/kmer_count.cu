@@ -822,7 +822,12 @@ myrio_svecs *count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k, 
     // ambiguity codes needs at most 2*(nb + (R-1)*min(nb, k*amb)).
     const std::vector<uint32_t> &amb = leaves->h_aux;
     std::vector<uint64_t> eoff(L + 1);
-    const size_t n_cls = sizeof(kSmemClasses) / sizeof(uint32_t);
+    // size classes whose work area fits in shared memory (the 16 k class of a leaf is 266 KB: leaves
+    // with many ambiguity codes take the global-scratch variant)
+    size_t n_cls = 0;
+    while (n_cls < sizeof(kSmemClasses) / sizeof(uint32_t) &&
+           leaf_work_bytes(kSmemClasses[n_cls]) + 4096 <= ctx->smem_optin)
+        ++n_cls;
     std::vector<std::vector<uint32_t>> cls(n_cls + 1);
     uint64_t acc = 0, max_cap = 0;
     for (uint64_t r = 0; r < L; ++r) {

@@ -16,6 +16,11 @@ myrio_svecs *count_leaves(myrio_ctx *ctx, const myrio_seqs *leaves, uint32_t k, 
 myrio_seqs *reads_from_fastq(myrio_ctx *ctx, const uint8_t *seq_ascii, const uint8_t *qual_ascii,
                              const uint64_t *base_off, uint64_t n, uint64_t min_length, float min_mean_qual,
                              uint8_t max_qual, uint8_t *keep_host);
+myrio_seqs *leaves_from_fasta(myrio_ctx *ctx, const uint8_t *seq_ascii, const uint64_t *base_off, uint64_t n,
+                              uint8_t *keep_host);
+
+// microbench.cu
+void bench_smem_bandwidth(myrio_ctx *ctx, double *gbps, double *ms);
 
 // svecs.cu
 myrio_svecs *svecs_normalize(myrio_ctx *ctx, const myrio_svecs *in);

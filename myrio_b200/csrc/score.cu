@@ -938,6 +938,7 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
 }
 
 static void reset_stats(myrio_ctx *ctx) {
+    ctx->twophase_ready = false;  // every scoring entry point rebuilds the plan / candidate scratch
     ctx->last_stats[0] = ctx->last_stats[1] = ctx->last_stats[2] = 0;
     ctx->score_counters.reserve(4);
     MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -1048,7 +1049,7 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
 // ranks' bounds is still a lower bound of the query's GLOBAL x-th best score (x leaves of some tile of some
 // rank reach it), so after an all-reduce(MAX) of Q x 4 bytes every rank sweeps with the strongest bound.
 // The shard-local result may then hold fewer than x entries (padded): only the merged list is exact.
-static uint64_t topx_batch_capacity(const myrio_index *ix, uint32_t x) {
+uint64_t score_topx_batch_capacity(const myrio_index *ix, uint32_t x) {
     const uint64_t n_tiles = std::max<uint64_t>(ix->tiles.size(), 1);
     return std::max<uint64_t>(1, (8ull << 30) / (n_tiles * x * 8));
 }
@@ -1058,9 +1059,9 @@ void score_topx_seed_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_s
     check_queries(queries, q_first, q_count);
     check_sim(sim);
     if (x == 0 || x > TX_MAX_X) fail(MYRIO_ERR_BAD_ARG, "x must be in 1..%d", TX_MAX_X);
-    if (q_count > topx_batch_capacity(ix, x))
+    if (q_count > score_topx_batch_capacity(ix, x))
         fail(MYRIO_ERR_UNSUPPORTED, "two-phase top-x needs the queries in one batch (%llu > %llu)",
-             (unsigned long long)q_count, (unsigned long long)topx_batch_capacity(ix, x));
+             (unsigned long long)q_count, (unsigned long long)score_topx_batch_capacity(ix, x));
     reset_stats(ctx);
     ctx->twophase_ready = false;
     if (q_count == 0) return;
@@ -1095,13 +1096,19 @@ void score_topx_seed_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_s
     ctx->twophase_ready = true;
     ctx->twophase_q = q_count;
     ctx->twophase_x = x;
+    ctx->twophase_ix = ix;
+    ctx->twophase_sim = sim;
 }
 
 void score_topx_sweep_device(myrio_ctx *ctx, const myrio_index *ix, uint64_t q_count, uint32_t x, int32_t sim,
                              const uint32_t *d_bound, uint64_t *d_top) {
     check_sim(sim);
-    if (!ctx->twophase_ready || ctx->twophase_q != q_count || ctx->twophase_x != x)
-        fail(MYRIO_ERR_BAD_ARG, "myrio_score_topx_sweep_async must follow myrio_score_topx_seed_async with the same queries");
+    // the plan, the candidate buffers and the seed flags of the seed pass live in the context: any other
+    // scoring call in between (it clears twophase_ready) or a different index / similarity invalidates them
+    if (!ctx->twophase_ready || ctx->twophase_q != q_count || ctx->twophase_x != x || ctx->twophase_ix != ix ||
+        ctx->twophase_sim != sim)
+        fail(MYRIO_ERR_BAD_ARG, "myrio_score_topx_sweep_async must directly follow myrio_score_topx_seed_async with the same "
+                                "index, similarity, x and query count");
     ctx->twophase_ready = false;
     if (q_count == 0) return;
     Plan &pl = *static_cast<Plan *>(ctx->plan);

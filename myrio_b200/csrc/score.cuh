@@ -23,6 +23,8 @@ void score_topx_sweep_device(myrio_ctx *ctx, const myrio_index *ix, uint64_t q_c
                              const uint32_t *d_bound, uint64_t *d_top);
 void topx_merge_composites_device(myrio_ctx *ctx, const uint64_t *d_in, uint32_t n_parts, uint64_t q_count,
                                   uint32_t x, float *d_scores_out, uint32_t *d_ids_out);
+// queries per two-phase batch on this shard (the per-tile candidate buffer is capped at 8 GB)
+uint64_t score_topx_batch_capacity(const myrio_index *ix, uint32_t x);
 void *plan_scratch_new();
 void plan_scratch_free(void *p);
 }  // namespace myrio

@@ -70,53 +70,37 @@ def allgather_topx(scores: torch.Tensor, ids: torch.Tensor, group=None):
     return gs, gi
 
 
-_TWO_PHASE_CAP: dict = {}
-
-
-def _two_phase_batch(ctx, ttcompute, x: int, group=None) -> int:
-    """Queries per two-phase batch: the library needs a batch's per-tile candidates in 8 GB (the capacity
-    depends on the shard's tile count), and every rank must cut the queries at the same places: the minimum
-    over the ranks, decided once per (index, x) with an all-reduce(MIN)."""
-    key = (id(ttcompute), x)
-    if key not in _TWO_PHASE_CAP:
-        n_tiles = max(1, ttcompute.info()["n_tiles"])
-        cap = max(1, (8 << 30) // (n_tiles * x * 8))
-        t = torch.tensor([cap], dtype=torch.int64, device=torch.device("cuda", ctx.device))
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
-        _TWO_PHASE_CAP[key] = int(t.item())
-    return _TWO_PHASE_CAP[key]
+def init_library_comm(ctx, group=None) -> dict:
+    """Gives the library its own NCCL communicator over the ranks of `group`: rank 0 draws the unique id
+    (myrio_comm_unique_id), torch.distributed only carries the 128 bytes, every rank calls myrio_comm_init.
+    From then on the collectives of the hot path (bound all-reduce, top-x all-gather, clustering's per-row
+    exchange) run inside libmyrio_b200.so on the context's stream."""
+    from .api import Context
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    info = ctx.comm_info()
+    if info["nranks"] == world and info["nccl_version"]:
+        return info
+    box = [Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ctx.comm_init(world, rank, box[0])
+    return ctx.comm_info()
 
 
 def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0):
-    """The multi-GPU step with the bound exchange, per batch of queries: seed pass on this rank's leaves,
-    all-reduce(MAX) of the per-query bounds (4 bytes each), sweep with the global bound, ONE all-gather of
-    the shard lists as 8-byte composites, merge (K7).  Everything is enqueued on the library's stream
-    (torch's collectives order themselves after it), no host synchronisation in between."""
+    """The multi-GPU step with the bound exchange -- one library call (myrio_score_topx_sharded): per batch
+    of queries the seed pass on this rank's leaves, ncclAllReduce(MAX) of the per-query bounds, the sweep with
+    the global bound, ONE ncclAllGather of the shard lists as 8-byte composites, the merge (K7); all on the
+    library's stream with the library's communicator (init_library_comm)."""
     from . import _lib
     Q = queries.n_rows
     dev = torch.device("cuda", ctx.device)
-    L = ctx._L
-    world = dist.get_world_size(group)
-    batch = _two_phase_batch(ctx, ttcompute, x, group)
-    if max_batch:
-        batch = min(batch, max_batch)
+    init_library_comm(ctx, group)
     with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=dev)):
         out_s = torch.empty((Q, x), dtype=torch.float32, device=dev)
         out_i = torch.empty((Q, x), dtype=torch.int32, device=dev)
-        for q0 in range(0, Q, batch):
-            qc = min(batch, Q - q0)
-            bound = torch.empty(qc, dtype=torch.int32, device=dev)
-            _lib.check(L.myrio_score_topx_seed_async(ctx.h, ttcompute.h, queries.h, q0, qc, x, similarity,
-                                                     C.c_void_p(bound.data_ptr())))
-            dist.all_reduce(bound, op=dist.ReduceOp.MAX, group=group)  # scores are >= +0: int order == float order
-            top = torch.empty((qc, x), dtype=torch.int64, device=dev)
-            _lib.check(L.myrio_score_topx_sweep_async(ctx.h, ttcompute.h, qc, x, similarity,
-                                                      C.c_void_p(bound.data_ptr()), C.c_void_p(top.data_ptr())))
-            g = torch.empty((world, qc, x), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(g.view(-1), top.view(-1), group=group)
-            _lib.check(L.myrio_topx_merge_composites_async(ctx.h, C.c_void_p(g.data_ptr()), world, qc, x,
-                                                           C.c_void_p(out_s[q0:q0 + qc].data_ptr()),
-                                                           C.c_void_p(out_i[q0:q0 + qc].data_ptr())))
+    _lib.check(ctx._L.myrio_score_topx_sharded(ctx.h, ttcompute.h, queries.h, 0, Q, x, similarity,
+                                               C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
+                                               max_batch))
     ctx.sync()
     return out_s, out_i
 
@@ -124,8 +108,9 @@ def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0,
 def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0):
     """The multi-GPU scoring step: shard-local top-x on this rank's leaves, exchange, merge (K7).
     Returns device tensors (scores [Q,x] f32, ids [Q,x] i32 holding u32 payload ids), identical on every
-    rank and identical to the single-GPU result: two-phase with the bound exchange over NCCL
-    (`sharded_topx_two_phase`); `sharded_topx_allgather` is the plain exchange of exact shard lists."""
+    rank and identical to the single-GPU result: two-phase with the bound exchange over NCCL inside the
+    library (`sharded_topx_two_phase`); `sharded_topx_allgather` is the plain exchange of exact shard lists
+    through torch.distributed (cross-check, and the gloo path of the CPU tests)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
         return sharded_topx_two_phase(ctx, ttcompute, queries, x, similarity, group, max_batch)
     return sharded_topx_allgather(ctx, ttcompute, queries, x, similarity, group)
@@ -200,7 +185,14 @@ def cluster_sharded(myrseqs, params, group=None):
     from . import api
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return api.cluster(myrseqs, params)
-    cb = make_allgather_callback(group)
+    if dist.get_backend(group) == "nccl":
+        # device-side exchange: ncclAllGather on the library's own communicator, no host staging
+        init_library_comm(myrseqs.ctx, group)
+        out = api.cluster(myrseqs, params, shard=(dist.get_rank(group), dist.get_world_size(group), None))
+        out.exchange = {"path": "ncclAllGather inside libmyrio_b200.so"}
+        return out
+    cb = make_allgather_callback(group)  # any other backend (gloo in the CPU tests): the callback form
     out = api.cluster(myrseqs, params, shard=(dist.get_rank(group), dist.get_world_size(group), cb))
     out.exchange = dict(cb.stats)  # calls / seconds / bytes spent in the all-gathers (includes waiting for peers)
+    out.exchange["path"] = "callback (torch.distributed)"
     return out

@@ -168,7 +168,8 @@ def _sample_cdf(rng, cdf: np.ndarray, n: int) -> np.ndarray:
 
 def make_reads(tree: SeqSet, n_reads: int, seed: int, *, q_shift: int = 0,
                min_window: int = 150, min_length: int = 50, min_mean_qual: float = 12.0,
-               leaf_ids: np.ndarray | None = None) -> SeqSet:
+               leaf_ids: np.ndarray | None = None, window_frac: float = 0.6, window_sd: float = 0.15,
+               max_window: int | None = None) -> SeqSet:
     """Simulated reads of random leaves of `tree` (see module docstring).  Returns
     exactly n_reads reads that pass pre_process; meta['src_leaf'] holds the source."""
     rng = np.random.default_rng([seed, 0xF00D])
@@ -180,8 +181,8 @@ def make_reads(tree: SeqSet, n_reads: int, seed: int, *, q_shift: int = 0,
         m = int(need * 1.15) + 8
         src = rng.integers(0, tree.n, m) if leaf_ids is None else rng.choice(leaf_ids, m)
         n = tl[src]
-        w = np.rint(rng.normal(0.6 * n, 0.15 * n)).astype(np.int64)
-        w = np.clip(w, np.minimum(min_window, n), n)
+        w = np.rint(rng.normal(window_frac * n, window_sd * n)).astype(np.int64)
+        w = np.clip(w, np.minimum(min_window, n), n if max_window is None else np.minimum(n, max_window))
         st = (rng.random(m) * (n - w + 1)).astype(np.int64)
         fwd = rng.random(m) < fwd_ratio
         # window bases in read orientation
@@ -237,6 +238,42 @@ def make_reads(tree: SeqSet, n_reads: int, seed: int, *, q_shift: int = 0,
     base_off[1:] = np.cumsum(lens)
     return SeqSet(np.concatenate(out_codes), base_off, np.concatenate(out_qual),
                   {"kind": "reads", "seed": seed, "src_leaf": np.concatenate(out_src)})
+
+
+def concat(parts: list) -> SeqSet:
+    """Concatenation of ragged batches (reads of several genes in one FASTQ)."""
+    lens = np.concatenate([p.lengths() for p in parts])
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    qual = None if parts[0].qual is None else np.concatenate([p.qual for p in parts])
+    return SeqSet(np.concatenate([p.codes for p in parts]), off, qual, {"kind": parts[0].meta.get("kind")})
+
+
+# BASELINE.json configs[2]: four gene trees (SURVEY.md §8d row C3): name, mean amplicon length, tree seed
+FOUR_GENES = [("matK", 850, 1003), ("rbcL", 1400, 1004), ("ITS", 650, 1005), ("trnH-psbA", 500, 1006)]
+
+
+def make_gene_tree(n_leaves: int, mean_len: int, seed: int) -> SeqSet:
+    return make_tree(n_leaves, seed, mean_len=mean_len, sd_len=int(0.06 * mean_len), min_len=int(0.7 * mean_len),
+                     max_len=int(1.35 * mean_len))
+
+
+def make_mixed_reads(trees: list, n_reads: int, seed: int, *, q_shift: int = -3, shuffle: bool = True) -> SeqSet:
+    """configs[2] reads: an equal mix over the gene trees, near-full-length amplicon reads (window ~0.95 n,
+    rbcL windowed to ~1 kb), Q shifted UP by 3 (`q_shift` = -3; the observed nanopore Q distribution alone
+    gives 9.6 %) so that the realised per-base error is ~5 % (4.7 %)
+    (meta['mean_phred_error']); meta['gene'] holds the tree of origin."""
+    per = n_reads // len(trees)
+    parts = [make_reads(t, per + (n_reads - per * len(trees) if i == 0 else 0), seed + i, q_shift=q_shift,
+                        window_frac=0.95, window_sd=0.04, max_window=1050) for i, t in enumerate(trees)]
+    gene = np.concatenate([np.full(p.n, i, np.int64) for i, p in enumerate(parts)])
+    out = concat(parts)
+    if shuffle:
+        order = np.random.default_rng([seed, 0x5EED]).permutation(out.n)
+        out, gene = out.subset(order), gene[order]
+    out.meta = {"kind": "reads", "seed": seed, "gene": gene,
+                "mean_phred_error": float(np.mean(np.power(10.0, -out.qual.astype(np.float64) / 10.0)))}
+    return out
 
 
 # ------------------------------------------------------------------ packing
@@ -305,3 +342,11 @@ ASCII = np.frombuffer(b"ACGT", np.uint8)
 
 def to_ascii(s: SeqSet, i: int) -> str:
     return ASCII[s.seq(i)].tobytes().decode()
+
+
+IUPAC_ASCII = np.frombuffer(b"-TGKCYSBAWRDMHVN", np.uint8)  # index = bio-seq's 4-bit Iupac code
+
+
+def iupac_to_ascii(codes4: np.ndarray) -> np.ndarray:
+    """FASTA text (one byte per symbol) of 4-bit IUPAC codes."""
+    return IUPAC_ASCII[np.asarray(codes4, np.uint8) & 15]

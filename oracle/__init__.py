@@ -107,19 +107,30 @@ def lib():
         L.myo_cluster.argtypes = [_u64p, _u64p, _f32p, _u64p, C.c_size_t,
                                   C.POINTER(_ClusterParams), _i32p, C.POINTER(C.c_uint32),
                                   C.c_void_p]
+        L.myo_set_silhouette_sample.restype = None
+        L.myo_set_silhouette_sample.argtypes = [C.c_void_p]
         L.myo_pairwise.restype = None
         L.myo_pairwise.argtypes = [C.c_int, _u64p, _u64p, _f32p, C.c_size_t, _u64p, _u64p, _f32p,
                                    C.c_size_t, C.c_int, _f32p]
         L.myo_max_threads.restype = C.c_int
+        L.myo_set_num_threads.restype = None
+        L.myo_set_num_threads.argtypes = [C.c_int]
         L.myo_fastq_preprocess.restype = C.c_longlong
         L.myo_fastq_preprocess.argtypes = [_u8p, _u8p, _u64p, C.c_size_t, C.c_size_t, C.c_float, C.c_uint8,
                                            _u8p, _u8p, _u8p, _u64p]
+        L.myo_fasta_to_iupac.restype = C.c_longlong
+        L.myo_fasta_to_iupac.argtypes = [_u8p, _u64p, C.c_size_t, _u8p, _u8p, _u64p]
         _lib = L
     return _lib
 
 
 def max_threads() -> int:
     return int(lib().myo_max_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """omp_set_num_threads (a launcher may have exported OMP_NUM_THREADS=1)."""
+    lib().myo_set_num_threads(int(n))
 
 
 @dataclass
@@ -189,6 +200,20 @@ def fastq_preprocess(seq_ascii: np.ndarray, qual_ascii: np.ndarray, base_off: np
         raise ValueError(f"non-ACGT base in record {-k - 1}")
     koff = koff[:k + 1]
     return codes[:int(koff[-1])], qual[:int(koff[-1])], koff, keep[:n]
+
+
+def fasta_to_iupac(seq_ascii: np.ndarray, base_off: np.ndarray):
+    """tax/store.rs:178-188. Returns (codes4 one per byte, kept_base_off, keep)."""
+    seq_ascii = np.ascontiguousarray(seq_ascii, np.uint8)
+    base_off = np.ascontiguousarray(base_off, np.uint64)
+    n = len(base_off) - 1
+    codes = np.zeros(max(1, len(seq_ascii)), np.uint8)
+    keep = np.zeros(max(1, n), np.uint8)
+    koff = np.zeros(n + 1, np.uint64)
+    sa = seq_ascii if len(seq_ascii) else np.zeros(1, np.uint8)
+    k = lib().myo_fasta_to_iupac(sa, base_off, n, codes, keep, koff)
+    koff = koff[:k + 1]
+    return codes[:int(koff[-1])], koff, keep[:n].astype(bool)
 
 
 def count_reads(bases: np.ndarray, qual: np.ndarray, base_off: np.ndarray, k: int, cutoff: float,
@@ -336,8 +361,10 @@ def invert(leaves: Csr):
 
 def cluster(counts: Csr, t2: int, init: Csr | None, expected_nb_of_clusters: int,
             eta_improvement: float = 1e-4, nb_iters_max: int = 20, silhouette: float | None = None,
-            sim: int = SIM_COSINE, threads: int = 0):
-    """clustering.rs:55-270 from the step-1 counts. Returns (assign, n_iters, sil)."""
+            sim: int = SIM_COSINE, threads: int = 0, silhouette_sample: np.ndarray | None = None):
+    """clustering.rs:55-270 from the step-1 counts. Returns (assign, n_iters, sil).
+    silhouette_sample (bool per read): compute the silhouette score of these reads only and skip the
+    trimming (full-size checks; see myo_set_silhouette_sample)."""
     n = counts.n_rows
     p = _ClusterParams()
     p.t2 = t2
@@ -366,8 +393,17 @@ def cluster(counts: Csr, t2: int, init: Csr | None, expected_nb_of_clusters: int
     ck = counts.keys if len(counts.keys) else np.zeros(1, np.uint64)
     cv = np.ascontiguousarray(counts.vals, np.float32) if len(counts.vals) else np.zeros(1, np.float32)
     hck = np.ascontiguousarray(counts.aux, np.uint64) if n else np.zeros(1, np.uint64)
-    e = lib().myo_cluster(counts.row_off, ck, cv, hck, n, C.byref(p), assign, C.byref(iters),
-                          sil.ctypes.data)
+    mask = None
+    if silhouette_sample is not None:
+        mask = np.ascontiguousarray(silhouette_sample, np.uint8)
+        assert len(mask) == n
+        lib().myo_set_silhouette_sample(mask.ctypes.data)
+    try:
+        e = lib().myo_cluster(counts.row_off, ck, cv, hck, n, C.byref(p), assign, C.byref(iters),
+                              sil.ctypes.data)
+    finally:
+        if mask is not None:
+            lib().myo_set_silhouette_sample(None)
     if e:
         raise ValueError(f"oracle cluster error {e}")
     return assign[:n], int(iters.value), sil[:n]

@@ -44,11 +44,45 @@ const float *myo_phred_correct_table(void) {
     return g_phred;
 }
 
+/* tax/store.rs:178-188: `Seq::<Iupac>::from_str(&string_seq)` of every FASTA record.  bio-seq Iupac:
+ * A=8 C=4 G=2 T=1, ambiguity codes = OR of their bases, '-' = X = 0; upper case only (assumed, see
+ * header).  A record with any other byte is reported and skipped (store.rs:181-187). */
+long long myo_fasta_to_iupac(const uint8_t *seq_ascii, const uint64_t *base_off, size_t n, uint8_t *codes_out,
+                             uint8_t *keep_out, uint64_t *kept_off_out) {
+    static const char sym[] = "-TGKCYSBAWRDMHVN"; /* index = 4-bit code */
+    size_t kept = 0;
+    uint64_t w = 0;
+    kept_off_out[0] = 0;
+    for (size_t r = 0; r < n; ++r) {
+        uint64_t b = base_off[r], e = base_off[r + 1];
+        int ok = 1;
+        for (uint64_t i = b; i < e && ok; ++i) {
+            const char *p = seq_ascii[i] ? strchr(sym, (int)seq_ascii[i]) : NULL;
+            if (!p) ok = 0;
+        }
+        keep_out[r] = (uint8_t)ok;
+        if (!ok) continue;
+        for (uint64_t i = b; i < e; ++i) codes_out[w++] = (uint8_t)(strchr(sym, (int)seq_ascii[i]) - sym);
+        kept_off_out[++kept] = w;
+    }
+    return (long long)kept;
+}
+
 int myo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
 #else
     return 1;
+#endif
+}
+
+/* bench.py --impl reference under torchrun: the launcher exports OMP_NUM_THREADS=1; the CPU arm must
+ * still use every host core it can */
+void myo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
 #endif
 }
 
@@ -901,6 +935,14 @@ static size_t cl_argmax(const cl_ctx *cx, const cluster_t *cl, size_t nc, size_t
     return best;
 }
 
+/* Full-size checks (tests/test_gpu_configs.py): the O(N^2) silhouette pass of a 100 k-read batch takes
+ * the CPU half an hour, so a test may restrict it to a SAMPLE of the reads.  With a mask set
+ * (mask[read] != 0 = compute), inner() (:323-336) runs for the masked reads only -- same code, same f32
+ * order -- every other read gets NaN, and the trimming step (:244-266), which needs all the scores of
+ * a cluster, is skipped.  NULL (the default) restores the reference behaviour. */
+static const uint8_t *g_sil_mask = NULL;
+void myo_set_silhouette_sample(const uint8_t *mask) { g_sil_mask = mask; }
+
 int myo_cluster(const uint64_t *row_off, const uint64_t *keys, const float *vals,
                 const uint64_t *nb_hck, size_t n_reads, const myo_cluster_params *p,
                 int32_t *assign_out, uint32_t *n_iters_out, float *sil_out) {
@@ -1084,6 +1126,10 @@ int myo_cluster(const uint64_t *row_off, const uint64_t *keys, const float *vals
 #pragma omp parallel for schedule(dynamic, 8) num_threads(nt)
             for (size_t t = 0; t < nm; ++t) { /* inner() :323-336 */
                 size_t i = own->members[t];
+                if (g_sil_mask && !g_sil_mask[cx.orig[i]]) {
+                    sil[t] = NAN;
+                    continue;
+                }
                 float a = 0.0f;
                 for (size_t u = 0; u < own->n_members; ++u) {
                     float d = 1.0f - cl_sim_read_read(&cx, i, own->members[u]);
@@ -1097,6 +1143,12 @@ int myo_cluster(const uint64_t *row_off, const uint64_t *keys, const float *vals
                 }
                 b = b / (float)nbr->n_members;
                 sil[t] = (b - a) / fmaxf(a, b);
+            }
+            if (g_sil_mask) { /* sampled check: scores only, no trimming */
+                for (size_t t = 0; t < nm; ++t)
+                    if (sil_out) sil_out[cx.orig[own->members[t]]] = sil[t];
+                free(sil);
+                continue;
             }
             /* :244-249 */
             float n = (float)nm;

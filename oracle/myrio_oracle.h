@@ -148,6 +148,10 @@ int myo_cluster(const uint64_t *row_off, const uint64_t *keys, const float *vals
                 const uint64_t *nb_hck, size_t n_reads, const myo_cluster_params *p,
                 int32_t *assign_out, uint32_t *n_iters_out, float *sil_out);
 
+/* test hook for full-size checks: restrict the silhouette pass of myo_cluster to the reads with
+ * mask[read] != 0 (no trimming then); NULL = the reference behaviour */
+void myo_set_silhouette_sample(const uint8_t *mask);
+
 /* pairwise similarity tile: out[i*n_cols+j] = sim(rows_i, cols_j) on pre-normalised rows */
 void myo_pairwise(int sim, const uint64_t *r_off, const uint64_t *r_keys, const float *r_vals,
                   size_t n_rows, const uint64_t *c_off, const uint64_t *c_keys, const float *c_vals,
@@ -163,7 +167,15 @@ long long myo_fastq_preprocess(const uint8_t *seq_ascii, const uint8_t *qual_asc
                                uint8_t *codes_out, uint8_t *qual_out, uint8_t *keep_out,
                                uint64_t *kept_off_out);
 
+/* tax/store.rs:178-188 Seq::<Iupac>::from_str per FASTA record: one 4-bit code per byte in codes_out
+ * (capacity = total symbols), keep_out[n], kept_off_out[n+1]; returns the number of kept records
+ * (a record with an invalid byte is skipped, store.rs:181-187). */
+long long myo_fasta_to_iupac(const uint8_t *seq_ascii, const uint64_t *base_off, size_t n, uint8_t *codes_out,
+                             uint8_t *keep_out, uint64_t *kept_off_out);
+
 int myo_max_threads(void);
+/* omp_set_num_threads: overrides an inherited OMP_NUM_THREADS (torchrun exports 1) */
+void myo_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

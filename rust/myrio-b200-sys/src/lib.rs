@@ -66,6 +66,8 @@ unsafe extern "C" {
     pub fn myrio_prof_reset(ctx: *mut myrio_ctx) -> i32;
     pub fn myrio_prof_query(ctx: *mut myrio_ctx, prefix: *const c_char, ms_total: *mut f64, launches: *mut u64) -> i32;
 
+    pub fn myrio_bench_smem_bandwidth(ctx: *mut myrio_ctx, gbps: *mut f64, ms: *mut f64) -> i32;
+
     pub fn myrio_reads_upload(ctx: *mut myrio_ctx, words: *const u64, word_off: *const u64, base_off: *const u64,
                               qual: *const u8, n_reads: u64, out: *mut *mut myrio_seqs) -> i32;
     pub fn myrio_reads_from_fastq(ctx: *mut myrio_ctx, seq_ascii: *const u8, qual_ascii: *const u8, base_off: *const u64,
@@ -73,7 +75,18 @@ unsafe extern "C" {
                                   out: *mut *mut myrio_seqs) -> i32;
     pub fn myrio_leaves_upload(ctx: *mut myrio_ctx, words: *const u64, word_off: *const u64, base_off: *const u64,
                                n_leaves: u64, out: *mut *mut myrio_seqs) -> i32;
+    pub fn myrio_leaves_from_fasta(ctx: *mut myrio_ctx, seq_ascii: *const u8, base_off: *const u64, n_records: u64,
+                                   keep: *mut u8, out: *mut *mut myrio_seqs) -> i32;
+    pub fn myrio_seqs_count(s: *const myrio_seqs, n_seqs: *mut u64) -> i32;
     pub fn myrio_seqs_free(s: *mut myrio_seqs);
+
+    pub fn myrio_comm_unique_id(id: *mut u8) -> i32;
+    pub fn myrio_comm_init(ctx: *mut myrio_ctx, nranks: u32, rank: u32, id: *const u8) -> i32;
+    pub fn myrio_comm_destroy(ctx: *mut myrio_ctx) -> i32;
+    pub fn myrio_comm_info(ctx: *const myrio_ctx, rank: *mut u32, nranks: *mut u32, nccl_version: *mut i32) -> i32;
+    pub fn myrio_score_topx_sharded(ctx: *mut myrio_ctx, ix: *const myrio_index, queries: *const myrio_svecs,
+                                    q_first: u64, q_count: u64, x: u32, similarity: i32, d_top_scores: *mut f32,
+                                    d_top_ids: *mut u32, max_batch: u64) -> i32;
 
     pub fn myrio_count_reads(ctx: *mut myrio_ctx, reads: *const myrio_seqs, k: u32, cutoff: f32,
                              out: *mut *mut myrio_svecs) -> i32;

@@ -696,3 +696,35 @@ def test_fastq_ingestion_matches_oracle_and_prepacked_path(api, ctx):
     # empty batch
     m0, k0 = api.MyrSeqs.from_fastq_records(ctx, np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(1, np.uint64))
     assert m0.n == 0 and len(k0) == 0
+
+
+def test_fasta_ingestion_matches_oracle_and_prepacked_path(api, ctx):
+    # tax/store.rs:166-195: Seq::<Iupac>::from_str per record on the device; ambiguity codes, gaps,
+    # an empty record, and records with an invalid byte (skipped like the reference, store.rs:181-187)
+    rng = np.random.default_rng(23)
+    tree = synth.make_tree(60, 111)
+    iupac = synth.tree_to_iupac(tree).copy()
+    pos = rng.choice(len(iupac), 300, replace=False)
+    iupac[pos] = rng.choice(np.array([0, 3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15], np.uint8), 300)
+    text = synth.iupac_to_ascii(iupac).copy()
+    off = tree.base_off.copy()
+    bad = {5: ord("a"), 17: ord("Z"), 40: ord("U")}
+    for r, ch in bad.items():
+        text[int(off[r]) + 11] = ch
+    # an empty record in the middle (header followed directly by the next header)
+    off = np.concatenate([off[:31], off[30:]])
+    st, keep = api.TaxTreeStore.from_fasta_records(ctx, text, off)
+    ocodes, ooff, okeep = oracle.fasta_to_iupac(text, off)
+    assert (keep == okeep).all() and keep.sum() == len(off) - 1 - len(bad)
+    assert not keep[5] and not keep[17] and keep[30] and not keep[41]  # record 40 moved to 41
+    assert st.n_leaves == keep.sum()
+    for k in (6, 18):
+        got = st._count(k, 32, 3).download()
+        exp = oracle.count_leaves(ocodes, ooff, k, 32, seed=3)
+        assert (got[0] == exp.row_off).all() and (got[1] == exp.keys).all() and (got[2] == exp.vals).all()
+        assert (bits(got[3]) == bits(exp.aux)).all()
+    # same bits as packing on the host
+    ref = api.TaxTreeStore(ctx, iupac=ocodes, base_off=ooff)._count(18, 32, 3).download()
+    assert all((a == b).all() for a, b in zip(got[:3], ref[:3]))
+    s0, k0 = api.TaxTreeStore.from_fasta_records(ctx, np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert s0.n_leaves == 0 and len(k0) == 0

@@ -256,3 +256,29 @@ def test_kmer_key_bit_orders():
             assert ma == mb and (np.diff(b.keys.astype(object)) > 0).all()
     finally:
         oracle.set_kmer_msb_first(False)
+
+
+def test_fasta_to_iupac_restatement():
+    # tax/store.rs:178-188: bio-seq Iupac codes (A=8 C=4 G=2 T=1, ambiguity = OR, '-' = X = 0)
+    recs = ["ACGT", "RYSWKMBDHVN-", "ACGU", "", "acgt", "NNAC"]
+    seq = np.frombuffer("".join(recs).encode(), np.uint8)
+    off = np.zeros(len(recs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(r) for r in recs])
+    codes, koff, keep = oracle.fasta_to_iupac(seq, off)
+    assert keep.tolist() == [True, True, False, True, False, True]
+    assert koff.tolist() == [0, 4, 16, 16, 20]
+    assert codes[:4].tolist() == [8, 4, 2, 1]
+    assert codes[4:16].tolist() == [8 | 2, 4 | 1, 4 | 2, 8 | 1, 2 | 1, 8 | 4, 7, 11, 13, 14, 15, 0]
+    assert codes[16:].tolist() == [15, 15, 8, 4]
+    assert (synth.iupac_to_ascii(codes) == np.frombuffer(b"ACGTRYSWKMBDHVN-NNAC", np.uint8)).all()
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    # the -sys crate cannot be compiled here (no cargo/rustc): at least keep its extern block complete
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "myrio_b200.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(myrio_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(root, "rust", "myrio-b200-sys", "src", "lib.rs")).read()
+    in_rust = set(re.findall(r"pub fn (myrio_[a-z0-9_]+)\s*\(", rs))
+    assert declared - in_rust == set(), sorted(declared - in_rust)
