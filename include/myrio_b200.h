@@ -70,6 +70,7 @@ typedef struct myrio_ctx myrio_ctx;       /* one GPU + stream + scratch         
 typedef struct myrio_seqs myrio_seqs;     /* device-resident packed sequences (+ quality)   */
 typedef struct myrio_svecs myrio_svecs;   /* device-resident batch of SparseVec<T> (CSR)    */
 typedef struct myrio_index myrio_index;   /* device-resident tiled inverted index of leaves */
+typedef struct myrio_store myrio_store;   /* host-side content of a .myrtree file (TaxTreeStore)  */
 
 const char *myrio_last_error(void);
 int32_t myrio_version(void);
@@ -165,6 +166,64 @@ int32_t myrio_svecs_upload(myrio_ctx *ctx, uint64_t n_rows, const uint64_t *row_
  * first converted with Float::from (tax/compute.rs:100-108). */
 int32_t myrio_svecs_normalize(myrio_ctx *ctx, const myrio_svecs *in, myrio_svecs **out);
 void myrio_svecs_free(myrio_svecs *v);
+
+/* ---- .myrtree files ----------------------------------------------------- *
+ * TaxTreeStore (myrio-core/src/tax/store.rs:43-48) and its byte format, to_bytes / from_bytes
+ * (store.rs:342-454): magic "MYRIO-\xCE\xA8", u64 header length, header {core chunk info, payload chunk
+ * infos, k_precomputed}, zstd(core without payloads), zstd(chunk of payloads) x C; bincode 2 fixed-int
+ * little endian inside (data/sparse.rs:413-436, tax/core.rs:332-410).  Two encodings are decided by code
+ * outside the reference tree and are ASSUMED (DESIGN.md lists them): Seq<Iupac> = u64 symbol count +
+ * Vec<usize> raw words; Rank = u32 discriminant.
+ *
+ * The taxonomy crosses the ABI as a flat PRE-ORDER node list: kind[i] (0 = branch, 1 = leaf),
+ * arg[i] (branch: number of children, leaf: payload_id), names concatenated with name_off[n+1].
+ * Leaf sequences use the packed Seq<Iupac> layout of myrio_leaves_upload. */
+int32_t myrio_store_new(const char *gene, uint32_t root_rank, uint64_t n_nodes, const uint8_t *node_kind,
+                        const uint64_t *node_arg, const uint64_t *name_off, const char *names,
+                        uint64_t n_payloads, const uint64_t *seq_words, const uint64_t *seq_word_off,
+                        const uint64_t *seq_base_off, myrio_store **out);
+/* TaxTreeStore::from_bytes (store.rs:408-454).  threads = 0 -> hardware concurrency.
+ * Malformed input -> MYRIO_ERR_FORMAT (the reference returns tax::Error). */
+int32_t myrio_store_from_bytes(const uint8_t *data, uint64_t len, uint32_t threads, myrio_store **out);
+/* TaxTreeStore::to_bytes (store.rs:342-405).  *out is library-allocated (myrio_bytes_free).  The payloads are
+ * cut into chunks of len < threads ? len : len / threads + 1 (store.rs:363-367: threads plays
+ * rayon::current_num_threads(); 0 -> hardware concurrency).  A store without payloads cannot be
+ * serialised (the reference panics in par_chunks(0)) -> MYRIO_ERR_EMPTY. */
+int32_t myrio_store_to_bytes(const myrio_store *st, int32_t zstd_level, uint32_t threads, uint8_t **out,
+                             uint64_t *len);
+void myrio_bytes_free(uint8_t *p);
+/* save_to_file / load_from_file (store.rs:53-93): the bytes above, written to / read from `path` */
+int32_t myrio_store_save(const myrio_store *st, const char *path, int32_t zstd_level, uint32_t threads);
+int32_t myrio_store_load(const char *path, uint32_t threads, myrio_store **out);
+int32_t myrio_store_info(const myrio_store *st, uint64_t *n_nodes, uint64_t *n_payloads, uint64_t *n_k,
+                         uint32_t *root_rank, uint64_t *names_bytes, uint64_t *gene_bytes,
+                         uint64_t *seq_words_total);
+/* any pointer may be NULL; sizes from myrio_store_info (gene: gene_bytes + 1 with the terminating 0) */
+int32_t myrio_store_tree(const myrio_store *st, char *gene, uint8_t *node_kind, uint64_t *node_arg,
+                         uint64_t *name_off, char *names, uint64_t *k_precomputed);
+int32_t myrio_store_seqs(const myrio_store *st, uint64_t *seq_words, uint64_t *seq_word_off,
+                         uint64_t *seq_base_off);
+/* size of / host copy of kmer_store_counts_vec[k_index] over all payloads (CSR, u16 counts, f32 rescale) */
+int32_t myrio_store_counts_info(const myrio_store *st, uint64_t k_index, uint64_t *nnz);
+int32_t myrio_store_counts_host(const myrio_store *st, uint64_t k_index, uint64_t *row_off, uint64_t *keys,
+                                uint16_t *counts, float *rescale);
+/* the payload sequences as a device batch for myrio_count_leaves */
+int32_t myrio_store_leaves(myrio_ctx *ctx, const myrio_store *st, myrio_seqs **out);
+/* the cached counts of k_precomputed[k_index] as a device batch (u16 values + rescale), ready for
+ * myrio_svecs_normalize + myrio_index_build: TaxTreeCompute::from_store_tree's cache hit (compute.rs:80-85) */
+int32_t myrio_store_counts(myrio_ctx *ctx, const myrio_store *st, uint64_t k_index, myrio_svecs **out);
+/* compute_and_append_kmer_counts / compute_and_overwrite_kmer_counts (store.rs:265-308), second half: the
+ * batch myrio_count_leaves produced for k is written back into the store (append: pushed after the existing
+ * entries; overwrite: replaces them all) -- the GPU-built counts reach the cache file without a host hop
+ * through the caller. */
+int32_t myrio_store_append_counts(myrio_ctx *ctx, myrio_store *st, uint64_t k, const myrio_svecs *counts);
+int32_t myrio_store_overwrite_counts(myrio_ctx *ctx, myrio_store *st, uint64_t k, const myrio_svecs *counts);
+/* the same from host arrays (CSR over the payloads; e.g. counts that never were on this GPU) */
+int32_t myrio_store_append_counts_host(myrio_store *st, uint64_t k, const uint64_t *row_off, const uint64_t *keys,
+                                       const uint16_t *counts, const float *rescale);
+/* TaxTreeStore::shrink (store.rs:259-262) */
+int32_t myrio_store_shrink(myrio_store *st);
+void myrio_store_free(myrio_store *st);
 
 /* ---- reference index ---------------------------------------------------- */
 

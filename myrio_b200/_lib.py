@@ -30,6 +30,10 @@ SYMBOLS = [
     "myrio_topx_merge_composites_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
     "myrio_cluster_sharded",
     "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_cluster_stats", "myrio_svecs_device_ptrs",
+    "myrio_store_new", "myrio_store_from_bytes", "myrio_store_to_bytes", "myrio_bytes_free", "myrio_store_save",
+    "myrio_store_load", "myrio_store_info", "myrio_store_tree", "myrio_store_seqs", "myrio_store_counts_info",
+    "myrio_store_counts_host", "myrio_store_leaves", "myrio_store_counts", "myrio_store_append_counts",
+    "myrio_store_overwrite_counts", "myrio_store_append_counts_host", "myrio_store_shrink", "myrio_store_free",
     "myrio_comm_unique_id", "myrio_comm_init", "myrio_comm_destroy", "myrio_comm_info", "myrio_score_topx_sharded",
 ]
 
@@ -125,6 +129,26 @@ def load() -> C.CDLL:
     L.myrio_topx_merge_composites_async.argtypes = [vp, vp, u32, u64, u32, vp, vp]
     L.myrio_topx_merge_async.argtypes = [vp, vp, vp, u32, u64, u32, vp, vp]
     L.myrio_score_stats.argtypes = [vp, P(u64), P(u64), P(u64)]
+    L.myrio_store_new.argtypes = [C.c_char_p, u32, u64, vp, vp, vp, vp, u64, vp, vp, vp, P(vp)]
+    L.myrio_store_from_bytes.argtypes = [vp, u64, u32, P(vp)]
+    L.myrio_store_to_bytes.argtypes = [vp, i32, u32, P(vp), P(u64)]
+    L.myrio_bytes_free.argtypes = [vp]
+    L.myrio_bytes_free.restype = None
+    L.myrio_store_save.argtypes = [vp, C.c_char_p, i32, u32]
+    L.myrio_store_load.argtypes = [C.c_char_p, u32, P(vp)]
+    L.myrio_store_info.argtypes = [vp, P(u64), P(u64), P(u64), P(u32), P(u64), P(u64), P(u64)]
+    L.myrio_store_tree.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.myrio_store_seqs.argtypes = [vp, vp, vp, vp]
+    L.myrio_store_counts_info.argtypes = [vp, u64, P(u64)]
+    L.myrio_store_counts_host.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.myrio_store_leaves.argtypes = [vp, vp, P(vp)]
+    L.myrio_store_counts.argtypes = [vp, vp, u64, P(vp)]
+    L.myrio_store_append_counts.argtypes = [vp, vp, u64, vp]
+    L.myrio_store_overwrite_counts.argtypes = [vp, vp, u64, vp]
+    L.myrio_store_append_counts_host.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.myrio_store_shrink.argtypes = [vp]
+    L.myrio_store_free.argtypes = [vp]
+    L.myrio_store_free.restype = None
     L.myrio_comm_unique_id.argtypes = [vp]
     L.myrio_comm_init.argtypes = [vp, u32, u32, vp]
     L.myrio_comm_destroy.argtypes = [vp]
@@ -138,7 +162,8 @@ def load() -> C.CDLL:
     for name in SYMBOLS:
         f = getattr(L, name)
         if name not in ("myrio_last_error", "myrio_ctx_destroy", "myrio_ctx_launch_count", "myrio_seqs_free",
-                        "myrio_svecs_free", "myrio_index_free", "myrio_version", "myrio_ctx_stream"):
+                        "myrio_svecs_free", "myrio_index_free", "myrio_version", "myrio_ctx_stream",
+                        "myrio_bytes_free", "myrio_store_free"):
             f.restype = i32
     _lib = L
     return L

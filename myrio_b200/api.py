@@ -229,9 +229,147 @@ class MyrSeqs:
         return out
 
 
+RANKS = {"Domain": 8, "Kingdom": 7, "Phylum": 6, "Class": 5, "Order": 4, "Family": 3, "Genus": 2, "Species": 1}
+
+
+class MyrTreeFile:
+    """Host-side content of a `.myrtree` file (myrio_store): TaxTreeStore::to_bytes / from_bytes / save_to_file /
+    load_from_file (tax/store.rs:53-93, 342-454).  The taxonomy is a flat PRE-ORDER node list: kind (0 branch,
+    1 leaf), arg (branch: number of children, leaf: payload_id), names.  No GPU is needed for the byte format;
+    `leaves` / `counts` / `append_counts` move the payloads between the file content and device batches."""
+
+    def __init__(self, handle):
+        self._L = _lib.load()
+        self.h = handle
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._L.myrio_store_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    @classmethod
+    def new(cls, gene: str, root_rank: int, node_kind, node_arg, node_names, iupac, base_off) -> "MyrTreeFile":
+        """TaxTreeCore::new over payloads without cached counts (store.rs:238-246).  iupac: one 4-bit code per byte."""
+        L = _lib.load()
+        kind = np.ascontiguousarray(node_kind, np.uint8)
+        arg = np.ascontiguousarray(node_arg, np.uint64)
+        enc = [n.encode() for n in node_names]
+        name_off = np.zeros(len(enc) + 1, np.uint64)
+        name_off[1:] = np.cumsum([len(e) for e in enc])
+        names = b"".join(enc)
+        base_off = np.ascontiguousarray(base_off, np.uint64)
+        words, word_off = pack_iupac4(np.ascontiguousarray(iupac, np.uint8), base_off)
+        h = C.c_void_p()
+        _lib.check(L.myrio_store_new(gene.encode(), root_rank, len(kind), _p(kind), _p(arg), _p(name_off),
+                                     C.c_char_p(names), len(base_off) - 1, _p(words), _p(word_off), _p(base_off),
+                                     C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_bytes(cls, data: bytes, threads: int = 0) -> "MyrTreeFile":
+        L = _lib.load()
+        buf = np.frombuffer(data, np.uint8)
+        h = C.c_void_p()
+        _lib.check(L.myrio_store_from_bytes(_p(buf) if len(buf) else None, len(buf), threads, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def load_from_file(cls, path: str, threads: int = 0) -> "MyrTreeFile":
+        L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(L.myrio_store_load(str(path).encode(), threads, C.byref(h)))
+        return cls(h)
+
+    def to_bytes(self, zstd_compression_level: int = 6, threads: int = 0) -> bytes:
+        out, n = C.c_void_p(), C.c_uint64(0)
+        _lib.check(self._L.myrio_store_to_bytes(self.h, zstd_compression_level, threads, C.byref(out), C.byref(n)))
+        try:
+            return C.string_at(out, n.value)
+        finally:
+            self._L.myrio_bytes_free(out)
+
+    def save_to_file(self, path: str, zstd_compression_level: int = 6, threads: int = 0):
+        _lib.check(self._L.myrio_store_save(self.h, str(path).encode(), zstd_compression_level, threads))
+
+    def info(self):
+        a, b, c, e, f, g = (C.c_uint64(0) for _ in range(6))
+        r = C.c_uint32(0)
+        _lib.check(self._L.myrio_store_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(r), C.byref(e),
+                                            C.byref(f), C.byref(g)))
+        return {"n_nodes": int(a.value), "n_payloads": int(b.value), "n_k": int(c.value), "root_rank": int(r.value),
+                "names_bytes": int(e.value), "gene_bytes": int(f.value), "seq_words": int(g.value)}
+
+    def tree(self):
+        i = self.info()
+        gene = C.create_string_buffer(i["gene_bytes"] + 1)
+        kind = np.zeros(i["n_nodes"], np.uint8)
+        arg = np.zeros(i["n_nodes"], np.uint64)
+        off = np.zeros(i["n_nodes"] + 1, np.uint64)
+        names = np.zeros(max(1, i["names_bytes"]), np.uint8)
+        kp = np.zeros(max(1, i["n_k"]), np.uint64)
+        _lib.check(self._L.myrio_store_tree(self.h, gene, _p(kind), _p(arg), _p(off), _p(names), _p(kp)))
+        raw = names.tobytes()
+        return {"gene": gene.value.decode(), "root_rank": i["root_rank"], "kind": kind, "arg": arg,
+                "names": [raw[int(off[j]):int(off[j + 1])].decode() for j in range(i["n_nodes"])],
+                "k_precomputed": [int(v) for v in kp[:i["n_k"]]]}
+
+    @property
+    def k_precomputed(self):
+        return self.tree()["k_precomputed"]
+
+    def seqs(self):
+        """(words, word_off, base_off): the packed Seq<Iupac> of every payload."""
+        i = self.info()
+        words = np.zeros(max(1, i["seq_words"]), np.uint64)
+        woff = np.zeros(i["n_payloads"] + 1, np.uint64)
+        boff = np.zeros(i["n_payloads"] + 1, np.uint64)
+        _lib.check(self._L.myrio_store_seqs(self.h, _p(words), _p(woff), _p(boff)))
+        return words[:i["seq_words"]], woff, boff
+
+    def counts_host(self, k_index: int):
+        """kmer_store_counts_vec[k_index] of every payload: (row_off, keys, u16 counts, f32 rescale)."""
+        n = C.c_uint64(0)
+        _lib.check(self._L.myrio_store_counts_info(self.h, k_index, C.byref(n)))
+        L = self.info()["n_payloads"]
+        ro = np.zeros(L + 1, np.uint64)
+        keys = np.zeros(max(1, n.value), np.uint64)
+        vals = np.zeros(max(1, n.value), np.uint16)
+        resc = np.zeros(max(1, L), np.float32)
+        _lib.check(self._L.myrio_store_counts_host(self.h, k_index, _p(ro), _p(keys), _p(vals), _p(resc)))
+        return ro, keys[:n.value], vals[:n.value], resc[:L]
+
+    def counts(self, ctx: Context, k_index: int) -> "SFVecs":
+        h = C.c_void_p()
+        _lib.check(self._L.myrio_store_counts(ctx.h, self.h, k_index, C.byref(h)))
+        out = SFVecs(ctx, h, True)
+        out.aux_is_u64 = False
+        return out
+
+    def append_counts(self, ctx: Context, k: int, counts: "SFVecs"):
+        _lib.check(self._L.myrio_store_append_counts(ctx.h, self.h, k, counts.h))
+
+    def append_counts_host(self, k: int, row_off, keys, counts, rescale):
+        ro = np.ascontiguousarray(row_off, np.uint64)
+        kk = np.ascontiguousarray(keys, np.uint64)
+        vv = np.ascontiguousarray(counts, np.uint16)
+        rs = np.ascontiguousarray(rescale, np.float32)
+        _lib.check(self._L.myrio_store_append_counts_host(self.h, k, _p(ro), _p(kk), _p(vv), _p(rs)))
+
+    def overwrite_counts(self, ctx: Context, k: int, counts: "SFVecs"):
+        _lib.check(self._L.myrio_store_overwrite_counts(ctx.h, self.h, k, counts.h))
+
+    def shrink(self):
+        """TaxTreeStore::shrink (store.rs:259-262)"""
+        _lib.check(self._L.myrio_store_shrink(self.h))
+
+
 class TaxTreeStore:
-    """The leaf sequences + cached k-mer counts of a .myrtree (tax/store.rs:28-50);
-    the taxonomy itself stays on the host (out of scope)."""
+    """The leaf sequences + cached k-mer counts of a .myrtree (tax/store.rs:28-50) on the GPU.  When the store
+    comes from (or is attached to) a MyrTreeFile, counts computed on the GPU are written back into it, so
+    `save_to_file` produces the reference's cache file (compute.rs:86-91: --cache-counts)."""
 
     def __init__(self, ctx: Context, leaves: SeqSet | None = None, *, iupac=None, base_off=None,
                  gene: str = "", leaf_id_base: int = 0):
@@ -247,6 +385,33 @@ class TaxTreeStore:
         self.h = h
         self.k_precomputed: list[int] = []
         self.kmer_store_counts_vec: list[SFVecs] = []
+
+    file: "MyrTreeFile | None" = None
+
+    @classmethod
+    def from_file(cls, ctx: Context, f: "MyrTreeFile", *, leaf_id_base: int = 0) -> "TaxTreeStore":
+        """TaxTreeStore::load_from_file (store.rs:77-93), GPU half: the payload sequences and every cached count
+        vector become device batches."""
+        self = cls.__new__(cls)
+        t = f.tree()
+        self.ctx, self.gene, self.leaf_id_base, self.file = ctx, t["gene"], leaf_id_base, f
+        h = C.c_void_p()
+        _lib.check(ctx._L.myrio_store_leaves(ctx.h, f.h, C.byref(h)))
+        self.h = h
+        self.n_leaves = f.info()["n_payloads"]
+        self.k_precomputed = list(t["k_precomputed"])
+        self.kmer_store_counts_vec = [f.counts(ctx, i) for i in range(len(self.k_precomputed))]
+        return self
+
+    @classmethod
+    def load_from_file(cls, ctx: Context, path: str, **kw) -> "TaxTreeStore":
+        return cls.from_file(ctx, MyrTreeFile.load_from_file(path), **kw)
+
+    def save_to_file(self, path: str, zstd_compression_level: int = 6):
+        """TaxTreeStore::save_to_file (store.rs:53-75)"""
+        if self.file is None:
+            raise MyrioError(_lib.ERR_BAD_ARG, "this store has no .myrtree content attached (MyrTreeFile)")
+        self.file.save_to_file(path, zstd_compression_level)
 
     @classmethod
     def from_fasta_records(cls, ctx: Context, seq_ascii, base_off, *, gene: str = "", leaf_id_base: int = 0):
@@ -286,11 +451,15 @@ class TaxTreeStore:
         """tax/store.rs:265-285"""
         self.kmer_store_counts_vec.append(self._count(k, nb_resamples, seed))
         self.k_precomputed.append(k)
+        if self.file is not None:
+            self.file.append_counts(self.ctx, k, self.kmer_store_counts_vec[-1])
 
     def compute_and_overwrite_kmer_counts(self, k: int, nb_resamples: int, seed: int = 0):
         """tax/store.rs:287-308"""
         self.kmer_store_counts_vec = [self._count(k, nb_resamples, seed)]
         self.k_precomputed = [k]
+        if self.file is not None:
+            self.file.overwrite_counts(self.ctx, k, self.kmer_store_counts_vec[0])
 
 
 class TaxTreeCompute:

@@ -240,6 +240,58 @@ def make_reads(tree: SeqSet, n_reads: int, seed: int, *, q_shift: int = 0,
                   {"kind": "reads", "seed": seed, "src_leaf": np.concatenate(out_src)})
 
 
+def taxonomy(tree: SeqSet) -> dict:
+    """The taxonomy of a make_tree() tree as the reference builds it from FASTA headers
+    (tax/store.rs:127-247): root rank Kingdom (`k:Plantae`), branches p > c > o > f > g, and the sequences as
+    LEAVES named by their species (several leaves may share a species name; a leaf's payload_id is its FASTA
+    order = its index in `tree`).  Returned as the flat PRE-ORDER node list of the C ABI (myrio_store_new):
+    kind (0 branch, 1 leaf), arg (number of children | payload_id), names; plus rank (Rank discriminant of every
+    node: branches 7..2, leaves 1) and root_rank."""
+    parents = tree.meta["parents"]  # per level p, c, o, f, g, s, leaf: index of the parent one level up
+    letters = ["p", "c", "o", "f", "g", "s"]
+    n_levels = len(parents)
+    # children ranges: parents are monotone, so the children of node j at level l are contiguous at level l + 1
+    starts = []
+    for li in range(1, n_levels):
+        par = parents[li]
+        n_par = len(parents[li - 1])
+        st = np.searchsorted(par, np.arange(n_par + 1), side="left")
+        starts.append(st)
+    kind, arg, names, rank = [0], [len(parents[0])], ["k:Plantae"], [7]
+    # iterative DFS over (level, index); species nodes (level 5) are not branches: their leaves hang under the genus
+    def leaves_of_genus(g):
+        out = []
+        s0, s1 = starts[4][g], starts[4][g + 1]          # species of genus g
+        for sp in range(s0, s1):
+            l0, l1 = starts[5][sp], starts[5][sp + 1]    # leaves of species sp
+            out.extend((int(leaf), f"s:Species{sp}") for leaf in range(l0, l1))
+        return out
+    stack = [(0, j) for j in range(len(parents[0]) - 1, -1, -1)]
+    while stack:
+        li, j = stack.pop()
+        if li == 4:  # genus: children are leaves
+            lv = leaves_of_genus(j)
+            kind.append(0)
+            arg.append(len(lv))
+            names.append(f"g:Genus{j}")
+            rank.append(2)
+            for pid, nm in lv:
+                kind.append(1)
+                arg.append(pid)
+                names.append(nm)
+                rank.append(1)
+            continue
+        c0, c1 = int(starts[li][j]), int(starts[li][j + 1])
+        kind.append(0)
+        arg.append(c1 - c0)
+        names.append(f"{letters[li]}:{letters[li].upper()}{j}")
+        rank.append(6 - li)
+        for c in range(c1 - 1, c0 - 1, -1):
+            stack.append((li + 1, c))
+    return {"kind": np.array(kind, np.uint8), "arg": np.array(arg, np.uint64), "names": names,
+            "rank": np.array(rank, np.uint8), "root_rank": 7}
+
+
 def concat(parts: list) -> SeqSet:
     """Concatenation of ragged batches (reads of several genes in one FASTQ)."""
     lens = np.concatenate([p.lengths() for p in parts])

@@ -23,8 +23,9 @@ def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
     src = os.path.join(_HERE, "myrio_oracle.c")
     hdr = os.path.join(_HERE, "myrio_oracle.h")
+    src2 = os.path.join(_HERE, "myrtree_oracle.c")
     stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, hdr)
+        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, src2, hdr)
     )
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
@@ -56,6 +57,15 @@ class _ClusterParams(C.Structure):
         ("has_silhouette", C.c_int),
         ("ssdcf", C.c_float),
         ("threads", C.c_int),
+    ]
+
+
+class _StoreDesc(C.Structure):
+    _fields_ = [
+        ("gene", C.c_char_p), ("root_rank", C.c_uint32), ("n_nodes", C.c_uint64), ("kind", C.c_void_p),
+        ("arg", C.c_void_p), ("name_off", C.c_void_p), ("names", C.c_void_p), ("n_payloads", C.c_uint64),
+        ("seq_codes", C.c_void_p), ("seq_off", C.c_void_p), ("n_k", C.c_uint64), ("k_precomputed", C.c_void_p),
+        ("row_off", C.c_void_p), ("keys", C.c_void_p), ("vals", C.c_void_p), ("rescale", C.c_void_p),
     ]
 
 
@@ -120,6 +130,19 @@ def lib():
                                            _u8p, _u8p, _u8p, _u64p]
         L.myo_fasta_to_iupac.restype = C.c_longlong
         L.myo_fasta_to_iupac.argtypes = [_u8p, _u64p, C.c_size_t, _u8p, _u8p, _u64p]
+        L.myo_store_encode.restype = C.c_int
+        L.myo_store_encode.argtypes = [C.POINTER(_StoreDesc), C.c_int, C.c_uint, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_uint64)]
+        L.myo_store_decode.restype = C.c_int
+        L.myo_store_decode.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.myo_store_view.restype = None
+        L.myo_store_view.argtypes = [C.c_void_p, C.POINTER(_StoreDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.myo_store_free.restype = None
+        L.myo_store_free.argtypes = [C.c_void_p]
+        L.myo_store_section.restype = C.c_int
+        L.myo_store_section.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.myo_bytes_free.restype = None
+        L.myo_bytes_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -417,3 +440,107 @@ def pairwise(rows: Csr, cols: Csr, sim: int = SIM_COSINE, threads: int = 0) -> n
                        rows.n_rows, cols.row_off, cols.keys,
                        np.ascontiguousarray(cols.vals, np.float32), cols.n_rows, threads, out)
     return out
+
+
+# ------------------------------------------------------------------ .myrtree (myrtree_oracle.c)
+
+@dataclass
+class StoreContent:
+    """A TaxTreeStore as flat arrays: taxonomy in pre-order, one 4-bit IUPAC code per byte, counts per k as Csr
+    (vals uint16, aux = rescale float32)."""
+    gene: str
+    root_rank: int
+    kind: np.ndarray        # uint8 [n_nodes]  0 branch, 1 leaf
+    arg: np.ndarray         # uint64 [n_nodes] children count | payload_id
+    names: list             # str per node
+    seq_codes: np.ndarray   # uint8 [total symbols]
+    seq_off: np.ndarray     # uint64 [n_payloads + 1]
+    k_precomputed: list
+    counts: list            # Csr per k
+
+
+def store_encode(st: StoreContent, zstd_level: int = 6, threads: int = 1) -> bytes:
+    """TaxTreeStore::to_bytes (tax/store.rs:342-405)."""
+    L = lib()
+    enc = [n.encode() for n in st.names]
+    name_off = np.zeros(len(enc) + 1, np.uint64)
+    name_off[1:] = np.cumsum([len(e) for e in enc])
+    names = np.frombuffer(b"".join(enc) + b"\0", np.uint8).copy()
+    kind = np.ascontiguousarray(st.kind, np.uint8)
+    arg = np.ascontiguousarray(st.arg, np.uint64)
+    codes = np.ascontiguousarray(st.seq_codes, np.uint8)
+    if len(codes) == 0:
+        codes = np.zeros(1, np.uint8)
+    soff = np.ascontiguousarray(st.seq_off, np.uint64)
+    nk = len(st.k_precomputed)
+    kp = np.ascontiguousarray(st.k_precomputed if nk else [0], np.uint64)
+    keep = []
+    ptrs = [(C.c_void_p * max(1, nk))() for _ in range(4)]
+    for i, c in enumerate(st.counts):
+        arrs = (np.ascontiguousarray(c.row_off, np.uint64), np.ascontiguousarray(c.keys if len(c.keys) else [0], np.uint64),
+                np.ascontiguousarray(c.vals if len(c.vals) else [0], np.uint16),
+                np.ascontiguousarray(c.aux if len(c.aux) else [0], np.float32))
+        keep.append(arrs)
+        for j in range(4):
+            ptrs[j][i] = arrs[j].ctypes.data
+    d = _StoreDesc(st.gene.encode(), st.root_rank, len(kind), kind.ctypes.data, arg.ctypes.data, name_off.ctypes.data,
+                   names.ctypes.data, len(soff) - 1, codes.ctypes.data, soff.ctypes.data, nk, kp.ctypes.data,
+                   C.cast(ptrs[0], C.c_void_p), C.cast(ptrs[1], C.c_void_p), C.cast(ptrs[2], C.c_void_p),
+                   C.cast(ptrs[3], C.c_void_p))
+    out, n = C.c_void_p(), C.c_uint64(0)
+    e = L.myo_store_encode(C.byref(d), zstd_level, threads, C.byref(out), C.byref(n))
+    if e:
+        raise ValueError(f"oracle store_encode error {e}")
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        L.myo_bytes_free(out)
+
+
+def store_decode(data: bytes) -> StoreContent:
+    """TaxTreeStore::from_bytes (tax/store.rs:408-454)."""
+    L = lib()
+    buf = np.frombuffer(data, np.uint8)
+    h = C.c_void_p()
+    e = L.myo_store_decode(buf.ctypes.data if len(buf) else None, len(buf), C.byref(h))
+    if e:
+        raise ValueError(f"oracle store_decode error {e}")
+    try:
+        d = _StoreDesc()
+        ptrs = [(C.c_void_p * 64)() for _ in range(4)]
+        L.myo_store_view(h, C.byref(d), ptrs[0], ptrs[1], ptrs[2], ptrs[3])
+
+        def arr(ptr, n, dt):
+            if n == 0 or not ptr:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
+        nn, npay, nk = int(d.n_nodes), int(d.n_payloads), int(d.n_k)
+        name_off = arr(d.name_off, nn + 1, np.uint64)
+        names_raw = arr(d.names, int(name_off[-1]) if nn else 0, np.uint8).tobytes()
+        names = [names_raw[int(name_off[i]):int(name_off[i + 1])].decode() for i in range(nn)]
+        soff = arr(d.seq_off, npay + 1, np.uint64)
+        counts = []
+        for i in range(nk):
+            ro = arr(ptrs[0][i], npay + 1, np.uint64)
+            nnz = int(ro[-1])
+            counts.append(Csr(ro, arr(ptrs[1][i], nnz, np.uint64), arr(ptrs[2][i], nnz, np.uint16),
+                              arr(ptrs[3][i], npay, np.float32)))
+        return StoreContent(d.gene.decode(), int(d.root_rank), arr(d.kind, nn, np.uint8), arr(d.arg, nn, np.uint64), names,
+                            arr(d.seq_codes, int(soff[-1]), np.uint8), soff,
+                            [int(v) for v in arr(d.k_precomputed, nk, np.uint64)], counts)
+    finally:
+        L.myo_store_free(h)
+
+
+def store_section(data: bytes, which: int) -> bytes:
+    """Decompressed section of a .myrtree file: -1 header, 0 core, 1 + c payload chunk c."""
+    L = lib()
+    buf = np.frombuffer(data, np.uint8)
+    out, n = C.c_void_p(), C.c_uint64(0)
+    e = L.myo_store_section(buf.ctypes.data, len(buf), which, C.byref(out), C.byref(n))
+    if e:
+        raise ValueError(f"oracle store_section error {e}")
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        L.myo_bytes_free(out)

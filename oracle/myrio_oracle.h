@@ -173,6 +173,42 @@ long long myo_fastq_preprocess(const uint8_t *seq_ascii, const uint8_t *qual_asc
 long long myo_fasta_to_iupac(const uint8_t *seq_ascii, const uint64_t *base_off, size_t n, uint8_t *codes_out,
                              uint8_t *keep_out, uint64_t *kept_off_out);
 
+/* ---- .myrtree byte format (myrtree_oracle.c): tax/store.rs:314-454, data/sparse.rs:413-436,
+ * tax/core.rs:332-410.  A store is described by flat arrays: taxonomy in PRE-ORDER (kind 0 = branch with
+ * arg = number of children, 1 = leaf with arg = payload_id; names concatenated), leaf sequences as one 4-bit
+ * IUPAC code per byte, cached counts per k as CSR over the payloads. */
+typedef struct {
+    const char *gene;
+    uint32_t root_rank; /* Rank discriminant, tax/clade.rs:93-104 */
+    uint64_t n_nodes;
+    const uint8_t *kind;
+    const uint64_t *arg;
+    const uint64_t *name_off; /* [n_nodes + 1] */
+    const char *names;
+    uint64_t n_payloads;
+    const uint8_t *seq_codes;
+    const uint64_t *seq_off; /* [n_payloads + 1] */
+    uint64_t n_k;
+    const uint64_t *k_precomputed;
+    const uint64_t *const *row_off; /* [n_k][n_payloads + 1] */
+    const uint64_t *const *keys;
+    const uint16_t *const *vals;
+    const float *const *rescale; /* [n_k][n_payloads] */
+} myo_store_desc;
+typedef struct myo_store_owned myo_store_owned;
+/* TaxTreeStore::to_bytes; `threads` plays rayon::current_num_threads() in the chunk-size rule (store.rs:363-367).
+ * *out is malloc'd (myo_bytes_free). 0 ok; -23 = no payloads (the reference panics) */
+int myo_store_encode(const myo_store_desc *d, int zstd_level, unsigned threads, uint8_t **out, uint64_t *out_len);
+/* TaxTreeStore::from_bytes; 0 ok, -30 bad magic (NotATaxTreeStore), -31 truncated, -32 zstd, -33 bincode */
+int myo_store_decode(const uint8_t *data, uint64_t len, myo_store_owned **out);
+/* fills `d` with pointers into `s`; the four arrays of n_k pointers are caller-provided */
+void myo_store_view(const myo_store_owned *s, myo_store_desc *d, const uint64_t **row_off, const uint64_t **keys,
+                    const uint16_t **vals, const float **rescale);
+void myo_store_free(myo_store_owned *s);
+/* decompressed section of a file: -1 header, 0 core, 1 + c = payload chunk c */
+int myo_store_section(const uint8_t *data, uint64_t len, int which, uint8_t **out, uint64_t *out_len);
+void myo_bytes_free(uint8_t *p);
+
 int myo_max_threads(void);
 /* omp_set_num_threads: overrides an inherited OMP_NUM_THREADS (torchrun exports 1) */
 void myo_set_num_threads(int n);

@@ -6,6 +6,7 @@ use core::ffi::{c_char, c_void};
 #[repr(C)] pub struct myrio_seqs { _p: [u8; 0] }
 #[repr(C)] pub struct myrio_svecs { _p: [u8; 0] }
 #[repr(C)] pub struct myrio_index { _p: [u8; 0] }
+#[repr(C)] pub struct myrio_store { _p: [u8; 0] }
 
 pub const MYRIO_OK: i32 = 0;
 pub const MYRIO_ERR_INVALID_K: i32 = 1;
@@ -79,6 +80,32 @@ unsafe extern "C" {
                                    keep: *mut u8, out: *mut *mut myrio_seqs) -> i32;
     pub fn myrio_seqs_count(s: *const myrio_seqs, n_seqs: *mut u64) -> i32;
     pub fn myrio_seqs_free(s: *mut myrio_seqs);
+
+    // .myrtree reader / writer (TaxTreeStore::to_bytes / from_bytes, tax/store.rs:342-454)
+    pub fn myrio_store_new(gene: *const c_char, root_rank: u32, n_nodes: u64, node_kind: *const u8, node_arg: *const u64,
+                           name_off: *const u64, names: *const c_char, n_payloads: u64, seq_words: *const u64,
+                           seq_word_off: *const u64, seq_base_off: *const u64, out: *mut *mut myrio_store) -> i32;
+    pub fn myrio_store_from_bytes(data: *const u8, len: u64, threads: u32, out: *mut *mut myrio_store) -> i32;
+    pub fn myrio_store_to_bytes(st: *const myrio_store, zstd_level: i32, threads: u32, out: *mut *mut u8, len: *mut u64) -> i32;
+    pub fn myrio_bytes_free(p: *mut u8);
+    pub fn myrio_store_save(st: *const myrio_store, path: *const c_char, zstd_level: i32, threads: u32) -> i32;
+    pub fn myrio_store_load(path: *const c_char, threads: u32, out: *mut *mut myrio_store) -> i32;
+    pub fn myrio_store_info(st: *const myrio_store, n_nodes: *mut u64, n_payloads: *mut u64, n_k: *mut u64,
+                            root_rank: *mut u32, names_bytes: *mut u64, gene_bytes: *mut u64, seq_words_total: *mut u64) -> i32;
+    pub fn myrio_store_tree(st: *const myrio_store, gene: *mut c_char, node_kind: *mut u8, node_arg: *mut u64,
+                            name_off: *mut u64, names: *mut c_char, k_precomputed: *mut u64) -> i32;
+    pub fn myrio_store_seqs(st: *const myrio_store, seq_words: *mut u64, seq_word_off: *mut u64, seq_base_off: *mut u64) -> i32;
+    pub fn myrio_store_counts_info(st: *const myrio_store, k_index: u64, nnz: *mut u64) -> i32;
+    pub fn myrio_store_counts_host(st: *const myrio_store, k_index: u64, row_off: *mut u64, keys: *mut u64,
+                                   counts: *mut u16, rescale: *mut f32) -> i32;
+    pub fn myrio_store_leaves(ctx: *mut myrio_ctx, st: *const myrio_store, out: *mut *mut myrio_seqs) -> i32;
+    pub fn myrio_store_counts(ctx: *mut myrio_ctx, st: *const myrio_store, k_index: u64, out: *mut *mut myrio_svecs) -> i32;
+    pub fn myrio_store_append_counts(ctx: *mut myrio_ctx, st: *mut myrio_store, k: u64, counts: *const myrio_svecs) -> i32;
+    pub fn myrio_store_overwrite_counts(ctx: *mut myrio_ctx, st: *mut myrio_store, k: u64, counts: *const myrio_svecs) -> i32;
+    pub fn myrio_store_append_counts_host(st: *mut myrio_store, k: u64, row_off: *const u64, keys: *const u64,
+                                          counts: *const u16, rescale: *const f32) -> i32;
+    pub fn myrio_store_shrink(st: *mut myrio_store) -> i32;
+    pub fn myrio_store_free(st: *mut myrio_store);
 
     pub fn myrio_comm_unique_id(id: *mut u8) -> i32;
     pub fn myrio_comm_init(ctx: *mut myrio_ctx, nranks: u32, rank: u32, id: *const u8) -> i32;

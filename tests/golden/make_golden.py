@@ -53,5 +53,36 @@ def main():
         print(out, "ok")
 
 
+def make_tiny_myrtree():
+    """tests/golden/tiny.myrtree: a three-leaf store WRITTEN BY THE LIBRARY's writer (myrio_store_to_bytes, zstd
+    level 6, one chunk), with the cached counts of k = 6 and 18 taken from the CPU oracle (32 resamples, seed 0:
+    leaf 1 holds ambiguity codes, so its counts depend on the documented counter-based resampler).  No GPU and no
+    reference checkout needed; tests/test_myrtree.py re-reads it and compares its sections with hand-assembled
+    bincode bytes."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(os.path.dirname(here))
+    sys.path.insert(0, root)
+    import numpy as np
+    import oracle
+    from myrio_b200 import api
+    iupac = {c: i for i, c in enumerate("-TGKCYSBAWRDMHVN")}
+    seqs = ["ACGTACGTTTGACCA", "ACGTACGTTTGACCANNRY-ACGT", "GGGG"]
+    codes = np.array([iupac[c] for s in seqs for c in s], np.uint8)
+    off = np.zeros(len(seqs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    f = api.MyrTreeFile.new("trnH-psbA", api.RANKS["Family"], [0, 0, 1, 1, 0, 1], [2, 2, 0, 1, 1, 2],
+                            ["f:Pinaceae", "g:Abies", "s:Abies alba", "s:Abies alba", "g:Picea", "s:Picea abies"],
+                            codes, off)
+    for k in (6, 18):
+        c = oracle.count_leaves(codes, off, k, 32)
+        f.append_counts_host(k, c.row_off, c.keys, c.vals, c.aux)
+    f.save_to_file(os.path.join(here, "tiny.myrtree"), 6, threads=1)
+    print("tiny.myrtree ok", os.path.getsize(os.path.join(here, "tiny.myrtree")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "myrtree":
+        make_tiny_myrtree()
+    else:
+        main()
+        make_tiny_myrtree()
