@@ -299,6 +299,52 @@ int32_t myrio_score_topx_sweep_async(myrio_ctx *ctx, const myrio_index *ix, uint
 int32_t myrio_topx_merge_composites_async(myrio_ctx *ctx, const uint64_t *d_in, uint32_t n_parts,
                                           uint64_t q_count, uint32_t x, float *d_scores_out,
                                           uint32_t *d_ids_out);
+/* ---- results: everything TaxTreeResults::from_compute_tree does after the score loop -------------
+ * (myrio-core/src/tax/results.rs:96-252): per-branch nb_leaves / mean / max over ALL leaves (:96-143),
+ * trim(max_amount_of_leaves_per_branch) (:257-307), cut(nb_best_analysis) (:310-381), softmax pooling per
+ * rank and confidence (:160-248).  Scores, branch statistics and the per-branch leaf selection run on the GPU
+ * (the score rows never leave it); the tree rebuild, pooling and confidence run in the library's host code
+ * in the reference's f32 order.  Ties (itertools' k_largest_by_key leaves them unspecified, and the
+ * reference's child order comes from a HashMap): equal scores keep the input order of the taxonomy. */
+typedef struct myrio_taxonomy myrio_taxonomy; /* the taxonomy of one tree, prepared for the results pass */
+typedef struct myrio_results myrio_results;   /* TaxTreeResults of one query */
+/* search parameters (myrio-cli/src/app/config.rs:158-175; defaults 15, 100, 2, 20, 1.1, 2.5, 0.9, 0.55) */
+typedef struct {
+    uint64_t max_amount_of_leaves_per_branch;
+    uint64_t nb_best_analysis;
+    float lambda_leaf, lambda_branch, mu, gamma, delta, epsilon;
+} myrio_results_params;
+/* flat PRE-ORDER taxonomy as in myrio_store_new (kind 0 = branch with arg children, 1 = leaf with arg =
+ * payload_id); every payload id at most once; root_rank = Rank discriminant of the root (tax/clade.rs:93-104) */
+int32_t myrio_taxonomy_create(myrio_ctx *ctx, uint32_t root_rank, uint64_t n_nodes, const uint8_t *node_kind,
+                              const uint64_t *node_arg, uint64_t n_payloads, myrio_taxonomy **out);
+void myrio_taxonomy_free(myrio_taxonomy *t);
+/* TaxTreeResults::from_compute_tree(query, ttcompute, similarity, ...) for queries [q_first, q_first+q_count):
+ * out[q] receives one handle per query.  `ix` must index the whole tree (leaf_id_base 0).  leaf_vecs = NULL
+ * scores over the index (Cosine / JacardTanimoto); with the normalised leaf vectors the scores come from the
+ * merge-join path (every Similarity, incl. Overlap; ix may then be NULL). */
+int32_t myrio_results_from_compute_tree(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *leaf_vecs,
+                                        myrio_taxonomy *taxonomy, const myrio_svecs *queries, uint64_t q_first,
+                                        uint64_t q_count, int32_t similarity, const myrio_results_params *params,
+                                        myrio_results **out);
+/* TaxTreeResults::cut(nb_best) on an analysed tree (run.rs:392: nb_best_display); force_keep is honoured */
+int32_t myrio_results_cut(const myrio_results *r, uint64_t nb_best, myrio_results **out);
+int32_t myrio_results_info(const myrio_results *r, uint64_t *n_nodes, uint64_t *n_payloads, uint32_t *root_rank);
+/* the tree as flat PRE-ORDER arrays (any pointer may be NULL): node_kind, node_arg (children | payload index),
+ * src_node (index of the node in the taxonomy: its name), BRes per node (branches: nb_leaves, mean, max,
+ * pool_score, confidence state 0 None / 1 Some(None) / 2 Some(Some(conf)), conf, force_keep), then per payload
+ * its score and its payload_id in the scored tree */
+int32_t myrio_results_tree(const myrio_results *r, uint8_t *node_kind, uint64_t *node_arg, uint64_t *src_node,
+                           uint64_t *nb_leaves, float *mean, float *max, float *pool_score, uint8_t *conf_state,
+                           float *conf, uint8_t *force_keep, float *payload_score, uint64_t *payload_src_id);
+void myrio_results_free(myrio_results *r);
+/* the "in-database confidence" of a run over several genes (myrio-cli/src/app/process/run.rs:405-466).  Per gene
+ * g the genus branches of its results tree, genus_off[g] .. genus_off[g+1]: name ids (equal id = equal genus name),
+ * pool scores, confidence state / value. */
+int32_t myrio_in_database_confidence(uint64_t n_genes, const uint64_t *genus_off, const uint64_t *name_id,
+                                     const float *pool_score, const uint8_t *conf_state, const float *conf,
+                                     float *out);
+
 /* ---- multi-GPU: one process per GPU, reference leaves sharded, queries replicated -------------
  * The reference is a single-process rayon program; these calls are what a multi-GPU binding of
  * TaxTreeResults::from_compute_tree (tax/results.rs:82-93 + cut(), :310-329) uses.

@@ -34,6 +34,8 @@ SYMBOLS = [
     "myrio_store_load", "myrio_store_info", "myrio_store_tree", "myrio_store_seqs", "myrio_store_counts_info",
     "myrio_store_counts_host", "myrio_store_leaves", "myrio_store_counts", "myrio_store_append_counts",
     "myrio_store_overwrite_counts", "myrio_store_append_counts_host", "myrio_store_shrink", "myrio_store_free",
+    "myrio_taxonomy_create", "myrio_taxonomy_free", "myrio_results_from_compute_tree", "myrio_results_cut",
+    "myrio_results_info", "myrio_results_tree", "myrio_results_free", "myrio_in_database_confidence",
     "myrio_comm_unique_id", "myrio_comm_init", "myrio_comm_destroy", "myrio_comm_info", "myrio_score_topx_sharded",
 ]
 
@@ -65,6 +67,16 @@ class ClusterParams(C.Structure):
         ("nb_iters_max", C.c_uint64),
         ("has_silhouette_trimming", C.c_int32),
         ("silhouette_trimming", C.c_float),
+    ]
+
+
+class ResultsParams(C.Structure):
+    """myrio_results_params (search parameters, myrio-cli/src/app/config.rs:158-175)"""
+    _fields_ = [
+        ("max_amount_of_leaves_per_branch", C.c_uint64),
+        ("nb_best_analysis", C.c_uint64),
+        ("lambda_leaf", C.c_float), ("lambda_branch", C.c_float), ("mu", C.c_float),
+        ("gamma", C.c_float), ("delta", C.c_float), ("epsilon", C.c_float),
     ]
 
 
@@ -149,6 +161,16 @@ def load() -> C.CDLL:
     L.myrio_store_shrink.argtypes = [vp]
     L.myrio_store_free.argtypes = [vp]
     L.myrio_store_free.restype = None
+    L.myrio_taxonomy_create.argtypes = [vp, u32, u64, vp, vp, u64, P(vp)]
+    L.myrio_taxonomy_free.argtypes = [vp]
+    L.myrio_taxonomy_free.restype = None
+    L.myrio_results_from_compute_tree.argtypes = [vp, vp, vp, vp, vp, u64, u64, i32, P(ResultsParams), P(vp)]
+    L.myrio_results_cut.argtypes = [vp, u64, P(vp)]
+    L.myrio_results_info.argtypes = [vp, P(u64), P(u64), P(u32)]
+    L.myrio_results_tree.argtypes = [vp] + [vp] * 12
+    L.myrio_results_free.argtypes = [vp]
+    L.myrio_results_free.restype = None
+    L.myrio_in_database_confidence.argtypes = [u64, vp, vp, vp, vp, vp, P(C.c_float)]
     L.myrio_comm_unique_id.argtypes = [vp]
     L.myrio_comm_init.argtypes = [vp, u32, u32, vp]
     L.myrio_comm_destroy.argtypes = [vp]
@@ -163,7 +185,7 @@ def load() -> C.CDLL:
         f = getattr(L, name)
         if name not in ("myrio_last_error", "myrio_ctx_destroy", "myrio_ctx_launch_count", "myrio_seqs_free",
                         "myrio_svecs_free", "myrio_index_free", "myrio_version", "myrio_ctx_stream",
-                        "myrio_bytes_free", "myrio_store_free"):
+                        "myrio_bytes_free", "myrio_store_free", "myrio_taxonomy_free", "myrio_results_free"):
             f.restype = i32
     _lib = L
     return L

@@ -575,6 +575,136 @@ class TaxTreeResults:
         return cls(scores, ts, ti)
 
 
+class Taxonomy:
+    """The taxonomy of one tree prepared for the results pass (myrio_taxonomy): flat pre-order node list."""
+
+    def __init__(self, ctx: Context, root_rank: int, node_kind, node_arg, n_payloads: int, names=None):
+        self.ctx = ctx
+        self.kind = np.ascontiguousarray(node_kind, np.uint8)
+        self.arg = np.ascontiguousarray(node_arg, np.uint64)
+        self.names, self.root_rank, self.n_payloads = names, root_rank, n_payloads
+        h = C.c_void_p()
+        _lib.check(ctx._L.myrio_taxonomy_create(ctx.h, root_rank, len(self.kind), _p(self.kind), _p(self.arg),
+                                                n_payloads, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.ctx._L.myrio_taxonomy_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+
+@dataclass
+class SearchParameters:
+    """myrio-cli/src/app/config.rs:158-175 ([search] of config_default.toml)"""
+    max_amount_of_leaves_per_branch: int = 15
+    nb_best_analysis: int = 100
+    lambda_leaf: float = 2.0
+    lambda_branch: float = 20.0
+    mu: float = 1.1
+    gamma: float = 2.5
+    delta: float = 0.9
+    epsilon: float = 0.55
+    nb_best_display: int = 7
+
+
+class BResTree:
+    """TaxTreeResults (tax/results.rs:59-61): TaxTreeCore<BRes, SimScore> of one query as flat pre-order arrays.
+    kind / arg / src_node per node; nb_leaves, mean, max, pool_score, conf_state (0 None, 1 Some(None),
+    2 Some(Some(conf))), conf, force_keep per node (branches); payload_score / payload_src_id per kept leaf."""
+
+    def __init__(self, L, handle):
+        self._L, self.h = L, handle
+        n, npay, rr = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        _lib.check(L.myrio_results_info(handle, C.byref(n), C.byref(npay), C.byref(rr)))
+        n, npay = int(n.value), int(npay.value)
+        self.root_rank = int(rr.value)
+        self.kind = np.zeros(n, np.uint8)
+        self.arg = np.zeros(n, np.uint64)
+        self.src_node = np.zeros(n, np.uint64)
+        self.nb_leaves = np.zeros(n, np.uint64)
+        self.mean, self.max, self.pool_score, self.conf = (np.zeros(n, np.float32) for _ in range(4))
+        self.conf_state = np.zeros(n, np.uint8)
+        self.force_keep = np.zeros(n, np.uint8)
+        self.payload_score = np.zeros(npay, np.float32)
+        self.payload_src_id = np.zeros(npay, np.uint64)
+        _lib.check(L.myrio_results_tree(handle, _p(self.kind), _p(self.arg), _p(self.src_node), _p(self.nb_leaves),
+                                        _p(self.mean), _p(self.max), _p(self.pool_score), _p(self.conf_state),
+                                        _p(self.conf), _p(self.force_keep),
+                                        _p(self.payload_score) if npay else None,
+                                        _p(self.payload_src_id) if npay else None))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self._L.myrio_results_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    def cut(self, nb_best: int) -> "BResTree":
+        """TaxTreeResults::cut (results.rs:310-381)"""
+        h = C.c_void_p()
+        _lib.check(self._L.myrio_results_cut(self.h, nb_best, C.byref(h)))
+        return BResTree(self._L, h)
+
+    def depths(self) -> np.ndarray:
+        d = np.zeros(len(self.kind), np.int64)
+        stack = []
+        for i in range(len(self.kind)):
+            d[i] = len(stack)
+            if stack:
+                stack[-1] -= 1
+            if self.kind[i] == 0:
+                stack.append(int(self.arg[i]))
+            while stack and stack[-1] == 0:
+                stack.pop()
+        return d
+
+    def branches_at_rank(self, rank: int) -> np.ndarray:
+        """gather_branches_at_rank (tax/core.rs:180-208): node indices of the branches at `rank`."""
+        return np.nonzero((self.kind == 0) & (self.depths() == self.root_rank - rank))[0]
+
+
+def results_from_compute_tree(queries: SFVecs, ttcompute: TaxTreeCompute, taxonomy: Taxonomy,
+                              similarity: int = SIM_COSINE, params: SearchParameters | None = None, *,
+                              q_first: int = 0, q_count: int | None = None) -> list:
+    """TaxTreeResults::from_compute_tree (tax/results.rs:68-252), the whole of it, for a batch of queries: scores of
+    every leaf, branch nb_leaves / mean / max, trim, cut, pooling, confidence.  Returns one BResTree per query."""
+    ctx = ttcompute.ctx
+    params = params or SearchParameters()
+    q_count = queries.n_rows - q_first if q_count is None else q_count
+    p = _lib.ResultsParams(params.max_amount_of_leaves_per_branch, params.nb_best_analysis, params.lambda_leaf,
+                           params.lambda_branch, params.mu, params.gamma, params.delta, params.epsilon)
+    out = (C.c_void_p * max(1, q_count))()
+    leaf_vecs = ttcompute.leaf_vectors().h if similarity == SIM_OVERLAP else None
+    _lib.check(ctx._L.myrio_results_from_compute_tree(ctx.h, ttcompute.h, leaf_vecs, taxonomy.h, queries.h, q_first,
+                                                      q_count, similarity, C.byref(p), out))
+    return [BResTree(ctx._L, C.c_void_p(out[i])) for i in range(q_count)]
+
+
+def in_database_confidence(per_gene: list) -> float:
+    """myrio-cli/src/app/process/run.rs:405-466.  per_gene: one (BResTree, names) pair per gene, `names` the node
+    names of that gene's taxonomy (indexed by src_node)."""
+    ids, off, name_id, pool, state, conf = {}, [0], [], [], [], []
+    for tree, names in per_gene:
+        for i in tree.branches_at_rank(RANKS["Genus"]):
+            name_id.append(ids.setdefault(names[int(tree.src_node[i])], len(ids)))
+            pool.append(tree.pool_score[i])
+            state.append(tree.conf_state[i])
+            conf.append(tree.conf[i])
+        off.append(len(name_id))
+    a = [np.ascontiguousarray(off, np.uint64), np.ascontiguousarray(name_id, np.uint64),
+         np.ascontiguousarray(pool, np.float32), np.ascontiguousarray(state, np.uint8),
+         np.ascontiguousarray(conf, np.float32)]
+    out = C.c_float(0)
+    _lib.check(_lib.load().myrio_in_database_confidence(len(per_gene), *[_p(x) for x in a], C.byref(out)))
+    return float(np.float32(out.value))
+
+
 @dataclass
 class ClusteringParameters:
     """myrio-core/src/clustering.rs:15-36 (defaults: myrio-cli/src/app/config.rs:107-119)"""

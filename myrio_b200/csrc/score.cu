@@ -988,6 +988,29 @@ void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries
     sync(ctx);
 }
 
+// Score rows of up to `q_max` queries starting at q_first, left ON THE DEVICE in ctx->score_rows ([qn][n_leaves],
+// payload order) for the results pass (results.cu).  Returns the number of queries done (bounded by the 2 GB
+// row budget and by what the hit lists allow).
+uint64_t score_rows_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
+                           uint64_t q_max, int32_t sim) {
+    check_queries(queries, q_first, q_max);
+    check_sim(sim);
+    const uint64_t L = ix->n_leaves;
+    reset_stats(ctx);
+    if (q_max == 0 || L == 0) return q_max;
+    const uint64_t budget = 1ull << 31;
+    uint64_t qn = std::min<uint64_t>(std::max<uint64_t>(1, budget / (L * 4)), q_max);
+    if (!ctx->plan) ctx->plan = plan_scratch_new();
+    Plan &pl = *static_cast<Plan *>(ctx->plan);
+    while (!build_plan(ctx, ix, queries, q_first, qn, PLAN_BUDGET, pl)) qn = (qn + 1) / 2;
+    ctx->score_rows.reserve(qn * L);
+    MYRIO_CK(cudaMemsetAsync(ctx->score_counters.p, 0, sizeof(unsigned long long), ctx->stream));
+    ScoreArgs a = base_args(ctx, ix, pl, qn);
+    a.scores = ctx->score_rows.p;
+    launch_score<false>(ctx, ix, a, sim, false);
+    return qn;
+}
+
 void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
                        uint64_t q_first, uint64_t q_count, uint32_t x, int32_t sim, float *d_top_scores,
                        uint32_t *d_top_ids, bool collect_stats) {
@@ -1275,6 +1298,18 @@ static void direct_rows(myrio_ctx *ctx, const myrio_svecs *leaves, const myrio_s
     a.ld = leaves->n_rows;
     a.transposed = true;  // out[query][leaf]
     launch_merge_pairs(ctx, a, "k4d_score_direct");
+}
+
+// the same through the merge-join path (every Similarity, incl. Overlap); rows left in ctx->score_rows
+uint64_t score_rows_direct_device(myrio_ctx *ctx, const myrio_svecs *leaves, const myrio_svecs *queries,
+                                  uint64_t q_first, uint64_t q_max, int32_t sim) {
+    check_direct(leaves, queries, q_first, q_max, sim);
+    const uint64_t L = leaves->n_rows;
+    if (q_max == 0 || L == 0) return q_max;
+    const uint64_t qn = std::min<uint64_t>(std::max<uint64_t>(1, (1ull << 31) / (L * 4)), q_max);
+    ctx->score_rows.reserve(qn * L);
+    direct_rows(ctx, leaves, queries, q_first, qn, sim, ctx->score_rows.p);
+    return qn;
 }
 
 void score_all_direct(myrio_ctx *ctx, const myrio_svecs *leaves, const myrio_svecs *queries, uint64_t q_first,

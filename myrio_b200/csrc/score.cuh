@@ -5,6 +5,10 @@
 namespace myrio {
 void score_all(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
                uint64_t q_count, int32_t sim, float *scores_host);
+uint64_t score_rows_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
+                           uint64_t q_max, int32_t sim);
+uint64_t score_rows_direct_device(myrio_ctx *ctx, const myrio_svecs *leaves, const myrio_svecs *queries,
+                                  uint64_t q_first, uint64_t q_max, int32_t sim);
 void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries,
                        uint64_t q_first, uint64_t q_count, uint32_t x, int32_t sim, float *d_top_scores,
                        uint32_t *d_top_ids, bool collect_stats);

@@ -23,9 +23,9 @@ def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
     src = os.path.join(_HERE, "myrio_oracle.c")
     hdr = os.path.join(_HERE, "myrio_oracle.h")
-    src2 = os.path.join(_HERE, "myrtree_oracle.c")
+    extra = [os.path.join(_HERE, f) for f in ("myrtree_oracle.c", "results_oracle.c", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in (src, src2, hdr)
+        os.path.getmtime(p) > os.path.getmtime(_LIB_PATH) for p in [src, hdr] + extra
     )
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
@@ -67,6 +67,19 @@ class _StoreDesc(C.Structure):
         ("seq_codes", C.c_void_p), ("seq_off", C.c_void_p), ("n_k", C.c_uint64), ("k_precomputed", C.c_void_p),
         ("row_off", C.c_void_p), ("keys", C.c_void_p), ("vals", C.c_void_p), ("rescale", C.c_void_p),
     ]
+
+
+class _ResultsParams(C.Structure):
+    _fields_ = [("max_amount_of_leaves_per_branch", C.c_uint64), ("nb_best_analysis", C.c_uint64),
+                ("lambda_leaf", C.c_float), ("lambda_branch", C.c_float), ("mu", C.c_float), ("gamma", C.c_float),
+                ("delta", C.c_float), ("epsilon", C.c_float)]
+
+
+class _ResultsView(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("n_payloads", C.c_uint64), ("kind", C.c_void_p), ("arg", C.c_void_p),
+                ("src", C.c_void_p), ("nb_leaves", C.c_void_p), ("mean", C.c_void_p), ("max", C.c_void_p),
+                ("pool_score", C.c_void_p), ("conf", C.c_void_p), ("conf_state", C.c_void_p),
+                ("force_keep", C.c_void_p), ("payload_score", C.c_void_p), ("payload_orig", C.c_void_p)]
 
 
 def lib():
@@ -143,6 +156,17 @@ def lib():
         L.myo_store_section.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.myo_bytes_free.restype = None
         L.myo_bytes_free.argtypes = [C.c_void_p]
+        L.myo_results_from_scores.restype = C.c_int
+        L.myo_results_from_scores.argtypes = [C.c_uint32, C.c_uint64, _u8p, _u64p, _f32p, C.c_uint64,
+                                              C.POINTER(_ResultsParams), C.POINTER(C.c_void_p)]
+        L.myo_results_cut.restype = C.c_int
+        L.myo_results_cut.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.myo_results_view.restype = None
+        L.myo_results_view.argtypes = [C.c_void_p, C.POINTER(_ResultsView)]
+        L.myo_results_free.restype = None
+        L.myo_results_free.argtypes = [C.c_void_p]
+        L.myo_in_database_confidence.restype = C.c_float
+        L.myo_in_database_confidence.argtypes = [C.c_uint64, _u64p, _u64p, _f32p, _u8p, _f32p]
         _lib = L
     return _lib
 
@@ -544,3 +568,67 @@ def store_section(data: bytes, which: int) -> bytes:
         return C.string_at(out, n.value)
     finally:
         L.myo_bytes_free(out)
+
+
+# ------------------------------------------------------------------ results (results_oracle.c)
+
+class ResultsTree:
+    """TaxTreeResults of one query (tax/results.rs): same fields as myrio_b200.api.BResTree."""
+
+    def __init__(self, handle):
+        self.h = handle
+        v = _ResultsView()
+        lib().myo_results_view(handle, C.byref(v))
+        n, npay = int(v.n_nodes), int(v.n_payloads)
+
+        def arr(ptr, cnt, dt):
+            if cnt == 0 or not ptr:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(cnt,)).copy()
+        self.kind, self.arg, self.src_node = arr(v.kind, n, np.uint8), arr(v.arg, n, np.uint64), arr(v.src, n, np.uint64)
+        self.nb_leaves = arr(v.nb_leaves, n, np.uint64)
+        self.mean, self.max = arr(v.mean, n, np.float32), arr(v.max, n, np.float32)
+        self.pool_score, self.conf = arr(v.pool_score, n, np.float32), arr(v.conf, n, np.float32)
+        self.conf_state, self.force_keep = arr(v.conf_state, n, np.uint8), arr(v.force_keep, n, np.uint8)
+        self.payload_score = arr(v.payload_score, npay, np.float32)
+        self.payload_src_id = arr(v.payload_orig, npay, np.uint64)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().myo_results_free(self.h)
+            self.h = None
+        except Exception:
+            pass
+
+    def cut(self, nb_best: int) -> "ResultsTree":
+        h = C.c_void_p()
+        e = lib().myo_results_cut(self.h, nb_best, C.byref(h))
+        if e:
+            raise ValueError(f"oracle results_cut error {e}")
+        return ResultsTree(h)
+
+
+def results_from_scores(root_rank: int, kind, arg, scores, max_amount_of_leaves_per_branch: int = 15,
+                        nb_best_analysis: int = 100, lambda_leaf: float = 2.0, lambda_branch: float = 20.0,
+                        mu: float = 1.1, gamma: float = 2.5, delta: float = 0.9, epsilon: float = 0.55) -> ResultsTree:
+    """TaxTreeResults::from_compute_tree after the score loop (tax/results.rs:96-252)."""
+    kind = np.ascontiguousarray(kind, np.uint8)
+    arg = np.ascontiguousarray(arg, np.uint64)
+    scores = np.ascontiguousarray(scores, np.float32)
+    p = _ResultsParams(max_amount_of_leaves_per_branch, nb_best_analysis, lambda_leaf, lambda_branch, mu, gamma, delta,
+                       epsilon)
+    h = C.c_void_p()
+    e = lib().myo_results_from_scores(root_rank, len(kind), kind, arg, scores if len(scores) else np.zeros(1, np.float32),
+                                      len(scores), C.byref(p), C.byref(h))
+    if e:
+        raise ValueError(f"oracle results_from_scores error {e}")
+    return ResultsTree(h)
+
+
+def in_database_confidence(genus_off, name_id, pool_score, conf_state, conf) -> np.float32:
+    """myrio-cli/src/app/process/run.rs:405-466"""
+    a = (np.ascontiguousarray(genus_off, np.uint64), np.ascontiguousarray(name_id, np.uint64),
+         np.ascontiguousarray(pool_score, np.float32), np.ascontiguousarray(conf_state, np.uint8),
+         np.ascontiguousarray(conf, np.float32))
+    return np.float32(lib().myo_in_database_confidence(len(a[0]) - 1, *a))

@@ -209,6 +209,39 @@ void myo_store_free(myo_store_owned *s);
 int myo_store_section(const uint8_t *data, uint64_t len, int which, uint8_t **out, uint64_t *out_len);
 void myo_bytes_free(uint8_t *p);
 
+/* ---- host post-processing after the score loop (results_oracle.c): tax/results.rs:96-381,
+ * myrio-cli/src/app/process/run.rs:405-466.  Trees are flat PRE-ORDER node lists like the .myrtree ones. */
+typedef struct { /* myrio-cli/src/app/config.rs:158-175 (defaults 15, 100, 2, 20, 1.1, 2.5, 0.9, 0.55) */
+    uint64_t max_amount_of_leaves_per_branch;
+    uint64_t nb_best_analysis;
+    float lambda_leaf, lambda_branch, mu, gamma, delta, epsilon;
+} myo_results_params;
+typedef struct myo_results myo_results;
+typedef struct {
+    uint64_t n_nodes, n_payloads;
+    const uint8_t *kind;      /* 0 branch, 1 leaf */
+    const uint64_t *arg;      /* children count | payload id in THIS results tree */
+    const uint64_t *src;      /* node index in the input tree (names live there) */
+    const uint64_t *nb_leaves;
+    const float *mean, *max, *pool_score, *conf;
+    const uint8_t *conf_state; /* 0 None, 1 Some(None), 2 Some(Some(conf)) */
+    const uint8_t *force_keep;
+    const float *payload_score;
+    const uint64_t *payload_orig; /* payload id in the input tree */
+} myo_results_view_t;
+/* TaxTreeResults::from_compute_tree from the scores on (results.rs:96-252): branch statistics over all leaves,
+ * trim, cut, pooling, confidence.  0 ok; -40 non-finite pool score (the reference panics), -41 empty result */
+int myo_results_from_scores(uint32_t root_rank, uint64_t n_nodes, const uint8_t *kind, const uint64_t *arg,
+                            const float *simscores, uint64_t n_payloads, const myo_results_params *p,
+                            myo_results **out);
+/* TaxTreeResults::cut on an analysed tree (results.rs:310-381; run.rs:392) */
+int myo_results_cut(const myo_results *r, uint64_t nb_best, myo_results **out);
+void myo_results_view(const myo_results *r, myo_results_view_t *v);
+void myo_results_free(myo_results *r);
+/* run.rs:405-466 in-database confidence; per gene the genus branches (name ids, pool scores, confidences) */
+float myo_in_database_confidence(uint64_t n_genes, const uint64_t *genus_off, const uint64_t *name_id,
+                                 const float *pool_score, const uint8_t *conf_state, const float *conf);
+
 int myo_max_threads(void);
 /* omp_set_num_threads: overrides an inherited OMP_NUM_THREADS (torchrun exports 1) */
 void myo_set_num_threads(int n);

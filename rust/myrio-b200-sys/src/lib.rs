@@ -7,6 +7,22 @@ use core::ffi::{c_char, c_void};
 #[repr(C)] pub struct myrio_svecs { _p: [u8; 0] }
 #[repr(C)] pub struct myrio_index { _p: [u8; 0] }
 #[repr(C)] pub struct myrio_store { _p: [u8; 0] }
+#[repr(C)] pub struct myrio_taxonomy { _p: [u8; 0] }
+#[repr(C)] pub struct myrio_results { _p: [u8; 0] }
+
+/// search parameters (myrio-cli/src/app/config.rs:158-175)
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct myrio_results_params {
+    pub max_amount_of_leaves_per_branch: u64,
+    pub nb_best_analysis: u64,
+    pub lambda_leaf: f32,
+    pub lambda_branch: f32,
+    pub mu: f32,
+    pub gamma: f32,
+    pub delta: f32,
+    pub epsilon: f32,
+}
 
 pub const MYRIO_OK: i32 = 0;
 pub const MYRIO_ERR_INVALID_K: i32 = 1;
@@ -106,6 +122,24 @@ unsafe extern "C" {
                                           counts: *const u16, rescale: *const f32) -> i32;
     pub fn myrio_store_shrink(st: *mut myrio_store) -> i32;
     pub fn myrio_store_free(st: *mut myrio_store);
+
+    // TaxTreeResults::from_compute_tree after the score loop (tax/results.rs:96-381), run.rs:405-466
+    pub fn myrio_taxonomy_create(ctx: *mut myrio_ctx, root_rank: u32, n_nodes: u64, node_kind: *const u8,
+                                 node_arg: *const u64, n_payloads: u64, out: *mut *mut myrio_taxonomy) -> i32;
+    pub fn myrio_taxonomy_free(t: *mut myrio_taxonomy);
+    pub fn myrio_results_from_compute_tree(ctx: *mut myrio_ctx, ix: *const myrio_index, leaf_vecs: *const myrio_svecs,
+                                           taxonomy: *mut myrio_taxonomy, queries: *const myrio_svecs, q_first: u64,
+                                           q_count: u64, similarity: i32, params: *const myrio_results_params,
+                                           out: *mut *mut myrio_results) -> i32;
+    pub fn myrio_results_cut(r: *const myrio_results, nb_best: u64, out: *mut *mut myrio_results) -> i32;
+    pub fn myrio_results_info(r: *const myrio_results, n_nodes: *mut u64, n_payloads: *mut u64, root_rank: *mut u32) -> i32;
+    pub fn myrio_results_tree(r: *const myrio_results, node_kind: *mut u8, node_arg: *mut u64, src_node: *mut u64,
+                              nb_leaves: *mut u64, mean: *mut f32, max: *mut f32, pool_score: *mut f32,
+                              conf_state: *mut u8, conf: *mut f32, force_keep: *mut u8, payload_score: *mut f32,
+                              payload_src_id: *mut u64) -> i32;
+    pub fn myrio_results_free(r: *mut myrio_results);
+    pub fn myrio_in_database_confidence(n_genes: u64, genus_off: *const u64, name_id: *const u64, pool_score: *const f32,
+                                        conf_state: *const u8, conf: *const f32, out: *mut f32) -> i32;
 
     pub fn myrio_comm_unique_id(id: *mut u8) -> i32;
     pub fn myrio_comm_init(ctx: *mut myrio_ctx, nranks: u32, rank: u32, id: *const u8) -> i32;
