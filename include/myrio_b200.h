@@ -20,7 +20,13 @@
  *     (myrio_svecs, myrio_index) and are fetched with *_info + *_download.
  *   - a myrio_ctx is bound to one GPU and one stream and is NOT thread-safe;
  *     distinct contexts may be used concurrently.  Calls return after the
- *     work has completed unless the name ends in `_async`.
+ *     work has completed unless the name ends in `_async`: those leave their
+ *     kernels queued on the context's stream (results are valid after
+ *     myrio_ctx_sync or after later work on that stream); the scoring ones may
+ *     still synchronise the stream internally while they size their hit lists.
+ *   - scratch comes from the device's default stream-ordered memory pool, whose
+ *     release threshold myrio_ctx_create raises so that freed scratch stays cached
+ *     (process-wide for that device; MYRIO_POOL_RELEASE_THRESHOLD_MB bounds it).
  *   - there is no CPU fallback: without a CUDA device myrio_ctx_create fails.
  *
  * Encodings (bio-seq 0.14.2, the reference's sequence crate):
@@ -424,6 +430,14 @@ int32_t myrio_cluster_sharded(myrio_ctx *ctx, const myrio_seqs *reads, const myr
  * fingerprint; over the f32 batch of local fingerprints it returns the global one. */
 int32_t myrio_compute_cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts,
                                        const uint64_t *member_ids, uint64_t m, myrio_svecs **out);
+/* The re-weighting of a tree's local fingerprints before the second clustering pass of `myrio run`
+ * (myrio-cli/src/app/process/run.rs:243-262): out = normalize_l2(sum_i local_i * exp(1 + alpha *
+ * simfunc(local_i, naive_query))), the sum taken in row order.  local_fingerprints: the normalised local
+ * fingerprints (rows); naive_query: the centroid of the pass-1 cluster (a 1-row batch); alpha:
+ * config.fingerprint.alpha (default 2.5, config.rs:137).  out: a 1-row batch = the cluster's initial centroid. */
+int32_t myrio_reweight_fingerprints(myrio_ctx *ctx, const myrio_svecs *local_fingerprints,
+                                    const myrio_svecs *naive_query, int32_t similarity, float alpha,
+                                    myrio_svecs **out);
 /* the reads x reads (or reads x centroids) similarity tile used by the clustering
  * loop: out[i*n_cols + j] = simfunc(rows_i, cols_j), rows/cols pre-normalised */
 int32_t myrio_pairwise(myrio_ctx *ctx, const myrio_svecs *rows, const myrio_svecs *cols,

@@ -29,7 +29,7 @@ SYMBOLS = [
     "myrio_score_topx_direct_async", "myrio_score_topx_seed_async", "myrio_score_topx_sweep_async",
     "myrio_topx_merge_composites_async", "myrio_topx_merge_async", "myrio_score_stats", "myrio_cluster",
     "myrio_cluster_sharded",
-    "myrio_compute_cluster_centroid", "myrio_pairwise", "myrio_cluster_stats", "myrio_svecs_device_ptrs",
+    "myrio_compute_cluster_centroid", "myrio_reweight_fingerprints", "myrio_pairwise", "myrio_cluster_stats", "myrio_svecs_device_ptrs",
     "myrio_store_new", "myrio_store_from_bytes", "myrio_store_to_bytes", "myrio_bytes_free", "myrio_store_save",
     "myrio_store_load", "myrio_store_info", "myrio_store_tree", "myrio_store_seqs", "myrio_store_counts_info",
     "myrio_store_counts_host", "myrio_store_leaves", "myrio_store_counts", "myrio_store_append_counts",
@@ -179,6 +179,7 @@ def load() -> C.CDLL:
     L.myrio_cluster.argtypes = [vp, vp, P(ClusterParams), vp, vp, P(u32), vp]
     L.myrio_cluster_sharded.argtypes = [vp, vp, P(ClusterParams), vp, P(Shard), vp, P(u32), vp]
     L.myrio_compute_cluster_centroid.argtypes = [vp, vp, vp, u64, P(vp)]
+    L.myrio_reweight_fingerprints.argtypes = [vp, vp, vp, i32, C.c_float, P(vp)]
     L.myrio_pairwise.argtypes = [vp, vp, vp, i32, vp]
     L.myrio_cluster_stats.argtypes = [vp, P(u64), P(u64)]
     for name in SYMBOLS:

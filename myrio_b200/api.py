@@ -777,6 +777,27 @@ def compute_cluster_centroid(counts: SFVecs, member_ids) -> SFVecs:
     return SFVecs(counts.ctx, h)
 
 
+def stack_rows(ctx: Context, vecs: list) -> SFVecs:
+    """One batch from several 1-row batches (e.g. the local fingerprints of a tree)."""
+    rows = [v.download(aux=False) for v in vecs]
+    ro = np.zeros(len(rows) + 1, np.uint64)
+    ro[1:] = np.cumsum([len(r[1]) for r in rows])
+    keys = np.concatenate([r[1] for r in rows]) if rows else np.zeros(0, np.uint64)
+    vals = np.concatenate([r[2] for r in rows]) if rows else np.zeros(0, np.float32)
+    return SFVecs.upload(ctx, ro, keys, vals)
+
+
+def reweight_fingerprints(local_fingerprints: SFVecs, naive_query: SFVecs, similarity: int = SIM_COSINE,
+                          alpha: float = 2.5) -> SFVecs:
+    """myrio-cli/src/app/process/run.rs:243-262: the initial centroid of the second clustering pass,
+    normalize_l2(sum_i local_i * exp(1 + alpha * simfunc(local_i, naive_query)))."""
+    h = C.c_void_p()
+    ctx = local_fingerprints.ctx
+    _lib.check(ctx._L.myrio_reweight_fingerprints(ctx.h, local_fingerprints.h, naive_query.h, similarity,
+                                                  C.c_float(alpha), C.byref(h)))
+    return SFVecs(ctx, h)
+
+
 def pairwise(rows: SFVecs, cols: SFVecs, similarity: int = SIM_COSINE) -> np.ndarray:
     """The reads x reads / reads x centroids similarity tile of the clustering loop."""
     out = np.zeros((rows.n_rows, cols.n_rows), np.float32)

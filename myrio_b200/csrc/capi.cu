@@ -44,10 +44,14 @@ int32_t myrio_ctx_create(int32_t device, myrio_ctx **out) {
         ctx->sm_count = prop.multiProcessorCount;
         ctx->smem_optin = prop.sharedMemPerBlockOptin;
         MYRIO_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-        {  // keep freed scratch cached in the pool instead of returning it to the OS
+        {  // Keep freed scratch cached in the device's default stream-ordered pool instead of returning it to
+           // the driver at every synchronisation (a steady-state step then never calls the allocator).  This is a
+           // PROCESS-WIDE setting of that pool: MYRIO_POOL_RELEASE_THRESHOLD_MB bounds what stays cached (0 = the
+           // CUDA default, release everything at the next synchronisation; unset = keep everything).
             cudaMemPool_t pool;
             MYRIO_CK(cudaDeviceGetDefaultMemPool(&pool, device));
             uint64_t threshold = UINT64_MAX;
+            if (const char *e = getenv("MYRIO_POOL_RELEASE_THRESHOLD_MB")) threshold = strtoull(e, nullptr, 10) << 20;
             MYRIO_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
         }
         ScopedCtx sc(ctx.get());
@@ -581,6 +585,16 @@ int32_t myrio_compute_cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts
         if (!ctx || !counts || !out || (!member_ids && m)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
         ScopedCtx sc(ctx);
         *out = cluster_centroid(ctx, counts, member_ids, m);
+    });
+}
+
+int32_t myrio_reweight_fingerprints(myrio_ctx *ctx, const myrio_svecs *local_fingerprints,
+                                    const myrio_svecs *naive_query, int32_t similarity, float alpha,
+                                    myrio_svecs **out) {
+    return guarded([&] {
+        if (!ctx || !local_fingerprints || !naive_query || !out) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        *out = reweight_fingerprints(ctx, local_fingerprints, naive_query, similarity, alpha);
     });
 }
 

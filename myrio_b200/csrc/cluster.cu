@@ -1330,8 +1330,9 @@ __global__ void __launch_bounds__(256) cc_scale_kernel(float *__restrict__ v, ui
 }
 
 myrio_svecs *cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts, const uint64_t *member_ids,
-                              uint64_t m) {
+                              uint64_t m, const float *d_row_scale) {
     const bool leaf_counts = counts->vtype == MYRIO_VAL_U16;
+    if (leaf_counts && d_row_scale) fail(MYRIO_ERR_BAD_ARG, "explicit row factors go with f32 batches");
     if (leaf_counts && counts->aux_kind != 2)
         fail(MYRIO_ERR_BAD_ARG, "u16 counts need their rescale factors (a myrio_count_leaves batch)");
     for (uint64_t i = 0; i < m; ++i)
@@ -1359,8 +1360,8 @@ myrio_svecs *cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts, const u
                          k1.p, v1.p);
         else
             MYRIO_LAUNCH(ctx, "cc_gather", gather_members_kernel<float>, (unsigned)((m + 7) / 8), 256, 0,
-                         counts->row_off.p, counts->keys.p, counts->vals_f32.p, (const float *)nullptr, d_ids.p,
-                         d_dst.p, m, k1.p, v1.p);
+                         counts->row_off.p, counts->keys.p, counts->vals_f32.p, d_row_scale, d_ids.p, d_dst.p, m,
+                         k1.p, v1.p);
         const bool in_tmp = radix_sort_pairs_raw(ctx, k1.p, v1.p, k2.p, v2.p, total, 64, hist, offs);
         const uint64_t *sk = in_tmp ? k2.p : k1.p, *sv = in_tmp ? v2.p : v1.p;
         const unsigned g = (unsigned)((total + 255) / 256);
@@ -1386,6 +1387,29 @@ myrio_svecs *cluster_centroid(myrio_ctx *ctx, const myrio_svecs *counts, const u
     h2d(ctx, out->row_off.p, h_ro, 2);
     sync(ctx);
     return out.release();
+}
+
+// The re-weighting of the local fingerprints before the second clustering pass
+// (myrio-cli/src/app/process/run.rs:243-262): score_i = simfunc(local_i, naive_query) (pre-normalised),
+// adjustor_i = exp(1 + alpha * score_i), result = normalize_l2(sum_i local_i * adjustor_i).  The similarities
+// and the weighted sparse sum run on the device; the n_local scalars exp() go through libm's expf on the host,
+// which is what Rust's f32::exp calls.
+myrio_svecs *reweight_fingerprints(myrio_ctx *ctx, const myrio_svecs *local, const myrio_svecs *naive_query,
+                                   int32_t sim, float alpha) {
+    if (local->vtype != MYRIO_VAL_F32 || naive_query->vtype != MYRIO_VAL_F32)
+        fail(MYRIO_ERR_BAD_ARG, "fingerprints and the query are f32 (normalised) vectors");
+    if (naive_query->n_rows != 1) fail(MYRIO_ERR_BAD_ARG, "the naive query is one vector (a 1-row batch)");
+    const uint64_t n = local->n_rows;
+    std::vector<float> score(std::max<uint64_t>(n, 1)), adjustor(std::max<uint64_t>(n, 1));
+    if (n) pairwise(ctx, local, naive_query, sim, score.data());
+    for (uint64_t i = 0; i < n; ++i) adjustor[i] = expf(1.0f + alpha * score[i]);  // :255
+    DevBuf<float> d_adj(std::max<uint64_t>(n, 1));
+    h2d(ctx, d_adj.p, adjustor.data(), n);
+    std::vector<uint64_t> ids(n);
+    std::iota(ids.begin(), ids.end(), 0ull);
+    myrio_svecs *out = cluster_centroid(ctx, local, ids.data(), n, d_adj.p);  // :257-260 sum + into_normalized_l2
+    sync(ctx);
+    return out;
 }
 
 // --------------------------------------------------------------- pairwise

@@ -130,6 +130,11 @@ def lib():
         L.myo_cluster.argtypes = [_u64p, _u64p, _f32p, _u64p, C.c_size_t,
                                   C.POINTER(_ClusterParams), _i32p, C.POINTER(C.c_uint32),
                                   C.c_void_p]
+        L.myo_sort_reduce_pairs_f32.restype = C.c_size_t
+        L.myo_sort_reduce_pairs_f32.argtypes = [_u64p, _f32p, C.c_size_t, _u64p, _f32p]
+        L.myo_reweight_fingerprints.restype = C.c_size_t
+        L.myo_reweight_fingerprints.argtypes = [C.c_int, _u64p, _u64p, _f32p, C.c_size_t, _u64p, _f32p, C.c_size_t,
+                                                C.c_float, _u64p, _f32p]
         L.myo_set_silhouette_sample.restype = None
         L.myo_set_silhouette_sample.argtypes = [C.c_void_p]
         L.myo_pairwise.restype = None
@@ -247,6 +252,31 @@ def fastq_preprocess(seq_ascii: np.ndarray, qual_ascii: np.ndarray, base_off: np
         raise ValueError(f"non-ACGT base in record {-k - 1}")
     koff = koff[:k + 1]
     return codes[:int(koff[-1])], qual[:int(koff[-1])], koff, keep[:n]
+
+
+def sort_reduce_pairs_f32(pairs):
+    """data/sparse.rs:274-313 from_unsorted_pairs."""
+    k = np.array([p[0] for p in pairs], np.uint64)
+    v = np.array([p[1] for p in pairs], np.float32)
+    ko = np.zeros(max(1, len(k)), np.uint64)
+    vo = np.zeros(max(1, len(k)), np.float32)
+    if len(k) == 0:
+        return ko[:0], vo[:0]
+    d = lib().myo_sort_reduce_pairs_f32(k, v, len(k), ko, vo)
+    return ko[:d], vo[:d]
+
+
+def reweight_fingerprints(local: "Csr", qk, qv, alpha: float = 2.5, sim: int = SIM_COSINE):
+    """myrio-cli/src/app/process/run.rs:243-262"""
+    qk, qv, qn = _kv(qk, qv)
+    nnz = int(local.row_off[-1])
+    ck = np.zeros(nnz + 1, np.uint64)
+    cv = np.zeros(nnz + 1, np.float32)
+    n = lib().myo_reweight_fingerprints(sim, np.ascontiguousarray(local.row_off, np.uint64),
+                                        np.ascontiguousarray(local.keys, np.uint64) if nnz else np.zeros(1, np.uint64),
+                                        np.ascontiguousarray(local.vals, np.float32) if nnz else np.zeros(1, np.float32),
+                                        local.n_rows, qk, qv, qn, alpha, ck, cv)
+    return ck[:n], cv[:n]
 
 
 def fasta_to_iupac(seq_ascii: np.ndarray, base_off: np.ndarray):

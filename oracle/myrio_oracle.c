@@ -935,6 +935,64 @@ static size_t cl_argmax(const cl_ctx *cx, const cluster_t *cl, size_t nc, size_t
     return best;
 }
 
+/* data/sparse.rs:274-313 from_unsorted_pairs: sort by key (unstable; equal keys are summed, so the order among
+ * them only matters for f32 rounding -- this restatement keeps the input order), values of equal keys added.
+ * keys_out / vals_out capacity n; returns the number of distinct keys. */
+size_t myo_sort_reduce_pairs_f32(const uint64_t *keys, const float *vals, size_t n, uint64_t *keys_out, float *vals_out) {
+    if (n == 0) return 0;
+    size_t *ord = (size_t *)malloc(n * sizeof(size_t));
+    for (size_t i = 0; i < n; ++i) ord[i] = i;
+    for (size_t i = 1; i < n; ++i) { /* stable insertion sort */
+        size_t v = ord[i], j = i;
+        while (j > 0 && keys[ord[j - 1]] > keys[v]) {
+            ord[j] = ord[j - 1];
+            --j;
+        }
+        ord[j] = v;
+    }
+    size_t idx = 0;
+    uint64_t prev_key = keys[ord[0]];
+    float val_to_write = vals[ord[0]];
+    keys_out[0] = prev_key;
+    for (size_t i = 1; i < n; ++i) {
+        uint64_t key = keys[ord[i]];
+        float val = vals[ord[i]];
+        if (prev_key != key) {
+            vals_out[idx] = val_to_write;
+            idx += 1;
+            keys_out[idx] = key;
+            val_to_write = val;
+            prev_key = key;
+        } else {
+            val_to_write = val_to_write + val;
+        }
+    }
+    vals_out[idx] = val_to_write;
+    free(ord);
+    return idx + 1;
+}
+
+/* myrio-cli/src/app/process/run.rs:243-262: re-weighted local fingerprints -> initial centroid of pass 2.
+ * local: CSR of n normalised fingerprints; query: the naive centroid.  out capacity: local nnz. */
+size_t myo_reweight_fingerprints(int sim, const uint64_t *row_off, const uint64_t *keys, const float *vals, size_t n,
+                                 const uint64_t *qk, const float *qv, size_t qn, float alpha, uint64_t *ck,
+                                 float *cv) {
+    size_t nnz = (size_t)row_off[n];
+    float *scaled = (float *)malloc((nnz + 1) * sizeof(float));
+    uint64_t *ids = (uint64_t *)malloc((n + 1) * sizeof(uint64_t));
+    for (size_t i = 0; i < n; ++i) {
+        size_t b = (size_t)row_off[i], e = (size_t)row_off[i + 1];
+        float score = myo_similarity(sim, 1, keys + b, vals + b, e - b, qk, qv, qn); /* simfunc(local, naive_query) */
+        float adjustor = expf(1.0f + alpha * score);
+        for (size_t j = b; j < e; ++j) scaled[j] = vals[j] * adjustor; /* local_fingerprint * adjustor */
+        ids[i] = i;
+    }
+    size_t out = myo_centroid(row_off, keys, scaled, ids, n, ck, cv); /* .sum::<SFVec>().into_normalized_l2() */
+    free(scaled);
+    free(ids);
+    return out;
+}
+
 /* Full-size checks (tests/test_gpu_configs.py): the O(N^2) silhouette pass of a 100 k-read batch takes
  * the CPU half an hour, so a test may restrict it to a SAMPLE of the reads.  With a mask set
  * (mask[read] != 0 = compute), inner() (:323-336) runs for the masked reads only -- same code, same f32

@@ -148,6 +148,13 @@ int myo_cluster(const uint64_t *row_off, const uint64_t *keys, const float *vals
                 const uint64_t *nb_hck, size_t n_reads, const myo_cluster_params *p,
                 int32_t *assign_out, uint32_t *n_iters_out, float *sil_out);
 
+/* data/sparse.rs:274-313 from_unsorted_pairs (f32 values) */
+size_t myo_sort_reduce_pairs_f32(const uint64_t *keys, const float *vals, size_t n, uint64_t *keys_out, float *vals_out);
+/* myrio-cli/src/app/process/run.rs:243-262 (fingerprint re-weighting); out capacity = local nnz */
+size_t myo_reweight_fingerprints(int sim, const uint64_t *row_off, const uint64_t *keys, const float *vals, size_t n,
+                                 const uint64_t *qk, const float *qv, size_t qn, float alpha, uint64_t *ck,
+                                 float *cv);
+
 /* test hook for full-size checks: restrict the silhouette pass of myo_cluster to the reads with
  * mask[read] != 0 (no trimming then); NULL = the reference behaviour */
 void myo_set_silhouette_sample(const uint8_t *mask);

@@ -141,6 +141,10 @@ unsafe extern "C" {
     pub fn myrio_in_database_confidence(n_genes: u64, genus_off: *const u64, name_id: *const u64, pool_score: *const f32,
                                         conf_state: *const u8, conf: *const f32, out: *mut f32) -> i32;
 
+    pub fn myrio_reweight_fingerprints(ctx: *mut myrio_ctx, local_fingerprints: *const myrio_svecs,
+                                       naive_query: *const myrio_svecs, similarity: i32, alpha: f32,
+                                       out: *mut *mut myrio_svecs) -> i32;
+
     pub fn myrio_comm_unique_id(id: *mut u8) -> i32;
     pub fn myrio_comm_init(ctx: *mut myrio_ctx, nranks: u32, rank: u32, id: *const u8) -> i32;
     pub fn myrio_comm_destroy(ctx: *mut myrio_ctx) -> i32;

@@ -6,14 +6,13 @@ composed from the C-ABI calls the way INTEGRATION.md wires them into the referen
   run      : fingerprints at cluster_k=6 (explicit leaf samples)           (tax/compute.rs:51-77)
              pass 1  cluster(reads, init = global fingerprints)            (run.rs:216-231)
              naive centroids of the pass-1 clusters at k=6                 (run.rs:231-241)
-             pass 2  cluster(reads, init = those centroids, silhouette)    (run.rs:264-276)
+             local fingerprints re-weighted by exp(1 + alpha * sim)        (run.rs:243-262)
+             pass 2  cluster(reads, init = re-weighted fingerprints, silhouette) (run.rs:264-276)
              per cluster: read counts at search_k=18, centroid = the query (run.rs:301-309)
              per (tree, query): all leaf scores + cut(100)                 (tax/results.rs:82-93, 310-329)
 
-One stated simplification: run.rs re-weights the LOCAL fingerprints with exp(1 + alpha * sim) on the host
-before pass 2 (run.rs:245-262, libm `exp`); here pass 2 starts from the naive centroids.  Everything the
-device computes is compared with the oracle: counts, fingerprints, both cluster assignments, silhouette
-scores, queries, every score row and the top-100."""
+Everything the device computes is compared with the oracle: counts, fingerprints (local, global and
+re-weighted), both cluster assignments, silhouette scores, queries, every score row and the top-100."""
 import numpy as np
 import pytest
 
@@ -64,9 +63,9 @@ def test_config1_tree_new_and_run_match_oracle():
         o_leaves.append(oracle.normalize(ol))
 
     # ---- fingerprints at cluster_k = 6
-    g_init_rows, o_init_rows = [], []
+    g_init_rows, o_init_rows, g_locals, o_locals = [], [], [], []
     for t, st, smp in zip(trees, stores, samples):
-        _, glob = api.fingerprints(st, 6, smp, 32)
+        loc, glob = api.fingerprints(st, 6, smp, 32)
         _, gk, gv, _ = glob.download(aux=False)
         oc6 = oracle.count_leaves(synth.tree_to_iupac(t), t.base_off, 6, 32)
         scaled = oracle.Csr(oc6.row_off, oc6.keys, (oc6.vals.astype(np.float32) * np.repeat(
@@ -77,6 +76,8 @@ def test_config1_tree_new_and_run_match_oracle():
         assert (gk == ek).all() and (bits(gv) == bits(ev)).all()
         g_init_rows.append((gk, gv))
         o_init_rows.append((ek, ev))
+        g_locals.append(api.stack_rows(ctx, loc))
+        o_locals.append(oracle.Csr(lro, lkk, lvv))
     iro, ik, iv = csr_from_rows(o_init_rows)
     o_init = oracle.Csr(iro, ik, iv)
     g_init = api.SFVecs.upload(ctx, iro, ik, iv)
@@ -98,8 +99,14 @@ def test_config1_tree_new_and_run_match_oracle():
         _, gk, gv, _ = api.compute_cluster_centroid(gc6, members).download(aux=False)
         ek, ev = oracle.centroid(oc6, members)
         assert (gk == ek).all() and (bits(gv) == bits(ev)).all()
-        g_rows.append((gk, gv))
-        o_rows.append((ek, ev))
+        # run.rs:243-262: cluster c is paired with tree c; its local fingerprints are re-weighted by
+        # exp(1 + alpha * sim(local, naive query)), summed and normalised -> initial centroid of pass 2
+        rk, rv = oracle.reweight_fingerprints(o_locals[c], ek, ev, 2.5)
+        naive = api.compute_cluster_centroid(gc6, members)
+        _, wk, wv, _ = api.reweight_fingerprints(g_locals[c], naive, api.SIM_COSINE, 2.5).download(aux=False)
+        assert (wk == rk).all() and (bits(wv) == bits(rv)).all()
+        g_rows.append((wk, wv))
+        o_rows.append((rk, rv))
     cro, ck, cv = csr_from_rows(o_rows)
     o2, o2_iters, o2_sil = oracle.cluster(oc6, 20, oracle.Csr(cro, ck, cv), 2, silhouette=1.4)
     g2 = api.cluster(m, api.ClusteringParameters(k=6, t1=0.2, t2=20,

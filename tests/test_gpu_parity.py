@@ -728,3 +728,16 @@ def test_fasta_ingestion_matches_oracle_and_prepacked_path(api, ctx):
     assert all((a == b).all() for a, b in zip(got[:3], ref[:3]))
     s0, k0 = api.TaxTreeStore.from_fasta_records(ctx, np.zeros(0, np.uint8), np.zeros(1, np.uint64))
     assert s0.n_leaves == 0 and len(k0) == 0
+
+
+def test_reference_kat_from_unsorted_pairs_through_the_gpu(api, ctx):
+    # data/sparse.rs:623-633 (pairs half): the GPU's sort + sum of (key, value) pairs is the gather / radix sort /
+    # run reduction behind myrio_compute_cluster_centroid; six one-entry rows summed = from_unsorted_pairs, then L2
+    pairs = [(10, 1.0), (2, 4.0), (1, 1.0), (10, 7.0), (10, 2.0), (3, 9.0)]
+    ro = np.arange(7, dtype=np.uint64)
+    rows = api.SFVecs.upload(ctx, ro, np.array([p[0] for p in pairs], np.uint64), np.array([p[1] for p in pairs], np.float32))
+    _, k, v, _ = api.compute_cluster_centroid(rows, np.arange(6)).download(aux=False)
+    ek, ev = oracle.sort_reduce_pairs_f32(pairs)
+    assert k.tolist() == [1, 2, 3, 10] == ek.tolist()
+    norm = oracle.normalize(oracle.Csr(np.array([0, 4], np.uint64), ek, ev))
+    assert (bits(v) == bits(norm.vals)).all()

@@ -258,6 +258,14 @@ def test_kmer_key_bit_orders():
         oracle.set_kmer_msb_first(False)
 
 
+def test_from_unsorted_pairs_kat():
+    # myrio-core/src/data/sparse.rs:623-633, second half: from_unsorted_pairs
+    k, v = oracle.sort_reduce_pairs_f32([(10, 1.0), (2, 4.0), (1, 1.0), (10, 7.0), (10, 2.0), (3, 9.0)])
+    assert k.tolist() == [1, 2, 3, 10] and v.tolist() == [1.0, 4.0, 9.0, 10.0]
+    k, v = oracle.sort_reduce_pairs_f32([])
+    assert len(k) == 0 and len(v) == 0
+
+
 def test_fasta_to_iupac_restatement():
     # tax/store.rs:178-188: bio-seq Iupac codes (A=8 C=4 G=2 T=1, ambiguity = OR, '-' = X = 0)
     recs = ["ACGT", "RYSWKMBDHVN-", "ACGU", "", "acgt", "NNAC"]
