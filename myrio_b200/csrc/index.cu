@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) make_pairs_kernel(const uint64_t *__restr
                                                          uint64_t *__restrict__ pvals,
                                                          unsigned long long *__restrict__ key_or,
                                                          float *__restrict__ unit) {
+    // key_or[0]: OR of all keys; key_or[1]: longest row
     const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n_rows) return;
     const unsigned lane = threadIdx.x & 31;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) make_pairs_kernel(const uint64_t *__restr
     }
     if (lane == 0) {
         if (acc) atomicOr(key_or, (unsigned long long)acc);
+        atomicMax(key_or + 1, (unsigned long long)(e - b));
         unit[row] = e > b ? m : 0.0f;  // the leaf's smallest normalised value (count == common count)
     }
 }
@@ -141,6 +143,24 @@ __global__ void __launch_bounds__(256) classify_dense_kernel(const uint64_t *__r
         }
     }
     flags[u] = dense;
+}
+
+// postings whose value is not unit[leaf] get POSTING_ODD (see index.cuh); run last, on the final posting array
+__global__ void __launch_bounds__(256) flag_odd_postings_kernel(uint64_t *__restrict__ postings, uint64_t n,
+                                                                const uint64_t *__restrict__ bounds, uint32_t n_tiles,
+                                                                uint32_t tile_leaves, const float *__restrict__ unit,
+                                                                unsigned long long *__restrict__ n_odd) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool odd = false;
+    if (i < n) {
+        const uint64_t p = postings[i];
+        const uint32_t t = tile_of(bounds, n_tiles, i);
+        const uint64_t leaf = (uint64_t)t * tile_leaves + (uint32_t)(p >> 32);
+        odd = (uint32_t)p != __float_as_uint(unit[leaf]);
+        if (odd) postings[i] = p | POSTING_ODD;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, odd);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_odd, (unsigned long long)__popc(m));
 }
 
 // one warp per dense entry: lane l builds word l (leaves with leaf & 31 == l, bit = leaf >> 5)
@@ -245,15 +265,17 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
     // 1. pairs + unit values
     DevBuf<uint64_t> pk(std::max<uint64_t>(P, 1)), pv(std::max<uint64_t>(P, 1)),
         pk2(std::max<uint64_t>(P, 1)), pv2(std::max<uint64_t>(P, 1));
-    DevBuf<unsigned long long> key_or(1);
+    DevBuf<unsigned long long> key_or(3);  // [0] OR of the keys, [1] longest leaf vector, [2] odd postings
     ix->unit.alloc(L);
-    MYRIO_CK(cudaMemsetAsync(key_or.p, 0, sizeof(unsigned long long), ctx->stream));
+    MYRIO_CK(cudaMemsetAsync(key_or.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     MYRIO_LAUNCH(ctx, "k3_make_pairs", make_pairs_kernel, (unsigned)((L + 7) / 8), 256, 0,
                  leaves->row_off.p, leaves->keys.p, leaves->vals_f32.p, L, pk.p, pv.p, key_or.p,
                  ix->unit.p);
-    unsigned long long h_or = 0;
-    d2h(ctx, &h_or, key_or.p, 1);
+    unsigned long long h_or2[2] = {0, 0};
+    d2h(ctx, h_or2, key_or.p, 2);
     sync(ctx);
+    const unsigned long long h_or = h_or2[0];
+    ix->max_leaf_nnz = h_or2[1];
     int key_bits = 0;
     while (key_bits < 64 && (h_or >> key_bits) != 0) ++key_bits;
     if (key_bits == 0) key_bits = 1;
@@ -374,6 +396,14 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         ti.unit = ix->unit.p + ti.leaf_begin;
         ti.n_dense = dstart[t + 1] - dstart[t];
     }
+    if (P) {
+        MYRIO_LAUNCH(ctx, "k3_flag_odd", flag_odd_postings_kernel, (unsigned)((P + 255) / 256), 256, 0, sv, P,
+                     d_bounds.p, (uint32_t)n_tiles, tile_leaves, ix->unit.p, key_or.p + 2);
+        unsigned long long h_odd = 0;
+        d2h(ctx, &h_odd, key_or.p + 2, 1);
+        sync(ctx);
+        ix->n_odd_postings = h_odd;
+    }
     ix->postings = std::move(in_tmp ? pv2 : pv);
     ix->d_tiles.alloc(n_tiles);
     h2d(ctx, ix->d_tiles.p, ix->tiles.data(), n_tiles);
@@ -387,7 +417,7 @@ __global__ void __launch_bounds__(256) export_postings_kernel(const uint64_t *__
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const uint64_t p = postings[i];
-        leaf[i] = (uint32_t)(p >> 32);
+        leaf[i] = (uint32_t)(p >> 32) & POSTING_LEAF_MASK;
         val[i] = __uint_as_float((uint32_t)p);
     }
 }

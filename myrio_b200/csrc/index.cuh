@@ -52,6 +52,11 @@ struct __align__(8) Posting {
     float val;
     uint32_t leaf;
 };
+// bit 63 of a posting word: its value differs from unit[leaf] (a k-mer that occurs more than once in the
+// leaf, or a resampled ambiguity window).  The count-mode scoring kernel treats such postings one by one, in
+// key order; all others contribute the same product per (query, leaf) and are merely COUNTED.
+static constexpr uint64_t POSTING_ODD = 1ull << 63;
+static constexpr uint32_t POSTING_LEAF_MASK = 0x7FFFFFFFu;
 
 }  // namespace myrio
 
@@ -73,6 +78,8 @@ struct myrio_index {
     myrio::DevBuf<uint32_t> bitmaps;  // [n_dense_total][32]
     myrio::DevBuf<float> unit;        // [n_leaves]
     uint64_t n_dense_total = 0;
+    uint64_t n_odd_postings = 0;   // postings flagged POSTING_ODD
+    uint64_t max_leaf_nnz = 0;     // longest leaf vector (the u16 shared-key counters of count mode need < 65535)
 };
 
 namespace myrio {

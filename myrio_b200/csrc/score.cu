@@ -45,10 +45,13 @@ struct ScoreArgs {
     uint32_t *gthr;      // [q_count] running lower bound (score bits) of the query's x-th best score
     // seeding of the bound: pass 1 scores every query against its SEED tile only (the tile holding most of
     // its keys, i.e. its closest relatives), pass 2 sweeps all other tasks tile-major with the bound already high
+    const float *qv1;      // [q_count] the query's common value (count mode): its smallest value
     const uint32_t *seed;  // [q_count] seed tile (pass 1); its plan_off entry carries PLAN_SEED_FLAG (pass 2 skips it)
     uint32_t seed_mode;    // 0 = no seeding, 1 = seed pass (task == query), 2 = sweep
 };
 static constexpr uint64_t PLAN_SEED_FLAG = 1ull << 63;
+
+__device__ __forceinline__ uint32_t post_leaf(uint64_t p) { return (uint32_t)(p >> 32) & POSTING_LEAF_MASK; }
 
 __device__ __forceinline__ float finite_or_zero(float x) {
     return (fabsf(x) <= 3.402823466e+38f) ? x : 0.0f;  // false for NaN and inf
@@ -357,19 +360,19 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
                 float tacc[SC_U];
                 if (n == 32u * SC_U) {
 #pragma unroll
-                    for (int u = 0; u < SC_U; ++u) tacc[u] = acc[(uint32_t)(p[u] >> 32)];
+                    for (int u = 0; u < SC_U; ++u) tacc[u] = acc[post_leaf(p[u])];
 #pragma unroll
                     for (int u = 0; u < SC_U; ++u)
-                        acc[(uint32_t)(p[u] >> 32)] =
+                        acc[post_leaf(p[u])] =
                             __fadd_rn(tacc[u], __fmul_rn(v, __uint_as_float((uint32_t)p[u])));
                 } else {
 #pragma unroll
                     for (int u = 0; u < SC_U; ++u)
-                        if (u * 32u < n) tacc[u] = acc[(uint32_t)(p[u] >> 32)];
+                        if (u * 32u < n) tacc[u] = acc[post_leaf(p[u])];
 #pragma unroll
                     for (int u = 0; u < SC_U; ++u)
                         if (u * 32u < n)
-                            acc[(uint32_t)(p[u] >> 32)] =
+                            acc[post_leaf(p[u])] =
                                 __fadd_rn(tacc[u], __fmul_rn(v, __uint_as_float((uint32_t)p[u])));
                 }
                 __syncwarp();  // the next chunk may belong to another key and hit the same leaves
@@ -401,6 +404,289 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
                 __syncwarp();
             }
         }
+
+        if (FUSED) {
+            tile_topx<SIM>(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
+                           a.cand + slot * a.x, a.cand_cnt + slot, lane);
+        } else {
+            float *out = a.scores + (size_t)ql * a.ld + ti->leaf_begin;
+            for (uint32_t i = lane; i < nl; i += 32) out[i] = sim_transform<SIM>(acc[i]);
+        }
+        __syncwarp();
+    }
+    if (STATS && lane == 0 && st_post) atomicAdd(a.counters + 3, st_post);
+}
+
+
+// ------------------------------------------------------------------ K4, count mode
+//
+// The same scores with about half the instructions.  For one (query, leaf) pair almost every shared key
+// contributes THE SAME f32 product p = fl(v1 * unit[leaf]): the query's k-mers nearly all have count 1 (value
+// v1 after normalisation) and the leaf's nearly all the common count (value unit[leaf]).  Equal addends commute,
+// so the order of the reference's sequential sum only matters relative to the few ODD terms (a k-mer counted
+// twice in the read or in the leaf).  The kernel therefore COUNTS the common terms instead of adding them --
+// dense keys: one bitmap word per lane added into bit-sliced counters held in registers (12 logic instructions
+// for 32 leaves instead of 128); sparse postings: a u16 increment in shared memory -- and replays them as
+// n sequential additions of p per leaf at the end of the task:  score = fl(fl(fl(0 + p) + p) + ...).  An odd
+// term (query value != v1, or a posting flagged POSTING_ODD by the index build) first replays the leaf's pending
+// common terms, which are exactly the ones that precede it in key order, then is added itself: bit-identical to
+// the walk of score_tiles_kernel and to the reference's merge-join, whatever the data.
+static_assert(SC_U == 2, "scc_odd_sparse_chunk takes two postings");
+static constexpr int SCC_PLANES = 6;        // bit-sliced counters: up to 63 dense keys between two flushes
+static constexpr int SCC_MAX_WARPS = 24;
+
+__host__ __device__ inline size_t score_count_warp_smem_bytes(uint32_t tile_leaves, bool fused) {
+    return ((size_t)tile_leaves + 32 + (fused ? 256 : 0)) * sizeof(float) +            // acc (+ histogram)
+           (((size_t)tile_leaves + 32) * sizeof(uint16_t) + 15) / 16 * 16 +             // shared-key counters
+           SC_HITS * sizeof(HitRec);
+}
+
+// The odd terms are rare: their code lives out of line so that the hot loop of the kernel stays small (the
+// instruction cache is the first thing a 24-warp persistent kernel of this size runs out of: ncu `no_instruction`).
+// An odd term for `leaf`: replay its pending common terms, then add the term (reference order).
+__device__ __forceinline__ void scc_odd_update(float *acc, uint16_t *cnt, const float *unit, uint32_t nl, float v1,
+                                               uint32_t leaf, float term) {
+    const float p = __fmul_rn(v1, __ldg(unit + min(leaf, nl - 1)));
+    float s = acc[leaf];
+    for (uint32_t n = cnt[leaf]; n; --n) s = __fadd_rn(s, p);
+    cnt[leaf] = 0;
+    acc[leaf] = __fadd_rn(s, term);
+}
+// a sparse chunk that holds at least one odd posting (or belongs to a query key whose value is not v1)
+__device__ __noinline__ void scc_odd_sparse_chunk(float *acc, uint16_t *cnt, const float *unit, uint32_t nl,
+                                                  uint32_t tile_leaves, float v1, float v, uint64_t p0, uint64_t p1,
+                                                  uint32_t n, bool odd_key) {
+    const uint64_t p[SC_U] = {p0, p1};
+#pragma unroll
+    for (int u = 0; u < SC_U; ++u)
+        if (u * 32u < n) {
+            const uint32_t leaf = post_leaf(p[u]);
+            const bool odd = (odd_key || (p[u] & POSTING_ODD) != 0ull) && leaf < tile_leaves;
+            if (odd)
+                scc_odd_update(acc, cnt, unit, nl, v1, leaf, __fmul_rn(v, __uint_as_float((uint32_t)p[u])));
+            else
+                cnt[leaf] = (uint16_t)(cnt[leaf] + 1u);
+        }
+}
+// a dense key of a query value other than v1: every posting carries unit[leaf], the query value is the odd one
+__device__ __noinline__ void scc_odd_dense_key(float *acc, uint16_t *cnt, const float *unit, uint32_t nl, float v1,
+                                               float v, uint32_t w, uint32_t lane) {
+    for (int r = 0; r < 32; ++r)
+        if ((w >> r) & 1u) {
+            const uint32_t leaf = 32u * r + lane;
+            scc_odd_update(acc, cnt, unit, nl, v1, leaf, __fmul_rn(v, __ldg(unit + leaf)));
+        }
+}
+
+template <int SIM, bool FUSED, bool STATS>
+__global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(ScoreArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *wbase = smem_raw + (size_t)warp * score_count_warp_smem_bytes(a.tile_leaves, FUSED);
+    float *acc = reinterpret_cast<float *>(wbase);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(acc + a.tile_leaves + 32);
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(acc + a.tile_leaves + 32 + (FUSED ? 256 : 0));
+    HitRec *hits = reinterpret_cast<HitRec *>(reinterpret_cast<uint8_t *>(cnt) +
+                                              (((size_t)a.tile_leaves + 32) * sizeof(uint16_t) + 15) / 16 * 16);
+    const uint64_t dummy_posting = (uint64_t)a.tile_leaves << 32;  // leaf = dummy slot, not odd
+    unsigned long long st_post = 0;
+    uint32_t cached_tile = 0xFFFFFFFFu;
+    uint32_t nl = 0;
+    const uint64_t *post = nullptr;
+    const uint32_t *bitmaps = nullptr;
+    const float *unit = nullptr;
+    const TileInfo *ti = a.tiles;
+
+    uint32_t next_task = 0;
+    if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
+    for (;;) {
+        const uint32_t task = __shfl_sync(0xffffffffu, next_task, 0);
+        if (task >= a.n_tasks) break;
+        if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
+        uint32_t t, ql;
+        if (a.seed_mode == 1) {
+            ql = task;
+            t = __ldg(a.seed + ql);
+        } else {
+            t = task / a.q_count;
+            ql = task - t * a.q_count;
+        }
+        const size_t slot = (size_t)ql * a.n_tiles + t;
+        const uint64_t hb_raw = a.plan_off[slot];
+        const uint64_t hb = hb_raw & ~PLAN_SEED_FLAG, he = a.plan_off[slot + 1] & ~PLAN_SEED_FLAG;
+        if (a.seed_mode == 2 && (hb_raw & PLAN_SEED_FLAG)) continue;
+        const float v1 = __ldg(a.qv1 + ql);  // the query's common value
+        if (t != cached_tile) {
+            ti = a.tiles + t;
+            nl = ti->n_leaves;
+            post = a.postings + ti->post_begin;
+            bitmaps = ti->bitmaps;
+            unit = ti->unit;
+            cached_tile = t;
+        }
+        for (uint32_t i = lane; i < a.tile_leaves + 32; i += 32) {
+            acc[i] = 0.0f;
+            cnt[i] = 0;
+        }
+        __syncwarp();
+
+        // bit-sliced counters of the lane-owned leaves 32*r + lane (bit r of plane j = bit j of the count)
+        uint32_t pl[SCC_PLANES];
+#pragma unroll
+        for (int j = 0; j < SCC_PLANES; ++j) pl[j] = 0;
+        uint32_t pending = 0;  // dense keys counted since the last flush (warp-uniform)
+        auto flush_planes = [&]() {
+            if (pending == 0) return;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int j = 0; j < SCC_PLANES; ++j) c |= ((pl[j] >> r) & 1u) << j;
+                if (32u * r < a.tile_leaves && c) cnt[32 * r + lane] = (uint16_t)(cnt[32 * r + lane] + c);
+            }
+#pragma unroll
+            for (int j = 0; j < SCC_PLANES; ++j) pl[j] = 0;
+            pending = 0;
+            __syncwarp();
+        };
+        auto process_hits = [&](uint32_t n_hits) {
+            uint32_t hi = 0;
+            uint32_t cb = 0, cl = 0, coff = 0;
+            float cv = 0.0f;
+            bool cdense = false, open = false;
+            auto next_hit = [&]() {
+                if (hi >= n_hits) {
+                    open = false;
+                    return;
+                }
+                const HitRec h = hits[hi++];
+                cb = h.begin;
+                cdense = (h.len & DENSE_FLAG) != 0u;
+                cl = h.len & ~DENSE_FLAG;
+                cv = h.qv;
+                coff = 0;
+                open = true;
+                if (STATS) st_post += (lane == 0) ? cl : 0;
+            };
+            constexpr uint32_t DENSE_CHUNK = 0xFFFFFFFFu;
+            auto fetch = [&](uint64_t(&p)[SC_U], uint32_t &n, float &v) -> bool {
+                if (!open) return false;
+                v = cv;
+                if (cdense) {
+                    n = DENSE_CHUNK;
+                    p[0] = __ldg(bitmaps + (size_t)cb * 32 + lane);
+                    next_hit();
+                    return true;
+                }
+                n = min(cl - coff, 32u * SC_U);
+                const uint64_t *ptr = post + cb + coff + lane;
+                if (n == 32u * SC_U) {
+#pragma unroll
+                    for (int u = 0; u < SC_U; ++u) p[u] = __ldg(ptr + u * 32);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < SC_U; ++u)
+                        p[u] = (u * 32u + lane < n) ? __ldg(ptr + u * 32) : dummy_posting;
+                }
+                coff += n;
+                if (coff >= cl) next_hit();
+                return true;
+            };
+            auto process = [&](const uint64_t(&p)[SC_U], uint32_t n, float v) {
+                const bool odd_key = v != v1;  // warp-uniform
+                if (n == DENSE_CHUNK) {
+                    const uint32_t w = (uint32_t)p[0];
+                    if (!odd_key) {
+                        // ripple-carry add of one bit per leaf into the bit-sliced counters
+                        uint32_t carry = w;
+#pragma unroll
+                        for (int j = 0; j < SCC_PLANES; ++j) {
+                            const uint32_t t2 = pl[j] & carry;
+                            pl[j] ^= carry;
+                            carry = t2;
+                        }
+                        if (++pending == (1u << SCC_PLANES) - 1u) flush_planes();
+                    } else {
+                        // every posting of a dense key carries unit[leaf]; the query value is the odd one
+                        flush_planes();
+                        scc_odd_dense_key(acc, cnt, unit, nl, v1, v, w, lane);
+                        __syncwarp();
+                    }
+                    return;
+                }
+                bool any_odd = odd_key && n != 0u;
+#pragma unroll
+                for (int u = 0; u < SC_U; ++u) any_odd |= (p[u] & POSTING_ODD) != 0ull;  // dummy postings carry no flag
+                if (!__any_sync(0xffffffffu, any_odd)) {
+#pragma unroll
+                    for (int u = 0; u < SC_U; ++u)
+                        if (u * 32u < n) {
+                            const uint32_t leaf = post_leaf(p[u]);
+                            cnt[leaf] = (uint16_t)(cnt[leaf] + 1u);
+                        }
+                } else {
+                    flush_planes();
+                    scc_odd_sparse_chunk(acc, cnt, unit, nl, a.tile_leaves, v1, v, p[0], p[1], n, odd_key);
+                }
+                __syncwarp();  // the next chunk may belong to another key and hit the same leaves
+            };
+            next_hit();
+            uint64_t pa[SC_U], pb[SC_U];
+            uint32_t na = 0, nb = 0;
+            float va = 0.0f, vb = 0.0f;
+            bool have_a = fetch(pa, na, va);
+            while (have_a) {
+                const bool have_b = fetch(pb, nb, vb);
+                process(pa, na, va);
+                if (!have_b) break;
+                have_a = fetch(pa, na, va);
+                process(pb, nb, vb);
+            }
+        };
+
+        for (uint64_t h0 = hb; h0 < he; h0 += SC_HITS) {
+            const uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
+            for (uint32_t i = lane; i < n_hits; i += 32) hits[i] = a.plan[h0 + i];
+            __syncwarp();
+            process_hits(n_hits);
+            __syncwarp();
+        }
+        flush_planes();
+
+        // replay: n sequential additions of p per leaf; four leaves of a lane in flight (rows r0 .. r0+3 of its
+        // slots: conflict-free shared-memory accesses, 32 consecutive leaves across the warp), in lock step up to
+        // the shortest of the four, then predicated.  (Variants measured in profiles/r02_k4_variants.md: giving a
+        // lane four CONSECUTIVE leaves or finishing the remainders one chain at a time is slower -- the chains are
+        // latency-bound, four independent ones per lane are needed.)
+        for (uint32_t r0 = 0; he > hb && 32u * r0 < nl; r0 += 4) {  // a task without hits leaves all scores at +0
+            float s[4], p[4];
+            uint32_t n[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t leaf = 32u * (r0 + j) + lane;
+                const bool ok = leaf < nl;
+                n[j] = ok ? cnt[leaf] : 0u;
+                s[j] = ok ? acc[leaf] : 0.0f;
+                p[j] = ok ? __fmul_rn(v1, __ldg(unit + leaf)) : 0.0f;
+            }
+            const uint32_t nmin = min(min(n[0], n[1]), min(n[2], n[3]));
+            const uint32_t nmax = max(max(n[0], n[1]), max(n[2], n[3]));
+            uint32_t i = 0;
+            for (; i < nmin; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[j] = __fadd_rn(s[j], p[j]);
+            }
+            for (; i < nmax; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[j] = i < n[j] ? __fadd_rn(s[j], p[j]) : s[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t leaf = 32u * (r0 + j) + lane;
+                if (leaf < nl) acc[leaf] = s[j];
+            }
+        }
+        __syncwarp();
 
         if (FUSED) {
             tile_topx<SIM>(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
@@ -600,7 +886,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_probe_kernel(
     const uint64_t *__restrict__ q_row_off, const uint64_t *__restrict__ q_keys, uint64_t q_first,
     uint32_t q_count, const DictSlot *__restrict__ gdict, uint32_t gmask,
     const EntryRec *__restrict__ entries, uint32_t n_tiles, uint2 *__restrict__ kref,
-    uint32_t *__restrict__ hitcnt) {
+    uint32_t *__restrict__ hitcnt, const float *__restrict__ q_vals, float *__restrict__ qv1) {
     extern __shared__ uint32_t pl_count[];  // [PL_WARPS][n_tiles]: the warp's query owns one row of hitcnt
     const uint32_t ql = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
     if (ql >= q_count) return;
@@ -611,7 +897,9 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_probe_kernel(
     const uint64_t kbase = q_row_off[q_first];
     const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
     const uint4 *dict = reinterpret_cast<const uint4 *>(gdict);
+    float vmin = 3.402823466e+38f;
     for (uint64_t i = qb + lane; i < qe; i += 32) {
+        vmin = fminf(vmin, q_vals[i]);
         const uint64_t key = q_keys[i];
         uint32_t h = dict_hash(key) & gmask;
         uint32_t begin = 0, len = 0;
@@ -631,6 +919,10 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_probe_kernel(
     __syncwarp();
     uint32_t *out = hitcnt + (size_t)ql * n_tiles;
     for (uint32_t t = lane; t < n_tiles; t += 32) out[t] = cnt[t];
+    // the query's common value for the count-mode kernel: its smallest value (a read's k-mers of count 1)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+    if (lane == 0) qv1[ql] = qe > qb ? vmin : 0.0f;
 }
 
 // one warp per query: keys in ascending order, the lanes fan out over ONE key's entries
@@ -814,6 +1106,7 @@ struct Plan {
     DevBuf<uint64_t> off;
     DevBuf<HitRec> hits;
     DevBuf<uint32_t> seed;
+    DevBuf<float> qv1;
     uint64_t n_hits = 0;
 };
 
@@ -830,13 +1123,14 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     pl.kref.reserve(std::max<uint64_t>(nnz, 1));
     pl.hitcnt.reserve(std::max<uint64_t>(n_tasks, 1));
     pl.off.reserve(n_tasks + 1);
+    pl.qv1.reserve(std::max<uint64_t>(qn, 1));
     const unsigned grid = (unsigned)((qn + PL_WARPS - 1) / PL_WARPS);
     const size_t smem = (size_t)PL_WARPS * n_tiles * sizeof(uint32_t);
     if (smem > ctx->smem_optin) fail(MYRIO_ERR_UNSUPPORTED, "too many tiles (%llu) for the plan kernels", (unsigned long long)n_tiles);
     MYRIO_CK(cudaFuncSetAttribute(plan_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MYRIO_LAUNCH(ctx, "k4a_plan_probe", plan_probe_kernel, grid, PL_WARPS * 32, smem, queries->row_off.p,
                  queries->keys.p, q0, (uint32_t)qn, ix->gdict.p, ix->gdict_mask, ix->gentries.p, (uint32_t)n_tiles,
-                 pl.kref.p, pl.hitcnt.p);
+                 pl.kref.p, pl.hitcnt.p, queries->vals_f32.p, pl.qv1.p);
     exclusive_scan_u32_to_u64(ctx, pl.hitcnt.p, pl.off.p, n_tasks);
     d2h(ctx, &pl.n_hits, pl.off.p + n_tasks, 1);
     sync(ctx);
@@ -901,8 +1195,46 @@ static void launch_score_variant(myrio_ctx *ctx, const myrio_index *ix, ScoreArg
     MYRIO_LAUNCH(ctx, name, kern, grid, warps * 32, smem, a);
 }
 
+// MYRIO_K4_COUNT=0 selects the add-as-you-go kernel (score_tiles_kernel); count mode is the default where it
+// applies: u16 shared-key counters (no leaf vector of 65535+ keys) and an index whose postings are mostly
+// unit-valued (odd terms are exact but slow: they flush the register counters)
+static bool k4_count_mode(const myrio_index *ix) {
+    static const int v = [] {
+        const char *e = getenv("MYRIO_K4_COUNT");
+        return e ? atoi(e) : -1;
+    }();
+    if (v == 0) return false;
+    if (ix->max_leaf_nnz >= 65535) return false;  // u16 shared-key counters
+    if (v > 0) return true;
+    return ix->n_odd_postings * 50 <= ix->n_postings;  // <= 2 % odd postings
+}
+
+template <int SIM, bool FUSED, bool STATS>
+static void launch_score_count_variant(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a) {
+    const size_t per_warp = score_count_warp_smem_bytes(ix->tile_leaves, FUSED);
+    int warps = (int)std::min<size_t>(SCC_MAX_WARPS, (ctx->smem_optin - 1024) / per_warp);
+    if (warps < 1) fail(MYRIO_ERR_BAD_ARG, "tile_leaves=%u does not fit in shared memory", ix->tile_leaves);
+    const size_t smem = per_warp * warps;
+    if (a.n_tasks >= 0xFFF00000ull) fail(MYRIO_ERR_BAD_ARG, "too many (query, tile) tasks in one batch");
+    const unsigned grid = (unsigned)std::min<unsigned long long>(a.n_tasks, (unsigned long long)ctx->sm_count);
+    const char *name = FUSED ? "k4_score_tiles_topx" : "k4_score_tiles_rows";
+    auto kern = score_tiles_count_kernel<SIM, FUSED, STATS>;
+    MYRIO_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MYRIO_LAUNCH(ctx, name, kern, grid, warps * 32, smem, a);
+}
+
 template <bool FUSED>
 static void launch_score(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a, int32_t sim, bool stats) {
+    if (k4_count_mode(ix)) {
+        if (sim == MYRIO_SIM_COSINE) {
+            if (stats) launch_score_count_variant<MYRIO_SIM_COSINE, FUSED, true>(ctx, ix, a);
+            else launch_score_count_variant<MYRIO_SIM_COSINE, FUSED, false>(ctx, ix, a);
+        } else {
+            if (stats) launch_score_count_variant<MYRIO_SIM_JACARD_TANIMOTO, FUSED, true>(ctx, ix, a);
+            else launch_score_count_variant<MYRIO_SIM_JACARD_TANIMOTO, FUSED, false>(ctx, ix, a);
+        }
+        return;
+    }
     const bool ureg = k4_unit_in_registers();
 #define MYRIO_K4_DISPATCH(SIMV)                                                         \
     do {                                                                                \
@@ -927,6 +1259,7 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
     a.postings = ix->postings.p;
     a.plan = pl.hits.p;
     a.plan_off = pl.off.p;
+    a.qv1 = pl.qv1.p;
     a.q_count = (uint32_t)qn;
     a.tile_leaves = ix->tile_leaves;
     a.n_tiles = (uint32_t)ix->tiles.size();

@@ -741,3 +741,17 @@ def test_reference_kat_from_unsorted_pairs_through_the_gpu(api, ctx):
     assert k.tolist() == [1, 2, 3, 10] == ek.tolist()
     norm = oracle.normalize(oracle.Csr(np.array([0, 4], np.uint64), ek, ev))
     assert (bits(v) == bits(norm.vals)).all()
+
+
+@pytest.mark.parametrize("count_mode", ["1", "0"])
+def test_k4_kernel_variants(count_mode):
+    # both K4 kernels (count mode / add-as-you-go) forced through the odd-term cases in their own process
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MYRIO_K4_COUNT=count_mode)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "k4_variant_worker.py")], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert f"K4_VARIANT_OK count={count_mode}" in r.stdout
