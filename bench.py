@@ -116,18 +116,52 @@ def emit(line: dict):
 # ------------------------------------------------------------------ clocks
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  Read in-process
+    through NVML (the library nvidia-smi itself reads) every 500 ms by a thread that holds no lock of ours:
+    an `nvidia-smi -lms 200` child next to several busy ranks stalled CUDA calls for 100-800 ms a few times per
+    second on these boxes (profiles/r02_smi_hiccups.md), which is a property of the probe, not of the step.
+    Falls back to the nvidia-smi child (at -lms 1000) when pynvml is unavailable."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.sm, self.reasons, self.mx, self.stop_flag, self.thread, self.source = [], set(), None, False, None, None
+
+    def _nvml_loop(self, nv, h):
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, bit in names:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.5)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML wants the physical index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "NVML in-process (pynvml), every 500 ms"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.source = "nvidia-smi -lms 1000"
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "1000",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -138,6 +172,13 @@ class ClockSampler:
             self.rows.append([t.strip() for t in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0, "source": self.source}
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": self.source}
         if self.proc:
             self.proc.terminate()
             try:
@@ -156,9 +197,9 @@ class ClockSampler:
             except Exception:
                 continue
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------- data
@@ -438,18 +479,29 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    def timed(fn, steps):
-        """`steps` calls bracketed by barrier + synchronize, CUDA events on the library's stream, max over ranks."""
+    step_trace = {}
+
+    def timed(fn, steps, tag=None):
+        """`steps` calls bracketed by barrier + synchronize, CUDA events on the library's stream, max over ranks.
+        With a tag the end of every step is marked too (diagnostic: rank 0's per-step times in the JSON line)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record(ext)
         for _ in range(steps):
             fn()
+            if tag:
+                m = torch.cuda.Event(enable_timing=True)
+                m.record(ext)
+                marks.append(m)
         ctx.sync()
         torch.cuda.synchronize(dev)
         e1.record(ext)
         e1.synchronize()
         ms = allmax(e0.elapsed_time(e1))
+        if tag:
+            ts = [e0.elapsed_time(m) for m in marks]
+            step_trace[tag] = [round(b - a, 3) for a, b in zip([0.0] + ts[:-1], ts)]
         barrier()
         return ms
 
@@ -529,12 +581,12 @@ def run_ours(args, rank, local_rank, world):
         step_resident()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("MYRIO_BENCH_NO_SMI"):  # diagnosis only: the line then carries no clocks
         sampler.start()
     ctx.prof_reset()
     ctx.prof_enable(True)
     launches0 = ctx.launch_count
-    ms_value = timed(step_resident, args.steps)
+    ms_value = timed(step_resident, args.steps, "value")
     launches = ctx.launch_count - launches0
     k4_ms, k4_n = ctx.prof_query("k4_score")
     k1_ms, k1_n = ctx.prof_query("k1_")
@@ -546,7 +598,7 @@ def run_ours(args, rank, local_rank, world):
     ctx.prof_reset()
     for _ in range(max(1, min(args.warmup, 3))):
         step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, "e2e")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- k-mer counting THROUGH THE CALL (reads): myrio_count_reads + sync, wall clock, max over ranks
@@ -678,6 +730,7 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clocks,
         "kmers": kmers,
         "comm": comm_info,
+        "step_ms_rank0": step_trace,
         "setup_s": {"leaves_fasta_ingest": t_upload_leaves, "k2_count_leaves": t_count_leaves, "k3_index_build": t_index},
         "index": info,
         "kernel_ms_per_step": {"k1_count_reads": k1_ms / args.steps, "k4_score_tiles_topx": k4_ms / args.steps,

@@ -75,6 +75,9 @@ void myrio_ctx_destroy(myrio_ctx *ctx) {
     ctx->topx_cand.release();
     ctx->topx_cand_cnt.release();
     ctx->topx_gthr.release();
+    ctx->xchg_bound.release();
+    ctx->xchg_top.release();
+    ctx->xchg_all.release();
     comm_destroy(ctx);
     if (ctx->plan) plan_scratch_free(ctx->plan);
     ctx->plan = nullptr;

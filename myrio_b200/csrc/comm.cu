@@ -120,9 +120,22 @@ void comm_allreduce_max_u32(myrio_ctx *ctx, uint32_t *d_buf, uint64_t n) {
 
 // The multi-GPU scoring step.  Identical result on every rank, identical to the single-GPU top-x over the
 // union of the shards (the bound is a lower bound of the global x-th best score; ties are resolved by the
-// composite key in K7).  Error agreement: a rank whose seed pass fails still takes part in the bound
-// all-reduce with an error flag in the last element, so that its peers return MYRIO_ERR_COMM instead of
-// waiting for it in the all-gather.
+// composite key in K7).
+//
+// No host synchronisation between the collectives of a call: the whole sequence of every batch is queued on the
+// context's stream and the host waits once, at the end.  (A first version read an error flag back after every
+// all-reduce; with the queue drained twice per step any host-side hiccup -- an NVML query holding the driver lock
+// was enough -- left all N GPUs idle for its duration: profiles/r02_smi_hiccups.md.)
+// Error agreement without a mid-call sync: a rank whose seed pass fails joins the batch's collectives with zero
+// bounds, an empty list and flag = 1 in the extra element of the bound array; the MAX all-reduce spreads the
+// flag, a kernel ORs it into a per-call word, and every rank reads that word after its last batch: the failing
+// rank rethrows its own error, its peers return MYRIO_ERR_COMM.  Nobody waits for a rank that is not coming.
+// The batch size (the ranks must cut the queries at the same places) is agreed once per (index, x) with an
+// all-reduce and kept with the index.
+__global__ void or_flag_kernel(const uint32_t *__restrict__ flag, uint32_t *__restrict__ acc) {
+    if (*flag) *acc = 1u;
+}
+
 void score_topx_sharded(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q_first,
                         uint64_t q_count, uint32_t x, int32_t sim, float *d_top_scores, uint32_t *d_top_ids,
                         uint64_t max_batch) {
@@ -132,44 +145,65 @@ void score_topx_sharded(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs
     }
     const uint32_t W = ctx->comm_world;
     ncclComm_t comm = static_cast<ncclComm_t>(ctx->comm);
-    // every rank must cut the queries at the same places: the smallest capacity over the ranks (the tile
-    // count of a shard decides how many queries' candidates fit).  ~0 - cap so that MAX gives the minimum.
-    DevBuf<uint32_t> d_cap(2);
-    const uint64_t cap_local = std::min<uint64_t>(score_topx_batch_capacity(ix, x), 0x7FFFFFFFull);
-    uint32_t h_cap[2] = {0xFFFFFFFFu - (uint32_t)cap_local, (uint32_t)q_count};
-    h2d(ctx, d_cap.p, h_cap, 2);
-    MYRIO_NCCL(nccl().AllReduce(d_cap.p, d_cap.p, 2, ncclUint32, ncclMax, comm, ctx->stream));
-    d2h(ctx, h_cap, d_cap.p, 2);
-    sync(ctx);
-    if (h_cap[1] != (uint32_t)q_count) fail(MYRIO_ERR_COMM, "the ranks disagree on the number of queries");
-    uint64_t batch = 0xFFFFFFFFu - h_cap[0];
+    ctx->xchg_bound.reserve(std::min<uint64_t>(std::max<uint64_t>(q_count, 1), 0x7FFFFFFFull) + 4);
+    if (ix->agreed_x != x || ix->agreed_world != W) {
+        // smallest capacity over the ranks (the tile count of a shard decides how many queries' candidates fit):
+        // ~0 - cap so that MAX gives the minimum.  One synchronising exchange per (index, x), not per call.
+        const uint64_t cap_local = std::min<uint64_t>(score_topx_batch_capacity(ix, x), 0x7FFFFFFFull);
+        uint32_t h_cap = 0xFFFFFFFFu - (uint32_t)cap_local;
+        h2d(ctx, ctx->xchg_bound.p, &h_cap, 1);
+        MYRIO_NCCL(nccl().AllReduce(ctx->xchg_bound.p, ctx->xchg_bound.p, 1, ncclUint32, ncclMax, comm, ctx->stream));
+        d2h(ctx, &h_cap, ctx->xchg_bound.p, 1);
+        sync(ctx);
+        ix->agreed_cap = 0xFFFFFFFFu - h_cap;
+        ix->agreed_x = x;
+        ix->agreed_world = W;
+    }
+    uint64_t batch = ix->agreed_cap;
     if (max_batch) batch = std::min(batch, max_batch);
     batch = std::max<uint64_t>(batch, 1);
 
-    DevBuf<uint32_t> bound(std::min(batch, q_count) + 1);
-    DevBuf<uint64_t> top(std::min(batch, q_count) * x), all((uint64_t)W * std::min(batch, q_count) * x);
+    DevBuf<uint32_t> &bound = ctx->xchg_bound;
+    DevBuf<uint64_t> &top = ctx->xchg_top, &all = ctx->xchg_all;
+    const uint64_t bq = std::min(batch, std::max<uint64_t>(q_count, 1));
+    bound.reserve(bq + 4);  // [0, qc) bounds, [qc] this batch's error flag; the per-call flag word sits at the end
+    top.reserve(bq * x);
+    all.reserve((uint64_t)W * bq * x);
+    uint32_t *d_call_flag = bound.p + bound.n - 1;
+    MYRIO_CK(cudaMemsetAsync(d_call_flag, 0, sizeof(uint32_t), ctx->stream));
+    Failure local{MYRIO_OK, ""};
     for (uint64_t q0 = 0; q0 < q_count; q0 += batch) {
         const uint64_t qc = std::min(batch, q_count - q0);
-        uint32_t err_flag = 0;
-        Failure local{MYRIO_OK, ""};
-        try {
-            score_topx_seed_device(ctx, ix, queries, q_first + q0, qc, x, sim, bound.p);
-        } catch (const Failure &e) {
-            local = e;
-            err_flag = 1;
-            cudaMemsetAsync(bound.p, 0, qc * sizeof(uint32_t), ctx->stream);
+        bool ok = local.code == MYRIO_OK;
+        if (ok) {
+            try {
+                score_topx_seed_device(ctx, ix, queries, q_first + q0, qc, x, sim, bound.p);
+            } catch (const Failure &e) {
+                local = e;
+                ok = false;
+            }
         }
-        MYRIO_LAUNCH(ctx, "k7_set_flag", set_u32_kernel, 1, 1, 0, bound.p + qc, err_flag);
+        if (!ok) MYRIO_CK(cudaMemsetAsync(bound.p, 0, qc * sizeof(uint32_t), ctx->stream));
+        MYRIO_LAUNCH(ctx, "k7_set_flag", set_u32_kernel, 1, 1, 0, bound.p + qc, ok ? 0u : 1u);
         MYRIO_NCCL(nccl().AllReduce(bound.p, bound.p, qc + 1, ncclUint32, ncclMax, comm, ctx->stream));
-        uint32_t any_err = 0;
-        d2h(ctx, &any_err, bound.p + qc, 1);
-        sync(ctx);
-        if (err_flag) throw local;
-        if (any_err) fail(MYRIO_ERR_COMM, "the seed pass failed on another rank");
-        score_topx_sweep_device(ctx, ix, qc, x, sim, bound.p, top.p);
+        MYRIO_LAUNCH(ctx, "k7_or_flag", or_flag_kernel, 1, 1, 0, bound.p + qc, d_call_flag);
+        if (ok) {
+            try {
+                score_topx_sweep_device(ctx, ix, qc, x, sim, bound.p, top.p);
+            } catch (const Failure &e) {
+                local = e;
+                ok = false;
+            }
+        }
+        if (!ok) MYRIO_CK(cudaMemsetAsync(top.p, 0, qc * x * sizeof(uint64_t), ctx->stream));
         MYRIO_NCCL(nccl().AllGather(top.p, all.p, qc * x, ncclUint64, comm, ctx->stream));
         topx_merge_composites_device(ctx, all.p, W, qc, x, d_top_scores + q0 * x, d_top_ids + q0 * x);
     }
+    uint32_t any_err = 0;
+    d2h(ctx, &any_err, d_call_flag, 1);
+    sync(ctx);
+    if (local.code != MYRIO_OK) throw local;
+    if (any_err) fail(MYRIO_ERR_COMM, "the scoring pass failed on another rank");
 }
 
 }  // namespace myrio

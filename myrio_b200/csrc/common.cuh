@@ -147,6 +147,9 @@ struct myrio_ctx {
     // multi-GPU (comm.cu): ncclComm_t of this rank, bound by myrio_comm_init
     void *comm = nullptr;
     uint32_t comm_rank = 0, comm_world = 1;
+    // exchange buffers of myrio_score_topx_sharded (grow-only: a steady-state step never goes back to the allocator)
+    myrio::DevBuf<uint32_t> xchg_bound;
+    myrio::DevBuf<uint64_t> xchg_top, xchg_all;
     uint64_t last_stats[3] = {0, 0, 0};
     uint64_t cluster_stats[2] = {0, 0};  // pair similarities, multiply-add terms of the last K6 call
     // pinned staging for small D2H reads

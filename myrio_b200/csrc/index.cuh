@@ -78,6 +78,9 @@ struct myrio_index {
     myrio::DevBuf<uint32_t> bitmaps;  // [n_dense_total][32]
     myrio::DevBuf<float> unit;        // [n_leaves]
     uint64_t n_dense_total = 0;
+    // myrio_score_topx_sharded: queries per exchange batch agreed by all ranks for (x, world) -- see comm.cu
+    mutable uint32_t agreed_x = 0, agreed_world = 0;
+    mutable uint64_t agreed_cap = 0;
     uint64_t n_odd_postings = 0;   // postings flagged POSTING_ODD
     uint64_t max_leaf_nnz = 0;     // longest leaf vector (the u16 shared-key counters of count mode need < 65535)
 };
