@@ -163,6 +163,21 @@ __global__ void __launch_bounds__(256) flag_odd_postings_kernel(uint64_t *__rest
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_odd, (unsigned long long)__popc(m));
 }
 
+// a sparse (tile, key) entry whose posting list holds an odd posting gets ORDERED_FLAG (index.cuh); run after
+// flag_odd_postings_kernel.  One thread per entry (lists are ~12 postings long on average).
+__global__ void __launch_bounds__(256) flag_ordered_entries_kernel(EntryRec *__restrict__ entries, uint64_t n_unique,
+                                                                   const uint64_t *__restrict__ postings,
+                                                                   const uint64_t *__restrict__ bounds) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_unique) return;
+    const EntryRec e = entries[j];
+    if (e.len & DENSE_FLAG) return;  // every posting of a dense key carries unit[leaf]
+    const uint64_t *p = postings + bounds[e.tile] + e.begin;
+    uint64_t any = 0;
+    for (uint32_t i = 0; i < (e.len & LEN_MASK); ++i) any |= p[i];
+    if (any & POSTING_ODD) entries[j].len = e.len | ORDERED_FLAG;
+}
+
 // one warp per dense entry: lane l builds word l (leaves with leaf & 31 == l, bit = leaf >> 5)
 __global__ void __launch_bounds__(256) fill_bitmaps_kernel(const uint64_t *__restrict__ postings,
                                                            const uint32_t *__restrict__ ubegin,
@@ -403,6 +418,9 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         d2h(ctx, &h_odd, key_or.p + 2, 1);
         sync(ctx);
         ix->n_odd_postings = h_odd;
+        if (h_odd && U)
+            MYRIO_LAUNCH(ctx, "k3_flag_ordered", flag_ordered_entries_kernel, (unsigned)((U + 255) / 256), 256, 0,
+                         ix->gentries.p, U, sv, d_bounds.p);
     }
     ix->postings = std::move(in_tmp ? pv2 : pv);
     ix->d_tiles.alloc(n_tiles);

@@ -20,6 +20,12 @@ struct EntryRec {
     uint32_t len;
 };
 static constexpr uint32_t DENSE_FLAG = 0x80000000u;
+// bit 30 of EntryRec::len / HitRec::len: the term needs its place in key order -- a sparse posting list that
+// holds a POSTING_ODD posting (EntryRec, set by the index build) or, in a hit list, also a query value that is not
+// the query's common value (HitRec, set by the plan kernels).  A hit list without this bit consists of common
+// terms only, which commute: the count-mode scoring kernel then takes its dense and sparse keys in two sweeps.
+static constexpr uint32_t ORDERED_FLAG = 0x40000000u;
+static constexpr uint32_t LEN_MASK = 0x3FFFFFFFu;  // df <= tile_leaves <= 49152
 // dense keys need lane-owned accumulators: leaf = 32*r + lane with r < 32
 static constexpr uint32_t DENSE_MAX_TILE = 1024;
 

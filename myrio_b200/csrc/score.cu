@@ -21,7 +21,7 @@ namespace myrio {
 
 struct __align__(4) HitRec {  // one key of the query that occurs in the tile, in key order
     uint32_t begin;
-    uint32_t len;  // DENSE_FLAG | df
+    uint32_t len;  // DENSE_FLAG | ORDERED_FLAG | df
     float qv;
 };
 
@@ -48,6 +48,7 @@ struct ScoreArgs {
     const float *qv1;      // [q_count] the query's common value (count mode): its smallest value
     const uint32_t *seed;  // [q_count] seed tile (pass 1); its plan_off entry carries PLAN_SEED_FLAG (pass 2 skips it)
     uint32_t seed_mode;    // 0 = no seeding, 1 = seed pass (task == query), 2 = sweep
+    uint32_t ub_prune;     // count mode, fused top-x: finish only the scores whose upper bound reaches the bound
 };
 static constexpr uint64_t PLAN_SEED_FLAG = 1ull << 63;
 
@@ -91,13 +92,22 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32s(uint32_t v, unsigned lan
 // pass); only the first tiles of a query run the 4 x 8-bit warp radix select.
 // Pruning never drops a member of the global top-x: an element below the bound has
 // at least x better elements in the tile that produced the bound.
+// second half: acc[] holds the tile's final (transformed) scores, `cnt` of them are >= thr
+__device__ __forceinline__ void tile_topx_emit(float *acc, uint32_t *hist, uint32_t nl, uint32_t x,
+                                               uint32_t gid_base, uint32_t *gthr_q, uint64_t *cand,
+                                               uint32_t *cand_cnt, unsigned lane, uint32_t thr, uint32_t cnt);
+
+__device__ __forceinline__ uint32_t read_bound(const uint32_t *gthr_q, unsigned lane) {
+    uint32_t thr = 0;
+    if (lane == 0) thr = *reinterpret_cast<const volatile uint32_t *>(gthr_q);
+    return __shfl_sync(0xffffffffu, thr, 0);
+}
+
 template <int SIM>
 __device__ __forceinline__ void tile_topx(float *acc, uint32_t *hist, uint32_t nl, uint32_t x,
                                           uint32_t gid_base, uint32_t *gthr_q, uint64_t *cand,
                                           uint32_t *cand_cnt, unsigned lane) {
-    uint32_t thr = 0;
-    if (lane == 0) thr = *reinterpret_cast<volatile uint32_t *>(gthr_q);
-    thr = __shfl_sync(0xffffffffu, thr, 0);
+    const uint32_t thr = read_bound(gthr_q, lane);
     uint32_t cnt = 0;
     for (uint32_t i = lane; i < nl; i += 32) {
         const float s = sim_transform<SIM>(acc[i]);
@@ -106,6 +116,12 @@ __device__ __forceinline__ void tile_topx(float *acc, uint32_t *hist, uint32_t n
     }
     cnt = warp_sum_u32(cnt);
     __syncwarp();
+    tile_topx_emit(acc, hist, nl, x, gid_base, gthr_q, cand, cand_cnt, lane, thr, cnt);
+}
+
+__device__ __forceinline__ void tile_topx_emit(float *acc, uint32_t *hist, uint32_t nl, uint32_t x,
+                                               uint32_t gid_base, uint32_t *gthr_q, uint64_t *cand,
+                                               uint32_t *cand_cnt, unsigned lane, uint32_t thr, uint32_t cnt) {
     if (cnt == 0) {  // nothing in this tile can enter the query's top-x
         if (lane == 0) *cand_cnt = 0;
         return;
@@ -313,7 +329,7 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
                 const HitRec h = hits[hi++];  // same address for all lanes: broadcast
                 cb = h.begin;
                 cdense = (h.len & DENSE_FLAG) != 0u;
-                cl = h.len & ~DENSE_FLAG;
+                cl = h.len & LEN_MASK;
                 cv = h.qv;
                 coff = 0;
                 open = true;
@@ -537,7 +553,9 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         uint32_t pending = 0;  // dense keys counted since the last flush (warp-uniform)
         auto flush_planes = [&]() {
             if (pending == 0) return;
-#pragma unroll
+            // rolled on purpose: the flush is inlined at several (mostly cold) sites and the kernel is
+            // instruction-cache sensitive; with the bound pass of the fused top-x it rarely runs at all
+#pragma unroll 2
             for (int r = 0; r < 32; ++r) {
                 uint32_t c = 0;
 #pragma unroll
@@ -562,7 +580,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                 const HitRec h = hits[hi++];
                 cb = h.begin;
                 cdense = (h.len & DENSE_FLAG) != 0u;
-                cl = h.len & ~DENSE_FLAG;
+                cl = h.len & LEN_MASK;
                 cv = h.qv;
                 coff = 0;
                 open = true;
@@ -645,11 +663,100 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         };
 
         for (uint64_t h0 = hb; h0 < he; h0 += SC_HITS) {
-            const uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
-            for (uint32_t i = lane; i < n_hits; i += 32) hits[i] = a.plan[h0 + i];
+            uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
+            bool ordered = false;
+            for (uint32_t i = lane; i < n_hits; i += 32) {
+                const HitRec h = a.plan[h0 + i];
+                hits[i] = h;
+                ordered |= (h.len & ORDERED_FLAG) != 0u;
+            }
+            ordered = __any_sync(0xffffffffu, ordered);
             __syncwarp();
+            if (!ordered) {
+                // Common terms only: they commute, so the dense keys go first in a tight loop (four bitmap
+                // words in flight, no per-key state machine) and the sparse keys, compacted to the front of
+                // the list on the way, take the general walk below.
+                uint32_t ns = 0;
+                for (uint32_t hi = 0; hi < n_hits; hi += 4) {
+                    if (pending > (1u << SCC_PLANES) - 5u) flush_planes();
+                    HitRec h[4];
+                    uint32_t w[4];
+                    bool dn[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        h[u] = hits[min(hi + u, n_hits - 1u)];
+                        dn[u] = hi + u < n_hits && (h[u].len & DENSE_FLAG) != 0u;
+                        w[u] = dn[u] ? __ldg(bitmaps + (size_t)h[u].begin * 32 + lane) : 0u;
+                    }
+                    __syncwarp();  // all lanes have read the four records before any is overwritten
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (dn[u]) {
+                            uint32_t carry = w[u];
+#pragma unroll
+                            for (int j = 0; j < SCC_PLANES; ++j) {
+                                const uint32_t t2 = pl[j] & carry;
+                                pl[j] ^= carry;
+                                carry = t2;
+                            }
+                            ++pending;
+                            if (STATS) st_post += (lane == 0) ? (h[u].len & LEN_MASK) : 0;
+                        } else if (hi + u < n_hits) {
+                            if (lane == 0) hits[ns] = h[u];
+                            ++ns;
+                        }
+                    }
+                }
+                __syncwarp();
+                n_hits = ns;
+            }
             process_hits(n_hits);
             __syncwarp();
+        }
+        // ---- bound pass (fused top-x, once the query has a bound).  The score of a leaf is the f32 sequence
+        // s <- fl(s + p), n times, from its partial sum s0: every rounding adds at most 2^-24 relative, so
+        // score <= (s0 + n p)(1 + 2^-24)^n <= 1.004 (s0 + n p) for n < 65535.  A leaf whose bound (computed with
+        // the dense keys still pending in the bit-sliced counters taken as ALL present: n <= cnt + pending) stays
+        // below the query's running bound cannot enter its top-x: its shared keys were counted, its score is
+        // not finished (left at +0, below any non-zero bound).  Only the survivors -- the query's relatives --
+        // get their dense count unsliced and their additions replayed, exactly as in the full replay below.
+        if (FUSED && a.ub_prune) {
+            const uint32_t thr = read_bound(a.gthr + ql, lane);
+            if (thr != 0u) {
+                const float thr_f = __uint_as_float(thr);
+                const float pend_f = (float)pending;
+                uint32_t c_cnt = 0;
+                if (he > hb) {
+#pragma unroll 4
+                    for (uint32_t r = 0; 32u * r < nl; ++r) {
+                        const uint32_t leaf = 32u * r + lane;
+                        const bool ok = leaf < nl;
+                        const uint32_t li = ok ? leaf : a.tile_leaves;  // dummy slot
+                        float sc = acc[li];
+                        const uint32_t n0 = cnt[li];
+                        const float p = __fmul_rn(v1, __ldg(unit + min(leaf, nl - 1u)));
+                        float ub = __fmul_rn(__fadd_rn(sc, __fmul_rn(__fadd_rn((float)n0, pend_f), p)), 1.01f);
+                        if (SIM == MYRIO_SIM_JACARD_TANIMOTO)  // monotone in the dot product while it is < 2
+                            ub = ub < 1.5f ? sim_transform<SIM>(ub) : 3.0e38f;
+                        const bool need = ok && !(ub < thr_f);
+                        if (need) {
+                            uint32_t c = 0;
+#pragma unroll
+                            for (int j = 0; j < SCC_PLANES; ++j) c |= ((pl[j] >> r) & 1u) << j;
+                            for (uint32_t n = n0 + c; n; --n) sc = __fadd_rn(sc, p);
+                            sc = sim_transform<SIM>(sc);
+                            c_cnt += (__float_as_uint(sc) >= thr) ? 1u : 0u;
+                        }
+                        if (ok) acc[leaf] = need ? sc : 0.0f;
+                    }
+                }
+                c_cnt = warp_sum_u32(c_cnt);
+                __syncwarp();
+                tile_topx_emit(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
+                               a.cand + slot * a.x, a.cand_cnt + slot, lane, thr, c_cnt);
+                __syncwarp();
+                continue;
+            }
         }
         flush_planes();
 
@@ -931,13 +1038,14 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_fill_kernel(
     const uint64_t *__restrict__ q_row_off, const float *__restrict__ q_vals, uint64_t q_first,
     uint32_t q_count, const EntryRec *__restrict__ entries, uint32_t n_tiles,
     const uint2 *__restrict__ kref, const uint64_t *__restrict__ plan_off, HitRec *__restrict__ plan,
-    uint32_t skip_words) {
+    uint32_t skip_words, const float *__restrict__ qv1s) {
     extern __shared__ uint32_t pl_cursor[];  // [PL_WARPS][n_tiles], relative to the query's first hit
     const uint32_t ql = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
     if (ql >= q_count) return;
     // queries of at most 32*skip_words keys were placed by plan_fill_ranked_kernel
     if ((q_row_off[q_first + ql + 1] - q_row_off[q_first + ql] + 31) / 32 <= skip_words) return;
     const unsigned lane = threadIdx.x & 31;
+    const float qv1 = qv1s[ql];  // the query's common value (plan_probe_kernel)
     uint32_t *cur = pl_cursor + (size_t)(threadIdx.x >> 5) * n_tiles;
     const uint64_t *off = plan_off + (size_t)ql * n_tiles;
     const uint64_t base = off[0];
@@ -963,7 +1071,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_fill_kernel(
                 const EntryRec er = entries[eb + e];
                 HitRec h;
                 h.begin = er.begin;
-                h.len = er.len;
+                h.len = er.len | (v != qv1 ? ORDERED_FLAG : 0u);
                 h.qv = v;
                 plan[base + cur[er.tile]++] = h;
             }
@@ -981,13 +1089,15 @@ static constexpr int PF_THREADS = 256;
 __global__ void __launch_bounds__(PF_THREADS) plan_fill_ranked_kernel(
     const uint64_t *__restrict__ q_row_off, const float *__restrict__ q_vals, uint64_t q_first,
     const EntryRec *__restrict__ entries, uint32_t n_tiles, uint32_t words_cap,
-    const uint2 *__restrict__ kref, const uint64_t *__restrict__ plan_off, HitRec *__restrict__ plan) {
+    const uint2 *__restrict__ kref, const uint64_t *__restrict__ plan_off, HitRec *__restrict__ plan,
+    const float *__restrict__ qv1s) {
     // shared: present[n_tiles][words] | hit_prefix[32*words_cap + 1] | ent_begin[32*words_cap]
     // (staging the query's plan region in shared memory for coalesced stores was measured slower:
     // the extra shared memory costs more occupancy than the scattered 12-byte stores cost)
     extern __shared__ uint32_t pf_smem[];
     __shared__ uint32_t s_warp[PF_THREADS / 32 + 1];
     const uint32_t ql = blockIdx.x;
+    const float qv1 = qv1s[ql];  // the query's common value (plan_probe_kernel)
     const uint64_t kbase = q_row_off[q_first];
     const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
     const uint32_t nq = (uint32_t)(qe - qb);
@@ -1051,8 +1161,8 @@ __global__ void __launch_bounds__(PF_THREADS) plan_fill_ranked_kernel(
         for (uint32_t w = 0; w < (i >> 5); ++w) rank += __popc(row[w]);
         HitRec h;
         h.begin = er.begin;
-        h.len = er.len;
         h.qv = q_vals[qb + i];
+        h.len = er.len | (h.qv != qv1 ? ORDERED_FLAG : 0u);
         plan[off[er.tile] + rank] = h;
     }
 }
@@ -1150,13 +1260,13 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
         MYRIO_CK(cudaFuncSetAttribute(plan_fill_ranked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         MYRIO_LAUNCH(ctx, "k4a_plan_fill_ranked", plan_fill_ranked_kernel, (unsigned)qn, PF_THREADS, psm,
                      queries->row_off.p, queries->vals_f32.p, q0, ix->gentries.p, (uint32_t)n_tiles, words_cap,
-                     pl.kref.p, pl.off.p, pl.hits.p);
+                     pl.kref.p, pl.off.p, pl.hits.p, pl.qv1.p);
     }
     if ((max_q_keys + 31) / 32 > words_cap) {
         MYRIO_CK(cudaFuncSetAttribute(plan_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MYRIO_LAUNCH(ctx, "k4a_plan_fill", plan_fill_kernel, grid, PL_WARPS * 32, smem, queries->row_off.p,
                      queries->vals_f32.p, q0, (uint32_t)qn, ix->gentries.p, (uint32_t)n_tiles, pl.kref.p, pl.off.p,
-                     pl.hits.p, words_cap);
+                     pl.hits.p, words_cap, pl.qv1.p);
     }
     return true;
 }
@@ -1253,6 +1363,16 @@ static void launch_score(myrio_ctx *ctx, const myrio_index *ix, ScoreArgs &a, in
 #undef MYRIO_K4_DISPATCH
 }
 
+// MYRIO_K4_UB=0: the fused top-x finishes EVERY score of every task (the full replay) instead of only those
+// whose upper bound reaches the query's running bound (comparison runs; the result is the same)
+static bool k4_bound_pruning() {
+    static const bool v = [] {
+        const char *e = getenv("MYRIO_K4_UB");
+        return !(e && e[0] == '0');
+    }();
+    return v;
+}
+
 static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl, uint64_t qn) {
     ScoreArgs a{};
     a.tiles = ix->d_tiles.p;
@@ -1267,6 +1387,7 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
     a.ld = ix->n_leaves;
     a.leaf_id_base = ix->leaf_id_base;
     a.counters = ctx->score_counters.p;
+    a.ub_prune = k4_bound_pruning() ? 1u : 0u;
     return a;
 }
 
