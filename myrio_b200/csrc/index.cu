@@ -288,6 +288,8 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
                  ix->unit.p);
     unsigned long long h_or2[2] = {0, 0};
     d2h(ctx, h_or2, key_or.p, 2);
+    std::vector<float> h_unit(L);  // per-tile maxima (TileInfo::unit_max)
+    d2h(ctx, h_unit.data(), ix->unit.p, L);
     sync(ctx);
     const unsigned long long h_or = h_or2[0];
     ix->max_leaf_nnz = h_or2[1];
@@ -410,6 +412,7 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         ti.bitmaps = ix->bitmaps.p + dstart[t] * 32;
         ti.unit = ix->unit.p + ti.leaf_begin;
         ti.n_dense = dstart[t + 1] - dstart[t];
+        ti.unit_max = *std::max_element(h_unit.begin() + ti.leaf_begin, h_unit.begin() + ti.leaf_begin + ti.n_leaves);
     }
     if (P) {
         MYRIO_LAUNCH(ctx, "k3_flag_odd", flag_odd_postings_kernel, (unsigned)((P + 255) / 256), 256, 0, sv, P,

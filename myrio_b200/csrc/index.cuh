@@ -42,6 +42,7 @@ struct TileInfo {
     const uint32_t *bitmaps;  // [n_dense][32]
     const float *unit;        // [n_leaves] (slice of the index-wide array)
     uint64_t n_dense;
+    float unit_max;           // largest unit value of the tile (upper bounds of the count-mode top-x)
 };
 
 __device__ __forceinline__ uint32_t dict_hash(uint64_t key) {

@@ -3,10 +3,13 @@
 // One CTA per sequence.  The packed sequence is staged in shared memory with
 // 16-byte loads, every window's key is produced by a funnel shift over the 2-bit
 // words (forward key + reverse-complement key via brev), the keys are sorted in
-// shared memory (bitonic network) and run-length reduced into a sorted
-// (key, count) row.  Rows go to an over-allocated scratch at a per-row offset
-// known up front (2*(n-k+1) keys at most); compact_rows_kernel then packs them
-// into the final CSR once the exact row sizes have been prefix-summed.
+// shared memory -- one MSD counting pass into 1024 order-preserving buckets, then
+// every key finds its place inside its bucket (a handful of keys) by counting; a
+// bitonic network is the fallback for low-complexity sequences -- and run-length
+// reduced into a sorted (key, count) row with ballot-ranked compaction.  Rows go to
+// an over-allocated scratch at a per-row offset known up front (2*(n-k+1) keys at
+// most); compact_rows_kernel then packs them into the final CSR once the exact row
+// sizes have been prefix-summed.
 //
 // Reference semantics restated here:
 //   reads : MyrSeq::compute_kmer_counts      myrio-core/src/data/myrseq.rs:76-111
@@ -21,7 +24,6 @@
 namespace myrio {
 
 static constexpr int KC_THREADS = 256;  // largest CTA; small size classes launch fewer threads (kc_threads_for)
-static constexpr int KC_BUCKETS = 256;
 
 static const uint32_t h_phred_bits[128] = {
 #include "phred_table.inc"
@@ -122,67 +124,128 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *keys, uint16_t *w, uint32
     __syncthreads();
 }
 
-// Sort of E u64 keys (values < 2^key_bits) for the common case of keys spread over
-// their leading bits: one MSD counting pass into 256 order-preserving buckets
-// (a handful of keys each), then every thread insertion-sorts one bucket.  About
-// 8x fewer instructions than the bitonic network at E ~ 1000.  Returns false -- and
-// leaves `keys` untouched -- if some bucket holds more than 32 keys (low-complexity
-// sequence); the caller then falls back to the bitonic network.
-__device__ __forceinline__ bool bucket_sort(uint64_t *keys, uint64_t *keys2, uint32_t E, uint32_t key_bits,
-                                            uint32_t *s_hist, uint32_t *s_start, uint32_t *wbuf) {
+// ---- sort of E u64 keys (K1 and the unambiguous path of K2).
+// 1024 order-preserving buckets on the leading 10 bits of the key; the histogram is 512 packed pairs of u16
+// counters (E <= 4096 here, so a half never carries into its neighbour) and doubles as the scatter cursor:
+// after the scan a half holds its bucket's START, after the scatter its END (= the next bucket's start).
+// Inside a bucket (E/1024 keys on average) a key's place is the number of smaller keys (ties: lower index
+// first), counted by the key's own thread -- no per-thread insertion sort, no divergence beyond the bucket size.
+// Returns false, `keys` untouched, if a bucket holds more than 32 keys (the caller falls back to bitonic).
+static constexpr int KC_BINS = 1024;
+__device__ __forceinline__ uint32_t kc_half(const uint32_t *h32, uint32_t d) {
+    return (h32[d >> 1] >> ((d & 1u) * 16u)) & 0xFFFFu;
+}
+__device__ __forceinline__ bool bucket_rank_sort(uint64_t *keys, uint64_t *keys2, uint32_t E, uint32_t key_bits,
+                                                 uint32_t *h32, uint32_t *wbuf) {
     const uint32_t tid = threadIdx.x, T = blockDim.x;
-    const uint32_t BPT = KC_BUCKETS / T;  // buckets per thread (T is 64, 128 or 256)
-    const uint32_t shift = key_bits > 8 ? key_bits - 8 : 0;
-    for (uint32_t b = tid; b < KC_BUCKETS; b += T) s_hist[b] = 0;
+    const uint32_t WPT = (KC_BINS / 2) / T;  // packed words per thread (T is 64, 128 or 256)
+    const uint32_t shift = key_bits > 10 ? key_bits - 10 : 0;
+    for (uint32_t b = tid; b < KC_BINS / 2; b += T) h32[b] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < E; i += T) atomicAdd(&s_hist[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    for (uint32_t i = tid; i < E; i += T) {
+        const uint32_t d = (uint32_t)(keys[i] >> shift) & (KC_BINS - 1);
+        atomicAdd(&h32[d >> 1], 1u << ((d & 1u) * 16u));
+    }
     __syncthreads();
-    // thread t owns the contiguous buckets [t*BPT, (t+1)*BPT)
     uint32_t c = 0, cmax = 0;
-    for (uint32_t j = 0; j < BPT; ++j) {
-        const uint32_t cj = s_hist[tid * BPT + j];
-        c += cj;
-        cmax = max(cmax, cj);
+    for (uint32_t j = 0; j < WPT; ++j) {
+        const uint32_t w = h32[tid * WPT + j];
+        c += (w & 0xFFFFu) + (w >> 16);
+        cmax = max(cmax, max(w & 0xFFFFu, w >> 16));
     }
     uint32_t total;
-    const uint32_t start = block_excl_scan_u32(c, wbuf, &total);
-    const int too_big = __syncthreads_or(cmax > 32u);
-    if (too_big) return false;
-    {
-        uint32_t run = start;
-        for (uint32_t j = 0; j < BPT; ++j) {
-            const uint32_t cj = s_hist[tid * BPT + j];
-            s_start[tid * BPT + j] = run;
-            s_hist[tid * BPT + j] = 0;  // becomes the per-bucket cursor
-            run += cj;
-        }
+    uint32_t run = block_excl_scan_u32(c, wbuf, &total);
+    if (__syncthreads_or(cmax > 32u)) return false;
+    for (uint32_t j = 0; j < WPT; ++j) {
+        const uint32_t w = h32[tid * WPT + j];
+        const uint32_t lo = w & 0xFFFFu, hi = w >> 16;
+        h32[tid * WPT + j] = run | ((run + lo) << 16);
+        run += lo + hi;
     }
-    if (tid == T - 1) s_start[KC_BUCKETS] = E;
     __syncthreads();
     for (uint32_t i = tid; i < E; i += T) {
         const uint64_t key = keys[i];
-        const uint32_t d = (uint32_t)(key >> shift) & 255u;
-        keys2[s_start[d] + atomicAdd(&s_hist[d], 1u)] = key;
+        const uint32_t d = (uint32_t)(key >> shift) & (KC_BINS - 1);
+        const uint32_t old = atomicAdd(&h32[d >> 1], 1u << ((d & 1u) * 16u));
+        keys2[(old >> ((d & 1u) * 16u)) & 0xFFFFu] = key;
     }
     __syncthreads();
-    // insertion sort of the thread's own range: buckets are already in order, so an element never
-    // moves below the start of its bucket and one pass over [start, start + c) sorts them all
-    {
-        const uint32_t b = start, e = start + c;
-        for (uint32_t i = b + 1; i < e; ++i) {
-            const uint64_t x = keys2[i];
-            uint32_t j = i;
-            while (j > b && keys2[j - 1] > x) {
-                keys2[j] = keys2[j - 1];
-                --j;
-            }
-            keys2[j] = x;
+    for (uint32_t i = tid; i < E; i += T) {
+        const uint64_t x = keys2[i];
+        const uint32_t d = (uint32_t)(x >> shift) & (KC_BINS - 1);
+        const uint32_t e = kc_half(h32, d), b = d ? kc_half(h32, d - 1) : 0u;
+        uint32_t rank = b;
+        for (uint32_t j = b; j < e; ++j) {
+            const uint64_t y = keys2[j];
+            rank += (y < x || (y == x && j < i)) ? 1u : 0u;
         }
+        keys[rank] = x;
     }
-    __syncthreads();
-    for (uint32_t i = tid; i < E; i += T) keys[i] = keys2[i];
     __syncthreads();
     return true;
+}
+
+// Run-length reduce of the sorted keys[0..E) straight to the row's scratch, in key order: ballot-ranked
+// compaction in position order (segment = 32 consecutive positions of one warp), two sweeps with a scan of
+// the per-segment counts in between.  `emit(i, run) -> value` decides per run head whether the run is kept
+// (value != 0) and what is stored; returns the number of runs kept.  `seg` holds round_len/32 + 8 counters
+// (it aliases the sort buffer, dead by now); round_len positions are reduced per round.
+template <typename VT, typename F>
+__device__ __forceinline__ uint32_t reduce_runs(const uint64_t *keys, uint32_t E, uint32_t *seg, uint32_t round_len,
+                                                uint32_t *s_d, uint64_t *out_keys, VT *out_vals, F value_of) {
+    const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, warp = tid >> 5, nW = T >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t done = 0;  // runs emitted by earlier rounds
+    for (uint32_t r0 = 0; r0 < E; r0 += round_len) {
+        const uint32_t re = min(E, r0 + round_len);
+        const uint32_t iters = (re - r0 + T - 1) / T;
+        for (uint32_t m = 0; m < iters; ++m) {
+            const uint32_t i = r0 + m * T + tid;
+            bool keep = false;
+            if (i < re && (i == 0 || keys[i] != keys[i - 1])) {
+                uint32_t j = i + 1;
+                const uint64_t x = keys[i];
+                while (j < E && keys[j] == x) ++j;
+                keep = value_of(i, j - i) != (VT)0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) seg[m * nW + warp] = __popc(bal);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t ns = iters * nW;
+            uint32_t carry = 0;
+            for (uint32_t c0 = 0; c0 < ns; c0 += 32) {
+                const uint32_t v = c0 + lane < ns ? seg[c0 + lane] : 0u;
+                const uint32_t inc = warp_incl_scan_u32(v);
+                if (c0 + lane < ns) seg[c0 + lane] = carry + inc - v;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) *s_d = carry;
+        }
+        __syncthreads();
+        for (uint32_t m = 0; m < iters; ++m) {
+            const uint32_t i = r0 + m * T + tid;
+            VT v = (VT)0;
+            uint64_t x = 0;
+            if (i < re && (i == 0 || keys[i] != keys[i - 1])) {
+                uint32_t j = i + 1;
+                x = keys[i];
+                while (j < E && keys[j] == x) ++j;
+                v = value_of(i, j - i);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, v != (VT)0);
+            if (v != (VT)0) {
+                const uint32_t d = done + seg[m * nW + warp] + __popc(bal & lt);
+                out_keys[d] = x;
+                out_vals[d] = v;
+            }
+        }
+        __syncthreads();
+        done += *s_d;
+        __syncthreads();
+    }
+    return done;
 }
 
 // bucket sort needs a second key buffer: only the small size classes carry one
@@ -232,12 +295,15 @@ struct ReadCountArgs {
     uint64_t gstride;
 };
 
-// shared/global work area: keys[ecap] u64 | aux[ecap+64] u32 (conf factors, then run heads)
+// shared/global work area: keys[ecap] u64
+//                          | buf: keys2[ecap] u64 (small classes: bucket-sort buffer) or (ecap/2+64) f32
+//                            -- the per-base confidence factors live here until the sort starts
 //                          | words[ecap/64+4] u64
-//                          | keys2[ecap] u64 (bucket-sort buffer, small classes only)
+__host__ __device__ inline size_t read_buf_bytes(uint32_t ecap) {
+    return has_bucket_buffer(ecap) ? (size_t)ecap * 8 : ((size_t)ecap / 2 + 64) * 4;
+}
 __host__ __device__ inline size_t read_work_bytes(uint32_t ecap) {
-    return (size_t)ecap * 8 + ((size_t)ecap + 64) * 4 + ((size_t)ecap / 64 + 4) * 8 +
-           (has_bucket_buffer(ecap) ? (size_t)ecap * 8 : 0);
+    return (size_t)ecap * 8 + read_buf_bytes(ecap) + ((size_t)ecap / 64 + 4) * 8;
 }
 
 template <bool GLOBAL>
@@ -245,23 +311,22 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ float s_phred[128];
     __shared__ uint32_t s_wbuf[33];
-    __shared__ uint32_t s_cnt;
-    __shared__ uint32_t s_hist[KC_BUCKETS], s_start[KC_BUCKETS + 1];
+    __shared__ uint32_t s_cnt, s_d;
+    __shared__ uint32_t s_h32[KC_BINS / 2];
 
     uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
     uint64_t *keys = reinterpret_cast<uint64_t *>(work);
-    uint32_t *aux = reinterpret_cast<uint32_t *>(work + (size_t)a.ecap * 8);
-    uint64_t *words = reinterpret_cast<uint64_t *>(work + (size_t)a.ecap * 8 + ((size_t)a.ecap + 64) * 4);
-    uint64_t *keys2 = words + ((size_t)a.ecap / 64 + 4);
-    float *pfac = reinterpret_cast<float *>(aux);
+    uint64_t *keys2 = reinterpret_cast<uint64_t *>(work + (size_t)a.ecap * 8);
+    float *pfac = reinterpret_cast<float *>(keys2);  // dead before the sort writes keys2
+    uint64_t *words = reinterpret_cast<uint64_t *>(work + (size_t)a.ecap * 8 + read_buf_bytes(a.ecap));
 
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u;
     const uint32_t r = a.ids[blockIdx.x];
     const uint64_t b0 = a.base_off[r];
     const uint32_t n = (uint32_t)(a.base_off[r + 1] - b0);
     const uint32_t k = a.k;
 
-    for (uint32_t i = tid; i < 128; i += blockDim.x) s_phred[i] = g_phred[i];
+    for (uint32_t i = tid; i < 128; i += T) s_phred[i] = g_phred[i];
     if (tid == 0) s_cnt = 0;
     if (n < k) {  // kmers::<K>() yields nothing
         if (tid == 0) {
@@ -278,64 +343,95 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
         const uint32_t nw = (n + 31) >> 5;
         const uint4 *src = reinterpret_cast<const uint4 *>(a.words + w0);
         uint4 *dst = reinterpret_cast<uint4 *>(words);
-        for (uint32_t i = tid; i < (nw + 1) / 2; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (uint32_t i = tid; i < (nw + 1) / 2; i += T) dst[i] = __ldg(src + i);
         if (tid == 0) {  // window_key may touch one word past the end
             words[((nw + 1) / 2) * 2] = 0;
         }
     }
     __syncthreads();  // s_phred ready
-    // quality bytes -> per-base probability of a correct call, 16-byte loads
+    // quality bytes -> per-base probability of a correct call: one aligned 4-byte load per thread and round
     {
         const uint8_t *qp = a.qual + b0;
-        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(qp) & 15u);
-        const uint4 *q4 = reinterpret_cast<const uint4 *>(qp - mis);
-        const uint32_t nchunks = (mis + n + 15) >> 4;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(qp) & 3u);
+        const uint32_t *q4 = reinterpret_cast<const uint32_t *>(qp - mis);
+        const uint32_t nchunks = (mis + n + 3) >> 2;
         bool bad = false;
-        for (uint32_t c = tid; c < nchunks; c += blockDim.x) {
-            uint4 v = __ldg(q4 + c);
-            uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        for (uint32_t c = tid; c < nchunks; c += T) {
+            const uint32_t v = __ldg(q4 + c);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                int idx = (int)(c * 16 + j) - (int)mis;
+            for (int j = 0; j < 4; ++j) {
+                const int idx = (int)(c * 4 + j) - (int)mis;
                 if (idx >= 0 && idx < (int)n) {
-                    uint32_t q = (wv[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+                    const uint32_t q = (v >> (j * 8)) & 0xFFu;
                     bad |= q >= 128u;
                     pfac[idx] = s_phred[q & 127u];
                 }
             }
         }
+        if (tid < 4) pfac[n + tid] = 1.0f;  // a thread's four windows read three factors past its last window
         if (bad) atomicMax(a.err, MYRIO_ERR_BAD_QUALITY);
     }
     __syncthreads();
 
-    // windows: confidence = product of k factors (sequential f32, as the reference);
-    // every passing window emits its key and its reverse complement's key
-    for (uint32_t base = 0; base < nb; base += blockDim.x) {
-        const uint32_t i = base + tid;
-        bool pass = false;
-        uint64_t kf = 0, kr = 0;
-        if (i < nb) {
-            float conf = 1.0f;
-            for (uint32_t j = 0; j < k; ++j) conf = __fmul_rn(conf, pfac[i + j]);
-            pass = conf > a.cutoff;
-            if (pass) {
-                kf = window_key(words, i, k);
-                kr = revcomp_key(kf, k);
-                order_key_pair(kf, kr, k, a.msb_first);
+    // windows: confidence = product of k factors (sequential f32, left to right, as the reference); a thread
+    // takes FOUR consecutive windows so that a factor is loaded once and multiplied into every chain it belongs
+    // to (1.0 * v == v exactly, so a chain starts with its first factor).  Every passing window emits its key
+    // and its reverse complement's key.
+    const uint32_t ngroups = (nb + 3) >> 2;
+    for (uint32_t g0 = 0; g0 < ngroups; g0 += T) {
+        const uint32_t i0 = 4u * (g0 + tid);
+        float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (g0 + tid < ngroups) {
+            const float *pp = pfac + i0;
+            if (k >= 4) {
+                const float v0 = pp[0], v1 = pp[1], v2 = pp[2], v3 = pp[3];
+                c[0] = __fmul_rn(__fmul_rn(__fmul_rn(v0, v1), v2), v3);
+                c[1] = __fmul_rn(__fmul_rn(v1, v2), v3);
+                c[2] = __fmul_rn(v2, v3);
+                c[3] = v3;
+#pragma unroll 4
+                for (uint32_t j = 4; j < k; ++j) {
+                    const float v = pp[j];
+                    c[0] = __fmul_rn(c[0], v);
+                    c[1] = __fmul_rn(c[1], v);
+                    c[2] = __fmul_rn(c[2], v);
+                    c[3] = __fmul_rn(c[3], v);
+                }
+                const float e0 = pp[k], e1 = pp[k + 1], e2 = pp[k + 2];
+                c[1] = __fmul_rn(c[1], e0);
+                c[2] = __fmul_rn(__fmul_rn(c[2], e0), e1);
+                c[3] = __fmul_rn(__fmul_rn(__fmul_rn(c[3], e0), e1), e2);
+            } else {
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    float conf = 1.0f;
+                    for (uint32_t j = 0; j < k; ++j) conf = __fmul_rn(conf, pp[w + j]);
+                    c[w] = conf;
+                }
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            const unsigned lane = tid & 31;
-            const int leader = __ffs(m) - 1;
+        bool ps[4];
+        uint32_t np = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            ps[w] = g0 + tid < ngroups && i0 + w < nb && c[w] > a.cutoff;
+            np += ps[w] ? 1u : 0u;
+        }
+        const uint32_t incl = warp_incl_scan_u32(np);
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (tot) {
             uint32_t slot = 0;
-            if ((int)lane == leader) slot = atomicAdd(&s_cnt, 2u * __popc(m));
-            slot = __shfl_sync(0xffffffffu, slot, leader);
-            if (pass) {
-                slot += 2u * __popc(m & ((1u << lane) - 1u));
-                keys[slot] = kf;
-                keys[slot + 1] = kr;
-            }
+            if (lane == 31) slot = atomicAdd(&s_cnt, 2u * tot);
+            slot = __shfl_sync(0xffffffffu, slot, 31) + 2u * (incl - np);
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+                if (ps[w]) {
+                    uint64_t kf = window_key(words, i0 + w, k), kr = revcomp_key(kf, k);
+                    order_key_pair(kf, kr, k, a.msb_first);
+                    keys[slot] = kf;
+                    keys[slot + 1] = kr;
+                    slot += 2;
+                }
         }
     }
     __syncthreads();
@@ -347,21 +443,17 @@ __global__ void __launch_bounds__(KC_THREADS) count_reads_kernel(ReadCountArgs a
         }
         return;
     }
-    if (!(has_bucket_buffer(a.ecap) && bucket_sort(keys, keys2, E, 2u * k, s_hist, s_start, s_wbuf))) {
+    if (!(has_bucket_buffer(a.ecap) && bucket_rank_sort(keys, keys2, E, 2u * k, s_h32, s_wbuf))) {
         const uint32_t S = pow2_ceil(E);
-        for (uint32_t i = E + tid; i < S; i += blockDim.x) keys[i] = ~0ull;
+        for (uint32_t i = E + tid; i < S; i += T) keys[i] = ~0ull;
         bitonic_sort<false>(keys, nullptr, S);
     }
 
-    uint32_t *headpos = aux;  // conf factors are dead
-    const uint32_t D = find_run_heads(keys, E, headpos, s_wbuf);
     const uint64_t o = a.eoff[r];
-    for (uint32_t idx = tid; idx < D; idx += blockDim.x) {
-        const uint32_t i = headpos[idx];
-        const uint32_t nx = (idx + 1 < D) ? headpos[idx + 1] : E;
-        a.skeys[o + idx] = keys[i];
-        a.svals[o + idx] = (float)(nx - i);  // value += 1.0 per occurrence: exact
-    }
+    // value += 1.0 per occurrence: exact
+    // (the segment counters alias the sort buffer: (ecap/2 + 64) words at least, ecap/32 + 8 needed)
+    const uint32_t D = reduce_runs<float>(keys, E, reinterpret_cast<uint32_t *>(keys2), a.ecap, &s_d, a.skeys + o,
+                                          a.svals + o, [](uint32_t, uint32_t run) { return (float)run; });
     if (tid == 0) {
         a.d_out[r] = D;
         a.hck_out[r] = E;
@@ -422,9 +514,11 @@ struct LeafCountArgs {
 
 // work area: keys[ecap] u64 | aux[ecap+64] u32 | wts[ecap] u16 | raw[ecap+16] u8 | comp[ecap+16] u8
 //            | words2[ecap/32+4] u64
+// The unambiguous path sorts with a second key buffer keys2[ecap] u64 that ALIASES aux..comp (8*ecap + 288
+// bytes, all dead once the keys exist; aux then holds the segment counters of the run-length reduce).
 __host__ __device__ inline size_t leaf_work_bytes(uint32_t ecap) {
     return (size_t)ecap * 8 + ((size_t)ecap + 64) * 4 + (size_t)ecap * 2 + 2 * ((size_t)ecap + 16) +
-           ((size_t)ecap / 32 + 4) * 8 + 16 + (has_bucket_buffer(ecap) ? (size_t)ecap * 8 : 0);
+           ((size_t)ecap / 32 + 4) * 8 + 16;
 }
 
 template <bool GLOBAL>
@@ -432,8 +526,8 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint32_t s_wbuf[33];
     __shared__ uint32_t s_cnt, s_namb, s_over;
-    __shared__ uint32_t s_sum;
-    __shared__ uint32_t s_hist[KC_BUCKETS], s_start[KC_BUCKETS + 1];
+    __shared__ uint32_t s_sum, s_d;
+    __shared__ uint32_t s_h32[KC_BINS / 2];
 
     uint8_t *work = GLOBAL ? a.gscratch + (size_t)blockIdx.x * a.gstride : smem_raw;
     size_t o_ = 0;
@@ -449,7 +543,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
     o_ += (size_t)a.ecap + 16;
     o_ = (o_ + 15) & ~(size_t)15;
     uint64_t *words2 = reinterpret_cast<uint64_t *>(work + o_);
-    uint64_t *keys2 = words2 + ((size_t)a.ecap / 32 + 4);
+    uint64_t *keys2 = reinterpret_cast<uint64_t *>(aux);
 
     const uint32_t tid = threadIdx.x;
     const uint32_t r = a.ids[blockIdx.x];
@@ -465,37 +559,74 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
         s_over = 0;
         s_sum = 0;
     }
-    // unpack 4-bit symbols (16-byte loads: 32 symbols each)
+    // Fast front end: a leaf of plain A/C/G/T (every 4-bit symbol one-hot: no gap, no ambiguity code -- the
+    // normal case) goes from the 4-bit words straight to 2-bit words with word-wide bit tricks, two input
+    // words (32 symbols) per thread.  Anything else takes the symbol-by-symbol path below.
+    bool irregular = false;
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.words + a.word_off[r]);
-        const uint32_t nchunks = (n_in + 31) >> 5;
-        for (uint32_t c = tid; c < nchunks; c += blockDim.x) {
-            uint4 v = __ldg(src + c);
-            uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        const uint64_t *src = a.words + a.word_off[r];
+        const uint32_t nw2 = (n_in + 31) >> 5;
+        for (uint32_t wi = tid; wi <= nw2; wi += blockDim.x) {  // one zero word past the end for window_key
+            uint64_t out = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                uint32_t idx = c * 32 + j;
-                if (idx < n_in) raw[idx] = (uint8_t)((wv[j >> 3] >> ((j & 7) * 4)) & 15u);
+            for (uint32_t h = 0; h < 2; ++h) {
+                const uint32_t s0 = (2 * wi + h) * 16;
+                if (s0 < n_in) {
+                    const uint64_t w = __ldg(src + 2 * wi + h);
+                    const uint32_t valid = min(16u, n_in - s0);
+                    const uint64_t m = valid == 16 ? ~0ull : (1ull << (4 * valid)) - 1ull;
+                    const uint64_t ones = 0x1111111111111111ull;
+                    const uint64_t multi = ((w & (w >> 1)) & (7 * ones)) | ((w & (w >> 2)) & (3 * ones)) |
+                                           ((w & (w >> 3)) & ones);
+                    const uint64_t zero = ~(w | (w >> 1) | (w >> 2) | (w >> 3)) & ones;
+                    irregular |= ((multi | zero) & m) != 0ull;
+                    // A=8 -> 0, C=4 -> 1, G=2 -> 2, T=1 -> 3: high bit = G|T, low bit = C|T
+                    const uint64_t hi = ((w >> 1) | w) & ones, lo = ((w >> 2) | w) & ones;
+                    uint64_t x = ((hi << 1) | lo) & m;
+                    x = (x | (x >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+                    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+                    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+                    x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
+                    out |= x << (32 * h);
+                }
+            }
+            words2[wi] = out;
+        }
+    }
+    const bool fast = !__syncthreads_or(irregular);
+    uint32_t n = n_in;
+    if (!fast) {
+        // unpack 4-bit symbols (16-byte loads: 32 symbols each)
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.words + a.word_off[r]);
+            const uint32_t nchunks = (n_in + 31) >> 5;
+            for (uint32_t c = tid; c < nchunks; c += blockDim.x) {
+                uint4 v = __ldg(src + c);
+                uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    uint32_t idx = c * 32 + j;
+                    if (idx < n_in) raw[idx] = (uint8_t)((wv[j >> 3] >> ((j & 7) * 4)) & 15u);
+                }
             }
         }
-    }
-    __syncthreads();
-    // drop gaps (Iupac::X == 0), tax/mod.rs:98 -- ordered compaction
-    uint32_t n;
-    {
-        const uint32_t C = (n_in + blockDim.x - 1) / blockDim.x;
-        const uint32_t b = min(n_in, tid * C), e = min(n_in, b + C);
-        uint32_t cnt = 0, amb = 0;
-        for (uint32_t i = b; i < e; ++i) {
-            cnt += raw[i] != 0;
-            amb += __popc((uint32_t)raw[i]) > 1;
+        __syncthreads();
+        // drop gaps (Iupac::X == 0), tax/mod.rs:98 -- ordered compaction
+        {
+            const uint32_t C = (n_in + blockDim.x - 1) / blockDim.x;
+            const uint32_t b = min(n_in, tid * C), e = min(n_in, b + C);
+            uint32_t cnt = 0, amb = 0;
+            for (uint32_t i = b; i < e; ++i) {
+                cnt += raw[i] != 0;
+                amb += __popc((uint32_t)raw[i]) > 1;
+            }
+            uint32_t pos = block_excl_scan_u32(cnt, s_wbuf, &n);
+            for (uint32_t i = b; i < e; ++i)
+                if (raw[i] != 0) comp[pos++] = raw[i];
+            if (amb) atomicAdd(&s_namb, amb);
         }
-        uint32_t pos = block_excl_scan_u32(cnt, s_wbuf, &n);
-        for (uint32_t i = b; i < e; ++i)
-            if (raw[i] != 0) comp[pos++] = raw[i];
-        if (amb) atomicAdd(&s_namb, amb);
+        __syncthreads();
     }
-    __syncthreads();
     const uint32_t cutoff = (R + 5u) >> 3;  // tax/mod.rs:130
     if (n < k || R == 0) {                  // :99-102 / empty singles -> :136-139
         if (tid == 0) {
@@ -507,20 +638,22 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
         return;
     }
     const uint32_t nb = n - k + 1;
-    const bool ambiguous = s_namb != 0;
+    const bool ambiguous = !fast && s_namb != 0;
     uint32_t E;
     if (!ambiguous) {
         // all resamples are identical: count once, scale by R (wrapping u16 like the
         // release-mode `+=` of from_unsorted_singles)
-        const uint32_t nw = (n + 31) >> 5;
-        for (uint32_t wi = tid; wi <= nw; wi += blockDim.x) {
-            uint64_t w = 0;
-            const uint32_t lim = min(32u, n > wi * 32 ? n - wi * 32 : 0u);
-            for (uint32_t j = 0; j < lim; ++j)
-                w |= (uint64_t)((uint32_t)__clz((uint32_t)comp[wi * 32 + j]) - 28u) << (2 * j);
-            words2[wi] = w;
+        if (!fast) {  // gaps were dropped: pack the compacted symbols
+            const uint32_t nw = (n + 31) >> 5;
+            for (uint32_t wi = tid; wi <= nw; wi += blockDim.x) {
+                uint64_t w = 0;
+                const uint32_t lim = min(32u, n > wi * 32 ? n - wi * 32 : 0u);
+                for (uint32_t j = 0; j < lim; ++j)
+                    w |= (uint64_t)((uint32_t)__clz((uint32_t)comp[wi * 32 + j]) - 28u) << (2 * j);
+                words2[wi] = w;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         for (uint32_t i = tid; i < nb; i += blockDim.x) {
             uint64_t kf = window_key(words2, i, k), kr = revcomp_key(kf, k);
             order_key_pair(kf, kr, k, a.msb_first);
@@ -585,8 +718,7 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
         E = s_cnt;
     }
     __syncthreads();
-    if (!(!ambiguous && has_bucket_buffer(a.ecap) &&
-          bucket_sort(keys, keys2, E, 2u * k, s_hist, s_start, s_wbuf))) {
+    if (!(!ambiguous && has_bucket_buffer(a.ecap) && bucket_rank_sort(keys, keys2, E, 2u * k, s_h32, s_wbuf))) {
         const uint32_t S = pow2_ceil(E);
         for (uint32_t i = E + tid; i < S; i += blockDim.x) {
             keys[i] = ~0ull;
@@ -598,6 +730,33 @@ __global__ void __launch_bounds__(KC_THREADS) count_leaves_kernel(LeafCountArgs 
             bitonic_sort<false>(keys, nullptr, S);
     }
 
+    if (!ambiguous) {
+        // value = run length x R (u16, wrapping); strip values <= cutoff (:130-134); sum of the survivors
+        uint32_t sum = 0;
+        const uint32_t D = reduce_runs<uint16_t>(keys, E, aux, a.ecap, &s_d, a.skeys + o, a.svals + o,
+                                                 [&](uint32_t, uint32_t run) {
+                                                     const uint32_t v = (run * R) & 0xFFFFu;
+                                                     return (uint16_t)(v > cutoff ? v : 0u);
+                                                 });
+        // the survivors' sum: every thread re-reads its share of what was just written (L1-resident)
+        for (uint32_t i = tid; i < D; i += blockDim.x) sum += a.svals[o + i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if ((tid & 31u) == 0 && sum) atomicAdd(&s_sum, sum);  // u32 wrapping like sum::<u32>() in release
+        __syncthreads();
+        if (tid == 0) {
+            if (D == 0) {  // :136-139
+                a.skeys[o] = 0;
+                a.svals[o] = 1;
+                a.d_out[r] = 1;
+                a.rescale_out[r] = 1.0f;
+            } else {
+                a.d_out[r] = D;
+                a.rescale_out[r] = __fdiv_rn((float)(2u * nb), (float)s_sum);  // :144-145
+            }
+        }
+        return;
+    }
     uint32_t *headpos = aux;
     const uint32_t Dall = find_run_heads(keys, E, headpos, s_wbuf);
     // value per run, strip values <= cutoff (:130-134), ordered compaction of the survivors

@@ -227,7 +227,6 @@ template <int SIM, bool FUSED, bool STATS, bool UREG>
 __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) score_tiles_kernel(ScoreArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
     // per warp: tile accumulators + dummy slot for masked-off lanes (+ 256-bin histogram) + hit list
     uint8_t *wbase = smem_raw + (size_t)warp * score_warp_smem_bytes(a.tile_leaves, FUSED);
     float *acc = reinterpret_cast<float *>(wbase);
@@ -452,7 +451,8 @@ static constexpr int SCC_PLANES = 6;        // bit-sliced counters: up to 63 den
 static constexpr int SCC_MAX_WARPS = 24;
 
 __host__ __device__ inline size_t score_count_warp_smem_bytes(uint32_t tile_leaves, bool fused) {
-    return ((size_t)tile_leaves + 32 + (fused ? 256 : 0)) * sizeof(float) +            // acc (+ histogram)
+    (void)fused;  // the histogram's space doubles as the dense-key list of a split hit list: always there
+    return ((size_t)tile_leaves + 32 + 256) * sizeof(float) +                            // acc + histogram
            (((size_t)tile_leaves + 32) * sizeof(uint16_t) + 15) / 16 * 16 +             // shared-key counters
            SC_HITS * sizeof(HitRec);
 }
@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
     uint8_t *wbase = smem_raw + (size_t)warp * score_count_warp_smem_bytes(a.tile_leaves, FUSED);
     float *acc = reinterpret_cast<float *>(wbase);
     uint32_t *hist = reinterpret_cast<uint32_t *>(acc + a.tile_leaves + 32);
-    uint16_t *cnt = reinterpret_cast<uint16_t *>(acc + a.tile_leaves + 32 + (FUSED ? 256 : 0));
+    uint16_t *cnt = reinterpret_cast<uint16_t *>(acc + a.tile_leaves + 32 + 256);
     HitRec *hits = reinterpret_cast<HitRec *>(reinterpret_cast<uint8_t *>(cnt) +
                                               (((size_t)a.tile_leaves + 32) * sizeof(uint16_t) + 15) / 16 * 16);
     const uint64_t dummy_posting = (uint64_t)a.tile_leaves << 32;  // leaf = dummy slot, not odd
@@ -511,46 +511,67 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
     const uint64_t *post = nullptr;
     const uint32_t *bitmaps = nullptr;
     const float *unit = nullptr;
+    float unit_max = 0.0f;
     const TileInfo *ti = a.tiles;
 
+    // ---- task pipeline.  Task ids come from an atomic counter.  The id of the task after next is requested in
+    // the middle of the current task, where the next task's plan slice (two offsets) and common value are loaded
+    // as well: all three round trips to L2 are off the critical path.
+    const unsigned lt = (1u << lane) - 1u;
     uint32_t next_task = 0;
     if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
-    for (;;) {
-        const uint32_t task = __shfl_sync(0xffffffffu, next_task, 0);
-        if (task >= a.n_tasks) break;
-        if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
-        uint32_t t, ql;
+    auto load_desc = [&](uint32_t tk, uint32_t &tt, uint32_t &qq, uint64_t &b, uint64_t &e, float &v) {
+        if (tk >= a.n_tasks) return;
         if (a.seed_mode == 1) {
-            ql = task;
-            t = __ldg(a.seed + ql);
+            qq = tk;
+            tt = __ldg(a.seed + qq);
         } else {
-            t = task / a.q_count;
-            ql = task - t * a.q_count;
+            tt = tk / a.q_count;  // tile-major: a tile's index stays hot in L2
+            qq = tk - tt * a.q_count;
         }
+        const size_t sl = (size_t)qq * a.n_tiles + tt;
+        b = a.plan_off[sl];
+        e = a.plan_off[sl + 1];
+        v = __ldg(a.qv1 + qq);  // the query's common value
+    };
+    uint32_t task = __shfl_sync(0xffffffffu, next_task, 0);
+    uint32_t t = 0, ql = 0;
+    uint64_t hb_raw = 0, he_raw = 0;
+    float v1 = 0.0f;
+    load_desc(task, t, ql, hb_raw, he_raw, v1);
+    if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
+    while (task < a.n_tasks) {
         const size_t slot = (size_t)ql * a.n_tiles + t;
-        const uint64_t hb_raw = a.plan_off[slot];
-        const uint64_t hb = hb_raw & ~PLAN_SEED_FLAG, he = a.plan_off[slot + 1] & ~PLAN_SEED_FLAG;
-        if (a.seed_mode == 2 && (hb_raw & PLAN_SEED_FLAG)) continue;
-        const float v1 = __ldg(a.qv1 + ql);  // the query's common value
+        const uint64_t hb = hb_raw & ~PLAN_SEED_FLAG, he = he_raw & ~PLAN_SEED_FLAG;
+        const bool skip = a.seed_mode == 2 && (hb_raw & PLAN_SEED_FLAG);  // scored by the seed pass
+        // bit-sliced counters of the lane-owned leaves 32*r + lane (bit r of plane j = bit j of the count)
+        uint32_t pl[SCC_PLANES];
+#pragma unroll
+        for (int j = 0; j < SCC_PLANES; ++j) pl[j] = 0;
+        uint32_t pending = 0;  // dense keys counted since the last flush (warp-uniform)
+        if (!skip) {
         if (t != cached_tile) {
             ti = a.tiles + t;
             nl = ti->n_leaves;
             post = a.postings + ti->post_begin;
             bitmaps = ti->bitmaps;
             unit = ti->unit;
+            unit_max = ti->unit_max;
             cached_tile = t;
         }
-        for (uint32_t i = lane; i < a.tile_leaves + 32; i += 32) {
-            acc[i] = 0.0f;
-            cnt[i] = 0;
+        if ((a.tile_leaves & 7u) == 0u) {  // 16-byte stores (the per-warp slices are 16-byte aligned)
+            const uint32_t n4 = (a.tile_leaves + 32) >> 2, n8 = (a.tile_leaves + 32) >> 3;
+            for (uint32_t i = lane; i < n4; i += 32) reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t i = lane; i < n8; i += 32) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            for (uint32_t i = lane; i < a.tile_leaves + 32; i += 32) {
+                acc[i] = 0.0f;
+                cnt[i] = 0;
+            }
         }
         __syncwarp();
+        }
 
-        // bit-sliced counters of the lane-owned leaves 32*r + lane (bit r of plane j = bit j of the count)
-        uint32_t pl[SCC_PLANES];
-#pragma unroll
-        for (int j = 0; j < SCC_PLANES; ++j) pl[j] = 0;
-        uint32_t pending = 0;  // dense keys counted since the last flush (warp-uniform)
         auto flush_planes = [&]() {
             if (pending == 0) return;
             // rolled on purpose: the flush is inlined at several (mostly cold) sites and the kernel is
@@ -662,92 +683,149 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             }
         };
 
+        if (!skip)
         for (uint64_t h0 = hb; h0 < he; h0 += SC_HITS) {
-            uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
+            const uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
+            // Staging.  Common terms commute, so a hit list without an ORDERED hit (nearly all of them) is split on
+            // the way in: the bitmap indexes of its dense keys go to dlist[] (the radix-select histogram's space,
+            // idle until the top-x), its sparse keys are compacted to the front of the hit buffer as (begin, len).
+            uint32_t *dlist = hist;
+            uint2 *shits = reinterpret_cast<uint2 *>(hits);
+            uint32_t nd = 0, ns = 0;
             bool ordered = false;
-            for (uint32_t i = lane; i < n_hits; i += 32) {
-                const HitRec h = a.plan[h0 + i];
-                hits[i] = h;
+            unsigned long long tsum = 0;
+            for (uint32_t base = 0; base < n_hits; base += 32) {
+                const uint32_t i = base + lane;
+                HitRec h;
+                h.begin = 0;
+                h.len = 0;
+                if (i < n_hits) h = a.plan[h0 + i];
+                const bool is_d = (h.len & DENSE_FLAG) != 0u, is_s = !is_d && i < n_hits;
                 ordered |= (h.len & ORDERED_FLAG) != 0u;
+                const unsigned md = __ballot_sync(0xffffffffu, is_d), ms = __ballot_sync(0xffffffffu, is_s);
+                if (is_d) dlist[nd + __popc(md & lt)] = h.begin;
+                if (is_s) shits[ns + __popc(ms & lt)] = make_uint2(h.begin, h.len & LEN_MASK);
+                nd += __popc(md);
+                ns += __popc(ms);
+                if (STATS) tsum += h.len & LEN_MASK;
             }
             ordered = __any_sync(0xffffffffu, ordered);
             __syncwarp();
-            if (!ordered) {
-                // Common terms only: they commute, so the dense keys go first in a tight loop (four bitmap
-                // words in flight, no per-key state machine) and the sparse keys, compacted to the front of
-                // the list on the way, take the general walk below.
-                uint32_t ns = 0;
-                for (uint32_t hi = 0; hi < n_hits; hi += 4) {
-                    if (pending > (1u << SCC_PLANES) - 5u) flush_planes();
-                    HitRec h[4];
-                    uint32_t w[4];
-                    bool dn[4];
+            if (ordered) {  // rare: the list is walked in key order
+                for (uint32_t i = lane; i < n_hits; i += 32) hits[i] = a.plan[h0 + i];
+                __syncwarp();
+                process_hits(n_hits);
+                __syncwarp();
+                continue;
+            }
+            if (STATS) st_post += tsum;
+            // dense keys: eight bitmap words in flight, one ripple-carry add each into the bit-sliced counters
+            for (uint32_t d0 = 0; d0 < nd; d0 += 8) {
+                if (pending > (1u << SCC_PLANES) - 9u) flush_planes();
+                uint32_t w[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        h[u] = hits[min(hi + u, n_hits - 1u)];
-                        dn[u] = hi + u < n_hits && (h[u].len & DENSE_FLAG) != 0u;
-                        w[u] = dn[u] ? __ldg(bitmaps + (size_t)h[u].begin * 32 + lane) : 0u;
-                    }
-                    __syncwarp();  // all lanes have read the four records before any is overwritten
+                for (int u = 0; u < 8; ++u)
+                    w[u] = d0 + u < nd ? __ldg(bitmaps + (size_t)dlist[d0 + u] * 32 + lane) : 0u;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (dn[u]) {
-                            uint32_t carry = w[u];
+                for (int u = 0; u < 8; ++u) {
+                    uint32_t carry = w[u];  // an absent word (0) leaves the counters unchanged
 #pragma unroll
-                            for (int j = 0; j < SCC_PLANES; ++j) {
-                                const uint32_t t2 = pl[j] & carry;
-                                pl[j] ^= carry;
-                                carry = t2;
-                            }
-                            ++pending;
-                            if (STATS) st_post += (lane == 0) ? (h[u].len & LEN_MASK) : 0;
-                        } else if (hi + u < n_hits) {
-                            if (lane == 0) hits[ns] = h[u];
-                            ++ns;
-                        }
+                    for (int j = 0; j < SCC_PLANES; ++j) {
+                        const uint32_t t2 = pl[j] & carry;
+                        pl[j] ^= carry;
+                        carry = t2;
                     }
                 }
-                __syncwarp();
-                n_hits = ns;
+                pending += min(8u, nd - d0);
             }
-            process_hits(n_hits);
+            // sparse keys: the lanes fan out over one key's postings (distinct leaves); the first chunk of the
+            // next key is requested before the current one is applied
+            if (ns) {
+                uint2 cur = shits[0];
+                uint64_t p0 = lane < cur.y ? __ldg(post + cur.x + lane) : dummy_posting;
+                for (uint32_t si = 0; si < ns; ++si) {
+                    uint2 nxt = make_uint2(0u, 0u);
+                    uint64_t pn = dummy_posting;
+                    if (si + 1 < ns) {
+                        nxt = shits[si + 1];
+                        if (lane < nxt.y) pn = __ldg(post + nxt.x + lane);
+                    }
+                    {
+                        const uint32_t leaf = (uint32_t)(p0 >> 32);  // no flag bits in an unordered list
+                        cnt[leaf] = (uint16_t)(cnt[leaf] + 1u);      // lanes past the end bump the dummy slot
+                    }
+                    for (uint32_t off = 32 + lane; off < cur.y; off += 32) {
+                        const uint32_t leaf = (uint32_t)(__ldg(post + cur.x + off) >> 32);
+                        cnt[leaf] = (uint16_t)(cnt[leaf] + 1u);
+                    }
+                    __syncwarp();  // the next key may hit the same leaves
+                    cur = nxt;
+                    p0 = pn;
+                }
+            }
             __syncwarp();
         }
+
+        // ---- the next task's descriptor (its id was requested half a task ago), and the id after that
+        const uint32_t n_task = __shfl_sync(0xffffffffu, next_task, 0);
+        uint32_t n_t = 0, n_ql = 0;
+        uint64_t n_hb = 0, n_he = 0;
+        float n_v1 = 0.0f;
+        load_desc(n_task, n_t, n_ql, n_hb, n_he, n_v1);
+        if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
+        auto advance = [&]() {
+            task = n_task;
+            t = n_t;
+            ql = n_ql;
+            hb_raw = n_hb;
+            he_raw = n_he;
+            v1 = n_v1;
+        };
+        if (skip) {
+            advance();
+            continue;
+        }
+
         // ---- bound pass (fused top-x, once the query has a bound).  The score of a leaf is the f32 sequence
         // s <- fl(s + p), n times, from its partial sum s0: every rounding adds at most 2^-24 relative, so
-        // score <= (s0 + n p)(1 + 2^-24)^n <= 1.004 (s0 + n p) for n < 65535.  A leaf whose bound (computed with
-        // the dense keys still pending in the bit-sliced counters taken as ALL present: n <= cnt + pending) stays
-        // below the query's running bound cannot enter its top-x: its shared keys were counted, its score is
-        // not finished (left at +0, below any non-zero bound).  Only the survivors -- the query's relatives --
-        // get their dense count unsliced and their additions replayed, exactly as in the full replay below.
+        // score <= (s0 + n p)(1 + 2^-24)^n <= 1.004 (s0 + n p) for n < 65535.  The bound is formed with the largest
+        // unit value of the tile (p <= pmax = fl(v1 unit_max)) and with the dense keys still pending in the
+        // bit-sliced counters taken as ALL present (n <= cnt + pending); a leaf whose bound stays below the query's
+        // running bound cannot enter its top-x: its shared keys were counted, its score is not finished (left at
+        // +0, below any non-zero bound).  Only the survivors -- the query's relatives -- get their unit value
+        // loaded, their dense count unsliced and their additions replayed, exactly as in the full replay below.
         if (FUSED && a.ub_prune) {
             const uint32_t thr = read_bound(a.gthr + ql, lane);
             if (thr != 0u) {
                 const float thr_f = __uint_as_float(thr);
-                const float pend_f = (float)pending;
+                const float pmax = __fmul_rn(v1, unit_max);
+                const uint32_t magic = 0x4B000000u + pending;  // float(2^23 + n) for n < 2^23
                 uint32_t c_cnt = 0;
                 if (he > hb) {
 #pragma unroll 4
                     for (uint32_t r = 0; 32u * r < nl; ++r) {
-                        const uint32_t leaf = 32u * r + lane;
-                        const bool ok = leaf < nl;
-                        const uint32_t li = ok ? leaf : a.tile_leaves;  // dummy slot
-                        float sc = acc[li];
-                        const uint32_t n0 = cnt[li];
-                        const float p = __fmul_rn(v1, __ldg(unit + min(leaf, nl - 1u)));
-                        float ub = __fmul_rn(__fadd_rn(sc, __fmul_rn(__fadd_rn((float)n0, pend_f), p)), 1.01f);
+                        const uint32_t leaf = 32u * r + lane;  // leaf < tile_leaves + 32: inside the padded arrays
+                        const float s0 = acc[leaf];
+                        const uint32_t n0 = cnt[leaf];
+                        const float nf = __fadd_rn(__uint_as_float(magic + n0), -8388608.0f);
+                        float ub = __fmul_rn(__fadd_rn(s0, __fmul_rn(nf, pmax)), 1.01f);
                         if (SIM == MYRIO_SIM_JACARD_TANIMOTO)  // monotone in the dot product while it is < 2
                             ub = ub < 1.5f ? sim_transform<SIM>(ub) : 3.0e38f;
-                        const bool need = ok && !(ub < thr_f);
-                        if (need) {
-                            uint32_t c = 0;
+                        const bool need = leaf < nl && !(ub < thr_f);
+                        if (need || s0 != 0.0f) {
+                            float sc = 0.0f;
+                            if (need) {
+                                const float p = __fmul_rn(v1, __ldg(unit + leaf));
+                                uint32_t c = 0;
 #pragma unroll
-                            for (int j = 0; j < SCC_PLANES; ++j) c |= ((pl[j] >> r) & 1u) << j;
-                            for (uint32_t n = n0 + c; n; --n) sc = __fadd_rn(sc, p);
-                            sc = sim_transform<SIM>(sc);
-                            c_cnt += (__float_as_uint(sc) >= thr) ? 1u : 0u;
+                                for (int j = 0; j < SCC_PLANES; ++j) c |= ((pl[j] >> r) & 1u) << j;
+                                sc = s0;
+                                for (uint32_t n = n0 + c; n; --n) sc = __fadd_rn(sc, p);
+                                sc = sim_transform<SIM>(sc);
+                                c_cnt += (__float_as_uint(sc) >= thr) ? 1u : 0u;
+                            }
+                            acc[leaf] = sc;
                         }
-                        if (ok) acc[leaf] = need ? sc : 0.0f;
                     }
                 }
                 c_cnt = warp_sum_u32(c_cnt);
@@ -755,6 +833,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                 tile_topx_emit(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
                                a.cand + slot * a.x, a.cand_cnt + slot, lane, thr, c_cnt);
                 __syncwarp();
+                advance();
                 continue;
             }
         }
@@ -803,8 +882,13 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             for (uint32_t i = lane; i < nl; i += 32) out[i] = sim_transform<SIM>(acc[i]);
         }
         __syncwarp();
+        advance();
     }
-    if (STATS && lane == 0 && st_post) atomicAdd(a.counters + 3, st_post);
+    if (STATS) {  // lane 0 counted the walked lists, every lane its share of the split ones
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) st_post += __shfl_xor_sync(0xffffffffu, st_post, d);
+        if (lane == 0 && st_post) atomicAdd(a.counters + 3, st_post);
+    }
 }
 
 // ------------------------------------------------------------------ K5: top-x
