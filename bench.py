@@ -128,20 +128,23 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu, self.rows, self.proc = gpu_index, [], None
         self.sm, self.reasons, self.mx, self.stop_flag, self.thread, self.source = [], set(), None, False, None, None
+        self.period = float(os.environ.get("MYRIO_BENCH_NVML_PERIOD", "0.5"))
 
     def _nvml_loop(self, nv, h):
         names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
                  ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        mode = os.environ.get("MYRIO_BENCH_NVML", "full")  # diagnosis: "clock" skips the event-reason query
         while not self.stop_flag:
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                for name, bit in names:
-                    if mask & bit:
-                        self.reasons.add(name)
+                if mode != "clock":
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                    for name, bit in names:
+                        if mask & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.5)
+            time.sleep(self.period)
 
     def start(self):
         try:
@@ -601,6 +604,14 @@ def run_ours(args, rank, local_rank, world):
     ms_e2e = timed(step_e2e, args.steps, "e2e")
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the same step with EVERY score finished (the fused top-x normally finishes only the scores whose
+    # upper bound reaches the query's running bound; the top-x is bit-identical either way)
+    ctx.set_topx_bound_pruning(False)
+    step_resident()
+    ms_all = timed(step_resident, max(1, min(args.steps, 2)))
+    ctx.set_topx_bound_pruning(True)
+    step_resident()
+
     # ---- k-mer counting THROUGH THE CALL (reads): myrio_count_reads + sync, wall clock, max over ranks
     n_cr = max(5, args.steps)
     c_tmp = resident.compute_kmer_counts(k, 0.1)  # warm-up
@@ -642,11 +653,11 @@ def run_ours(args, rank, local_rank, world):
     k4_avg_ms = k4_ms / max(k4_n, 1)
     k4_step_ms = k4_ms / max(args.steps, 1)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    prof = latest_profile("r02_k4_ncu_summary") or latest_profile("r01_k4_v14_ncu_summary")
+    prof = latest_profile("_k4v") or latest_profile("r02_k4_ncu_summary")  # newest capture of the count-mode kernel
     issue_peak = 148 * 4 * sm_mhz * 1e6  # warp instructions / s: 148 SMs x 4 schedulers x 1 issue / clk
     roofline = {
         "bound": "issue",
-        "kernel": "k4_score_tiles_topx (score_tiles_kernel<COSINE, fused top-x>), seed pass + tile-major sweep",
+        "kernel": "k4_score_tiles_topx (score_tiles_count_kernel<COSINE, fused top-x>), seed pass + tile-major sweep",
         "unit": "Gwarp-inst/s", "peak": issue_peak / 1e9,
         "peak_source": f"148 SMs x 4 warp schedulers x SM clock under load ({sm_mhz:.0f} MHz, nvidia-smi during the timed region)",
         "launch_ms_avg": k4_avg_ms, "launches_per_step": k4_per_step, "kernel_ms_per_step": k4_step_ms,
@@ -726,6 +737,13 @@ def run_ours(args, rank, local_rank, world):
                 "h2d_bytes_per_step_per_rank": h2d_rank,
                 "note": "every rank uploads the read batch (queries are replicated) and downloads its 1/N of the merged top-x"},
         "gpu_launches": int(launches),
+        "all_scores_finished": {
+            "ms_per_step": ms_all / max(1, min(args.steps, 2)),
+            "value": n_gpu_scores * max(1, min(args.steps, 2)) / (ms_all * 1e-3), "unit": UNIT,
+            "note": "the same step with myrio_ctx_set_topx_bound_pruning(0): every (query, leaf) score is replayed to "
+                    "its final f32 value instead of only those whose upper bound reaches the query's running x-th best "
+                    "score; `value` counts every pair either way (each pair's shared keys are counted and its score "
+                    "bounded), the top-x is bit-identical"},
         "roofline": roofline,
         "clocks": clocks,
         "kmers": kmers,

@@ -94,6 +94,11 @@ uint64_t myrio_ctx_launch_count(const myrio_ctx *ctx);
  * constant; it decides the stored .myrtree keys and, through the sort order, the f32 summation order.
  * Applies to the myrio_count_* calls made on this context afterwards. */
 int32_t myrio_ctx_set_kmer_bit_order(myrio_ctx *ctx, int32_t msb_first);
+/* Fused top-x (myrio_score_topx*): 1 (default) = a (query, leaf) score is FINISHED only if its upper bound
+ * reaches the query's running x-th best score (every pair's shared keys are still counted; the top-x is
+ * bit-identical either way); 0 = every score of every pair is finished, as myrio_score_all does.  A
+ * measurement / comparison switch; the environment variable MYRIO_K4_UB=0 sets the default to 0. */
+int32_t myrio_ctx_set_topx_bound_pruning(myrio_ctx *ctx, int32_t on);
 /* optional per-kernel CUDA-event timing (events on the context's stream) */
 int32_t myrio_prof_enable(myrio_ctx *ctx, int32_t on);
 int32_t myrio_prof_reset(myrio_ctx *ctx);

@@ -20,7 +20,7 @@ VAL_F32, VAL_U16 = 0, 1
 # every symbol include/myrio_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
     "myrio_last_error", "myrio_version", "myrio_ctx_create", "myrio_ctx_destroy", "myrio_ctx_sync",
-    "myrio_ctx_launch_count", "myrio_ctx_set_kmer_bit_order", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query", "myrio_bench_smem_bandwidth",
+    "myrio_ctx_launch_count", "myrio_ctx_set_kmer_bit_order", "myrio_ctx_set_topx_bound_pruning", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query", "myrio_bench_smem_bandwidth",
     "myrio_reads_upload", "myrio_reads_from_fastq", "myrio_leaves_upload", "myrio_leaves_from_fasta", "myrio_seqs_count", "myrio_seqs_free", "myrio_count_reads",
     "myrio_count_leaves", "myrio_svecs_info", "myrio_svecs_download", "myrio_svecs_upload",
     "myrio_svecs_normalize", "myrio_svecs_free", "myrio_index_build", "myrio_index_info",
@@ -133,6 +133,7 @@ def load() -> C.CDLL:
     L.myrio_score_topx.argtypes = [vp, vp, vp, u64, u64, u32, i32, vp, vp]
     L.myrio_score_topx_async.argtypes = [vp, vp, vp, u64, u64, u32, i32, vp, vp]
     L.myrio_ctx_set_kmer_bit_order.argtypes = [vp, i32]
+    L.myrio_ctx_set_topx_bound_pruning.argtypes = [vp, i32]
     L.myrio_score_all_direct.argtypes = [vp, vp, vp, u64, u64, i32, vp]
     L.myrio_score_topx_direct.argtypes = [vp, vp, u32, vp, u64, u64, u32, i32, vp, vp]
     L.myrio_score_topx_direct_async.argtypes = [vp, vp, u32, vp, u64, u64, u32, i32, vp, vp]

@@ -50,6 +50,11 @@ class Context:
         """Integer value of a k-mer key: False (default) = bio-seq's LSB-first packing, True = MSB-first."""
         _lib.check(self._L.myrio_ctx_set_kmer_bit_order(self.h, int(bool(msb_first))))
 
+    def set_topx_bound_pruning(self, on: bool):
+        """Fused top-x: finish only the scores whose upper bound reaches the query's running bound (default) or
+        every score (comparison runs); the top-x is bit-identical either way."""
+        _lib.check(self._L.myrio_ctx_set_topx_bound_pruning(self.h, int(bool(on))))
+
     @property
     def stream(self) -> int:
         """cudaStream_t of the context as an integer (torch.cuda.ExternalStream(ctx.stream))."""

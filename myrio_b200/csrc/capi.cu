@@ -103,6 +103,13 @@ int32_t myrio_ctx_set_kmer_bit_order(myrio_ctx *ctx, int32_t msb_first) {
     });
 }
 
+int32_t myrio_ctx_set_topx_bound_pruning(myrio_ctx *ctx, int32_t on) {
+    return guarded([&] {
+        if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
+        ctx->topx_bound_pruning = on ? 1 : 0;
+    });
+}
+
 void *myrio_ctx_stream(const myrio_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int32_t myrio_prof_enable(myrio_ctx *ctx, int32_t on) {

@@ -290,12 +290,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_kernel(PairArgs a) {
 // Silhouette sums (clustering.rs:323-336) over a transposed tile: one thread per row adds
 // dist = 1 - sim in COLUMN ORDER (the member order of the reference's iterators), continuing
 // the running sums of the previous column pass.
+// Rows from swap_row on belong to the SECOND group of columns (two mutually nearest clusters scored in one
+// tile): for them the columns from `split` on are the own cluster and the first `split` the neighbour's -- the
+// two sums are independent sequences, so only their roles swap.
 __global__ void __launch_bounds__(128) silsum_rows_kernel(const float *__restrict__ tile, uint64_t ld,
                                                           uint32_t n_rows, uint32_t c_first, uint32_t n_cols,
-                                                          uint32_t split, float *__restrict__ sums) {
+                                                          uint32_t split, float *__restrict__ sums,
+                                                          uint32_t swap_row) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    float sa = sums[(size_t)r * 2], sb = sums[(size_t)r * 2 + 1];
+    const bool swp = r >= swap_row;
+    float sa = sums[(size_t)r * 2 + (swp ? 1 : 0)], sb = sums[(size_t)r * 2 + (swp ? 0 : 1)];
     uint32_t c = 0;
     for (; c + 8 <= n_cols; c += 8) {
         float s[8];
@@ -317,8 +322,8 @@ __global__ void __launch_bounds__(128) silsum_rows_kernel(const float *__restric
         else
             sb = __fadd_rn(sb, d);
     }
-    sums[(size_t)r * 2] = sa;
-    sums[(size_t)r * 2 + 1] = sb;
+    sums[(size_t)r * 2 + (swp ? 1 : 0)] = sa;
+    sums[(size_t)r * 2 + (swp ? 0 : 1)] = sb;
 }
 
 // argmax over the columns of a transposed tile; max_by_key keeps the LAST maximum
@@ -596,6 +601,11 @@ struct CanonArgs {
     int sim;
     float *out;  // transposed: out[c * ld + row]
     uint64_t ld;
+    // The first sym_cols columns are the rows themselves, in the same order (a cluster's members against
+    // themselves): sim(i, j) == sim(j, i) bit for bit (the products commute, the key order is shared), so a
+    // column chunk that lies inside that square only takes the rows at or below its first column and every
+    // score is also stored at its mirror position.  Needs c_first == 0 and n_cols >= sym_cols.
+    uint32_t sym_cols;
 };
 
 // shared memory: plane A (columns 0-3) = PC_REPLICAS x plane_rows float4, then plane B (columns 4-7)
@@ -613,6 +623,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_canon_kernel(CanonArg
         const uint32_t slice = task / n_chunks, chunk = task % n_chunks;
         const uint32_t c0 = chunk * CB;
         const uint32_t nc = min((uint32_t)CB, a.n_cols - c0);
+        const bool sym = c0 + CB <= a.sym_cols;  // the chunk lies inside the symmetric square
+        uint32_t g_lo = (uint32_t)((uint64_t)a.n_groups * slice / a.n_slices);
+        const uint32_t g_hi = (uint32_t)((uint64_t)a.n_groups * (slice + 1) / a.n_slices);
+        if (sym) g_lo = max(g_lo, c0 >> 5);  // rows above the chunk come from the mirror stores
+        if (g_lo >= g_hi) continue;           // (uniform over the CTA: nothing staged for an empty task)
         if (chunk != staged) {
             __syncthreads();
             for (uint32_t i = tid; i < 2 * plane_f4; i += PT_THREADS) sm4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -644,8 +659,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_canon_kernel(CanonArg
             staged = chunk;
             __syncthreads();
         }
-        const uint32_t g_lo = (uint32_t)((uint64_t)a.n_groups * slice / a.n_slices);
-        const uint32_t g_hi = (uint32_t)((uint64_t)a.n_groups * (slice + 1) / a.n_slices);
         for (uint32_t g = g_lo + warp; g < g_hi; g += PT_WARPS) {
             const uint32_t quads = a.grp_len[g];
             const uint64_t base = a.grp_off[g] * 128ull + lane * 4u;
@@ -688,6 +701,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) pair_tile_canon_kernel(CanonArg
 #pragma unroll
                 for (int c = 0; c < CB; ++c)
                     if ((uint32_t)c < nc) a.out[(size_t)(c0 + c) * a.ld + ri] = pk_sim(a.sim, acc[c]);
+                if (sym && ri >= c0 + CB && ri < a.sym_cols) {  // mirror: column ri, rows c0 .. c0+7
+#pragma unroll
+                    for (int c = 0; c < CB; ++c) a.out[(size_t)ri * a.ld + c0 + c] = pk_sim(a.sim, acc[c]);
+                }
             }
         }
     }
@@ -712,8 +729,8 @@ static void launch_pair_tile_canon(myrio_ctx *ctx, CanonArgs a, const RowSlab &s
     a.n_groups = s.n_groups;
     a.canon = ct.idx.p;
     a.plane_rows = ct.plane_rows;
-    ctx->cluster_stats[0] += (uint64_t)s.n_rows * a.n_cols;
-    ctx->cluster_stats[1] += s.nnz * a.n_cols;
+    ctx->cluster_stats[0] += (uint64_t)s.n_rows * a.n_cols;  // similarities delivered (mirrored ones included)
+    if (a.sym_cols == 0) ctx->cluster_stats[1] += s.nnz * a.n_cols;  // terms: the caller counts a symmetric launch
     const uint32_t n_chunks = (a.n_cols + 7) / 8;
     const uint64_t slab_bytes = (uint64_t)s.keys.n * 2 + (uint64_t)s.vals.n * 4;
     uint32_t n_slices = (uint32_t)((slab_bytes + pt_slice_bytes() - 1) / pt_slice_bytes());
@@ -749,21 +766,64 @@ __global__ void __launch_bounds__(256) recenter_accumulate_kernel(const uint64_t
     if (lane == 0) atomicAdd(&members[c], 1u);
 }
 
-// one thread per cluster: centroid = normalize_l2(sum of raw member counts)
-// (clustering.rs:44-53, 288-295); empty clusters keep their centroid.
-__global__ void recenter_finalize_kernel(const uint32_t *__restrict__ sums, const uint32_t *__restrict__ members,
-                                         uint32_t n_clusters, uint32_t dim, float *__restrict__ cen) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+// The same sums with shared-memory privatisation (n_clusters * dim counters fit in shared memory: the reference
+// default of a handful of clusters at k = 6): a persistent grid, one warp per kept read at a time, shared-memory
+// atomics, then ONE global atomic per non-zero counter and CTA -- ~25x fewer global atomics on 16 k addresses.
+__global__ void __launch_bounds__(256) recenter_accumulate_smem_kernel(const uint64_t *__restrict__ r_off,
+                                                                       const uint64_t *__restrict__ r_keys,
+                                                                       const float *__restrict__ raw,
+                                                                       const uint32_t *__restrict__ kept,
+                                                                       const uint32_t *__restrict__ target,
+                                                                       uint32_t n_kept, uint32_t dim, uint32_t n_clusters,
+                                                                       uint32_t *__restrict__ sums,
+                                                                       uint32_t *__restrict__ members) {
+    extern __shared__ uint32_t rc_smem[];  // [n_clusters * dim] sums | [n_clusters] members
+    const uint32_t total = n_clusters * dim + n_clusters;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) rc_smem[i] = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n_kept; i += gridDim.x * wpb) {
+        const uint32_t r = kept[i], c = target[i];
+        const uint64_t b = r_off[r], e = r_off[r + 1];
+        for (uint64_t j = b + lane; j < e; j += 32)
+            atomicAdd(&rc_smem[c * dim + (uint32_t)r_keys[j]], (uint32_t)raw[j]);
+        if (lane == 0) atomicAdd(&rc_smem[n_clusters * dim + c], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_clusters * dim; i += blockDim.x)
+        if (rc_smem[i]) atomicAdd(&sums[i], rc_smem[i]);
+    for (uint32_t c = threadIdx.x; c < n_clusters; c += blockDim.x)
+        if (rc_smem[n_clusters * dim + c]) atomicAdd(&members[c], rc_smem[n_clusters * dim + c]);
+}
+
+// one CTA per cluster: centroid = normalize_l2(sum of raw member counts)
+// (clustering.rs:44-53, 288-295); empty clusters keep their centroid.  The squares are formed in parallel,
+// their sum runs sequentially in key order on one thread (data/sparse.rs:366: a zero square leaves it unchanged).
+__global__ void __launch_bounds__(256) recenter_finalize_kernel(const uint32_t *__restrict__ sums,
+                                                                const uint32_t *__restrict__ members,
+                                                                uint32_t n_clusters, uint32_t dim,
+                                                                float *__restrict__ cen) {
+    extern __shared__ float rf_sq[];  // [dim]
+    __shared__ float s_m;
+    const uint32_t c = blockIdx.x;
     if (c >= n_clusters || members[c] == 0) return;
     const uint32_t *s = sums + (size_t)c * dim;
     float *o = cen + (size_t)c * dim;
-    float nrm = 0.0f;
-    for (uint32_t k = 0; k < dim; ++k) {
+    for (uint32_t k = threadIdx.x; k < dim; k += blockDim.x) {
         const float v = (float)s[k];
-        nrm = __fadd_rn(nrm, __fmul_rn(v, v));
+        rf_sq[k] = __fmul_rn(v, v);
     }
-    const float m = __fsqrt_rn(nrm);
-    for (uint32_t k = 0; k < dim; ++k) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float nrm = 0.0f;
+#pragma unroll 8
+        for (uint32_t k = 0; k < dim; ++k) nrm = __fadd_rn(nrm, rf_sq[k]);
+        s_m = __fsqrt_rn(nrm);
+    }
+    __syncthreads();
+    const float m = s_m;
+    for (uint32_t k = threadIdx.x; k < dim; k += blockDim.x) {
         const uint32_t u = s[k];
         o[k] = u ? __fdiv_rn((float)u, m) : 0.0f;
     }
@@ -1122,10 +1182,21 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         // recenter (:167)
         MYRIO_CK(cudaMemsetAsync(d_sums.p, 0, (size_t)nc * dim * sizeof(uint32_t), ctx->stream));
         MYRIO_CK(cudaMemsetAsync(d_members.p, 0, nc * sizeof(uint32_t), ctx->stream));
-        MYRIO_LAUNCH(ctx, "k6_recenter_accumulate", recenter_accumulate_kernel, (nk + 7) / 8, 256, 0,
-                     counts->row_off.p, counts->keys.p, counts->vals_f32.p, d_kept.p, d_target.p, nk, dim,
-                     d_sums.p, d_members.p);
-        MYRIO_LAUNCH(ctx, "k6_recenter_finalize", recenter_finalize_kernel, (nc + 31) / 32, 32, 0, d_sums.p,
+        const size_t rc_bytes = ((size_t)nc * dim + nc) * sizeof(uint32_t);
+        if (rc_bytes + 2048 <= ctx->smem_optin) {
+            MYRIO_CK(cudaFuncSetAttribute(recenter_accumulate_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)rc_bytes));
+            MYRIO_LAUNCH(ctx, "k6_recenter_accumulate", recenter_accumulate_smem_kernel,
+                         (unsigned)std::min<uint32_t>((nk + 7) / 8, ctx->sm_count), 256, rc_bytes, counts->row_off.p,
+                         counts->keys.p, counts->vals_f32.p, d_kept.p, d_target.p, nk, dim, nc, d_sums.p, d_members.p);
+        } else {
+            MYRIO_LAUNCH(ctx, "k6_recenter_accumulate", recenter_accumulate_kernel, (nk + 7) / 8, 256, 0,
+                         counts->row_off.p, counts->keys.p, counts->vals_f32.p, d_kept.p, d_target.p, nk, dim,
+                         d_sums.p, d_members.p);
+        }
+        MYRIO_CK(cudaFuncSetAttribute(recenter_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(dim * sizeof(float))));
+        MYRIO_LAUNCH(ctx, "k6_recenter_finalize", recenter_finalize_kernel, nc, 256, dim * sizeof(float), d_sums.p,
                      d_members.p, nc, dim, cen.p);
         nb_iters += 1;
     }
@@ -1150,97 +1221,122 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
     CanonTable canon;
     const bool canon_path = !merge_path && p->k <= 6 && canon_path_enabled();
     if (canon_path) build_canon_table(ctx, p->k, canon);
+    // neighbour of every cluster: last maximum over j != c of sim(centroid_c, centroid_j) (:345-351)
+    std::vector<uint32_t> nbr(nc, 0xFFFFFFFFu);
     for (uint32_t c = 0; c < nc; ++c) {
-        const uint32_t nm = (uint32_t)members[c].size();
-        if (nm == 0) continue;
-        // neighbour: last maximum over j != c of sim(centroid_c, centroid_j) (:345-351)
-        uint32_t nb = 0xFFFFFFFFu;
         float bs = 0.0f;
         for (uint32_t j = 0; j < nc; ++j) {
             if (j == c) continue;
             const float s = host_dense_sim(sim, &hcen[(size_t)c * dim], &hcen[(size_t)j * dim], dim);
-            if (nb == 0xFFFFFFFFu || s >= bs) {
+            if (nbr[c] == 0xFFFFFFFFu || s >= bs) {
                 bs = s;
-                nb = j;
+                nbr[c] = j;
             }
         }
-        const uint32_t nn = (uint32_t)members[nb].size();
-        std::vector<uint32_t> cols(members[c]);
-        cols.insert(cols.end(), members[nb].begin(), members[nb].end());
-        mark("silhouette cluster");
-        uint32_t mlo, mcnt, mchunk;  // this rank's share of the cluster's members (rows of the tile)
-        share(nm, mlo, mcnt, mchunk);
-        std::vector<float> sums((size_t)W * mchunk * 2);
-        DevBuf<float> d_sums2(std::max<size_t>((size_t)mcnt * 2, 1));
-        if (mcnt) {
-            DevBuf<uint32_t> d_rows(mcnt), d_cols(cols.size());
-            h2d(ctx, d_rows.p, members[c].data() + mlo, mcnt);
-            h2d(ctx, d_cols.p, cols.data(), cols.size());
-            MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)mcnt * 2 * sizeof(float), ctx->stream));
-            RowSlab mslab;  // the rank's members as rows
-            if (canon_path)
-                build_row_slab_scheduled(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, mcnt, canon,
-                                         mslab);
-            else if (!merge_path)
-                build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, mcnt, mslab);
-            PairArgs sa{};
-            sa.c_off = norm->row_off.p;
-            sa.c_keys = norm->keys.p;
-            sa.c_vals = norm->vals_f32.p;
-            sa.col_ids = d_cols.p;
-            sa.dim = dim;
-            sa.sim = sim;
-            sa.ld = mcnt;
-            // column passes of at most PT_TILE_BUDGET bytes of [column][member] similarities; the row
-            // sums continue from pass to pass, so the f32 addition order is the member order
-            const uint32_t n_cols_all = (uint32_t)cols.size();
-            uint32_t pass_cols = (uint32_t)std::min<uint64_t>(
-                n_cols_all, std::max<uint64_t>(8, PT_TILE_BUDGET / (4ull * mcnt) / 8 * 8));
-            DevBuf<float> d_sil_tile((size_t)pass_cols * mcnt);
-            sa.out = d_sil_tile.p;
-            for (uint32_t cf = 0; cf < n_cols_all; cf += pass_cols) {
-                sa.c_first = cf;
-                sa.n_cols = std::min(pass_cols, n_cols_all - cf);
-                if (canon_path) {
-                    CanonArgs ca{};
-                    ca.c_off = sa.c_off;
-                    ca.c_keys = sa.c_keys;
-                    ca.c_vals = sa.c_vals;
-                    ca.col_ids = sa.col_ids;
-                    ca.c_first = cf;
-                    ca.n_cols = sa.n_cols;
-                    ca.sim = sim;
-                    ca.out = d_sil_tile.p;
-                    ca.ld = mcnt;
-                    launch_pair_tile_canon(ctx, ca, mslab, canon, "k6_pair_silhouette");
-                } else if (!merge_path) {
-                    launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
-                } else {
-                    MergeArgs m{};
-                    m.r_off = norm->row_off.p;
-                    m.r_keys = norm->keys.p;
-                    m.r_vals = norm->vals_f32.p;
-                    m.row_ids = d_rows.p;
-                    m.n_rows = mcnt;
-                    m.c_off = norm->row_off.p;
-                    m.c_keys = norm->keys.p;
-                    m.c_vals = norm->vals_f32.p;
-                    m.col_ids = d_cols.p;
-                    m.c_first = cf;
-                    m.n_cols = sa.n_cols;
-                    m.sim = sim;
-                    m.out = d_sil_tile.p;
-                    m.ld = mcnt;
-                    m.transposed = true;
-                    ctx->cluster_stats[0] += (uint64_t)mcnt * sa.n_cols;
-                    launch_merge_pairs(ctx, m, "k6_pair_silhouette");
+    }
+    // row lengths of the normalised reads (exact term counts of the symmetric launches)
+    std::vector<uint64_t> h_roff;
+    const bool sym_ok = canon_path && W == 1 && !(getenv("MYRIO_K6_SYM") && getenv("MYRIO_K6_SYM")[0] == '0');
+    if (sym_ok) {
+        h_roff.resize(N + 1);
+        d2h(ctx, h_roff.data(), norm->row_off.p, N + 1);
+        sync(ctx);
+    }
+    uint64_t sym_budget = PT_TILE_BUDGET;  // bytes of similarity tile a symmetric launch may hold
+    if (sym_ok) {
+        size_t free_b = 0, total_b = 0;
+        MYRIO_CK(cudaMemGetInfo(&free_b, &total_b));
+        sym_budget = std::max<uint64_t>(PT_TILE_BUDGET, std::min<uint64_t>(free_b / 2, 48ull << 30));
+    }
+
+    // Silhouette sums (a, b) of `rows` against the columns `cols`: columns [0, split) are the rows' own cluster
+    // (for the rows before swap_row; the other way round after it).  sym_cols > 0: the first sym_cols columns
+    // ARE the rows (same reads, same order) and the whole square is held in one tile.
+    auto tile_sums = [&](const uint32_t *rows_h, uint32_t n_rows, const std::vector<uint32_t> &cols, uint32_t split,
+                         uint32_t swap_row, uint32_t sym_cols, DevBuf<float> &d_sums2) {
+        DevBuf<uint32_t> d_rows(n_rows), d_cols(cols.size());
+        h2d(ctx, d_rows.p, rows_h, n_rows);
+        h2d(ctx, d_cols.p, cols.data(), cols.size());
+        MYRIO_CK(cudaMemsetAsync(d_sums2.p, 0, (size_t)n_rows * 2 * sizeof(float), ctx->stream));
+        RowSlab mslab;  // the rows of the tile
+        if (canon_path)
+            build_row_slab_scheduled(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, n_rows, canon, mslab);
+        else if (!merge_path)
+            build_row_slab(ctx, norm->row_off.p, norm->keys.p, norm->vals_f32.p, d_rows.p, n_rows, mslab);
+        PairArgs sa{};
+        sa.c_off = norm->row_off.p;
+        sa.c_keys = norm->keys.p;
+        sa.c_vals = norm->vals_f32.p;
+        sa.col_ids = d_cols.p;
+        sa.dim = dim;
+        sa.sim = sim;
+        sa.ld = n_rows;
+        // column passes of at most PT_TILE_BUDGET bytes of [column][member] similarities; the row
+        // sums continue from pass to pass, so the f32 addition order is the member order
+        const uint32_t n_cols_all = (uint32_t)cols.size();
+        const uint64_t budget = sym_cols ? sym_budget : PT_TILE_BUDGET;
+        uint32_t pass_cols = (uint32_t)std::min<uint64_t>(
+            n_cols_all, std::max<uint64_t>(8, budget / (4ull * n_rows) / 8 * 8));
+        if (sym_cols && pass_cols < sym_cols) sym_cols = 0;  // (the callers check the budget; belt and braces)
+        DevBuf<float> d_sil_tile((size_t)pass_cols * n_rows);
+        sa.out = d_sil_tile.p;
+        for (uint32_t cf = 0; cf < n_cols_all; cf += pass_cols) {
+            sa.c_first = cf;
+            sa.n_cols = std::min(pass_cols, n_cols_all - cf);
+            if (canon_path) {
+                CanonArgs ca{};
+                ca.c_off = sa.c_off;
+                ca.c_keys = sa.c_keys;
+                ca.c_vals = sa.c_vals;
+                ca.col_ids = sa.col_ids;
+                ca.c_first = cf;
+                ca.n_cols = sa.n_cols;
+                ca.sim = sim;
+                ca.out = d_sil_tile.p;
+                ca.ld = n_rows;
+                ca.sym_cols = cf == 0 ? sym_cols : 0;
+                if (ca.sym_cols) {
+                    // terms actually formed: inside the square a 32-row group meets the column chunks that start
+                    // below its last row; outside it, every column
+                    const uint32_t sq = ca.sym_cols / 8 * 8;  // columns in symmetric chunks
+                    uint64_t terms = 0;
+                    for (uint32_t i = 0; i < n_rows; ++i) {
+                        const uint64_t nnz_i = h_roff[rows_h[i] + 1] - h_roff[rows_h[i]];
+                        const uint32_t inside = std::min<uint32_t>(sq, ((i >> 5) * 32 + 32) / 8 * 8);  // whole 32-row groups
+                        terms += nnz_i * (inside + (sa.n_cols - sq));
+                    }
+                    ctx->cluster_stats[1] += terms;
                 }
-                // columns [0, nm) are the cluster's own members (sum a), the rest the neighbour's (sum b)
-                MYRIO_LAUNCH(ctx, "k6_silsum_rows", silsum_rows_kernel, (mcnt + 127) / 128, 128, 0, d_sil_tile.p,
-                             (uint64_t)mcnt, mcnt, cf, sa.n_cols, nm, d_sums2.p);
+                launch_pair_tile_canon(ctx, ca, mslab, canon, "k6_pair_silhouette");
+            } else if (!merge_path) {
+                launch_pair_tile<true>(ctx, sa, mslab, "k6_pair_silhouette");
+            } else {
+                MergeArgs m{};
+                m.r_off = norm->row_off.p;
+                m.r_keys = norm->keys.p;
+                m.r_vals = norm->vals_f32.p;
+                m.row_ids = d_rows.p;
+                m.n_rows = n_rows;
+                m.c_off = norm->row_off.p;
+                m.c_keys = norm->keys.p;
+                m.c_vals = norm->vals_f32.p;
+                m.col_ids = d_cols.p;
+                m.c_first = cf;
+                m.n_cols = sa.n_cols;
+                m.sim = sim;
+                m.out = d_sil_tile.p;
+                m.ld = n_rows;
+                m.transposed = true;
+                ctx->cluster_stats[0] += (uint64_t)n_rows * sa.n_cols;
+                launch_merge_pairs(ctx, m, "k6_pair_silhouette");
             }
+            MYRIO_LAUNCH(ctx, "k6_silsum_rows", silsum_rows_kernel, (n_rows + 127) / 128, 128, 0, d_sil_tile.p,
+                         (uint64_t)n_rows, n_rows, cf, sa.n_cols, split, d_sums2.p, swap_row);
         }
-        gather_rows(d_sums2.p, 2 * sizeof(float), mlo, mcnt, mchunk, sums.data());
+    };
+    // silhouette scores of cluster c from its members' sums -> trimming (:244-266)
+    auto finish_cluster = [&](uint32_t c, const float *sums, uint32_t nn) {
+        const uint32_t nm = (uint32_t)members[c].size();
         std::vector<float> sil(nm);
         for (uint32_t t = 0; t < nm; ++t) {  // inner() :323-336
             const float a = sums[(size_t)t * 2] / (float)(nm - 1);
@@ -1263,6 +1359,44 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
             if (silhouette) silhouette[r] = sil[t];
             if (sil[t] < left_cutoff) assign[r] = -2;  // :257-262
         }
+    };
+    std::vector<uint8_t> done(nc, 0);
+    for (uint32_t c = 0; c < nc; ++c) {
+        const uint32_t nm = (uint32_t)members[c].size();
+        if (nm == 0 || done[c]) continue;
+        const uint32_t nb = nbr[c];
+        const uint32_t nn = (uint32_t)members[nb].size();
+        mark("silhouette cluster");
+        // Two clusters that are each other's neighbour need the same similarities: ONE symmetric tile over
+        // both member lists gives the four sums of both (half the work of two separate rectangles).
+        if (sym_ok && nb > c && nbr[nb] == c && nn > 0 && !done[nb] &&
+            (uint64_t)(nm + nn) * (nm + nn) * 4ull <= sym_budget) {
+            std::vector<uint32_t> both(members[c]);
+            both.insert(both.end(), members[nb].begin(), members[nb].end());
+            DevBuf<float> d_sums2((size_t)(nm + nn) * 2);
+            tile_sums(both.data(), nm + nn, both, nm, nm, nm + nn, d_sums2);
+            std::vector<float> sums((size_t)(nm + nn) * 2);
+            d2h(ctx, sums.data(), d_sums2.p, sums.size());
+            sync(ctx);
+            finish_cluster(c, sums.data(), nn);
+            finish_cluster(nb, sums.data() + (size_t)nm * 2, nm);
+            done[c] = done[nb] = 1;
+            continue;
+        }
+        std::vector<uint32_t> cols(members[c]);
+        cols.insert(cols.end(), members[nb].begin(), members[nb].end());
+        uint32_t mlo, mcnt, mchunk;  // this rank's share of the cluster's members (rows of the tile)
+        share(nm, mlo, mcnt, mchunk);
+        std::vector<float> sums((size_t)W * mchunk * 2);
+        DevBuf<float> d_sums2(std::max<size_t>((size_t)mcnt * 2, 1));
+        if (mcnt) {
+            // one rank: the members x members square is symmetric as well (when it fits one tile pass)
+            const bool own_sym = sym_ok && (uint64_t)nm * (nm + 8) * 4ull <= sym_budget;
+            tile_sums(members[c].data() + mlo, mcnt, cols, nm, 0xFFFFFFFFu, own_sym ? nm : 0, d_sums2);
+        }
+        gather_rows(d_sums2.p, 2 * sizeof(float), mlo, mcnt, mchunk, sums.data());
+        finish_cluster(c, sums.data(), nn);
+        done[c] = 1;
     }
 }
 

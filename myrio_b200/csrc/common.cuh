@@ -130,6 +130,7 @@ struct myrio_ctx {
     size_t smem_optin = 0;
     uint64_t launches = 0;
     uint32_t kmer_msb_first = 0;  // key bit order of K1/K2 (0 = bio-seq's LSB-first)
+    int topx_bound_pruning = -1;  // myrio_ctx_set_topx_bound_pruning; -1 = the process default (MYRIO_K4_UB)
     bool prof_on = false;
     std::vector<myrio::ProfEntry> prof;
     // scoring scratch (grow-only)

@@ -29,7 +29,8 @@ struct ScoreArgs {
     const TileInfo *tiles;
     const uint64_t *postings;
     const HitRec *plan;         // hit lists of all (query, tile) tasks of the batch
-    const uint64_t *plan_off;   // [q_count * n_tiles + 1]
+    const uint64_t *plan_off;   // [q_count * plan_stride (+ 1)]: a task's hit list is [off[s], off[s + 1])
+    uint32_t plan_stride;       // entries per query: n_tiles + 1 (plan_build_kernel) or n_tiles (contiguous lists)
     uint32_t q_count;
     uint32_t tile_leaves;
     unsigned long long n_tasks;
@@ -259,9 +260,9 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
             ql = task - t * a.q_count;
         }
         // the task's slice of the plan (requested first: everything below overlaps its latency)
-        const size_t slot = (size_t)ql * a.n_tiles + t;
-        const uint64_t hb_raw = a.plan_off[slot];
-        const uint64_t hb = hb_raw & ~PLAN_SEED_FLAG, he = a.plan_off[slot + 1] & ~PLAN_SEED_FLAG;
+        const size_t slot = (size_t)ql * a.n_tiles + t, pslot = (size_t)ql * a.plan_stride + t;
+        const uint64_t hb_raw = a.plan_off[pslot];
+        const uint64_t hb = hb_raw & ~PLAN_SEED_FLAG, he = a.plan_off[pslot + 1] & ~PLAN_SEED_FLAG;
         if (a.seed_mode == 2 && (hb_raw & PLAN_SEED_FLAG)) continue;  // scored by the seed pass
         if (t != cached_tile) {
             ti = a.tiles + t;
@@ -518,8 +519,9 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
     // the middle of the current task, where the next task's plan slice (two offsets) and common value are loaded
     // as well: all three round trips to L2 are off the critical path.
     const unsigned lt = (1u << lane) - 1u;
+    constexpr uint32_t TASK_BATCH = 4;  // consecutive tasks (same tile, neighbouring queries) per atomic
     uint32_t next_task = 0;
-    if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
+    if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, (unsigned long long)TASK_BATCH);
     auto load_desc = [&](uint32_t tk, uint32_t &tt, uint32_t &qq, uint64_t &b, uint64_t &e, float &v) {
         if (tk >= a.n_tasks) return;
         if (a.seed_mode == 1) {
@@ -529,17 +531,18 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             tt = tk / a.q_count;  // tile-major: a tile's index stays hot in L2
             qq = tk - tt * a.q_count;
         }
-        const size_t sl = (size_t)qq * a.n_tiles + tt;
+        const size_t sl = (size_t)qq * a.plan_stride + tt;
         b = a.plan_off[sl];
         e = a.plan_off[sl + 1];
         v = __ldg(a.qv1 + qq);  // the query's common value
     };
     uint32_t task = __shfl_sync(0xffffffffu, next_task, 0);
+    uint32_t task_end = task + TASK_BATCH;  // end of the batch `task` belongs to
     uint32_t t = 0, ql = 0;
     uint64_t hb_raw = 0, he_raw = 0;
     float v1 = 0.0f;
     load_desc(task, t, ql, hb_raw, he_raw, v1);
-    if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
+    if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, (unsigned long long)TASK_BATCH);
     while (task < a.n_tasks) {
         const size_t slot = (size_t)ql * a.n_tiles + t;
         const uint64_t hb = hb_raw & ~PLAN_SEED_FLAG, he = he_raw & ~PLAN_SEED_FLAG;
@@ -719,62 +722,79 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                 continue;
             }
             if (STATS) st_post += tsum;
-            // dense keys: eight bitmap words in flight, one ripple-carry add each into the bit-sliced counters
-            for (uint32_t d0 = 0; d0 < nd; d0 += 8) {
-                if (pending > (1u << SCC_PLANES) - 9u) flush_planes();
-                uint32_t w[8];
+            // dense keys: one ripple-carry add of a bitmap word each into the bit-sliced counters; two half-groups
+            // of four words, each reloaded as soon as it has been applied (4-8 loads in flight throughout)
+            {
+                uint32_t wa[4], wb[4];
+                auto load4 = [&](uint32_t(&w)[4], uint32_t b0) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    w[u] = d0 + u < nd ? __ldg(bitmaps + (size_t)dlist[d0 + u] * 32 + lane) : 0u;
+                    for (int u = 0; u < 4; ++u)
+                        w[u] = b0 + u < nd ? __ldg(bitmaps + (size_t)dlist[b0 + u] * 32 + lane) : 0u;
+                };
+                auto ripple4 = [&](const uint32_t(&w)[4]) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    uint32_t carry = w[u];  // an absent word (0) leaves the counters unchanged
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t carry = w[u];  // an absent word (0) leaves the counters unchanged
 #pragma unroll
-                    for (int j = 0; j < SCC_PLANES; ++j) {
-                        const uint32_t t2 = pl[j] & carry;
-                        pl[j] ^= carry;
-                        carry = t2;
+                        for (int j = 0; j < SCC_PLANES; ++j) {
+                            const uint32_t t2 = pl[j] & carry;
+                            pl[j] ^= carry;
+                            carry = t2;
+                        }
                     }
+                };
+                load4(wa, 0);
+                load4(wb, 4);
+                for (uint32_t d0 = 0; d0 < nd; d0 += 8) {
+                    if (pending > (1u << SCC_PLANES) - 9u) flush_planes();
+                    ripple4(wa);
+                    load4(wa, d0 + 8);
+                    ripple4(wb);
+                    load4(wb, d0 + 12);
+                    pending += min(8u, nd - d0);
                 }
-                pending += min(8u, nd - d0);
             }
-            // sparse keys: the lanes fan out over one key's postings (distinct leaves); the first chunk of the
-            // next key is requested before the current one is applied
-            if (ns) {
-                uint2 cur = shits[0];
-                uint64_t p0 = lane < cur.y ? __ldg(post + cur.x + lane) : dummy_posting;
-                for (uint32_t si = 0; si < ns; ++si) {
-                    uint2 nxt = make_uint2(0u, 0u);
-                    uint64_t pn = dummy_posting;
-                    if (si + 1 < ns) {
-                        nxt = shits[si + 1];
-                        if (lane < nxt.y) pn = __ldg(post + nxt.x + lane);
+            // sparse keys: the lanes fan out over a key's postings; the first chunks of four keys are requested
+            // together, and the counters are bumped with shared-memory atomics on the u32 that holds two of them
+            // (two keys may hit the same leaf: no barrier between keys is needed this way)
+            {
+                uint32_t *cnt32 = reinterpret_cast<uint32_t *>(cnt);
+                auto bump = [&](uint64_t p) {
+                    const uint32_t leaf = (uint32_t)(p >> 32);  // no flag bits in an unordered list
+                    atomicAdd(cnt32 + (leaf >> 1), 1u << ((leaf & 1u) * 16u));
+                };
+                for (uint32_t s0 = 0; s0 < ns; s0 += 4) {
+                    uint2 rec[4];
+                    uint64_t p[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        rec[u] = s0 + u < ns ? shits[s0 + u] : make_uint2(0u, 0u);
+                        p[u] = lane < rec[u].y ? __ldg(post + rec[u].x + lane) : 0ull;
                     }
-                    {
-                        const uint32_t leaf = (uint32_t)(p0 >> 32);  // no flag bits in an unordered list
-                        cnt[leaf] = (uint16_t)(cnt[leaf] + 1u);      // lanes past the end bump the dummy slot
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (lane < rec[u].y) bump(p[u]);
+                        for (uint32_t off = 32 + lane; off < rec[u].y; off += 32) bump(__ldg(post + rec[u].x + off));
                     }
-                    for (uint32_t off = 32 + lane; off < cur.y; off += 32) {
-                        const uint32_t leaf = (uint32_t)(__ldg(post + cur.x + off) >> 32);
-                        cnt[leaf] = (uint16_t)(cnt[leaf] + 1u);
-                    }
-                    __syncwarp();  // the next key may hit the same leaves
-                    cur = nxt;
-                    p0 = pn;
                 }
             }
             __syncwarp();
         }
 
         // ---- the next task's descriptor (its id was requested half a task ago), and the id after that
-        const uint32_t n_task = __shfl_sync(0xffffffffu, next_task, 0);
+        uint32_t n_task = task + 1, n_end = task_end;
+        if (n_task == task_end) {  // the batch is used up: take the one requested a batch ago, request another
+            n_task = __shfl_sync(0xffffffffu, next_task, 0);
+            n_end = n_task + TASK_BATCH;
+            if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, (unsigned long long)TASK_BATCH);
+        }
         uint32_t n_t = 0, n_ql = 0;
         uint64_t n_hb = 0, n_he = 0;
         float n_v1 = 0.0f;
         load_desc(n_task, n_t, n_ql, n_hb, n_he, n_v1);
-        if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
         auto advance = [&]() {
             task = n_task;
+            task_end = n_end;
             t = n_t;
             ql = n_ql;
             hb_raw = n_hb;
@@ -1251,6 +1271,202 @@ __global__ void __launch_bounds__(PF_THREADS) plan_fill_ranked_kernel(
     }
 }
 
+// ---- plan, second generation: two kernels and a scan over the QUERIES (not over the (query, tile) tasks).
+// plan_count_kernel: one warp per query -- dictionary lookups only; a key's slot already says in how many tiles
+// it occurs, so the query's total number of hits is known without touching the entry lists.
+__global__ void __launch_bounds__(PL_WARPS * 32) plan_count_kernel(
+    const uint64_t *__restrict__ q_row_off, const uint64_t *__restrict__ q_keys, uint64_t q_first,
+    uint32_t q_count, const DictSlot *__restrict__ gdict, uint32_t gmask, uint2 *__restrict__ kref,
+    uint32_t *__restrict__ qhits, const float *__restrict__ q_vals, float *__restrict__ qv1) {
+    const uint32_t ql = blockIdx.x * PL_WARPS + (threadIdx.x >> 5);
+    if (ql >= q_count) return;
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t kbase = q_row_off[q_first];
+    const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
+    const uint4 *dict = reinterpret_cast<const uint4 *>(gdict);
+    float vmin = 3.402823466e+38f;
+    uint32_t total = 0;
+    for (uint64_t i = qb + lane; i < qe; i += 32) {
+        vmin = fminf(vmin, q_vals[i]);
+        const uint64_t key = q_keys[i];
+        uint32_t h = dict_hash(key) & gmask;
+        uint32_t begin = 0, len = 0;
+        for (;;) {
+            const uint4 s = __ldg(dict + h);
+            if (s.w == 0u) break;  // empty slot: the key occurs nowhere in this index
+            if ((((uint64_t)s.y << 32) | s.x) == key) {
+                begin = s.z;
+                len = s.w;
+                break;
+            }
+            h = (h + 1) & gmask;
+        }
+        kref[i - kbase] = make_uint2(begin, len);
+        total += len;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+        total += __shfl_xor_sync(0xffffffffu, total, d);
+    }
+    if (lane == 0) {
+        qv1[ql] = qe > qb ? vmin : 0.0f;  // the query's common value for the count-mode kernel
+        qhits[ql] = total;
+    }
+}
+
+// plan_build_kernel: one CTA per query.  Sweep 1 sets present[tile][key] for every hit (each warp flattens the
+// entry lists of 32 keys over its lanes); the tiles' hit counts and the prefix popcounts of the bit rows give the
+// place of every hit -- rank of key i in tile t = keys below i present in t -- so sweep 2 writes all hit records
+// in ascending key order without any serialisation.  The query's tile offsets (plan_off row of n_tiles + 1
+// entries) start at qoff[q]; its seed tile (most hits, lowest tile on ties) is chosen on the way.
+static constexpr int PB_THREADS = 256;
+static constexpr int PB_WARP_WORDS = 100;  // per warp: prefix[33] | entry begins[32] | query values[32]
+__host__ __device__ inline size_t plan_build_smem_bytes(uint32_t n_tiles, uint32_t words) {
+    return ((size_t)n_tiles * words * 6 + 3) / 4 * 4 + ((size_t)n_tiles + 1) * sizeof(uint32_t) +
+           (PB_THREADS / 32) * PB_WARP_WORDS * sizeof(uint32_t);
+}
+__global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
+    const uint64_t *__restrict__ q_row_off, const float *__restrict__ q_vals, uint64_t q_first,
+    const EntryRec *__restrict__ entries, uint32_t n_tiles, uint32_t words_cap, const uint2 *__restrict__ kref,
+    const uint64_t *__restrict__ qoff, const float *__restrict__ qv1s, uint64_t *__restrict__ plan_off,
+    HitRec *__restrict__ plan, uint32_t *__restrict__ seed) {
+    extern __shared__ uint32_t pb_smem[];
+    __shared__ uint32_t s_scan[PB_THREADS / 32 + 1];
+    __shared__ unsigned long long s_best;
+    const uint32_t ql = blockIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t kbase = q_row_off[q_first];
+    const uint64_t qb = q_row_off[q_first + ql], qe = q_row_off[q_first + ql + 1];
+    const uint32_t nq = (uint32_t)(qe - qb);
+    const uint32_t words = max((nq + 31) >> 5, 1u);  // <= words_cap (the host checked the longest query)
+    const uint64_t base = qoff[ql];
+    uint64_t *off_row = plan_off + (size_t)ql * (n_tiles + 1);
+    uint32_t *present = pb_smem;                                                      // [n_tiles][words]
+    uint16_t *pfx = reinterpret_cast<uint16_t *>(present + (size_t)n_tiles * words);  // [n_tiles][words]
+    uint32_t *toff = pb_smem + ((size_t)n_tiles * words_cap * 6 + 3) / 4;             // [n_tiles + 1]
+    uint32_t *wpre = toff + n_tiles + 1 + (size_t)warp * PB_WARP_WORDS;
+    uint32_t *wbeg = wpre + 33;
+    float *wval = reinterpret_cast<float *>(wbeg + 32);
+    const float qv1 = qv1s[ql];
+    for (uint32_t i = tid; i < n_tiles * words; i += PB_THREADS) present[i] = 0;
+    if (tid == 0) s_best = 0;
+    __syncthreads();
+
+    // the hits of 32 consecutive keys flattened over the lanes of a warp, FOUR hits of a lane at a time so that
+    // their (dependent, L2-latency) entry loads overlap: f(key index[4], slot[4], entry index[4], n)
+    auto sweep = [&](auto f) {
+        for (uint32_t k0 = warp * 32; k0 < nq; k0 += PB_THREADS) {
+            const uint32_t i = k0 + lane;
+            uint2 kr = make_uint2(0u, 0u);
+            float v = 0.0f;
+            if (i < nq) {
+                kr = kref[qb + i - kbase];
+                v = q_vals[qb + i];
+            }
+            uint32_t inc = kr.y;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= (unsigned)d) inc += t;
+            }
+            __syncwarp();  // the previous round's readers are done
+            wpre[lane + 1] = inc;
+            if (lane == 0) wpre[0] = 0;
+            wbeg[lane] = kr.x;
+            wval[lane] = v;
+            __syncwarp();
+            const uint32_t H = wpre[32];
+            for (uint32_t j0 = lane; j0 < H; j0 += 128) {
+                uint32_t ki[4], sl[4], en[4];
+                uint32_t n = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t j = j0 + 32u * u;
+                    uint32_t lo = 0;  // last slot with wpre[slot] <= j (empty lists are skipped)
+                    if (j < H) {
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1)
+                            if (wpre[lo + step] <= j) lo += step;
+                        n = u + 1;
+                    }
+                    ki[u] = k0 + lo;
+                    sl[u] = lo;
+                    en[u] = wbeg[lo] + (min(j, H - 1) - wpre[lo]);
+                }
+                f(ki, sl, en, n);
+            }
+        }
+    };
+    sweep([&](const uint32_t(&ki)[4], const uint32_t(&)[4], const uint32_t(&en)[4], uint32_t n) {
+        uint32_t tl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((uint32_t)u < n) tl[u] = entries[en[u]].tile;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((uint32_t)u < n) atomicOr(&present[tl[u] * words + (ki[u] >> 5)], 1u << (ki[u] & 31));
+    });
+    __syncthreads();
+    // hit count of every tile + prefix popcounts of its bit row
+    const uint32_t C = (n_tiles + PB_THREADS - 1) / PB_THREADS;  // consecutive tiles per thread
+    uint32_t mine = 0;
+    unsigned long long best = 0;
+    for (uint32_t t = tid * C; t < min(n_tiles, (tid + 1) * C); ++t) {
+        uint32_t run = 0;
+        for (uint32_t w = 0; w < words; ++w) {
+            pfx[t * words + w] = (uint16_t)run;
+            run += __popc(present[t * words + w]);
+        }
+        toff[t] = run;
+        mine += run;
+        best = max(best, ((unsigned long long)run << 32) | (unsigned long long)(0xFFFFFFFFu - t));
+    }
+    // exclusive scan of the tile counts (block scan over the per-thread chunk sums)
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += t;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+    if (lane == 31) s_scan[warp] = inc;
+    if (lane == 0) atomicMax(&s_best, best);
+    __syncthreads();
+    uint32_t run = inc - mine;
+    for (uint32_t w = 0; w < warp; ++w) run += s_scan[w];
+    for (uint32_t t = tid * C; t < min(n_tiles, (tid + 1) * C); ++t) {
+        const uint32_t c = toff[t];
+        toff[t] = run;
+        run += c;
+    }
+    if (tid == PB_THREADS - 1) toff[n_tiles] = run;
+    __syncthreads();
+    const uint32_t seed_tile = 0xFFFFFFFFu - (uint32_t)s_best;
+    for (uint32_t t = tid; t <= n_tiles; t += PB_THREADS)
+        off_row[t] = (base + toff[t]) | ((seed && t == seed_tile) ? PLAN_SEED_FLAG : 0ull);
+    if (seed && tid == 0) seed[ql] = seed_tile;
+    sweep([&](const uint32_t(&ki)[4], const uint32_t(&sl)[4], const uint32_t(&en)[4], uint32_t n) {
+        EntryRec er[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((uint32_t)u < n) er[u] = entries[en[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if ((uint32_t)u < n) {
+                const uint32_t i = ki[u], w = i >> 5;
+                const uint32_t rank =
+                    pfx[er[u].tile * words + w] + __popc(present[er[u].tile * words + w] & ((1u << (i & 31)) - 1u));
+                HitRec h;
+                h.begin = er[u].begin;
+                h.qv = wval[sl[u]];
+                h.len = er[u].len | (h.qv != qv1 ? ORDERED_FLAG : 0u);
+                plan[base + toff[er[u].tile] + rank] = h;
+            }
+    });
+}
+
 // one warp per query: its seed tile = the tile that holds most of its keys (ties: the lowest tile); the
 // tile's plan_off entry is flagged so that the sweep skips the (query, seed tile) task
 __global__ void __launch_bounds__(256) seed_tile_kernel(const uint32_t *__restrict__ hitcnt, uint32_t q_count,
@@ -1301,24 +1517,71 @@ struct Plan {
     DevBuf<HitRec> hits;
     DevBuf<uint32_t> seed;
     DevBuf<float> qv1;
+    DevBuf<uint32_t> qhits;  // hits per query (plan_count_kernel)
+    DevBuf<uint64_t> qoff;   // their exclusive scan: where a query's hit lists start
     uint64_t n_hits = 0;
+    uint32_t stride = 0;     // plan_off entries per query: n_tiles + 1 (plan_build_kernel) or n_tiles (fallback)
+    bool seeded = false;     // plan_build_kernel chose the seed tiles and flagged them
 };
 
-// plan for queries [q0, q0+qn); returns false (nothing built) when the hit lists would not fit `budget`
+static bool plan_second_generation() {  // MYRIO_K4A_PLAN=1 keeps the probe / scan / ranked-fill kernels of round 1
+    static const bool v = [] {
+        const char *e = getenv("MYRIO_K4A_PLAN");
+        return !(e && e[0] == '1');
+    }();
+    return v;
+}
+
+// plan for queries [q0, q0+qn); returns false (nothing built) when the hit lists would not fit `budget`.
+// want_seed: also choose every query's seed tile (fused top-x with seeding).
 static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs *queries, uint64_t q0, uint64_t qn,
-                       uint64_t budget_bytes, Plan &pl) {
+                       uint64_t budget_bytes, Plan &pl, bool want_seed = false) {
     const uint64_t n_tiles = ix->tiles.size();
     const uint64_t n_tasks = qn * n_tiles;
+    pl.seeded = false;
+    pl.kref.reserve(std::max<uint64_t>(queries->nnz, 1));
+    pl.qv1.reserve(std::max<uint64_t>(qn, 1));
+    const unsigned grid = (unsigned)((qn + PL_WARPS - 1) / PL_WARPS);
+    const uint64_t max_q_keys = std::max<uint64_t>(queries_max_keys(ctx, queries), 1);
+    const uint32_t words_all = (uint32_t)((max_q_keys + 31) / 32);
+    if (plan_second_generation() && max_q_keys < 65536 &&
+        plan_build_smem_bytes((uint32_t)n_tiles, words_all) + 4096 <= ctx->smem_optin) {
+        pl.qhits.reserve(qn);
+        pl.qoff.reserve(qn + 1);
+        MYRIO_LAUNCH(ctx, "k4a_plan_count", plan_count_kernel, grid, PL_WARPS * 32, 0, queries->row_off.p,
+                     queries->keys.p, q0, (uint32_t)qn, ix->gdict.p, ix->gdict_mask, pl.kref.p, pl.qhits.p,
+                     queries->vals_f32.p, pl.qv1.p);
+        exclusive_scan_u32_to_u64(ctx, pl.qhits.p, pl.qoff.p, qn);
+        uint64_t kb[2];
+        d2h(ctx, &kb[0], queries->row_off.p + q0, 1);
+        d2h(ctx, &kb[1], queries->row_off.p + q0 + qn, 1);
+        d2h(ctx, &pl.n_hits, pl.qoff.p + qn, 1);
+        sync(ctx);
+        if (pl.n_hits * sizeof(HitRec) > budget_bytes && qn > 1) return false;
+        ctx->last_stats[0] += kb[1] - kb[0];
+        ctx->last_stats[1] += pl.n_hits;
+        pl.hits.reserve(std::max<uint64_t>(pl.n_hits, 1));
+        pl.stride = (uint32_t)n_tiles + 1;
+        pl.off.reserve(qn * pl.stride + 1);
+        const bool seed = want_seed && n_tiles > 1;
+        if (seed) pl.seed.reserve(qn);
+        const size_t psm = plan_build_smem_bytes((uint32_t)n_tiles, words_all);
+        MYRIO_CK(cudaFuncSetAttribute(plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        MYRIO_LAUNCH(ctx, "k4a_plan_build", plan_build_kernel, (unsigned)qn, PB_THREADS, psm, queries->row_off.p,
+                     queries->vals_f32.p, q0, ix->gentries.p, (uint32_t)n_tiles, words_all, pl.kref.p, pl.qoff.p,
+                     pl.qv1.p, pl.off.p, pl.hits.p, seed ? pl.seed.p : (uint32_t *)nullptr);
+        pl.seeded = seed;
+        return true;
+    }
+    // ---- round-1 path (very long queries x very many tiles): per-task hit counts, a scan over all tasks
     uint64_t kb[2];
     d2h(ctx, &kb[0], queries->row_off.p + q0, 1);
     d2h(ctx, &kb[1], queries->row_off.p + q0 + qn, 1);
     sync(ctx);
     const uint64_t nnz = kb[1] - kb[0];
-    pl.kref.reserve(std::max<uint64_t>(nnz, 1));
     pl.hitcnt.reserve(std::max<uint64_t>(n_tasks, 1));
     pl.off.reserve(n_tasks + 1);
-    pl.qv1.reserve(std::max<uint64_t>(qn, 1));
-    const unsigned grid = (unsigned)((qn + PL_WARPS - 1) / PL_WARPS);
+    pl.stride = (uint32_t)n_tiles;
     const size_t smem = (size_t)PL_WARPS * n_tiles * sizeof(uint32_t);
     if (smem > ctx->smem_optin) fail(MYRIO_ERR_UNSUPPORTED, "too many tiles (%llu) for the plan kernels", (unsigned long long)n_tiles);
     MYRIO_CK(cudaFuncSetAttribute(plan_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1334,7 +1597,6 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     pl.hits.reserve(std::max<uint64_t>(pl.n_hits, 1));
     // queries whose presence bit-matrix fits in shared memory take the parallel kernel, the rest
     // (very long queries on indexes with very many tiles) the per-key sequential one
-    const uint64_t max_q_keys = std::max<uint64_t>(queries_max_keys(ctx, queries), 1);
     const size_t smem_budget = std::min<size_t>(ctx->smem_optin, 96 * 1024);
     // shared memory per word of query keys: n_tiles presence words + 64 prefix/begin words
     uint32_t words_cap = (uint32_t)std::min<uint64_t>((max_q_keys + 31) / 32,
@@ -1353,6 +1615,14 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
                      pl.hits.p, words_cap, pl.qv1.p);
     }
     return true;
+}
+
+// seed tiles of a fused top-x step, unless plan_build_kernel chose them already
+static void choose_seed_tiles(myrio_ctx *ctx, const myrio_index *ix, Plan &pl, uint64_t qn) {
+    if (pl.seeded) return;
+    pl.seed.reserve(qn);
+    MYRIO_LAUNCH(ctx, "k4a_seed_tiles", seed_tile_kernel, (unsigned)((qn + 7) / 8), 256, 0, pl.hitcnt.p, (uint32_t)qn,
+                 (uint32_t)ix->tiles.size(), pl.off.p, pl.seed.p);
 }
 
 // ------------------------------------------------------------------ host side
@@ -1463,6 +1733,7 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
     a.postings = ix->postings.p;
     a.plan = pl.hits.p;
     a.plan_off = pl.off.p;
+    a.plan_stride = pl.stride;
     a.qv1 = pl.qv1.p;
     a.q_count = (uint32_t)qn;
     a.tile_leaves = ix->tile_leaves;
@@ -1471,7 +1742,7 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
     a.ld = ix->n_leaves;
     a.leaf_id_base = ix->leaf_id_base;
     a.counters = ctx->score_counters.p;
-    a.ub_prune = k4_bound_pruning() ? 1u : 0u;
+    a.ub_prune = (ctx->topx_bound_pruning < 0 ? k4_bound_pruning() : ctx->topx_bound_pruning != 0) ? 1u : 0u;
     return a;
 }
 
@@ -1567,7 +1838,8 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     Plan &pl = *static_cast<Plan *>(ctx->plan);
     for (uint64_t q0 = 0; q0 < q_count;) {
         uint64_t qn = std::min(per, q_count - q0);
-        while (!build_plan(ctx, ix, queries, q_first + q0, qn, PLAN_BUDGET, pl)) qn = (qn + 1) / 2;
+        const bool seeding = ix->tiles.size() > 1 && topx_seeding();
+        while (!build_plan(ctx, ix, queries, q_first + q0, qn, PLAN_BUDGET, pl, seeding)) qn = (qn + 1) / 2;
         cand.reserve(qn * n_tiles * x);
         cand_cnt.reserve(qn * n_tiles);
         gthr.reserve(qn);
@@ -1580,11 +1852,9 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
             a.cand = cand.p;
             a.cand_cnt = cand_cnt.p;
             a.gthr = gthr.p;
-            if (ix->tiles.size() > 1 && topx_seeding()) {
+            if (seeding) {
                 // pass 1: every query against its seed tile; pass 2: everything else, tile-major
-                pl.seed.reserve(qn);
-                MYRIO_LAUNCH(ctx, "k4a_seed_tiles", seed_tile_kernel, (unsigned)((qn + 7) / 8), 256, 0, pl.hitcnt.p,
-                             (uint32_t)qn, (uint32_t)ix->tiles.size(), pl.off.p, pl.seed.p);
+                choose_seed_tiles(ctx, ix, pl, qn);
                 ScoreArgs s1 = a;
                 s1.seed = pl.seed.p;
                 s1.seed_mode = 1;
@@ -1629,7 +1899,7 @@ void score_topx_seed_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_s
     const uint64_t n_tiles = std::max<uint64_t>(ix->tiles.size(), 1);
     if (!ctx->plan) ctx->plan = plan_scratch_new();
     Plan &pl = *static_cast<Plan *>(ctx->plan);
-    if (!build_plan(ctx, ix, queries, q_first, q_count, ~0ull, pl))
+    if (!build_plan(ctx, ix, queries, q_first, q_count, ~0ull, pl, ix->tiles.size() > 1))
         fail(MYRIO_ERR_UNSUPPORTED, "two-phase top-x: the hit lists do not fit");
     ctx->topx_cand.reserve(q_count * n_tiles * x);
     ctx->topx_cand_cnt.reserve(q_count * n_tiles);
@@ -1639,9 +1909,7 @@ void score_topx_seed_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_s
     MYRIO_CK(cudaMemsetAsync(ctx->topx_cand_cnt.p, 0, q_count * n_tiles * sizeof(uint32_t), ctx->stream));
     ctx->twophase_seeded = false;
     if (ix->tiles.size() > 1) {
-        pl.seed.reserve(q_count);
-        MYRIO_LAUNCH(ctx, "k4a_seed_tiles", seed_tile_kernel, (unsigned)((q_count + 7) / 8), 256, 0, pl.hitcnt.p,
-                     (uint32_t)q_count, (uint32_t)ix->tiles.size(), pl.off.p, pl.seed.p);
+        choose_seed_tiles(ctx, ix, pl, q_count);
         ScoreArgs s1 = base_args(ctx, ix, pl, q_count);
         s1.x = x;
         s1.cand = ctx->topx_cand.p;

@@ -77,6 +77,7 @@ unsafe extern "C" {
     pub fn myrio_ctx_destroy(ctx: *mut myrio_ctx);
     pub fn myrio_ctx_sync(ctx: *mut myrio_ctx) -> i32;
     pub fn myrio_ctx_set_kmer_bit_order(ctx: *mut myrio_ctx, msb_first: i32) -> i32;
+    pub fn myrio_ctx_set_topx_bound_pruning(ctx: *mut myrio_ctx, on: i32) -> i32;
     pub fn myrio_ctx_stream(ctx: *const myrio_ctx) -> *mut c_void;
     pub fn myrio_ctx_launch_count(ctx: *const myrio_ctx) -> u64;
     pub fn myrio_prof_enable(ctx: *mut myrio_ctx, on: i32) -> i32;
