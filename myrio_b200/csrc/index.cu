@@ -414,6 +414,18 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         ti.n_dense = dstart[t + 1] - dstart[t];
         ti.unit_max = *std::max_element(h_unit.begin() + ti.leaf_begin, h_unit.begin() + ti.leaf_begin + ti.n_leaves);
     }
+    {
+        std::vector<uint32_t> moff(n_tiles + 1, 0);
+        for (uint64_t t = 0; t < n_tiles; ++t) {
+            ix->tiles[t].mask_off = moff[t];
+            ix->tiles[t].mask_words = (uint32_t)((ix->tiles[t].n_dense + 31) / 32);
+            moff[t + 1] = moff[t] + ix->tiles[t].mask_words;
+        }
+        ix->mask_words_total = moff[n_tiles];
+        ix->mask_off.alloc(n_tiles + 1);
+        h2d(ctx, ix->mask_off.p, moff.data(), n_tiles + 1);
+        sync(ctx);  // moff is a local
+    }
     if (P) {
         MYRIO_LAUNCH(ctx, "k3_flag_odd", flag_odd_postings_kernel, (unsigned)((P + 255) / 256), 256, 0, sv, P,
                      d_bounds.p, (uint32_t)n_tiles, tile_leaves, ix->unit.p, key_or.p + 2);

@@ -43,6 +43,9 @@ struct TileInfo {
     const float *unit;        // [n_leaves] (slice of the index-wide array)
     uint64_t n_dense;
     float unit_max;           // largest unit value of the tile (upper bounds of the count-mode top-x)
+    // dense-key masks of the plan: a query's common dense keys in this tile are bits of mask_words words
+    // (bit = the key's bitmap index) at word mask_off of the query's mask row (index-wide: mask_words_total)
+    uint32_t mask_off, mask_words;
 };
 
 __device__ __forceinline__ uint32_t dict_hash(uint64_t key) {
@@ -85,6 +88,8 @@ struct myrio_index {
     myrio::DevBuf<uint32_t> bitmaps;  // [n_dense_total][32]
     myrio::DevBuf<float> unit;        // [n_leaves]
     uint64_t n_dense_total = 0;
+    uint32_t mask_words_total = 0;    // words of one query's dense-key mask row (sum of the tiles' mask_words)
+    myrio::DevBuf<uint32_t> mask_off; // [n_tiles + 1] (device copy for the plan kernels)
     // myrio_score_topx_sharded: queries per exchange batch agreed by all ranks for (x, world) -- see comm.cu
     mutable uint32_t agreed_x = 0, agreed_world = 0;
     mutable uint64_t agreed_cap = 0;

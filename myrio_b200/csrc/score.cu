@@ -50,6 +50,10 @@ struct ScoreArgs {
     const uint32_t *seed;  // [q_count] seed tile (pass 1); its plan_off entry carries PLAN_SEED_FLAG (pass 2 skips it)
     uint32_t seed_mode;    // 0 = no seeding, 1 = seed pass (task == query), 2 = sweep
     uint32_t ub_prune;     // count mode, fused top-x: finish only the scores whose upper bound reaches the bound
+    // count mode: a query's common dense keys per tile as bits (bit = bitmap index in the tile) instead of hit
+    // records: row ql of mask_stride words, the tile's words at TileInfo::mask_off (0 = everything is a record)
+    const uint32_t *dmask;
+    uint32_t mask_stride;
 };
 static constexpr uint64_t PLAN_SEED_FLAG = 1ull << 63;
 
@@ -513,6 +517,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
     const uint32_t *bitmaps = nullptr;
     const float *unit = nullptr;
     float unit_max = 0.0f;
+    uint32_t t_mo = 0, t_mw = 0;  // the tile's words in a query's dense-key mask row
     const TileInfo *ti = a.tiles;
 
     // ---- task pipeline.  Task ids come from an atomic counter.  The id of the task after next is requested in
@@ -552,6 +557,9 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
 #pragma unroll
         for (int j = 0; j < SCC_PLANES; ++j) pl[j] = 0;
         uint32_t pending = 0;  // dense keys counted since the last flush (warp-uniform)
+        bool had_ordered = false;  // some batch of the task took the ordered walk (partial sums may be non-zero)
+        uint32_t mask0 = 0;
+        bool any_hits = he > hb;  // hit records, or (below) bits in the dense-key mask
         if (!skip) {
         if (t != cached_tile) {
             ti = a.tiles + t;
@@ -560,8 +568,12 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             bitmaps = ti->bitmaps;
             unit = ti->unit;
             unit_max = ti->unit_max;
+            t_mo = ti->mask_off;
+            t_mw = a.mask_stride ? ti->mask_words : 0u;
             cached_tile = t;
         }
+        // first words of the query's dense-key mask for this tile (requested before the accumulators are cleared)
+        if (t_mw && lane < 8 && lane < t_mw) mask0 = __ldg(a.dmask + (size_t)ql * a.mask_stride + t_mo + lane);
         if ((a.tile_leaves & 7u) == 0u) {  // 16-byte stores (the per-warp slices are 16-byte aligned)
             const uint32_t n4 = (a.tile_leaves + 32) >> 2, n8 = (a.tile_leaves + 32) >> 3;
             for (uint32_t i = lane; i < n4; i += 32) reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -686,13 +698,79 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             }
         };
 
+        uint32_t *dlist = hist;  // dense-key list of a split hit list / of a mask chunk (the radix-select
+                                  // histogram's space, idle until the top-x)
+        // dense keys dlist[0, nd): eight bitmap words at a time go through a carry-save adder tree into the
+        // bit-sliced counters (a full adder is two LOP3: 20 logic instructions per eight words instead of 96 for
+        // eight ripple-carry additions); the next eight words are requested before the current ones are added
+        auto dense_sweep = [&](uint32_t nd) {
+            uint32_t w[8], wn[8];
+            auto load8 = [&](uint32_t(&x)[8], uint32_t b0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    x[u] = b0 + u < nd ? __ldg(bitmaps + (size_t)dlist[b0 + u] * 32 + lane) : 0u;
+            };
+            // full adder on 32 independent bit positions
+            auto csa = [](uint32_t x, uint32_t y, uint32_t z, uint32_t &sum, uint32_t &car) {
+                sum = x ^ y ^ z;
+                car = (x & y) | (z & (x | y));
+            };
+            load8(w, 0);
+            for (uint32_t d0 = 0; d0 < nd; d0 += 8) {
+                if (pending > (1u << SCC_PLANES) - 9u) flush_planes();
+                load8(wn, d0 + 8);
+                if (STATS) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) st_post += __popc(w[u]);  // summed over the lanes at the end: df
+                }
+                uint32_t s1, c1, s2, c2, s3, c3, c4, c5, c6, c7, t0;
+                csa(w[0], w[1], w[2], s1, c1);          // weight 1
+                csa(w[3], w[4], w[5], s2, c2);
+                csa(w[6], w[7], pl[0], s3, c3);
+                csa(s1, s2, s3, pl[0], c4);
+                csa(c1, c2, c3, t0, c5);                // weight 2
+                csa(t0, c4, pl[1], pl[1], c6);
+                csa(c5, c6, pl[2], pl[2], c7);          // weight 4
+#pragma unroll
+                for (int j = 3; j < SCC_PLANES; ++j) {  // weight 8 and up: ripple the single carry
+                    const uint32_t t2 = pl[j] & c7;
+                    pl[j] ^= c7;
+                    c7 = t2;
+                }
+                pending += min(8u, nd - d0);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = wn[u];
+            }
+        };
+
+        if (!skip && t_mw) {
+            // the query's common dense keys in this tile: bits of its mask row (plan_build_kernel), 8 words
+            // (256 keys) at a time expanded to bitmap indexes
+            const uint32_t *mrow = a.dmask + (size_t)ql * a.mask_stride + t_mo;
+            for (uint32_t w0 = 0; w0 < t_mw; w0 += 8) {
+                uint32_t m = w0 == 0 ? mask0 : ((lane < 8 && w0 + lane < t_mw) ? __ldg(mrow + w0 + lane) : 0u);
+                const uint32_t nb = __popc(m);
+                const uint32_t incl = warp_incl_scan_u32s(nb, lane);
+                const uint32_t nd = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t pos = incl - nb;
+                any_hits |= nd != 0u;
+                while (m) {
+                    const uint32_t b = __ffs(m) - 1;
+                    m &= m - 1;
+                    dlist[pos++] = (w0 + lane) * 32 + b;
+                }
+                __syncwarp();
+                dense_sweep(nd);
+                __syncwarp();
+            }
+        }
+
         if (!skip)
         for (uint64_t h0 = hb; h0 < he; h0 += SC_HITS) {
             const uint32_t n_hits = (uint32_t)min((uint64_t)SC_HITS, he - h0);
             // Staging.  Common terms commute, so a hit list without an ORDERED hit (nearly all of them) is split on
             // the way in: the bitmap indexes of its dense keys go to dlist[] (the radix-select histogram's space,
             // idle until the top-x), its sparse keys are compacted to the front of the hit buffer as (begin, len).
-            uint32_t *dlist = hist;
             uint2 *shits = reinterpret_cast<uint2 *>(hits);
             uint32_t nd = 0, ns = 0;
             bool ordered = false;
@@ -710,11 +788,12 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                 if (is_s) shits[ns + __popc(ms & lt)] = make_uint2(h.begin, h.len & LEN_MASK);
                 nd += __popc(md);
                 ns += __popc(ms);
-                if (STATS) tsum += h.len & LEN_MASK;
+                if (STATS && is_s) tsum += h.len & LEN_MASK;  // (a dense key's df is counted from its bitmap)
             }
             ordered = __any_sync(0xffffffffu, ordered);
             __syncwarp();
             if (ordered) {  // rare: the list is walked in key order
+                had_ordered = true;
                 for (uint32_t i = lane; i < n_hits; i += 32) hits[i] = a.plan[h0 + i];
                 __syncwarp();
                 process_hits(n_hits);
@@ -722,38 +801,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                 continue;
             }
             if (STATS) st_post += tsum;
-            // dense keys: one ripple-carry add of a bitmap word each into the bit-sliced counters; two half-groups
-            // of four words, each reloaded as soon as it has been applied (4-8 loads in flight throughout)
-            {
-                uint32_t wa[4], wb[4];
-                auto load4 = [&](uint32_t(&w)[4], uint32_t b0) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        w[u] = b0 + u < nd ? __ldg(bitmaps + (size_t)dlist[b0 + u] * 32 + lane) : 0u;
-                };
-                auto ripple4 = [&](const uint32_t(&w)[4]) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint32_t carry = w[u];  // an absent word (0) leaves the counters unchanged
-#pragma unroll
-                        for (int j = 0; j < SCC_PLANES; ++j) {
-                            const uint32_t t2 = pl[j] & carry;
-                            pl[j] ^= carry;
-                            carry = t2;
-                        }
-                    }
-                };
-                load4(wa, 0);
-                load4(wb, 4);
-                for (uint32_t d0 = 0; d0 < nd; d0 += 8) {
-                    if (pending > (1u << SCC_PLANES) - 9u) flush_planes();
-                    ripple4(wa);
-                    load4(wa, d0 + 8);
-                    ripple4(wb);
-                    load4(wb, d0 + 12);
-                    pending += min(8u, nd - d0);
-                }
-            }
+            dense_sweep(nd);
             // sparse keys: the lanes fan out over a key's postings; the first chunks of four keys are requested
             // together, and the counters are bumped with shared-memory atomics on the u32 that holds two of them
             // (two keys may hit the same leaf: no barrier between keys is needed this way)
@@ -819,9 +867,66 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             if (thr != 0u) {
                 const float thr_f = __uint_as_float(thr);
                 const float pmax = __fmul_rn(v1, unit_max);
+                // Integer form of the same test for the usual task (no ordered batch: every partial sum is +0;
+                // Cosine): ub(n) = 1.01 n pmax is monotone in n, so "ub < bound" is "n < n_need" with
+                // n_need = floor(bound / (1.0101 pmax)) - 1 (the margin of 1e-4 and of one count covers the roundings
+                // of the division).  Eight counters per 16-byte load, one add + one OR per pair of counters: a
+                // counter c >= T sets bit 15 of (c + 0x8000 - T).  Survivors (rare) are listed, the pending dense
+                // counts flushed, and each survivor is finished by its own lane.
+                if (SIM == MYRIO_SIM_COSINE && !had_ordered && (a.tile_leaves & 7u) == 0u && any_hits) {
+                    const float q = __fdiv_rn(thr_f, __fmul_rn(pmax, 1.0101f));  // +inf for pmax == 0
+                    uint32_t n_need = q < 1.0e9f ? (uint32_t)q : 1000000000u;
+                    n_need = n_need > 1u ? n_need - 1u : 0u;
+                    const uint32_t T = n_need > pending ? n_need - pending : 0u;
+                    if (T >= 1u && T <= 0x8000u) {
+                        // (counters stay below 0x8000 + T: a count is at most the query's length, and count mode
+                        // is off for leaf vectors of 65 535+ keys; the general pass below needs no such assumption)
+                        const uint32_t KK = (0x8000u - T) * 0x00010001u;
+                        uint32_t *slist = hist;  // [0, 255): survivor leaves, [255]: their number
+                        if (lane == 0) slist[255] = 0;
+                        __syncwarp();
+                        const uint4 *cnt4 = reinterpret_cast<const uint4 *>(cnt);
+                        for (uint32_t i = lane; i * 8u < nl; i += 32) {
+                            const uint4 v = cnt4[i];
+                            if ((((v.x + KK) | (v.y + KK) | (v.z + KK) | (v.w + KK)) & 0x80008000u) == 0u) continue;
+                            const uint32_t ww[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const uint32_t c = (ww[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu, leaf = i * 8u + e;
+                                if (c >= T && leaf < nl) {
+                                    const uint32_t pos = atomicAdd(&slist[255], 1u);
+                                    if (pos < 255u) slist[pos] = leaf;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        const uint32_t n_surv = slist[255];
+                        if (n_surv <= 255u) {
+                            uint32_t c_cnt = 0;
+                            if (n_surv) {
+                                flush_planes();  // the survivors' counts become complete
+                                for (uint32_t j = lane; j < n_surv; j += 32) {
+                                    const uint32_t leaf = slist[j];
+                                    const float p = __fmul_rn(v1, __ldg(unit + leaf));
+                                    float sc = 0.0f;
+                                    for (uint32_t n = cnt[leaf]; n; --n) sc = __fadd_rn(sc, p);
+                                    acc[leaf] = sc;  // Cosine: the dot product is the score
+                                    c_cnt += (__float_as_uint(sc) >= thr) ? 1u : 0u;
+                                }
+                                c_cnt = warp_sum_u32(c_cnt);
+                                __syncwarp();
+                            }
+                            tile_topx_emit(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
+                                           a.cand + slot * a.x, a.cand_cnt + slot, lane, thr, c_cnt);
+                            __syncwarp();
+                            advance();
+                            continue;
+                        }
+                    }
+                }
                 const uint32_t magic = 0x4B000000u + pending;  // float(2^23 + n) for n < 2^23
                 uint32_t c_cnt = 0;
-                if (he > hb) {
+                if (any_hits) {
 #pragma unroll 4
                     for (uint32_t r = 0; 32u * r < nl; ++r) {
                         const uint32_t leaf = 32u * r + lane;  // leaf < tile_leaves + 32: inside the padded arrays
@@ -864,7 +969,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         // the shortest of the four, then predicated.  (Variants measured in profiles/r02_k4_variants.md: giving a
         // lane four CONSECUTIVE leaves or finishing the remainders one chain at a time is slower -- the chains are
         // latency-bound, four independent ones per lane are needed.)
-        for (uint32_t r0 = 0; he > hb && 32u * r0 < nl; r0 += 4) {  // a task without hits leaves all scores at +0
+        for (uint32_t r0 = 0; any_hits && 32u * r0 < nl; r0 += 4) {  // a task without hits leaves all scores at +0
             float s[4], p[4];
             uint32_t n[4];
 #pragma unroll
@@ -1320,17 +1425,26 @@ __global__ void __launch_bounds__(PL_WARPS * 32) plan_count_kernel(
 // place of every hit -- rank of key i in tile t = keys below i present in t -- so sweep 2 writes all hit records
 // in ascending key order without any serialisation.  The query's tile offsets (plan_off row of n_tiles + 1
 // entries) start at qoff[q]; its seed tile (most hits, lowest tile on ties) is chosen on the way.
+//
+// Dense-key masks (mask_stride > 0; count-mode scoring).  A COMMON dense hit -- dense key, query value == the
+// query's common value -- needs no record at all: in a hit list without ordered hits its whole content is "bitmap
+// b of the tile", so it is one bit (bit b of the tile's words in the query's mask row).  On barcode-shaped data
+// three hits out of four are of this kind.  A tile whose list holds an ordered hit keeps records for everything
+// (the walk in key order needs them) and gets an empty mask.
 static constexpr int PB_THREADS = 256;
 static constexpr int PB_WARP_WORDS = 100;  // per warp: prefix[33] | entry begins[32] | query values[32]
-__host__ __device__ inline size_t plan_build_smem_bytes(uint32_t n_tiles, uint32_t words) {
-    return ((size_t)n_tiles * words * 6 + 3) / 4 * 4 + ((size_t)n_tiles + 1) * sizeof(uint32_t) +
+__host__ __device__ inline size_t plan_build_smem_bytes(uint32_t n_tiles, uint32_t words, uint32_t mask_stride) {
+    const size_t per_bit = mask_stride ? 10 : 6;  // present (+ dense-common) bit rows + u16 prefix popcounts
+    return ((size_t)n_tiles * words * per_bit + 3) / 4 * 4 + ((size_t)n_tiles + 1) * sizeof(uint32_t) +
+           (mask_stride ? ((size_t)(n_tiles + 31) / 32 + mask_stride) * sizeof(uint32_t) : 0) +
            (PB_THREADS / 32) * PB_WARP_WORDS * sizeof(uint32_t);
 }
 __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
     const uint64_t *__restrict__ q_row_off, const float *__restrict__ q_vals, uint64_t q_first,
     const EntryRec *__restrict__ entries, uint32_t n_tiles, uint32_t words_cap, const uint2 *__restrict__ kref,
     const uint64_t *__restrict__ qoff, const float *__restrict__ qv1s, uint64_t *__restrict__ plan_off,
-    HitRec *__restrict__ plan, uint32_t *__restrict__ seed) {
+    HitRec *__restrict__ plan, uint32_t *__restrict__ seed, const uint32_t *__restrict__ mask_off,
+    uint32_t mask_stride, uint32_t *__restrict__ dmask_out) {
     extern __shared__ uint32_t pb_smem[];
     __shared__ uint32_t s_scan[PB_THREADS / 32 + 1];
     __shared__ unsigned long long s_best;
@@ -1342,14 +1456,20 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
     const uint32_t words = max((nq + 31) >> 5, 1u);  // <= words_cap (the host checked the longest query)
     const uint64_t base = qoff[ql];
     uint64_t *off_row = plan_off + (size_t)ql * (n_tiles + 1);
+    const bool masks = mask_stride != 0;
     uint32_t *present = pb_smem;                                                      // [n_tiles][words]
-    uint16_t *pfx = reinterpret_cast<uint16_t *>(present + (size_t)n_tiles * words);  // [n_tiles][words]
-    uint32_t *toff = pb_smem + ((size_t)n_tiles * words_cap * 6 + 3) / 4;             // [n_tiles + 1]
-    uint32_t *wpre = toff + n_tiles + 1 + (size_t)warp * PB_WARP_WORDS;
+    uint32_t *pdc = present + (masks ? (size_t)n_tiles * words : 0);                  // [n_tiles][words] dense-common
+    uint16_t *pfx = reinterpret_cast<uint16_t *>(pdc + (size_t)n_tiles * words);      // [n_tiles][words]
+    uint32_t *toff = pb_smem + ((size_t)n_tiles * words_cap * (masks ? 10 : 6) + 3) / 4;  // [n_tiles + 1]
+    uint32_t *tord = toff + n_tiles + 1;                                              // [(n_tiles+31)/32] ordered tiles
+    uint32_t *dm = tord + (n_tiles + 31) / 32;                                        // [mask_stride]
+    uint32_t *wpre = toff + n_tiles + 1 + (masks ? (n_tiles + 31) / 32 + mask_stride : 0) + (size_t)warp * PB_WARP_WORDS;
     uint32_t *wbeg = wpre + 33;
     float *wval = reinterpret_cast<float *>(wbeg + 32);
     const float qv1 = qv1s[ql];
-    for (uint32_t i = tid; i < n_tiles * words; i += PB_THREADS) present[i] = 0;
+    for (uint32_t i = tid; i < n_tiles * words * (masks ? 2u : 1u); i += PB_THREADS) present[i] = 0;
+    if (masks)
+        for (uint32_t i = tid; i < (n_tiles + 31) / 32 + mask_stride; i += PB_THREADS) tord[i] = 0;
     if (tid == 0) s_best = 0;
     __syncthreads();
 
@@ -1398,29 +1518,60 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
             }
         }
     };
-    sweep([&](const uint32_t(&ki)[4], const uint32_t(&)[4], const uint32_t(&en)[4], uint32_t n) {
-        uint32_t tl[4];
+    if (!masks) {
+        sweep([&](const uint32_t(&ki)[4], const uint32_t(&)[4], const uint32_t(&en)[4], uint32_t n) {
+            uint32_t tl[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if ((uint32_t)u < n) tl[u] = entries[en[u]].tile;
+            for (int u = 0; u < 4; ++u)
+                if ((uint32_t)u < n) tl[u] = entries[en[u]].tile;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if ((uint32_t)u < n) atomicOr(&present[tl[u] * words + (ki[u] >> 5)], 1u << (ki[u] & 31));
-    });
+            for (int u = 0; u < 4; ++u)
+                if ((uint32_t)u < n) atomicOr(&present[tl[u] * words + (ki[u] >> 5)], 1u << (ki[u] & 31));
+        });
+    } else {
+        sweep([&](const uint32_t(&ki)[4], const uint32_t(&sl)[4], const uint32_t(&en)[4], uint32_t n) {
+            EntryRec er[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((uint32_t)u < n) er[u] = entries[en[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((uint32_t)u < n) {
+                    const uint32_t t = er[u].tile, w = ki[u] >> 5, bit = 1u << (ki[u] & 31);
+                    atomicOr(&present[t * words + w], bit);
+                    const bool ord = (er[u].len & ORDERED_FLAG) != 0u || wval[sl[u]] != qv1;
+                    if (ord) {
+                        atomicOr(&tord[t >> 5], 1u << (t & 31));
+                    } else if (er[u].len & DENSE_FLAG) {
+                        atomicOr(&pdc[t * words + w], bit);
+                        atomicOr(&dm[__ldg(mask_off + t) + (er[u].begin >> 5)], 1u << (er[u].begin & 31));
+                    }
+                }
+        });
+    }
     __syncthreads();
     // hit count of every tile + prefix popcounts of its bit row
     const uint32_t C = (n_tiles + PB_THREADS - 1) / PB_THREADS;  // consecutive tiles per thread
     uint32_t mine = 0;
     unsigned long long best = 0;
     for (uint32_t t = tid * C; t < min(n_tiles, (tid + 1) * C); ++t) {
-        uint32_t run = 0;
+        uint32_t all = 0, run = 0;
+        const bool keep_all = masks && ((tord[t >> 5] >> (t & 31)) & 1u);
+        if (keep_all)  // an ordered list: records for every hit, no mask
+            for (uint32_t w = __ldg(mask_off + t); w < __ldg(mask_off + t + 1); ++w) dm[w] = 0;
         for (uint32_t w = 0; w < words; ++w) {
+            uint32_t bits = present[t * words + w];
+            all += __popc(bits);
+            if (masks && !keep_all) {
+                bits &= ~pdc[t * words + w];  // the common dense hits live in the mask
+                present[t * words + w] = bits;
+            }
             pfx[t * words + w] = (uint16_t)run;
-            run += __popc(present[t * words + w]);
+            run += __popc(bits);
         }
         toff[t] = run;
         mine += run;
-        best = max(best, ((unsigned long long)run << 32) | (unsigned long long)(0xFFFFFFFFu - t));
+        best = max(best, ((unsigned long long)all << 32) | (unsigned long long)(0xFFFFFFFFu - t));
     }
     // exclusive scan of the tile counts (block scan over the per-thread chunk sums)
     uint32_t inc = mine;
@@ -1447,6 +1598,8 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
     for (uint32_t t = tid; t <= n_tiles; t += PB_THREADS)
         off_row[t] = (base + toff[t]) | ((seed && t == seed_tile) ? PLAN_SEED_FLAG : 0ull);
     if (seed && tid == 0) seed[ql] = seed_tile;
+    if (masks)
+        for (uint32_t i = tid; i < mask_stride; i += PB_THREADS) dmask_out[(size_t)ql * mask_stride + i] = dm[i];
     sweep([&](const uint32_t(&ki)[4], const uint32_t(&sl)[4], const uint32_t(&en)[4], uint32_t n) {
         EntryRec er[4];
 #pragma unroll
@@ -1456,8 +1609,9 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
         for (int u = 0; u < 4; ++u)
             if ((uint32_t)u < n) {
                 const uint32_t i = ki[u], w = i >> 5;
-                const uint32_t rank =
-                    pfx[er[u].tile * words + w] + __popc(present[er[u].tile * words + w] & ((1u << (i & 31)) - 1u));
+                const uint32_t bits = present[er[u].tile * words + w];
+                if (!((bits >> (i & 31)) & 1u)) continue;  // a common dense hit: in the mask
+                const uint32_t rank = pfx[er[u].tile * words + w] + __popc(bits & ((1u << (i & 31)) - 1u));
                 HitRec h;
                 h.begin = er[u].begin;
                 h.qv = wval[sl[u]];
@@ -1522,7 +1676,10 @@ struct Plan {
     uint64_t n_hits = 0;
     uint32_t stride = 0;     // plan_off entries per query: n_tiles + 1 (plan_build_kernel) or n_tiles (fallback)
     bool seeded = false;     // plan_build_kernel chose the seed tiles and flagged them
+    DevBuf<uint32_t> dmask;  // [queries][mask_stride] dense-key masks (count mode)
+    uint32_t mask_stride = 0;
 };
+static bool k4_count_mode(const myrio_index *ix);
 
 static bool plan_second_generation() {  // MYRIO_K4A_PLAN=1 keeps the probe / scan / ranked-fill kernels of round 1
     static const bool v = [] {
@@ -1544,8 +1701,17 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     const unsigned grid = (unsigned)((qn + PL_WARPS - 1) / PL_WARPS);
     const uint64_t max_q_keys = std::max<uint64_t>(queries_max_keys(ctx, queries), 1);
     const uint32_t words_all = (uint32_t)((max_q_keys + 31) / 32);
+    pl.mask_stride = 0;
+    // dense-key masks: count-mode scoring only (the add-as-you-go kernel needs a record with the query value for
+    // every hit), and only while the CTA's bit matrices stay small enough for several CTAs per SM
+    static const bool masks_on = [] {
+        const char *e = getenv("MYRIO_K4A_MASKS");
+        return !(e && e[0] == '0');
+    }();
+    uint32_t mask_stride = masks_on && k4_count_mode(ix) ? ix->mask_words_total : 0;
+    if (mask_stride && plan_build_smem_bytes((uint32_t)n_tiles, words_all, mask_stride) > 100 * 1024) mask_stride = 0;
     if (plan_second_generation() && max_q_keys < 65536 &&
-        plan_build_smem_bytes((uint32_t)n_tiles, words_all) + 4096 <= ctx->smem_optin) {
+        plan_build_smem_bytes((uint32_t)n_tiles, words_all, mask_stride) + 4096 <= ctx->smem_optin) {
         pl.qhits.reserve(qn);
         pl.qoff.reserve(qn + 1);
         MYRIO_LAUNCH(ctx, "k4a_plan_count", plan_count_kernel, grid, PL_WARPS * 32, 0, queries->row_off.p,
@@ -1565,12 +1731,15 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
         pl.off.reserve(qn * pl.stride + 1);
         const bool seed = want_seed && n_tiles > 1;
         if (seed) pl.seed.reserve(qn);
-        const size_t psm = plan_build_smem_bytes((uint32_t)n_tiles, words_all);
+        if (mask_stride) pl.dmask.reserve(qn * mask_stride);
+        const size_t psm = plan_build_smem_bytes((uint32_t)n_tiles, words_all, mask_stride);
         MYRIO_CK(cudaFuncSetAttribute(plan_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         MYRIO_LAUNCH(ctx, "k4a_plan_build", plan_build_kernel, (unsigned)qn, PB_THREADS, psm, queries->row_off.p,
                      queries->vals_f32.p, q0, ix->gentries.p, (uint32_t)n_tiles, words_all, pl.kref.p, pl.qoff.p,
-                     pl.qv1.p, pl.off.p, pl.hits.p, seed ? pl.seed.p : (uint32_t *)nullptr);
+                     pl.qv1.p, pl.off.p, pl.hits.p, seed ? pl.seed.p : (uint32_t *)nullptr, ix->mask_off.p,
+                     mask_stride, mask_stride ? pl.dmask.p : (uint32_t *)nullptr);
         pl.seeded = seed;
+        pl.mask_stride = mask_stride;
         return true;
     }
     // ---- round-1 path (very long queries x very many tiles): per-task hit counts, a scan over all tasks
@@ -1734,6 +1903,8 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
     a.plan = pl.hits.p;
     a.plan_off = pl.off.p;
     a.plan_stride = pl.stride;
+    a.dmask = pl.mask_stride ? pl.dmask.p : nullptr;
+    a.mask_stride = pl.mask_stride;
     a.qv1 = pl.qv1.p;
     a.q_count = (uint32_t)qn;
     a.tile_leaves = ix->tile_leaves;

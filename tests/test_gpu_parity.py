@@ -743,16 +743,17 @@ def test_reference_kat_from_unsorted_pairs_through_the_gpu(api, ctx):
     assert (bits(v) == bits(norm.vals)).all()
 
 
-@pytest.mark.parametrize("count_mode,ub,plan", [("1", "1", "2"), ("1", "0", "2"), ("0", "1", "2"), ("1", "1", "1")])
-def test_k4_kernel_variants(count_mode, ub, plan):
-    # the K4 kernels (count mode with / without the bound pass of the fused top-x, add-as-you-go) and both
-    # generations of the plan kernels forced through the odd-term cases, each in its own process (the switches
-    # are read once per process)
+@pytest.mark.parametrize("count_mode,ub,plan,masks", [("1", "1", "2", "1"), ("1", "0", "2", "1"), ("0", "1", "2", "1"),
+                                                      ("1", "1", "1", "1"), ("1", "1", "2", "0")])
+def test_k4_kernel_variants(count_mode, ub, plan, masks):
+    # the K4 kernels (count mode with / without the bound pass of the fused top-x, add-as-you-go), both
+    # generations of the plan kernels and the plan with / without dense-key masks, forced through the odd-term
+    # cases, each in its own process (the switches are read once per process)
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MYRIO_K4_COUNT=count_mode, MYRIO_K4_UB=ub, MYRIO_K4A_PLAN=plan)
+    env = dict(os.environ, MYRIO_K4_COUNT=count_mode, MYRIO_K4_UB=ub, MYRIO_K4A_PLAN=plan, MYRIO_K4A_MASKS=masks)
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "k4_variant_worker.py")], env=env,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
