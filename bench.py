@@ -146,6 +146,42 @@ class ClockSampler:
                 pass
             time.sleep(self.period)
 
+    def start_inline(self):
+        """In-line mode (default): no thread; `poll()` is called by the timing loop itself at step boundaries
+        INSIDE the timed region (a few times per region).  A concurrent NVML query from another thread or
+        process stalls this process's CUDA calls for 20-900 ms every now and then (profiles/r02_smi_hiccups.md);
+        a query made between two steps costs only its own duration, which is recorded (`poll_ms`)."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.gpu
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
+            self.source = "NVML in-process (pynvml), polled by the timing loop at step boundaries inside the timed regions"
+            self.inline, self.poll_ms = True, []
+        except Exception:
+            self.inline = False
+            self.start()
+
+    def poll(self):
+        if not getattr(self, "inline", False):
+            return
+        nv = self._nv
+        t0 = time.perf_counter()
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+            for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                              ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                              ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+        self.poll_ms.append((time.perf_counter() - t0) * 1e3)
+
     def start(self):
         try:
             import pynvml as nv
@@ -175,6 +211,12 @@ class ClockSampler:
             self.rows.append([t.strip() for t in line.split(",")])
 
     def stop(self):
+        if getattr(self, "inline", False):
+            if not self.sm:
+                return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0, "source": self.source}
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": self.source,
+                    "poll_ms_max": round(max(self.poll_ms), 3), "poll_ms_total": round(sum(self.poll_ms), 3)}
         if self.thread is not None:
             self.stop_flag = True
             self.thread.join(timeout=2)
@@ -483,6 +525,7 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     step_trace = {}
+    sampler = None  # ClockSampler of rank 0 while the headline regions are timed
 
     def timed(fn, steps, tag=None):
         """`steps` calls bracketed by barrier + synchronize, CUDA events on the library's stream, max over ranks.
@@ -491,7 +534,10 @@ def run_ours(args, rank, local_rank, world):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
         e0.record(ext)
-        for _ in range(steps):
+        poll_at = {steps // 4, steps // 2, (3 * steps) // 4} if tag else set()  # inside the timed region
+        for it in range(steps):
+            if it in poll_at and sampler is not None:
+                sampler.poll()
             fn()
             if tag:
                 m = torch.cuda.Event(enable_timing=True)
@@ -583,9 +629,12 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(args.warmup):
         step_resident()
 
-    sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("MYRIO_BENCH_NO_SMI"):  # diagnosis only: the line then carries no clocks
-        sampler.start()
+        sampler = ClockSampler(local_rank)
+        if os.environ.get("MYRIO_BENCH_NVML_THREAD"):
+            sampler.start()
+        else:
+            sampler.start_inline()
     ctx.prof_reset()
     ctx.prof_enable(True)
     launches0 = ctx.launch_count
@@ -602,7 +651,8 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(max(1, min(args.warmup, 3))):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps, "e2e")
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if sampler is not None else None
+    sampler = None
 
     # ---- the same step with EVERY score finished (the fused top-x normally finishes only the scores whose
     # upper bound reaches the query's running bound; the top-x is bit-identical either way)
@@ -653,7 +703,8 @@ def run_ours(args, rank, local_rank, world):
     k4_avg_ms = k4_ms / max(k4_n, 1)
     k4_step_ms = k4_ms / max(args.steps, 1)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    prof = latest_profile("_k4v") or latest_profile("r02_k4_ncu_summary")  # newest capture of the count-mode kernel
+    # the committed ncu capture of the CURRENT K4 (instructions per posting, DRAM bytes), older ones as fall-backs
+    prof = latest_profile("r02_k4v11") or latest_profile("r02_k4v9") or latest_profile("r02_k4_ncu_summary")
     issue_peak = 148 * 4 * sm_mhz * 1e6  # warp instructions / s: 148 SMs x 4 schedulers x 1 issue / clk
     roofline = {
         "bound": "issue",

@@ -115,34 +115,76 @@ __global__ void __launch_bounds__(256) emit_unique_kernel(const uint64_t *__rest
     if (i == 0) ubegin[uidx[n]] = (uint32_t)n;
 }
 
-// A unique (tile, key) entry is DENSE when the key occurs in at least max(32, n_leaves/4)
-// leaves of the tile and every one of its postings carries exactly unit[leaf].
+// A unique (tile, key) entry is DENSE when the key occurs in at least min_df leaves of the tile and every one of
+// its postings carries exactly unit[leaf]: it is then also stored as a 128-byte bitmap.  flags: 2 = HOT (in at
+// least max(32, n_leaves/4) leaves: the plan keeps such keys as mask bits), 1 = cold dense, 0 = sparse.
+// min_df = 0 means "hot only" (the add-as-you-go kernel pays 32 slots per dense key whatever its df; the
+// count-mode kernel pays three logic instructions: measured best from 32 postings on).
 __global__ void __launch_bounds__(256) classify_dense_kernel(const uint64_t *__restrict__ postings,
                                                              const uint32_t *__restrict__ ubegin,
                                                              uint64_t n_unique,
                                                              const uint64_t *__restrict__ ustart,
                                                              uint32_t n_tiles, uint64_t n_leaves,
                                                              uint32_t tile_leaves,
-                                                             const float *__restrict__ unit,
-                                                             uint32_t *__restrict__ flags) {
+                                                             const float *__restrict__ unit, uint32_t min_df,
+                                                             uint32_t *__restrict__ hot, uint32_t *__restrict__ cold) {
     const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_unique) return;
     const uint32_t b = ubegin[u], e = ubegin[u + 1];
-    uint32_t dense = 0;
-    if (e - b >= 32u) {
+    uint32_t cls = 0;
+    if (e - b >= (min_df ? min(min_df, 32u) : 32u)) {
         const uint32_t t = tile_of(ustart, n_tiles, u);
         const uint64_t leaf0 = (uint64_t)t * tile_leaves;
         const uint32_t nl = (uint32_t)min((uint64_t)tile_leaves, n_leaves - leaf0);
-        if (e - b >= max(32u, nl / 4u)) {
-            dense = 1;
+        const uint32_t hot_df = max(32u, nl / 4u);
+        if (e - b >= hot_df)
+            cls = 2;
+        else if (min_df && e - b >= min_df)
+            cls = 1;
+        if (cls) {
             const float *un = unit + leaf0;
-            for (uint32_t i = b; dense && i < e; ++i) {
+            for (uint32_t i = b; cls && i < e; ++i) {
                 const uint64_t p = postings[i];
-                if ((uint32_t)p != __float_as_uint(un[(uint32_t)(p >> 32)])) dense = 0u;
+                if ((uint32_t)p != __float_as_uint(un[(uint32_t)(p >> 32)])) cls = 0u;
             }
         }
     }
-    flags[u] = dense;
+    hot[u] = cls == 2u;
+    cold[u] = cls == 1u;
+}
+
+// bitmap index of every dense entry: inside a tile the hot keys come first (their indexes are the bit positions
+// of the plan's dense-key masks), then the cold ones; tiles follow one another.  dflags[u] = dense at all.
+__global__ void __launch_bounds__(256) dense_index_kernel(const uint32_t *__restrict__ hot,
+                                                          const uint32_t *__restrict__ cold,
+                                                          const uint64_t *__restrict__ hidx,
+                                                          const uint64_t *__restrict__ cidx, uint64_t n_unique,
+                                                          const uint64_t *__restrict__ ustart, uint32_t n_tiles,
+                                                          uint32_t *__restrict__ dflags, uint64_t *__restrict__ didx) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_unique) return;
+    const uint32_t t = tile_of(ustart, n_tiles, u);
+    const uint64_t us = ustart[t], ue = ustart[t + 1];
+    const uint64_t hot0 = hidx[us], cold0 = cidx[us], n_hot = hidx[ue] - hot0;
+    dflags[u] = hot[u] | cold[u];
+    didx[u] = hot0 + cold0 + (hot[u] ? hidx[u] - hot0 : n_hot + (cidx[u] - cold0));
+}
+
+// number of postings whose value is not unit[leaf] (what flag_odd_postings_kernel will flag), counted before the
+// dense classification: it decides whether the index is scored in count mode, hence how low the dense bar is
+__global__ void __launch_bounds__(256) count_odd_postings_kernel(const uint64_t *__restrict__ postings, uint64_t n,
+                                                                 const uint64_t *__restrict__ bounds, uint32_t n_tiles,
+                                                                 uint32_t tile_leaves, const float *__restrict__ unit,
+                                                                 unsigned long long *__restrict__ n_odd) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool odd = false;
+    if (i < n) {
+        const uint64_t p = postings[i];
+        const uint32_t t = tile_of(bounds, n_tiles, i);
+        odd = (uint32_t)p != __float_as_uint(unit[(uint64_t)t * tile_leaves + (uint32_t)(p >> 32)]);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, odd);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_odd, (unsigned long long)__popc(m));
 }
 
 // postings whose value is not unit[leaf] get POSTING_ODD (see index.cuh); run last, on the final posting array
@@ -309,6 +351,7 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
 
     uint64_t U = 0, n_dense = 0;
     std::vector<uint64_t> ustart(n_tiles + 1, 0), dstart(n_tiles + 1, 0);
+    std::vector<uint32_t> n_hot_of(n_tiles, 0);  // hot dense keys per tile (the plan's mask bits)
     DevBuf<uint64_t> d_ustart(n_tiles + 1);
     DevBuf<uint32_t> dflags;
     DevBuf<uint64_t> didx;
@@ -334,19 +377,49 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         // 4. dense entries -> bitmaps
         dflags.alloc(U);
         didx.alloc(U + 1);
+        DevBuf<uint64_t> d_dstart(n_tiles + 1);
+        std::vector<uint64_t> hstart(n_tiles + 1, 0);
         if (tile_leaves <= DENSE_MAX_TILE) {
+            // will the index be scored in count mode (score.cu: <= 2 % odd postings, short leaf vectors)?
+            unsigned long long h_odd0 = 0;
+            MYRIO_CK(cudaMemsetAsync(key_or.p + 2, 0, sizeof(unsigned long long), ctx->stream));
+            MYRIO_LAUNCH(ctx, "k3_count_odd", count_odd_postings_kernel, g, 256, 0, sv, P, d_bounds.p,
+                         (uint32_t)n_tiles, tile_leaves, ix->unit.p, key_or.p + 2);
+            d2h(ctx, &h_odd0, key_or.p + 2, 1);
+            sync(ctx);
+            MYRIO_CK(cudaMemsetAsync(key_or.p + 2, 0, sizeof(unsigned long long), ctx->stream));
+            static const uint32_t cold_df = [] {  // MYRIO_DENSE_MIN_DF: 0 = hot keys only (round-1 behaviour)
+                const char *e = getenv("MYRIO_DENSE_MIN_DF");
+                return e ? (uint32_t)atoi(e) : 32u;
+            }();
+            const bool count_mode = h_odd0 * 50 <= P && ix->max_leaf_nnz < 65535;
+            DevBuf<uint32_t> hot(U), cold(U);
+            DevBuf<uint64_t> hidx(U + 1), cidx(U + 1), d_hstart(n_tiles + 1);
             MYRIO_LAUNCH(ctx, "k3_classify_dense", classify_dense_kernel, (unsigned)((U + 255) / 256), 256, 0, sv,
-                         ix->ubegin.p, U, d_ustart.p, (uint32_t)n_tiles, L, tile_leaves, ix->unit.p, dflags.p);
+                         ix->ubegin.p, U, d_ustart.p, (uint32_t)n_tiles, L, tile_leaves, ix->unit.p,
+                         count_mode ? cold_df : 0u, hot.p, cold.p);
+            exclusive_scan_u32_to_u64(ctx, hot.p, hidx.p, U);
+            exclusive_scan_u32_to_u64(ctx, cold.p, cidx.p, U);
+            MYRIO_LAUNCH(ctx, "k3_dense_index", dense_index_kernel, (unsigned)((U + 255) / 256), 256, 0, hot.p, cold.p,
+                         hidx.p, cidx.p, U, d_ustart.p, (uint32_t)n_tiles, dflags.p, didx.p);
+            // per tile: first bitmap (hot + cold before the tile) and number of hot keys
+            MYRIO_LAUNCH(ctx, "k3_gather", gather_u64_kernel, (unsigned)((n_tiles + 256) / 256), 256, 0, hidx.p,
+                         d_ustart.p, n_tiles + 1, d_hstart.p);
+            MYRIO_LAUNCH(ctx, "k3_gather", gather_u64_kernel, (unsigned)((n_tiles + 256) / 256), 256, 0, cidx.p,
+                         d_ustart.p, n_tiles + 1, d_dstart.p);
+            std::vector<uint64_t> cstart(n_tiles + 1, 0);
+            d2h(ctx, hstart.data(), d_hstart.p, n_tiles + 1);
+            d2h(ctx, cstart.data(), d_dstart.p, n_tiles + 1);
+            sync(ctx);
+            for (uint64_t t = 0; t <= n_tiles; ++t) dstart[t] = hstart[t] + cstart[t];
         } else {
             MYRIO_CK(cudaMemsetAsync(dflags.p, 0, U * sizeof(uint32_t), ctx->stream));
+            MYRIO_CK(cudaMemsetAsync(didx.p, 0, (U + 1) * sizeof(uint64_t), ctx->stream));
+            sync(ctx);
         }
-        exclusive_scan_u32_to_u64(ctx, dflags.p, didx.p, U);
-        DevBuf<uint64_t> d_dstart(n_tiles + 1);
-        MYRIO_LAUNCH(ctx, "k3_gather", gather_u64_kernel, (unsigned)((n_tiles + 256) / 256), 256, 0, didx.p,
-                     d_ustart.p, n_tiles + 1, d_dstart.p);
-        d2h(ctx, dstart.data(), d_dstart.p, n_tiles + 1);
-        sync(ctx);
         n_dense = dstart[n_tiles];
+        n_hot_of.assign(n_tiles, 0);
+        for (uint64_t t = 0; t < n_tiles; ++t) n_hot_of[t] = (uint32_t)(hstart[t + 1] - hstart[t]);
         if (n_dense) {
             ix->bitmaps.alloc(n_dense * 32);
             MYRIO_LAUNCH(ctx, "k3_fill_bitmaps", fill_bitmaps_kernel, (unsigned)((U + 7) / 8), 256, 0, sv,
@@ -418,7 +491,7 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         std::vector<uint32_t> moff(n_tiles + 1, 0);
         for (uint64_t t = 0; t < n_tiles; ++t) {
             ix->tiles[t].mask_off = moff[t];
-            ix->tiles[t].mask_words = (uint32_t)((ix->tiles[t].n_dense + 31) / 32);
+            ix->tiles[t].mask_words = (n_hot_of[t] + 31) / 32;  // hot keys first: their bitmap indexes are the bits
             moff[t + 1] = moff[t] + ix->tiles[t].mask_words;
         }
         ix->mask_words_total = moff[n_tiles];

@@ -1543,8 +1543,13 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
                     if (ord) {
                         atomicOr(&tord[t >> 5], 1u << (t & 31));
                     } else if (er[u].len & DENSE_FLAG) {
-                        atomicOr(&pdc[t * words + w], bit);
-                        atomicOr(&dm[__ldg(mask_off + t) + (er[u].begin >> 5)], 1u << (er[u].begin & 31));
+                        // the tile's mask covers its HOT dense keys (bitmap indexes below 32 * mask words); a cold
+                        // dense key stays a record (its DENSE_FLAG sends it through the dense sweep all the same)
+                        const uint32_t mo = __ldg(mask_off + t), mw = __ldg(mask_off + t + 1) - mo;
+                        if ((er[u].begin >> 5) < mw) {
+                            atomicOr(&pdc[t * words + w], bit);
+                            atomicOr(&dm[mo + (er[u].begin >> 5)], 1u << (er[u].begin & 31));
+                        }
                     }
                 }
         });
