@@ -49,6 +49,7 @@ struct ScoreArgs {
     const float *qv1;      // [q_count] the query's common value (count mode): its smallest value
     const uint32_t *seed;  // [q_count] seed tile (pass 1); its plan_off entry carries PLAN_SEED_FLAG (pass 2 skips it)
     uint32_t seed_mode;    // 0 = no seeding, 1 = seed pass (task == query), 2 = sweep
+    const uint32_t *seed_order;  // seed pass: task i scores query seed_order[i] (queries grouped by seed tile) or i
     uint32_t ub_prune;     // count mode, fused top-x: finish only the scores whose upper bound reaches the bound
     // count mode: a query's common dense keys per tile as bits (bit = bitmap index in the tile) instead of hit
     // records: row ql of mask_stride words, the tile's words at TileInfo::mask_off (0 = everything is a record)
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__((UREG ? SC_UREG_WARPS : SC_MAX_WARPS) * 32) sc
         if (lane == 0) next_task = (uint32_t)atomicAdd(a.counters, 1ull);
         uint32_t t, ql;
         if (a.seed_mode == 1) {
-            ql = task;
+            ql = a.seed_order ? __ldg(a.seed_order + task) : task;
             t = __ldg(a.seed + ql);
         } else {
             t = task / a.q_count;  // tile-major: a tile's index stays hot in L2
@@ -499,6 +500,58 @@ __device__ __noinline__ void scc_odd_dense_key(float *acc, uint16_t *cnt, const 
         }
 }
 
+// x-th largest of the u16 counters cnt[0, n) (n >= x >= 1), by a two-pass radix select over a per-warp 256-bin
+// histogram (high byte, then low byte inside the chosen high byte).
+__device__ __forceinline__ uint32_t warp_xth_largest_u16(const uint16_t *cnt, uint32_t n, uint32_t x, uint32_t *hist,
+                                                         unsigned lane) {
+    uint32_t prefix = 0, need = x;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int shift = 8 - 8 * pass;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+        __syncwarp();
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            uint32_t bin = 0xFFFFFFFFu;
+            if (i < n) {
+                const uint32_t c = cnt[i];
+                if (pass == 0 || (c >> 8) == prefix) bin = (c >> shift) & 255u;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (bin != 0xFFFFFFFFu && (int)lane == __ffs(peers) - 1) hist[bin] += __popc(peers);
+            __syncwarp();
+        }
+        // lane l owns bins 255-8l .. 248-8l (descending): where does the running count reach `need`?
+        uint32_t local[8], lsum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            local[j] = hist[255 - 8 * lane - j];
+            lsum += local[j];
+        }
+        const uint32_t incl = warp_incl_scan_u32s(lsum, lane);
+        const unsigned reach = __ballot_sync(0xffffffffu, incl >= need);
+        const int owner = __ffs(reach) - 1;
+        uint32_t bin = 0, rest = 0;
+        if ((int)lane == owner) {
+            uint32_t run = incl - lsum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (run + local[j] >= need) {
+                    bin = 255 - 8 * lane - j;
+                    rest = need - run;
+                    break;
+                }
+                run += local[j];
+            }
+        }
+        bin = __shfl_sync(0xffffffffu, bin, owner);
+        need = __shfl_sync(0xffffffffu, rest, owner);
+        prefix = (prefix << 8) | bin;
+        __syncwarp();
+    }
+    return prefix;
+}
+
 template <int SIM, bool FUSED, bool STATS>
 __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(ScoreArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -516,8 +569,9 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
     const uint64_t *post = nullptr;
     const uint32_t *bitmaps = nullptr;
     const float *unit = nullptr;
-    float unit_max = 0.0f;
+    float unit_max = 0.0f, unit_min = 0.0f;
     uint32_t t_mo = 0, t_mw = 0;  // the tile's words in a query's dense-key mask row
+    bool acc_dirty = true;        // acc[] may hold something else than +0
     const TileInfo *ti = a.tiles;
 
     // ---- task pipeline.  Task ids come from an atomic counter.  The id of the task after next is requested in
@@ -530,7 +584,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
     auto load_desc = [&](uint32_t tk, uint32_t &tt, uint32_t &qq, uint64_t &b, uint64_t &e, float &v) {
         if (tk >= a.n_tasks) return;
         if (a.seed_mode == 1) {
-            qq = tk;
+            qq = a.seed_order ? __ldg(a.seed_order + tk) : tk;  // grouped by seed tile: neighbours share the tile
             tt = __ldg(a.seed + qq);
         } else {
             tt = tk / a.q_count;  // tile-major: a tile's index stays hot in L2
@@ -568,22 +622,27 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             bitmaps = ti->bitmaps;
             unit = ti->unit;
             unit_max = ti->unit_max;
+            unit_min = ti->unit_min;
             t_mo = ti->mask_off;
             t_mw = a.mask_stride ? ti->mask_words : 0u;
             cached_tile = t;
         }
         // first words of the query's dense-key mask for this tile (requested before the accumulators are cleared)
         if (t_mw && lane < 8 && lane < t_mw) mask0 = __ldg(a.dmask + (size_t)ql * a.mask_stride + t_mo + lane);
+        // the counters are cleared for every task; the partial sums only if the previous task touched them (the
+        // usual task -- no ordered batch, no survivor of the bound pass -- never does)
         if ((a.tile_leaves & 7u) == 0u) {  // 16-byte stores (the per-warp slices are 16-byte aligned)
             const uint32_t n4 = (a.tile_leaves + 32) >> 2, n8 = (a.tile_leaves + 32) >> 3;
-            for (uint32_t i = lane; i < n4; i += 32) reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (acc_dirty)
+                for (uint32_t i = lane; i < n4; i += 32) reinterpret_cast<float4 *>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             for (uint32_t i = lane; i < n8; i += 32) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
         } else {
             for (uint32_t i = lane; i < a.tile_leaves + 32; i += 32) {
-                acc[i] = 0.0f;
+                if (acc_dirty) acc[i] = 0.0f;
                 cnt[i] = 0;
             }
         }
+        acc_dirty = true;  // until the task proves otherwise
         __syncwarp();
         }
 
@@ -651,7 +710,9 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                 if (n == DENSE_CHUNK) {
                     const uint32_t w = (uint32_t)p[0];
                     if (!odd_key) {
-                        // ripple-carry add of one bit per leaf into the bit-sliced counters
+                        // ripple-carry add of one bit per leaf into the bit-sliced counters (an earlier batch of
+                        // the task may have left them full: the dense sweep stops at 63 as well)
+                        if (pending >= (1u << SCC_PLANES) - 1u) flush_planes();
                         uint32_t carry = w;
 #pragma unroll
                         for (int j = 0; j < SCC_PLANES; ++j) {
@@ -659,7 +720,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                             pl[j] ^= carry;
                             carry = t2;
                         }
-                        if (++pending == (1u << SCC_PLANES) - 1u) flush_planes();
+                        ++pending;
                     } else {
                         // every posting of a dense key carries unit[leaf]; the query value is the odd one
                         flush_planes();
@@ -863,7 +924,17 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         // +0, below any non-zero bound).  Only the survivors -- the query's relatives -- get their unit value
         // loaded, their dense count unsliced and their additions replayed, exactly as in the full replay below.
         if (FUSED && a.ub_prune) {
-            const uint32_t thr = read_bound(a.gthr + ql, lane);
+            uint32_t thr = read_bound(a.gthr + ql, lane);
+            // A query without a bound yet (its seed tile): a valid one comes from the counters alone.  The x leaves
+            // with the largest counts each score at least n_x pmin (1 - 2^-24)^n > 0.99 n_x pmin (n_x = the x-th
+            // largest count, pmin = fl(v1 unit_min)), so the tile's x-th best score is at least that, and the bound
+            // pass below finishes the ~x leaves that can reach it instead of all of them.
+            if (thr == 0u && (a.ub_prune & 2u) && SIM == MYRIO_SIM_COSINE && !had_ordered && any_hits && nl > a.x) {
+                flush_planes();
+                const uint32_t n_x = warp_xth_largest_u16(cnt, nl, a.x, hist, lane);
+                thr = __float_as_uint(__fmul_rn(__fmul_rn((float)n_x, __fmul_rn(v1, unit_min)), 0.99f));
+                if (lane == 0 && thr) atomicMax(a.gthr + ql, thr);  // x leaves of this tile reach it: a valid bound
+            }
             if (thr != 0u) {
                 const float thr_f = __uint_as_float(thr);
                 const float pmax = __fmul_rn(v1, unit_max);
@@ -919,6 +990,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                             tile_topx_emit(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
                                            a.cand + slot * a.x, a.cand_cnt + slot, lane, thr, c_cnt);
                             __syncwarp();
+                            acc_dirty = n_surv != 0u;
                             advance();
                             continue;
                         }
@@ -1436,7 +1508,7 @@ static constexpr int PB_WARP_WORDS = 100;  // per warp: prefix[33] | entry begin
 __host__ __device__ inline size_t plan_build_smem_bytes(uint32_t n_tiles, uint32_t words, uint32_t mask_stride) {
     const size_t per_bit = mask_stride ? 10 : 6;  // present (+ dense-common) bit rows + u16 prefix popcounts
     return ((size_t)n_tiles * words * per_bit + 3) / 4 * 4 + ((size_t)n_tiles + 1) * sizeof(uint32_t) +
-           (mask_stride ? ((size_t)(n_tiles + 31) / 32 + mask_stride) * sizeof(uint32_t) : 0) +
+           (mask_stride ? ((size_t)(n_tiles + 31) / 32 + mask_stride + words + 1) * sizeof(uint32_t) : 0) +
            (PB_THREADS / 32) * PB_WARP_WORDS * sizeof(uint32_t);
 }
 __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
@@ -1463,19 +1535,21 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
     uint32_t *toff = pb_smem + ((size_t)n_tiles * words_cap * (masks ? 10 : 6) + 3) / 4;  // [n_tiles + 1]
     uint32_t *tord = toff + n_tiles + 1;                                              // [(n_tiles+31)/32] ordered tiles
     uint32_t *dm = tord + (n_tiles + 31) / 32;                                        // [mask_stride]
-    uint32_t *wpre = toff + n_tiles + 1 + (masks ? (n_tiles + 31) / 32 + mask_stride : 0) + (size_t)warp * PB_WARP_WORDS;
+    uint32_t *krec = dm + mask_stride;  // [words_cap] keys with a hit that is NOT a mask bit | [1] any ordered tile
+    uint32_t *wpre = toff + n_tiles + 1 + (masks ? (n_tiles + 31) / 32 + mask_stride + words_cap + 1 : 0) +
+                     (size_t)warp * PB_WARP_WORDS;
     uint32_t *wbeg = wpre + 33;
     float *wval = reinterpret_cast<float *>(wbeg + 32);
     const float qv1 = qv1s[ql];
     for (uint32_t i = tid; i < n_tiles * words * (masks ? 2u : 1u); i += PB_THREADS) present[i] = 0;
     if (masks)
-        for (uint32_t i = tid; i < (n_tiles + 31) / 32 + mask_stride; i += PB_THREADS) tord[i] = 0;
+        for (uint32_t i = tid; i < (n_tiles + 31) / 32 + mask_stride + words_cap + 1; i += PB_THREADS) tord[i] = 0;
     if (tid == 0) s_best = 0;
     __syncthreads();
 
     // the hits of 32 consecutive keys flattened over the lanes of a warp, FOUR hits of a lane at a time so that
     // their (dependent, L2-latency) entry loads overlap: f(key index[4], slot[4], entry index[4], n)
-    auto sweep = [&](auto f) {
+    auto sweep = [&](bool only_record_keys, auto f) {
         for (uint32_t k0 = warp * 32; k0 < nq; k0 += PB_THREADS) {
             const uint32_t i = k0 + lane;
             uint2 kr = make_uint2(0u, 0u);
@@ -1483,6 +1557,8 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
             if (i < nq) {
                 kr = kref[qb + i - kbase];
                 v = q_vals[qb + i];
+                // second sweep: a key all of whose hits became mask bits has nothing to write
+                if (only_record_keys && !((krec[i >> 5] >> (i & 31)) & 1u)) kr.y = 0;
             }
             uint32_t inc = kr.y;
 #pragma unroll
@@ -1519,7 +1595,7 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
         }
     };
     if (!masks) {
-        sweep([&](const uint32_t(&ki)[4], const uint32_t(&)[4], const uint32_t(&en)[4], uint32_t n) {
+        sweep(false, [&](const uint32_t(&ki)[4], const uint32_t(&)[4], const uint32_t(&en)[4], uint32_t n) {
             uint32_t tl[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -1529,7 +1605,7 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
                 if ((uint32_t)u < n) atomicOr(&present[tl[u] * words + (ki[u] >> 5)], 1u << (ki[u] & 31));
         });
     } else {
-        sweep([&](const uint32_t(&ki)[4], const uint32_t(&sl)[4], const uint32_t(&en)[4], uint32_t n) {
+        sweep(false, [&](const uint32_t(&ki)[4], const uint32_t(&sl)[4], const uint32_t(&en)[4], uint32_t n) {
             EntryRec er[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -1540,8 +1616,10 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
                     const uint32_t t = er[u].tile, w = ki[u] >> 5, bit = 1u << (ki[u] & 31);
                     atomicOr(&present[t * words + w], bit);
                     const bool ord = (er[u].len & ORDERED_FLAG) != 0u || wval[sl[u]] != qv1;
+                    bool masked = false;
                     if (ord) {
                         atomicOr(&tord[t >> 5], 1u << (t & 31));
+                        krec[words_cap] = 1u;  // some tile keeps records for everything: no key may be skipped
                     } else if (er[u].len & DENSE_FLAG) {
                         // the tile's mask covers its HOT dense keys (bitmap indexes below 32 * mask words); a cold
                         // dense key stays a record (its DENSE_FLAG sends it through the dense sweep all the same)
@@ -1549,8 +1627,10 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
                         if ((er[u].begin >> 5) < mw) {
                             atomicOr(&pdc[t * words + w], bit);
                             atomicOr(&dm[mo + (er[u].begin >> 5)], 1u << (er[u].begin & 31));
+                            masked = true;
                         }
                     }
+                    if (!masked) atomicOr(&krec[w], bit);
                 }
         });
     }
@@ -1605,7 +1685,8 @@ __global__ void __launch_bounds__(PB_THREADS) plan_build_kernel(
     if (seed && tid == 0) seed[ql] = seed_tile;
     if (masks)
         for (uint32_t i = tid; i < mask_stride; i += PB_THREADS) dmask_out[(size_t)ql * mask_stride + i] = dm[i];
-    sweep([&](const uint32_t(&ki)[4], const uint32_t(&sl)[4], const uint32_t(&en)[4], uint32_t n) {
+    sweep(masks && krec[words_cap] == 0u,
+          [&](const uint32_t(&ki)[4], const uint32_t(&sl)[4], const uint32_t(&en)[4], uint32_t n) {
         EntryRec er[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -1681,6 +1762,8 @@ struct Plan {
     uint64_t n_hits = 0;
     uint32_t stride = 0;     // plan_off entries per query: n_tiles + 1 (plan_build_kernel) or n_tiles (fallback)
     bool seeded = false;     // plan_build_kernel chose the seed tiles and flagged them
+    DevBuf<uint32_t> seed_order;  // queries grouped by seed tile (seed pass)
+    bool has_seed_order = false;
     DevBuf<uint32_t> dmask;  // [queries][mask_stride] dense-key masks (count mode)
     uint32_t mask_stride = 0;
 };
@@ -1791,12 +1874,60 @@ static bool build_plan(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
     return true;
 }
 
-// seed tiles of a fused top-x step, unless plan_build_kernel chose them already
+// Queries in the order of their seed tiles (a counting sort by one CTA: the seed pass then works tile by tile
+// like the sweep -- a warp's consecutive tasks share the tile's unit values, bitmaps and postings -- instead of
+// jumping to a random tile per task).
+static constexpr uint32_t SO_MAX_TILES = 8192;
+__global__ void __launch_bounds__(1024) seed_order_kernel(const uint32_t *__restrict__ seed, uint32_t q_count,
+                                                          uint32_t n_tiles, uint32_t *__restrict__ order) {
+    extern __shared__ uint32_t so_cnt[];  // [n_tiles]
+    __shared__ uint32_t s_warp[33];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t t = tid; t < n_tiles; t += blockDim.x) so_cnt[t] = 0;
+    __syncthreads();
+    for (uint32_t q = tid; q < q_count; q += blockDim.x) atomicAdd(&so_cnt[seed[q]], 1u);
+    __syncthreads();
+    // exclusive scan of the counters (consecutive tiles per thread)
+    const uint32_t C = (n_tiles + blockDim.x - 1) / blockDim.x;
+    uint32_t mine = 0;
+    for (uint32_t t = tid * C; t < min(n_tiles, (tid + 1) * C); ++t) mine += so_cnt[t];
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= (unsigned)d) inc += v;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t run = inc - mine;
+    for (uint32_t w = 0; w < warp; ++w) run += s_warp[w];
+    for (uint32_t t = tid * C; t < min(n_tiles, (tid + 1) * C); ++t) {
+        const uint32_t c = so_cnt[t];
+        so_cnt[t] = run;
+        run += c;
+    }
+    __syncthreads();
+    for (uint32_t q = tid; q < q_count; q += blockDim.x) order[atomicAdd(&so_cnt[seed[q]], 1u)] = q;
+}
+
+// seed tiles of a fused top-x step (unless plan_build_kernel chose them already) and the queries grouped by them
 static void choose_seed_tiles(myrio_ctx *ctx, const myrio_index *ix, Plan &pl, uint64_t qn) {
-    if (pl.seeded) return;
-    pl.seed.reserve(qn);
-    MYRIO_LAUNCH(ctx, "k4a_seed_tiles", seed_tile_kernel, (unsigned)((qn + 7) / 8), 256, 0, pl.hitcnt.p, (uint32_t)qn,
-                 (uint32_t)ix->tiles.size(), pl.off.p, pl.seed.p);
+    if (!pl.seeded) {
+        pl.seed.reserve(qn);
+        MYRIO_LAUNCH(ctx, "k4a_seed_tiles", seed_tile_kernel, (unsigned)((qn + 7) / 8), 256, 0, pl.hitcnt.p,
+                     (uint32_t)qn, (uint32_t)ix->tiles.size(), pl.off.p, pl.seed.p);
+    }
+    static const bool order_on = [] {  // MYRIO_K4_SEED_ORDER=0: seed tasks in query order (comparison runs)
+        const char *e = getenv("MYRIO_K4_SEED_ORDER");
+        return !(e && e[0] == '0');
+    }();
+    pl.has_seed_order = order_on && ix->tiles.size() <= SO_MAX_TILES && qn < 0xFFFFFFFFull;
+    if (pl.has_seed_order) {
+        pl.seed_order.reserve(qn);
+        const size_t smem = ix->tiles.size() * sizeof(uint32_t);
+        MYRIO_LAUNCH(ctx, "k4a_seed_order", seed_order_kernel, 1, 1024, smem, pl.seed.p, (uint32_t)qn,
+                     (uint32_t)ix->tiles.size(), pl.seed_order.p);
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -1919,6 +2050,11 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
     a.leaf_id_base = ix->leaf_id_base;
     a.counters = ctx->score_counters.p;
     a.ub_prune = (ctx->topx_bound_pruning < 0 ? k4_bound_pruning() : ctx->topx_bound_pruning != 0) ? 1u : 0u;
+    static const bool seed_bound = [] {  // MYRIO_K4_SEED_BOUND=0: a query without a bound finishes the whole tile
+        const char *e = getenv("MYRIO_K4_SEED_BOUND");
+        return !(e && e[0] == '0');
+    }();
+    if (a.ub_prune && seed_bound) a.ub_prune |= 2u;  // bit 1: bound of a seed tile from the x-th largest count
     return a;
 }
 
@@ -2033,6 +2169,7 @@ void score_topx_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_svecs 
                 choose_seed_tiles(ctx, ix, pl, qn);
                 ScoreArgs s1 = a;
                 s1.seed = pl.seed.p;
+                s1.seed_order = pl.has_seed_order ? pl.seed_order.p : nullptr;
                 s1.seed_mode = 1;
                 s1.n_tasks = qn;
                 launch_score<true>(ctx, ix, s1, sim, collect_stats);
@@ -2092,6 +2229,7 @@ void score_topx_seed_device(myrio_ctx *ctx, const myrio_index *ix, const myrio_s
         s1.cand_cnt = ctx->topx_cand_cnt.p;
         s1.gthr = ctx->topx_gthr.p;
         s1.seed = pl.seed.p;
+        s1.seed_order = pl.has_seed_order ? pl.seed_order.p : nullptr;
         s1.seed_mode = 1;
         s1.n_tasks = q_count;
         launch_score<true>(ctx, ix, s1, sim, false);

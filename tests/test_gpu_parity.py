@@ -585,12 +585,12 @@ def test_leaves_as_queries_self_score_and_long_hit_lists(api, ctx):
     res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 5, q_first=1000, q_count=200,
                                                full_scores=True)
     oln = oracle.normalize(oracle.count_leaves(synth.tree_to_iupac(tree), tree.base_off, 18, 32))
-    for j in range(0, 200, 7):
+    for j in range(200):  # every query: a hit list that mixes ordered and split batches is a rare event
         k, v = oln.row(1000 + j)
         s = oracle.score_all(oln, k, v)
-        assert (bits(s) == bits(res.scores[j])).all()
+        assert (bits(s) == bits(res.scores[j])).all(), j
         ts, ti = oracle.topx(s, 5)
-        assert (ti == res.top_ids[j]).all() and (bits(ts) == bits(res.top_scores[j])).all()
+        assert (ti == res.top_ids[j]).all() and (bits(ts) == bits(res.top_scores[j])).all(), j
     assert (res.top_ids[:, 0] == np.arange(1000, 1200)).all()
     # ~1266 sequential f32 additions: the self-score is 1 only up to the rounding the reference has too
     assert np.allclose(res.top_scores[:, 0], 1.0, atol=1e-4)
