@@ -486,7 +486,6 @@ myrio_index *index_build(myrio_ctx *ctx, const myrio_svecs *leaves, uint32_t lea
         ti.unit = ix->unit.p + ti.leaf_begin;
         ti.n_dense = dstart[t + 1] - dstart[t];
         ti.unit_max = *std::max_element(h_unit.begin() + ti.leaf_begin, h_unit.begin() + ti.leaf_begin + ti.n_leaves);
-        ti.unit_min = *std::min_element(h_unit.begin() + ti.leaf_begin, h_unit.begin() + ti.leaf_begin + ti.n_leaves);
     }
     {
         std::vector<uint32_t> moff(n_tiles + 1, 0);

@@ -43,7 +43,6 @@ struct TileInfo {
     const float *unit;        // [n_leaves] (slice of the index-wide array)
     uint64_t n_dense;
     float unit_max;           // largest unit value of the tile (upper bounds of the count-mode top-x)
-    float unit_min;           // smallest one (lower bound of a seed tile's x-th best score)
     // dense-key masks of the plan: a query's common dense keys in this tile are bits of mask_words words
     // (bit = the key's bitmap index) at word mask_off of the query's mask row (index-wide: mask_words_total)
     uint32_t mask_off, mask_words;

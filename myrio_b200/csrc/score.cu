@@ -500,58 +500,6 @@ __device__ __noinline__ void scc_odd_dense_key(float *acc, uint16_t *cnt, const 
         }
 }
 
-// x-th largest of the u16 counters cnt[0, n) (n >= x >= 1), by a two-pass radix select over a per-warp 256-bin
-// histogram (high byte, then low byte inside the chosen high byte).
-__device__ __forceinline__ uint32_t warp_xth_largest_u16(const uint16_t *cnt, uint32_t n, uint32_t x, uint32_t *hist,
-                                                         unsigned lane) {
-    uint32_t prefix = 0, need = x;
-    for (int pass = 0; pass < 2; ++pass) {
-        const int shift = 8 - 8 * pass;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
-        __syncwarp();
-        for (uint32_t base = 0; base < n; base += 32) {
-            const uint32_t i = base + lane;
-            uint32_t bin = 0xFFFFFFFFu;
-            if (i < n) {
-                const uint32_t c = cnt[i];
-                if (pass == 0 || (c >> 8) == prefix) bin = (c >> shift) & 255u;
-            }
-            const unsigned peers = __match_any_sync(0xffffffffu, bin);
-            if (bin != 0xFFFFFFFFu && (int)lane == __ffs(peers) - 1) hist[bin] += __popc(peers);
-            __syncwarp();
-        }
-        // lane l owns bins 255-8l .. 248-8l (descending): where does the running count reach `need`?
-        uint32_t local[8], lsum = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            local[j] = hist[255 - 8 * lane - j];
-            lsum += local[j];
-        }
-        const uint32_t incl = warp_incl_scan_u32s(lsum, lane);
-        const unsigned reach = __ballot_sync(0xffffffffu, incl >= need);
-        const int owner = __ffs(reach) - 1;
-        uint32_t bin = 0, rest = 0;
-        if ((int)lane == owner) {
-            uint32_t run = incl - lsum;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (run + local[j] >= need) {
-                    bin = 255 - 8 * lane - j;
-                    rest = need - run;
-                    break;
-                }
-                run += local[j];
-            }
-        }
-        bin = __shfl_sync(0xffffffffu, bin, owner);
-        need = __shfl_sync(0xffffffffu, rest, owner);
-        prefix = (prefix << 8) | bin;
-        __syncwarp();
-    }
-    return prefix;
-}
-
 template <int SIM, bool FUSED, bool STATS>
 __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(ScoreArgs a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -569,7 +517,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
     const uint64_t *post = nullptr;
     const uint32_t *bitmaps = nullptr;
     const float *unit = nullptr;
-    float unit_max = 0.0f, unit_min = 0.0f;
+    float unit_max = 0.0f;
     uint32_t t_mo = 0, t_mw = 0;  // the tile's words in a query's dense-key mask row
     bool acc_dirty = true;        // acc[] may hold something else than +0
     const TileInfo *ti = a.tiles;
@@ -622,7 +570,6 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             bitmaps = ti->bitmaps;
             unit = ti->unit;
             unit_max = ti->unit_max;
-            unit_min = ti->unit_min;
             t_mo = ti->mask_off;
             t_mw = a.mask_stride ? ti->mask_words : 0u;
             cached_tile = t;
@@ -924,17 +871,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         // +0, below any non-zero bound).  Only the survivors -- the query's relatives -- get their unit value
         // loaded, their dense count unsliced and their additions replayed, exactly as in the full replay below.
         if (FUSED && a.ub_prune) {
-            uint32_t thr = read_bound(a.gthr + ql, lane);
-            // A query without a bound yet (its seed tile): a valid one comes from the counters alone.  The x leaves
-            // with the largest counts each score at least n_x pmin (1 - 2^-24)^n > 0.99 n_x pmin (n_x = the x-th
-            // largest count, pmin = fl(v1 unit_min)), so the tile's x-th best score is at least that, and the bound
-            // pass below finishes the ~x leaves that can reach it instead of all of them.
-            if (thr == 0u && (a.ub_prune & 2u) && SIM == MYRIO_SIM_COSINE && !had_ordered && any_hits && nl > a.x) {
-                flush_planes();
-                const uint32_t n_x = warp_xth_largest_u16(cnt, nl, a.x, hist, lane);
-                thr = __float_as_uint(__fmul_rn(__fmul_rn((float)n_x, __fmul_rn(v1, unit_min)), 0.99f));
-                if (lane == 0 && thr) atomicMax(a.gthr + ql, thr);  // x leaves of this tile reach it: a valid bound
-            }
+            const uint32_t thr = read_bound(a.gthr + ql, lane);
             if (thr != 0u) {
                 const float thr_f = __uint_as_float(thr);
                 const float pmax = __fmul_rn(v1, unit_max);
@@ -953,8 +890,10 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                         // (counters stay below 0x8000 + T: a count is at most the query's length, and count mode
                         // is off for leaf vectors of 65 535+ keys; the general pass below needs no such assumption)
                         const uint32_t KK = (0x8000u - T) * 0x00010001u;
-                        uint32_t *slist = hist;  // [0, 255): survivor leaves, [255]: their number
-                        if (lane == 0) slist[255] = 0;
+                        // survivor leaves [0, SL_CAP) and their number [SL_CAP] live in the hit buffer (idle now)
+                        constexpr uint32_t SL_CAP = SC_HITS * sizeof(HitRec) / sizeof(uint32_t) - 1;
+                        uint32_t *slist = reinterpret_cast<uint32_t *>(hits);
+                        if (lane == 0) slist[SL_CAP] = 0;
                         __syncwarp();
                         const uint4 *cnt4 = reinterpret_cast<const uint4 *>(cnt);
                         for (uint32_t i = lane; i * 8u < nl; i += 32) {
@@ -965,14 +904,14 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                             for (int e = 0; e < 8; ++e) {
                                 const uint32_t c = (ww[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu, leaf = i * 8u + e;
                                 if (c >= T && leaf < nl) {
-                                    const uint32_t pos = atomicAdd(&slist[255], 1u);
-                                    if (pos < 255u) slist[pos] = leaf;
+                                    const uint32_t pos = atomicAdd(&slist[SL_CAP], 1u);
+                                    if (pos < SL_CAP) slist[pos] = leaf;
                                 }
                             }
                         }
                         __syncwarp();
-                        const uint32_t n_surv = slist[255];
-                        if (n_surv <= 255u) {
+                        const uint32_t n_surv = slist[SL_CAP];
+                        if (n_surv <= SL_CAP) {
                             uint32_t c_cnt = 0;
                             if (n_surv) {
                                 flush_planes();  // the survivors' counts become complete
@@ -2050,11 +1989,6 @@ static ScoreArgs base_args(myrio_ctx *ctx, const myrio_index *ix, const Plan &pl
     a.leaf_id_base = ix->leaf_id_base;
     a.counters = ctx->score_counters.p;
     a.ub_prune = (ctx->topx_bound_pruning < 0 ? k4_bound_pruning() : ctx->topx_bound_pruning != 0) ? 1u : 0u;
-    static const bool seed_bound = [] {  // MYRIO_K4_SEED_BOUND=0: a query without a bound finishes the whole tile
-        const char *e = getenv("MYRIO_K4_SEED_BOUND");
-        return !(e && e[0] == '0');
-    }();
-    if (a.ub_prune && seed_bound) a.ub_prune |= 2u;  // bit 1: bound of a seed tile from the x-th largest count
     return a;
 }
 
