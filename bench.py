@@ -704,7 +704,7 @@ def run_ours(args, rank, local_rank, world):
     k4_step_ms = k4_ms / max(args.steps, 1)
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     # the committed ncu capture of the CURRENT K4 (instructions per posting, DRAM bytes), older ones as fall-backs
-    prof = latest_profile("r02_k4v11") or latest_profile("r02_k4v9") or latest_profile("r02_k4_ncu_summary")
+    prof = latest_profile("r02_k4v12") or latest_profile("r02_k4v11") or latest_profile("r02_k4_ncu_summary")
     issue_peak = 148 * 4 * sm_mhz * 1e6  # warp instructions / s: 148 SMs x 4 schedulers x 1 issue / clk
     roofline = {
         "bound": "issue",

@@ -712,11 +712,21 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         // bit-sliced counters (a full adder is two LOP3: 20 logic instructions per eight words instead of 96 for
         // eight ripple-carry additions); the next eight words are requested before the current ones are added
         auto dense_sweep = [&](uint32_t nd) {
-            uint32_t w[8], wn[8];
+            uint32_t w[8], wn[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            const uint32_t *bm_lane = bitmaps + lane;
             auto load8 = [&](uint32_t(&x)[8], uint32_t b0) {
+                uint32_t idx[8];
+                if ((a.tile_leaves & 3u) == 0u) {  // the list is 16-byte aligned, b0 a multiple of 8
+                    const uint4 i0 = *reinterpret_cast<const uint4 *>(dlist + b0);
+                    const uint4 i1 = *reinterpret_cast<const uint4 *>(dlist + b0 + 4);
+                    idx[0] = i0.x, idx[1] = i0.y, idx[2] = i0.z, idx[3] = i0.w;
+                    idx[4] = i1.x, idx[5] = i1.y, idx[6] = i1.z, idx[7] = i1.w;
+                } else {
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    x[u] = b0 + u < nd ? __ldg(bitmaps + (size_t)dlist[b0 + u] * 32 + lane) : 0u;
+                    for (int u = 0; u < 8; ++u) idx[u] = dlist[b0 + u];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = b0 + u < nd ? __ldg(bm_lane + idx[u] * 32u) : 0u;
             };
             // full adder on 32 independent bit positions
             auto csa = [](uint32_t x, uint32_t y, uint32_t z, uint32_t &sum, uint32_t &car) {
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
             load8(w, 0);
             for (uint32_t d0 = 0; d0 < nd; d0 += 8) {
                 if (pending > (1u << SCC_PLANES) - 9u) flush_planes();
-                load8(wn, d0 + 8);
+                if (d0 + 8 < nd) load8(wn, d0 + 8);
                 if (STATS) {
 #pragma unroll
                     for (int u = 0; u < 8; ++u) st_post += __popc(w[u]);  // summed over the lanes at the end: df
@@ -870,6 +880,8 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         // running bound cannot enter its top-x: its shared keys were counted, its score is not finished (left at
         // +0, below any non-zero bound).  Only the survivors -- the query's relatives -- get their unit value
         // loaded, their dense count unsliced and their additions replayed, exactly as in the full replay below.
+        bool emit_ready = false;  // acc[] holds the final scores that matter, e_cnt of them reach the bound e_thr
+        uint32_t e_thr = 0, e_cnt = 0;
         if (FUSED && a.ub_prune) {
             const uint32_t thr = read_bound(a.gthr + ql, lane);
             if (thr != 0u) {
@@ -926,18 +938,16 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                                 c_cnt = warp_sum_u32(c_cnt);
                                 __syncwarp();
                             }
-                            tile_topx_emit(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
-                                           a.cand + slot * a.x, a.cand_cnt + slot, lane, thr, c_cnt);
-                            __syncwarp();
                             acc_dirty = n_surv != 0u;
-                            advance();
-                            continue;
+                            e_thr = thr;
+                            e_cnt = c_cnt;
+                            emit_ready = true;
                         }
                     }
                 }
                 const uint32_t magic = 0x4B000000u + pending;  // float(2^23 + n) for n < 2^23
                 uint32_t c_cnt = 0;
-                if (any_hits) {
+                if (!emit_ready && any_hits) {
 #pragma unroll 4
                     for (uint32_t r = 0; 32u * r < nl; ++r) {
                         const uint32_t leaf = 32u * r + lane;  // leaf < tile_leaves + 32: inside the padded arrays
@@ -964,15 +974,15 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
                         }
                     }
                 }
-                c_cnt = warp_sum_u32(c_cnt);
-                __syncwarp();
-                tile_topx_emit(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
-                               a.cand + slot * a.x, a.cand_cnt + slot, lane, thr, c_cnt);
-                __syncwarp();
-                advance();
-                continue;
+                if (!emit_ready) {
+                    e_cnt = warp_sum_u32(c_cnt);
+                    e_thr = thr;
+                    emit_ready = true;
+                    __syncwarp();
+                }
             }
         }
+        if (!emit_ready) {
         flush_planes();
 
         // replay: n sequential additions of p per leaf; four leaves of a lane in flight (rows r0 .. r0+3 of its
@@ -1010,13 +1020,25 @@ __global__ void __launch_bounds__(SCC_MAX_WARPS * 32) score_tiles_count_kernel(S
         }
         __syncwarp();
 
-        if (FUSED) {
-            tile_topx<SIM>(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql,
-                           a.cand + slot * a.x, a.cand_cnt + slot, lane);
+        if (FUSED) {  // all scores are finished: how many reach the bound?
+            e_thr = read_bound(a.gthr + ql, lane);
+            uint32_t c = 0;
+            for (uint32_t i = lane; i < nl; i += 32) {
+                const float sc = sim_transform<SIM>(acc[i]);
+                acc[i] = sc;
+                c += (__float_as_uint(sc) >= e_thr) ? 1u : 0u;
+            }
+            e_cnt = warp_sum_u32(c);
+            __syncwarp();
         } else {
             float *out = a.scores + (size_t)ql * a.ld + ti->leaf_begin;
             for (uint32_t i = lane; i < nl; i += 32) out[i] = sim_transform<SIM>(acc[i]);
         }
+        }
+        // one top-x tail for the three ways a task ends (integer bound pass, general bound pass, full replay)
+        if (FUSED)
+            tile_topx_emit(acc, hist, nl, a.x, a.leaf_id_base + ti->leaf_begin, a.gthr + ql, a.cand + slot * a.x,
+                           a.cand_cnt + slot, lane, e_thr, e_cnt);
         __syncwarp();
         advance();
     }
