@@ -531,6 +531,9 @@ def run_ours(args, rank, local_rank, world):
         """`steps` calls bracketed by barrier + synchronize, CUDA events on the library's stream, max over ranks.
         With a tag the end of every step is marked too (diagnostic: rank 0's per-step times in the JSON line)."""
         barrier()
+        import gc
+        gc.collect()
+        gc.disable()  # no collector pauses on any rank while the K steps are timed (re-enabled below)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
         e0.record(ext)
@@ -547,6 +550,7 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
         e1.record(ext)
         e1.synchronize()
+        gc.enable()
         ms = allmax(e0.elapsed_time(e1))
         if tag:
             ts = [e0.elapsed_time(m) for m in marks]
@@ -602,15 +606,23 @@ def run_ours(args, rank, local_rank, world):
     d2h_total = int(Q * x * 8)
     resident = api.MyrSeqs.from_packed(ctx, p_words, p_woff, p_boff, p_qual)
 
+    # result tensors of the step, allocated once (a caller's loop owns its output buffers)
+    res_s = torch.empty((Q, x), dtype=torch.float32, device=dev)
+    res_i = torch.empty((Q, x), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    sync_mode = os.environ.get("MYRIO_BENCH_STEP_SYNC", "")  # diagnosis: "device" ends a resident step with a device-wide sync
+
     def topx(qn):
         if world > 1:
-            return mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
-        return mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE)  # one rank: K4 + K5, no exchange
+            return mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch, out=(res_s, res_i))
+        return mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE, out=(res_s, res_i))  # one rank: K4 + K5
 
     def step_resident():
         counts = resident.compute_kmer_counts(k, 0.1)
         qn = counts.into_normalized_l2()
         s, i = topx(qn)
+        if sync_mode == "device":
+            torch.cuda.synchronize(dev)
         return counts, s, i
 
     def step_e2e():
@@ -916,11 +928,15 @@ def bench_strong(args, ctx, api, mdist, synth, rank, world, timed, allmax, dev):
     resident = api.MyrSeqs(ctx, reads)
     Q = reads.n
 
+    import torch
+    res = (torch.empty((Q, x), dtype=torch.float32, device=dev), torch.empty((Q, x), dtype=torch.int32, device=dev))
+    torch.cuda.synchronize(dev)
+
     def step():
         qn = resident.compute_kmer_counts(k, 0.1).into_normalized_l2()
         if world > 1:
-            return mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch)
-        return mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE)
+            return mdist.sharded_topx(ctx, ttc, qn, x, api.SIM_COSINE, max_batch=args.topx_batch, out=res)
+        return mdist.sharded_topx_allgather(ctx, ttc, qn, x, api.SIM_COSINE, out=res)
 
     step()
     ms = timed(step, args.strong_steps)

@@ -86,7 +86,8 @@ def init_library_comm(ctx, group=None) -> dict:
     return ctx.comm_info()
 
 
-def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0):
+def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0,
+                           out=None):
     """The multi-GPU step with the bound exchange -- one library call (myrio_score_topx_sharded): per batch
     of queries the seed pass on this rank's leaves, ncclAllReduce(MAX) of the per-query bounds, the sweep with
     the global bound, ONE ncclAllGather of the shard lists as 8-byte composites, the merge (K7); all on the
@@ -95,9 +96,12 @@ def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0,
     Q = queries.n_rows
     dev = torch.device("cuda", ctx.device)
     init_library_comm(ctx, group)
-    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=dev)):
-        out_s = torch.empty((Q, x), dtype=torch.float32, device=dev)
-        out_i = torch.empty((Q, x), dtype=torch.int32, device=dev)
+    if out is not None:  # caller-owned result tensors (a steady-state loop then never touches the allocator)
+        out_s, out_i = out
+    else:
+        with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=dev)):
+            out_s = torch.empty((Q, x), dtype=torch.float32, device=dev)
+            out_i = torch.empty((Q, x), dtype=torch.int32, device=dev)
     _lib.check(ctx._L.myrio_score_topx_sharded(ctx.h, ttcompute.h, queries.h, 0, Q, x, similarity,
                                                C.c_void_p(out_s.data_ptr()), C.c_void_p(out_i.data_ptr()),
                                                max_batch))
@@ -105,25 +109,29 @@ def sharded_topx_two_phase(ctx, ttcompute, queries, x: int, similarity: int = 0,
     return out_s, out_i
 
 
-def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0):
+def sharded_topx(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, max_batch: int = 0, out=None):
     """The multi-GPU scoring step: shard-local top-x on this rank's leaves, exchange, merge (K7).
     Returns device tensors (scores [Q,x] f32, ids [Q,x] i32 holding u32 payload ids), identical on every
     rank and identical to the single-GPU result: two-phase with the bound exchange over NCCL inside the
     library (`sharded_topx_two_phase`); `sharded_topx_allgather` is the plain exchange of exact shard lists
     through torch.distributed (cross-check, and the gloo path of the CPU tests)."""
     if dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
-        return sharded_topx_two_phase(ctx, ttcompute, queries, x, similarity, group, max_batch)
-    return sharded_topx_allgather(ctx, ttcompute, queries, x, similarity, group)
+        return sharded_topx_two_phase(ctx, ttcompute, queries, x, similarity, group, max_batch, out)
+    return sharded_topx_allgather(ctx, ttcompute, queries, x, similarity, group, out)
 
 
-def sharded_topx_allgather(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None):
+def sharded_topx_allgather(ctx, ttcompute, queries, x: int, similarity: int = 0, group=None, out=None):
     """Exact shard-local top-x (K4+K5), all-gather of Q x x (score, id) pairs, merge (K7)."""
     from . import _lib
     Q = queries.n_rows
     dev = torch.device("cuda", ctx.device)
-    ls = torch.empty((Q, x), dtype=torch.float32, device=dev)
-    li = torch.empty((Q, x), dtype=torch.int32, device=dev)
-    torch.cuda.current_stream(dev).synchronize()
+    single = not dist.is_initialized() or dist.get_world_size(group) == 1
+    if out is not None and single:
+        ls, li = out
+    else:
+        ls = torch.empty((Q, x), dtype=torch.float32, device=dev)
+        li = torch.empty((Q, x), dtype=torch.int32, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
     _lib.check(ctx._L.myrio_score_topx_async(ctx.h, ttcompute.h, queries.h, 0, Q, x, similarity,
                                              C.c_void_p(ls.data_ptr()), C.c_void_p(li.data_ptr())))
     ctx.sync()
