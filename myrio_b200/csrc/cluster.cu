@@ -326,11 +326,11 @@ __global__ void __launch_bounds__(128) silsum_rows_kernel(const float *__restric
     sums[(size_t)r * 2 + (swp ? 0 : 1)] = sb;
 }
 
-// argmax over the columns of a transposed tile; max_by_key keeps the LAST maximum
+// argmax over the columns of a transposed tile; max_by_key keeps the LAST maximum.  One 8-byte record per
+// row (best similarity bits, best column): a row-sharded run exchanges both with ONE all-gather per iteration.
 __global__ void __launch_bounds__(128) argmax_rows_kernel(const float *__restrict__ tile, uint64_t ld,
                                                           uint32_t n_rows, uint32_t n_cols,
-                                                          float *__restrict__ best_out,
-                                                          uint32_t *__restrict__ idx_out) {
+                                                          uint2 *__restrict__ best_out) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     float best = 0.0f;
@@ -342,8 +342,7 @@ __global__ void __launch_bounds__(128) argmax_rows_kernel(const float *__restric
             best_idx = c;
         }
     }
-    best_out[r] = best;
-    idx_out[r] = best_idx;
+    best_out[r] = make_uint2(__float_as_uint(best), best_idx);
 }
 
 static uint64_t pt_slice_bytes() {  // MYRIO_K6_SLICE_MB overrides (tuning)
@@ -1138,8 +1137,9 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
 
     mark("centroids filled");
     // Step 3 (:132-169)
-    DevBuf<float> d_best(std::max<uint32_t>(kcnt, 1));
-    DevBuf<uint32_t> d_target_loc(std::max<uint32_t>(kcnt, 1)), d_target(nk), d_sums((size_t)nc * dim), d_members(nc);
+    DevBuf<uint2> d_best(std::max<uint32_t>(kcnt, 1));  // (best similarity bits, target) of this rank's rows
+    DevBuf<uint32_t> d_target(nk), d_sums((size_t)nc * dim), d_members(nc);
+    std::vector<uint2> best_target((size_t)W * kchunk);
     std::vector<float> best((size_t)W * kchunk);
     std::vector<uint32_t> target((size_t)W * kchunk);
     DevBuf<float> d_tile(std::max<size_t>((size_t)nc * kcnt, 1));  // reads x centroids similarities, [centroid][read]
@@ -1151,10 +1151,13 @@ void cluster_reads(myrio_ctx *ctx, const myrio_seqs *reads, const myrio_cluster_
         if (kcnt) {
             centroid_tile(true, "k6_pair_argmax");
             MYRIO_LAUNCH(ctx, "k6_argmax_rows", argmax_rows_kernel, (kcnt + 127) / 128, 128, 0, d_tile.p,
-                         (uint64_t)kcnt, kcnt, nc, d_best.p, d_target_loc.p);
+                         (uint64_t)kcnt, kcnt, nc, d_best.p);
         }
-        gather_rows(d_best.p, sizeof(float), klo, kcnt, kchunk, best.data());
-        gather_rows(d_target_loc.p, sizeof(uint32_t), klo, kcnt, kchunk, target.data());
+        gather_rows(d_best.p, sizeof(uint2), klo, kcnt, kchunk, best_target.data());
+        for (uint32_t i = 0; i < nk; ++i) {
+            std::memcpy(&best[i], &best_target[i].x, sizeof(float));
+            target[i] = best_target[i].y;
+        }
         h2d(ctx, d_target.p, target.data(), nk);
     };
     float previous_mean_wcsss = 1E-6f;

@@ -1201,24 +1201,40 @@ __global__ void __launch_bounds__(256) topx_merge_composites_kernel(const uint64
                                                                     uint32_t n_parts, uint64_t q_count, uint32_t x,
                                                                     float *__restrict__ out_s,
                                                                     uint32_t *__restrict__ out_i) {
-    extern __shared__ uint64_t mk[];
+    // Every part is sorted (best first, 0 = padding) and the composites are distinct (payload ids), so the place
+    // of an element in the merged list is its place in its own part + the number of greater elements in every
+    // other part (a binary search each): no sort, one barrier.
+    extern __shared__ uint64_t mk[];  // [n_parts][x]
     const uint64_t q = blockIdx.x;
     const uint32_t total = n_parts * x;
-    uint32_t S = 2;
-    while (S < total) S <<= 1;
-    for (uint32_t j = threadIdx.x; j < S; j += blockDim.x) {
-        uint64_t c = 0;
-        if (j < total) {
-            const uint32_t p = j / x, e = j % x;
-            c = in_c[((size_t)p * q_count + q) * x + e];
-        }
-        mk[j] = c;
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
+        const uint32_t p = j / x, e = j % x;
+        mk[j] = in_c[((size_t)p * q_count + q) * x + e];
     }
-    bitonic_desc(mk, S);
-    for (uint32_t j = threadIdx.x; j < x; j += blockDim.x) {
+    for (uint32_t j = threadIdx.x; j < x; j += blockDim.x) {  // places nobody reaches stay padding
+        out_s[q * x + j] = 0.0f;
+        out_i[q * x + j] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < total; j += blockDim.x) {
         const uint64_t c = mk[j];
-        out_s[q * x + j] = __uint_as_float((uint32_t)(c >> 32));
-        out_i[q * x + j] = 0xFFFFFFFFu - (uint32_t)c;
+        if (c == 0ull) continue;
+        const uint32_t p = j / x;
+        uint32_t rank = j - p * x;
+        for (uint32_t o = 0; o < n_parts && rank < x; ++o) {
+            if (o == p) continue;
+            const uint64_t *lst = mk + (size_t)o * x;
+            uint32_t lo = 0, hi = x;  // first position whose element is not greater than c
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (lst[mid] > c) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < x) {
+            out_s[q * x + rank] = __uint_as_float((uint32_t)(c >> 32));
+            out_i[q * x + rank] = 0xFFFFFFFFu - (uint32_t)c;
+        }
     }
 }
 
