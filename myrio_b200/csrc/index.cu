@@ -13,10 +13,13 @@
 //      inside a tile, ordered by (key, leaf);
 //   3. run heads -> unique (tile, key) entries + absolute posting offsets;
 //   4. unit[leaf] = smallest value of the leaf; a key that occurs in >= 1/4 of a tile's
-//      leaves, always with value == unit[leaf], is DENSE: one 128-byte bitmap;
+//      leaves (HOT) -- or, on an index that will be scored in count mode, in >= 32 leaves (cold) --
+//      always with value == unit[leaf], is DENSE: one 128-byte bitmap; hot keys are numbered first
+//      inside a tile (their bitmap indexes are the bits of the plan's dense-key masks);
 //   5. the (tile, key) entries re-sorted by key + ONE open-addressing dictionary
-//      key -> [EntryRec{tile, begin, len | DENSE_FLAG}] (tiles ascending): a query key is looked
-//      up once per query, not once per tile.
+//      key -> [EntryRec{tile, begin, len | DENSE_FLAG | ORDERED_FLAG}] (tiles ascending): a query key is
+//      looked up once per query, not once per tile;
+//   6. postings whose value is not unit[leaf] get POSTING_ODD, the sparse entries that hold one ORDERED_FLAG.
 #include <algorithm>
 
 #include "index.cuh"

@@ -10,6 +10,13 @@
 // pair and walks the query's keys in ascending order; the lanes fan out over
 // the posting list of ONE key at a time (a leaf occurs at most once per list),
 // so no two lanes ever update the same accumulator and no atomics are needed.
+// That is score_tiles_kernel (round 1).  The default since round 2 is COUNT MODE
+// (score_tiles_count_kernel): nearly all terms of a (query, leaf) pair are the same
+// f32 product, equal addends commute, so they are counted (bitmaps into bit-sliced
+// counters, sparse postings into u16 counters) and added n times at the end -- only
+// for the leaves whose upper bound can still reach the query's top-x -- while the
+// rare odd terms keep their place in key order.  File map: tile_topx (K5 fused),
+// score_tiles_kernel, count mode, K5 / K7 merges, the plan kernels (K4a), host side.
 #include <algorithm>
 
 #include "index.cuh"

@@ -264,6 +264,23 @@ def test_score_all_and_topx_bit_exact(api, ctx, tile_leaves):
     assert st["key_hits"] > 0 and st["postings_touched"] >= st["key_hits"]
 
 
+def test_topx_bound_pruning_switch_gives_the_same_topx(api, ctx):
+    # myrio_ctx_set_topx_bound_pruning: finishing only the scores that can reach a query's running bound, or
+    # every score, is the same top-x bit for bit (multi-tile tree, so the sweep runs with a bound)
+    tree, reads, ttc, q, oln, oqn = build_case(api, ctx, 3000, 60, 33, tile_leaves=256)
+    a = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 25)
+    ctx.set_topx_bound_pruning(False)
+    try:
+        b = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_COSINE, 25)
+    finally:
+        ctx.set_topx_bound_pruning(True)
+    assert (a.top_ids == b.top_ids).all() and (bits(a.top_scores) == bits(b.top_scores)).all()
+    for i in range(0, reads.n, 5):
+        k, v = oqn.row(i)
+        ts, ti = oracle.topx(oracle.score_all(oln, k, v), 25)
+        assert (ti == a.top_ids[i]).all() and (bits(ts) == bits(a.top_scores[i])).all()
+
+
 def test_score_jacard_tanimoto_and_k12(api, ctx):
     tree, reads, ttc, q, oln, oqn = build_case(api, ctx, 400, 12, 31, k=12)
     res = api.TaxTreeResults.from_compute_tree(q, ttc, api.SIM_JACARD_TANIMOTO, 7, full_scores=True)
