@@ -537,7 +537,7 @@ def run_ours(args, rank, local_rank, world):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
         e0.record(ext)
-        poll_at = {steps // 4, steps // 2, (3 * steps) // 4} if tag else set()  # inside the timed region
+        poll_at = {steps // 3, (2 * steps) // 3} if tag else set()  # inside the timed region
         for it in range(steps):
             if it in poll_at and sampler is not None:
                 sampler.poll()
