@@ -129,6 +129,7 @@ class ClockSampler:
         self.gpu, self.rows, self.proc = gpu_index, [], None
         self.sm, self.reasons, self.mx, self.stop_flag, self.thread, self.source = [], set(), None, False, None, None
         self.period = float(os.environ.get("MYRIO_BENCH_NVML_PERIOD", "0.5"))
+        self.device_mhz = []  # on-device measurements inside the timed regions (myrio_bench_clock_probe)
 
     def _nvml_loop(self, nv, h):
         names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
@@ -147,10 +148,10 @@ class ClockSampler:
             time.sleep(self.period)
 
     def start_inline(self):
-        """In-line mode (default): no thread; `poll()` is called by the timing loop itself at step boundaries
-        INSIDE the timed region (a few times per region).  A concurrent NVML query from another thread or
-        process stalls this process's CUDA calls for 20-900 ms every now and then (profiles/r02_smi_hiccups.md);
-        a query made between two steps costs only its own duration, which is recorded (`poll_ms`)."""
+        """In-line mode (default): no thread; `poll()` (NVML clock + throttle reasons) is called by the timing loop
+        at the two ends of every timed region, the SM clock inside the region comes from on-device probes.  A
+        concurrent NVML query from another thread or process stalls this process's CUDA calls for 20-900 ms every
+        now and then (profiles/r02_smi_hiccups.md); the duration of every poll is recorded (`poll_ms`)."""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -158,7 +159,9 @@ class ClockSampler:
             idx = int(vis.split(",")[self.gpu]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else self.gpu
             self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(idx)
             self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM))
-            self.source = "NVML in-process (pynvml), polled by the timing loop at step boundaries inside the timed regions"
+            self.source = ("sm_mhz: on-device probes (SM cycles per %globaltimer ns over ~0.5 ms) enqueued between steps INSIDE "
+                           "the timed regions; sm_max_mhz / reasons: NVML in-process (pynvml) before the first timed region "
+                           "and right after the last event of each")
             self.inline, self.poll_ms = True, []
         except Exception:
             self.inline = False
@@ -212,11 +215,15 @@ class ClockSampler:
 
     def stop(self):
         if getattr(self, "inline", False):
-            if not self.sm:
+            if not self.sm and not self.device_mhz:
                 return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0, "source": self.source}
-            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
-                    "samples": len(self.sm), "source": self.source,
-                    "poll_ms_max": round(max(self.poll_ms), 3), "poll_ms_total": round(sum(self.poll_ms), 3)}
+            under_load = self.device_mhz or self.sm
+            return {"sm_mhz": float(np.median(under_load)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(under_load), "source": self.source,
+                    "sm_mhz_device_probes": [round(m, 1) for m in self.device_mhz],
+                    "sm_mhz_nvml_at_region_boundaries": self.sm,
+                    "poll_ms_max": round(max(self.poll_ms), 3) if self.poll_ms else None,
+                    "poll_ms_total": round(sum(self.poll_ms), 3) if self.poll_ms else None}
         if self.thread is not None:
             self.stop_flag = True
             self.thread.join(timeout=2)
@@ -536,11 +543,19 @@ def run_ours(args, rank, local_rank, world):
         gc.disable()  # no collector pauses on any rank while the K steps are timed (re-enabled below)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = []
+        # Clocks.  INSIDE the timed region the SM clock is measured on the device (myrio_bench_clock_probe: SM
+        # cycles against %globaltimer over ~0.5 ms, enqueued on the library's stream between two steps) -- no
+        # driver call, so nothing is perturbed.  NVML (clock + throttle reasons) is polled once before the first
+        # region (followed by one more warm-up step) and immediately after the last event of every region: a
+        # query cost 2-100 ms on these boxes, slowed the step after it, and stalled other ranks for 100-900 ms
+        # when it ran inside a region (profiles/r02_smi_hiccups.md).
+        probe_at = sorted({steps // 4, steps // 2, (3 * steps) // 4, steps - 1}) if (tag and sampler is not None) else []
         e0.record(ext)
-        poll_at = {steps // 3, (2 * steps) // 3} if tag else set()  # inside the timed region
+        n_probe = 0
         for it in range(steps):
-            if it in poll_at and sampler is not None:
-                sampler.poll()
+            if it in probe_at:
+                ctx.clock_probe(n_probe)
+                n_probe += 1
             fn()
             if tag:
                 m = torch.cuda.Event(enable_timing=True)
@@ -550,6 +565,9 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
         e1.record(ext)
         e1.synchronize()
+        if tag and sampler is not None:
+            sampler.poll()
+            sampler.device_mhz.extend(m for m in ctx.clock_read(n_probe) if m > 0)
         gc.enable()
         ms = allmax(e0.elapsed_time(e1))
         if tag:
@@ -647,6 +665,8 @@ def run_ours(args, rank, local_rank, world):
             sampler.start()
         else:
             sampler.start_inline()
+            sampler.poll()
+    step_resident()  # one more warm-up step after the clock query (every rank: the step holds collectives)
     ctx.prof_reset()
     ctx.prof_enable(True)
     launches0 = ctx.launch_count

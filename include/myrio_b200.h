@@ -108,6 +108,11 @@ int32_t myrio_prof_query(myrio_ctx *ctx, const char *prefix, double *ms_total, u
 /* measured aggregate shared-memory read bandwidth (GB/s; conflict-free 16-byte loads, one 1024-thread CTA
  * per SM) -- the denominator of the roofline fraction of the clustering tile kernels (bench.py) */
 int32_t myrio_bench_smem_bandwidth(myrio_ctx *ctx, double *gbps, double *ms);
+/* SM clock under load without a driver call: myrio_bench_clock_probe enqueues a ~0.5 ms one-warp kernel on the
+ * context's stream that counts SM cycles (%clock64) against %globaltimer into `slot` (< 64);
+ * myrio_bench_clock_read synchronises and returns the first n slots in MHz (0 = never written). */
+int32_t myrio_bench_clock_probe(myrio_ctx *ctx, uint32_t slot);
+int32_t myrio_bench_clock_read(myrio_ctx *ctx, uint32_t n, double *mhz);
 
 /* ---- sequences ---------------------------------------------------------- */
 

@@ -20,7 +20,7 @@ VAL_F32, VAL_U16 = 0, 1
 # every symbol include/myrio_b200.h declares (tests/test_capi_symbols.py checks the header against this)
 SYMBOLS = [
     "myrio_last_error", "myrio_version", "myrio_ctx_create", "myrio_ctx_destroy", "myrio_ctx_sync",
-    "myrio_ctx_launch_count", "myrio_ctx_set_kmer_bit_order", "myrio_ctx_set_topx_bound_pruning", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query", "myrio_bench_smem_bandwidth",
+    "myrio_ctx_launch_count", "myrio_ctx_set_kmer_bit_order", "myrio_ctx_set_topx_bound_pruning", "myrio_ctx_stream", "myrio_prof_enable", "myrio_prof_reset", "myrio_prof_query", "myrio_bench_smem_bandwidth", "myrio_bench_clock_probe", "myrio_bench_clock_read",
     "myrio_reads_upload", "myrio_reads_from_fastq", "myrio_leaves_upload", "myrio_leaves_from_fasta", "myrio_seqs_count", "myrio_seqs_free", "myrio_count_reads",
     "myrio_count_leaves", "myrio_svecs_info", "myrio_svecs_download", "myrio_svecs_upload",
     "myrio_svecs_normalize", "myrio_svecs_free", "myrio_index_build", "myrio_index_info",
@@ -108,6 +108,8 @@ def load() -> C.CDLL:
     L.myrio_prof_reset.argtypes = [vp]
     L.myrio_prof_query.argtypes = [vp, C.c_char_p, P(C.c_double), P(u64)]
     L.myrio_bench_smem_bandwidth.argtypes = [vp, P(C.c_double), P(C.c_double)]
+    L.myrio_bench_clock_probe.argtypes = [vp, u32]
+    L.myrio_bench_clock_read.argtypes = [vp, u32, P(C.c_double)]
     L.myrio_reads_upload.argtypes = [vp, vp, vp, vp, vp, u64, P(vp)]
     L.myrio_reads_from_fastq.argtypes = [vp, vp, vp, vp, u64, u64, C.c_float, C.c_uint8, vp, P(vp)]
     L.myrio_leaves_upload.argtypes = [vp, vp, vp, vp, u64, P(vp)]

@@ -97,6 +97,16 @@ class Context:
         _lib.check(self._L.myrio_comm_info(self.h, C.byref(r), C.byref(w), C.byref(v)))
         return {"rank": int(r.value), "nranks": int(w.value), "nccl_version": int(v.value)}
 
+    def clock_probe(self, slot: int):
+        """Enqueue an on-device SM clock measurement (cycles per ns over ~0.5 ms) into `slot` on the ctx stream."""
+        _lib.check(self._L.myrio_bench_clock_probe(self.h, int(slot)))
+
+    def clock_read(self, n: int):
+        """The first n clock-probe slots in MHz (synchronises the stream)."""
+        out = (C.c_double * max(n, 1))()
+        _lib.check(self._L.myrio_bench_clock_read(self.h, int(n), out))
+        return [float(out[i]) for i in range(n)]
+
     def bench_smem_bandwidth(self):
         """Measured shared-memory read bandwidth of this GPU (the K6 roofline denominator)."""
         g, ms = C.c_double(0), C.c_double(0)

@@ -78,6 +78,7 @@ void myrio_ctx_destroy(myrio_ctx *ctx) {
     ctx->xchg_bound.release();
     ctx->xchg_top.release();
     ctx->xchg_all.release();
+    ctx->clock_probes.release();
     comm_destroy(ctx);
     if (ctx->plan) plan_scratch_free(ctx->plan);
     ctx->plan = nullptr;
@@ -152,6 +153,22 @@ int32_t myrio_bench_smem_bandwidth(myrio_ctx *ctx, double *gbps, double *ms) {
         if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
         ScopedCtx sc(ctx);
         bench_smem_bandwidth(ctx, gbps, ms);
+    });
+}
+
+int32_t myrio_bench_clock_probe(myrio_ctx *ctx, uint32_t slot) {
+    return guarded([&] {
+        if (!ctx) fail(MYRIO_ERR_BAD_ARG, "NULL ctx");
+        ScopedCtx sc(ctx);
+        bench_clock_probe(ctx, slot);
+    });
+}
+
+int32_t myrio_bench_clock_read(myrio_ctx *ctx, uint32_t n, double *mhz) {
+    return guarded([&] {
+        if (!ctx || (n && !mhz)) fail(MYRIO_ERR_BAD_ARG, "NULL argument");
+        ScopedCtx sc(ctx);
+        bench_clock_read(ctx, n, mhz);
     });
 }
 

@@ -151,6 +151,7 @@ struct myrio_ctx {
     // exchange buffers of myrio_score_topx_sharded (grow-only: a steady-state step never goes back to the allocator)
     myrio::DevBuf<uint32_t> xchg_bound;
     myrio::DevBuf<uint64_t> xchg_top, xchg_all;
+    myrio::DevBuf<unsigned long long> clock_probes;  // myrio_bench_clock_probe: (cycles, ns) per slot
     uint64_t last_stats[3] = {0, 0, 0};
     uint64_t cluster_stats[2] = {0, 0};  // pair similarities, multiply-add terms of the last K6 call
     // pinned staging for small D2H reads

@@ -21,6 +21,8 @@ myrio_seqs *leaves_from_fasta(myrio_ctx *ctx, const uint8_t *seq_ascii, const ui
 
 // microbench.cu
 void bench_smem_bandwidth(myrio_ctx *ctx, double *gbps, double *ms);
+void bench_clock_probe(myrio_ctx *ctx, uint32_t slot);
+void bench_clock_read(myrio_ctx *ctx, uint32_t n, double *mhz);
 
 // svecs.cu
 myrio_svecs *svecs_normalize(myrio_ctx *ctx, const myrio_svecs *in);

@@ -58,4 +58,39 @@ void bench_smem_bandwidth(myrio_ctx *ctx, double *gbps, double *ms_out) {
     if (ms_out) *ms_out = best_ms;
 }
 
+// ---- SM clock under load, measured on the device: cycles of %clock64 per nanosecond of %globaltimer over a
+// ~0.5 ms spin of one warp, enqueued on the context's stream between two steps of a timed region.  No driver or
+// NVML call is involved (an NVML query inside a timed region costs 2-36 ms on these boxes and can stall the CUDA
+// calls of other ranks: profiles/r02_smi_hiccups.md).
+__global__ void clock_probe_kernel(unsigned long long *__restrict__ out) {
+    if (threadIdx.x != 0) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    long long c1 = c0;
+    while (c1 - c0 < 1000000) c1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    out[0] = (unsigned long long)(c1 - c0);
+    out[1] = t1 - t0;
+}
+
+static constexpr uint32_t CLOCK_PROBE_SLOTS = 64;
+
+void bench_clock_probe(myrio_ctx *ctx, uint32_t slot) {
+    if (slot >= CLOCK_PROBE_SLOTS) fail(MYRIO_ERR_BAD_ARG, "clock probe slot %u out of range (%u)", slot, CLOCK_PROBE_SLOTS);
+    if (ctx->clock_probes.n == 0) {
+        ctx->clock_probes.alloc(2 * CLOCK_PROBE_SLOTS);
+        MYRIO_CK(cudaMemsetAsync(ctx->clock_probes.p, 0, 2 * CLOCK_PROBE_SLOTS * sizeof(unsigned long long), ctx->stream));
+    }
+    MYRIO_LAUNCH(ctx, "mb_clock_probe", clock_probe_kernel, 1, 32, 0, ctx->clock_probes.p + 2 * slot);
+}
+
+void bench_clock_read(myrio_ctx *ctx, uint32_t n, double *mhz) {
+    if (n > CLOCK_PROBE_SLOTS) fail(MYRIO_ERR_BAD_ARG, "at most %u clock probes", CLOCK_PROBE_SLOTS);
+    std::vector<unsigned long long> h(2 * (size_t)n, 0ull);
+    if (ctx->clock_probes.n && n) d2h(ctx, h.data(), ctx->clock_probes.p, 2 * (size_t)n);
+    sync(ctx);
+    for (uint32_t i = 0; i < n; ++i) mhz[i] = h[2 * i + 1] ? (double)h[2 * i] * 1e3 / (double)h[2 * i + 1] : 0.0;
+}
+
 }  // namespace myrio

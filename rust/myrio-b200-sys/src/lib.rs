@@ -85,6 +85,8 @@ unsafe extern "C" {
     pub fn myrio_prof_query(ctx: *mut myrio_ctx, prefix: *const c_char, ms_total: *mut f64, launches: *mut u64) -> i32;
 
     pub fn myrio_bench_smem_bandwidth(ctx: *mut myrio_ctx, gbps: *mut f64, ms: *mut f64) -> i32;
+    pub fn myrio_bench_clock_probe(ctx: *mut myrio_ctx, slot: u32) -> i32;
+    pub fn myrio_bench_clock_read(ctx: *mut myrio_ctx, n: u32, mhz: *mut f64) -> i32;
 
     pub fn myrio_reads_upload(ctx: *mut myrio_ctx, words: *const u64, word_off: *const u64, base_off: *const u64,
                               qual: *const u8, n_reads: u64, out: *mut *mut myrio_seqs) -> i32;
