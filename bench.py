@@ -549,7 +549,9 @@ def run_ours(args, rank, local_rank, world):
         # region (followed by one more warm-up step) and immediately after the last event of every region: a
         # query cost 2-100 ms on these boxes, slowed the step after it, and stalled other ranks for 100-900 ms
         # when it ran inside a region (profiles/r02_smi_hiccups.md).
-        probe_at = sorted({steps // 4, steps // 2, (3 * steps) // 4, steps - 1}) if (tag and sampler is not None) else []
+        probe_at = []
+        if tag and sampler is not None:  # N > 1: one probe, before the last step (rank 0 must not drift from its peers)
+            probe_at = sorted({steps // 4, steps // 2, (3 * steps) // 4, steps - 1}) if world == 1 else [steps - 1]
         e0.record(ext)
         n_probe = 0
         for it in range(steps):
