@@ -82,6 +82,10 @@ def config_dict(args, world):
                     f"{args.reads} reads, k={args.k}, top-{args.x}, cosine",
         "leaves_per_gpu": args.leaves, "leaves_total": args.leaves * world, "reads": args.reads,
         "k": args.k, "x": args.x, "read_cutoff_t1": 0.1, "nb_resamples": 32,
+        "topx": f"fused top-{args.x} (the cut() of tax/results.rs:310-329): every (query, leaf) pair's shared k-mers are "
+                "counted and its score bounded from above; a score is finished to its exact f32 value only if the bound "
+                "reaches the query's running x-th best -- the returned top-x is bit-identical to a full scoring; "
+                "`all_scores_finished` is the same step with every score finished",
         "parallelism": f"leaf-shard x{world} (contiguous payload-id blocks), queries replicated; seed pass, "
                        f"ncclAllReduce(MAX) of the per-query bounds, sweep, ncclAllGather of 8-byte composites, merge "
                        f"-- all inside myrio_score_topx_sharded" if world > 1 else "single GPU",
