@@ -761,8 +761,9 @@ def run_ours(args, rank, local_rank, world):
         dram = float(sum(l.get("dram_bytes", 0.0) for l in pl))
         # the round-1 capture predates the field: its workload touched 2.4347e11 postings per step (BENCH_r01)
         post_prof = float(pj.get("postings_touched_per_step") or (2.4347e11 if pname.startswith("r01_k4_v14") else 0.0))
-        # warp instructions of THIS run = instructions per posting of the committed capture (same code, same
-        # workload) x the postings counted in this run; / measured kernel time / issue peak
+        # warp instructions of THIS run = instructions per posting of the committed capture (same workload; the
+        # capture's `state` names the commit it was taken at) x the postings counted in this run; / measured
+        # kernel time / issue peak
         if wi > 0:
             wi_run = wi * (t_q / post_prof) if post_prof > 0 else wi
             roofline.update({
